@@ -1,0 +1,151 @@
+/* srt.h — C ABI of libsrt.so: the B200-native per-sample radiance loop of scheme-raytrace.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; its de-facto
+ * operator interface is the closure-vector protocol evaluated by trace-all / color
+ * (main.scm:100-121, 471-491).  The host (Scheme scene scripts, or the Python mirror in
+ * scheme_raytrace_b200/host) keeps the reference's constructor API and flattens the scene into
+ * the POD tables below; everything behind these entry points is hand-written sm_100a CUDA.
+ *
+ * Conventions: every function returns 0 on success and a negative SrtError otherwise; nothing
+ * throws or aborts across the ABI; srt_last_error() gives a thread-local message.  There is NO
+ * CPU fallback: without an sm_100 device srt_init() fails.  The caller owns all input and output
+ * arrays (inputs are copied during set_ / commit); the library owns device memory behind the
+ * opaque handle.  A handle is not thread-safe.  Calls are synchronous on return unless the name
+ * ends in _async.
+ */
+#ifndef SRT_H
+#define SRT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SRT_OK = 0, SRT_ERR_NO_DEVICE = -1, SRT_ERR_CUDA = -2, SRT_ERR_ARG = -3, SRT_ERR_NOT_COMMITTED = -4,
+  SRT_ERR_BVH_DEPTH = -5, SRT_ERR_IO = -6
+} SrtError;
+
+/* primitive kinds — replace the hit closures of geometry.scm / bezier.scm */
+enum {
+  SRT_PRIM_SPHERE = 0,        /* geometry.scm:146 make-sphere         p = cx cy cz r                       */
+  SRT_PRIM_MOVING_SPHERE = 1, /* geometry.scm:177 make-moving-sphere  p = c0.xyz r c1.xyz time0 time1      */
+  SRT_PRIM_XY_RECT = 2,       /* geometry.scm:376 make-xy-rect        p = x0 x1 y0 y1 k                    */
+  SRT_PRIM_XZ_RECT = 3,       /* geometry.scm:395 make-xz-rect        p = x0 x1 z0 z1 k                    */
+  SRT_PRIM_YZ_RECT = 4,       /* geometry.scm:414 make-yz-rect        p = y0 y1 z0 z1 k                    */
+  SRT_PRIM_BEZIER = 5         /* bezier.scm:61   make-bezier          p = a.xyz b.xyz c.xyz d.xyz width    */
+};
+#define SRT_PRIM_FLAG_FLIP 1  /* geometry.scm:433 flip-normals (parity of the flips above the leaf)        */
+
+/* One flattened leaf primitive.  Position in the array = primitive id = position in the
+ * reference's flattened top-level object list (box faces in make-box order, geometry.scm:446-457);
+ * the id drives the exact-tie rule. */
+typedef struct {
+  int32_t type;      /* SRT_PRIM_*            */
+  int32_t flags;     /* SRT_PRIM_FLAG_*       */
+  int32_t material;  /* index into materials  */
+  int32_t xform;     /* index into xforms, -1 = none */
+  float p[16];
+} SrtPrim;
+
+/* Rigid instance transform = the composition of a translate / rotate-y chain
+ * (geometry.scm:465 translate, :483 rotate-y):  world = Ry * object + offset with
+ * Ry*(x,y,z) = (cos*x + sin*z, y, -sin*x + cos*z)  (geometry.scm:526-530). */
+typedef struct { float sin_t, cos_t, off[3]; } SrtXform;
+
+enum { SRT_MAT_LAMBERTIAN = 0, SRT_MAT_METAL = 1, SRT_MAT_DIELECTRIC = 2, SRT_MAT_DIFFUSE_LIGHT = 3, SRT_MAT_ISOTROPIC = 4 };
+/* material.scm:24 make-lambertian, :45 make-metal (param = fuzz), :76 make-dielectric
+ * (param = ref-idx), :103 make-diffuse-light; isotropic is the book's (absent upstream). */
+typedef struct { int32_t kind; int32_t tex; float param; float pad; } SrtMaterial;
+
+enum { SRT_TEX_CONSTANT = 0, SRT_TEX_CHECKER = 1, SRT_TEX_NOISE = 2, SRT_TEX_MARBLE = 3 };
+/* texture.scm:12 constant-texture (rgb), :16 checker-texture (even, odd = texture indices),
+ * :25 noise-texture (scale), :30 marble-texture (scale). */
+typedef struct { int32_t kind; int32_t even, odd; float scale; float rgb[3]; float pad; } SrtTexture;
+
+/* the 10 slots of camera.scm:70-78 */
+typedef struct { float llc[3], horiz[3], vert[3], origin[3], w[3], u[3], v[3]; float lens_radius, time0, time1; } SrtCamera;
+
+enum { SRT_SKY_GRADIENT = 0 /* main.scm:91 sky-color */, SRT_SKY_BLACK = 1 /* main.scm:97 black */ };
+
+/* quirk bits.  SRT_QUIRKS_REFERENCE reproduces upstream HEAD. */
+#define SRT_Q1_COSINE_X2 1          /* util.scm:42-43     */
+#define SRT_Q4_PERLIN_ALIAS 2       /* perlin.scm:76      */
+#define SRT_Q6_SCATTER_TIME0 4      /* ray.scm:8-9        */
+#define SRT_Q10_DIELECTRIC_UNNORM 8 /* material.scm:59-67 */
+#define SRT_QUIRKS_REFERENCE 15
+
+typedef struct {
+  int32_t width, height;       /* main.scm:126-127 *size-x* *size-y*                     */
+  int32_t spp_begin, spp_end;  /* sample range [begin,end) rendered by this call         */
+  int32_t max_depth;           /* main.scm:26 +max-depth+                                */
+  int32_t sky;                 /* SRT_SKY_*                                              */
+  uint32_t seed;               /* Philox key word 1                                      */
+  int32_t quirks;              /* SRT_Q* bits                                            */
+  float t_min;                 /* main.scm:104: 0.001                                    */
+  int32_t wave_spp;            /* samples per pixel per wavefront wave; 0 = auto         */
+  int32_t reserved[6];
+} SrtRenderParams;
+
+typedef struct {
+  uint64_t rays;               /* closest-hit queries (primary + every bounce)           */
+  uint64_t paths;              /* camera samples                                         */
+  float ms_total;              /* device time, first ray-gen launch .. accumulation done */
+  float ms_commit;             /* last commit: H2D + LBVH build                          */
+  int32_t kernel_launches;     /* kernels launched by this call                          */
+  int32_t waves;
+  int32_t bvh_nodes, bvh_depth;
+  uint64_t rays_per_bounce[8]; /* first 8 bounces                                        */
+} SrtStats;
+
+/* 64-byte node of the LBVH as the traversal kernel reads it; child < 0 is leaf ~child. */
+typedef struct { float lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, parent, sibling; } SrtBvhNode;
+
+/* ray / hit records of the parity hook (replaces (g:hit scene r t-min t-max), geometry.scm:14) */
+typedef struct { float o[3], d[3], time; } SrtRay;
+typedef struct { int32_t prim; int32_t material; float t, u, v; float p[3], n[3]; } SrtHit;
+
+typedef struct SrtScene SrtScene;
+
+int srt_device_count(void);
+int srt_init(int device);                         /* selects the device; fails without sm_100  */
+const char* srt_last_error(void);
+void srt_shutdown(void);
+
+SrtScene* srt_scene_create(void);
+void srt_scene_destroy(SrtScene*);
+int srt_scene_set_prims(SrtScene*, const SrtPrim*, int n);
+int srt_scene_set_xforms(SrtScene*, const SrtXform*, int n);
+int srt_scene_set_materials(SrtScene*, const SrtMaterial*, int n);
+int srt_scene_set_textures(SrtScene*, const SrtTexture*, int n);
+int srt_scene_set_perlin(SrtScene*, const float* ranvec768, const int32_t* perm_x, const int32_t* perm_y, const int32_t* perm_z);
+int srt_scene_set_camera(SrtScene*, const SrtCamera*);
+int srt_scene_commit(SrtScene*);                  /* H2D + GPU LBVH build                      */
+
+/* LBVH inspection (bit-exact check against the host reference build) */
+int srt_bvh_node_count(SrtScene*);
+int srt_bvh_readback(SrtScene*, SrtBvhNode* nodes, int cap);
+int srt_bvh_keys_readback(SrtScene*, uint64_t* keys_sorted, int32_t* order, int cap);
+int srt_prim_bounds_readback(SrtScene*, float* aabbs6, int cap);
+
+/* fixed-ray-batch closest hit through the SAME extend kernel the renderer uses */
+int srt_trace_batch(SrtScene*, const SrtRay* rays, int n, float t_min, float t_max, SrtHit* out);
+
+/* Render samples [spp_begin, spp_end) and ADD them to rgb_sum (W*H*3 floats, y = 0 bottom row,
+ * main.scm:471-491 trace-all).  _host: rgb_sum in host memory (D2H inside); _device: rgb_sum is
+ * a device pointer on the scene's device (multi-GPU reduce is done by the caller on it). */
+int srt_render_host(SrtScene*, const SrtRenderParams*, float* rgb_sum, SrtStats* stats);
+int srt_render_device(SrtScene*, const SrtRenderParams*, float* d_rgb_sum, SrtStats* stats);
+
+/* main.scm:123-124,481-487 correct-gamma + quantise; :439-450 save-as-ppm */
+int srt_resolve_device(const float* d_rgb_sum, int width, int height, int spp, uint8_t* d_image);
+int srt_resolve_host(const float* rgb_sum, int width, int height, int spp, uint8_t* image);
+int srt_save_ppm(const char* path, const uint8_t* image, int width, int height);
+
+/* unit hooks used by the parity tests (each runs the device function the shade kernel uses) */
+int srt_eval_texture(SrtScene*, int tex, const float* uvp5, int n, int quirks, float* rgb);
+int srt_eval_raygen(SrtScene*, const SrtRenderParams*, int n, const int32_t* pixel, const int32_t* sample, SrtRay* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+"""Scene flattening: object tree (geometry.py) -> the POD tables of include/srt.h.
+
+Primitive id = position in the depth-first, list-order walk of the reference's object list
+(box faces in make-box order) — the order `hit-obj-list` (geometry.scm:33-50) visits them, which
+is what the exact-tie rule is defined on.
+"""
+import math
+from dataclasses import dataclass
+import numpy as np
+from . import geometry as g
+from . import texture as t
+from .camera import camera_to_floats
+
+PRIM_DTYPE = np.dtype([("type", "<i4"), ("flags", "<i4"), ("material", "<i4"), ("xform", "<i4"), ("p", "<f4", (16,))])
+XFORM_DTYPE = np.dtype([("sin_t", "<f4"), ("cos_t", "<f4"), ("off", "<f4", (3,))])
+MATERIAL_DTYPE = np.dtype([("kind", "<i4"), ("tex", "<i4"), ("param", "<f4"), ("pad", "<f4")])
+TEXTURE_DTYPE = np.dtype([("kind", "<i4"), ("even", "<i4"), ("odd", "<i4"), ("scale", "<f4"), ("rgb", "<f4", (3,)), ("pad", "<f4")])
+CAMERA_DTYPE = np.dtype([("llc", "<f4", (3,)), ("horiz", "<f4", (3,)), ("vert", "<f4", (3,)), ("origin", "<f4", (3,)),
+                         ("w", "<f4", (3,)), ("u", "<f4", (3,)), ("v", "<f4", (3,)),
+                         ("lens_radius", "<f4"), ("time0", "<f4"), ("time1", "<f4")])
+assert PRIM_DTYPE.itemsize == 80 and XFORM_DTYPE.itemsize == 20 and MATERIAL_DTYPE.itemsize == 16
+assert TEXTURE_DTYPE.itemsize == 32 and CAMERA_DTYPE.itemsize == 96
+
+SKY_GRADIENT, SKY_BLACK = 0, 1
+
+
+@dataclass
+class FlatScene:
+    prims: np.ndarray
+    xforms: np.ndarray
+    materials: np.ndarray
+    textures: np.ndarray
+    camera: np.ndarray
+    sky: int
+    leaves: list            # leaf Obj per primitive id (host bookkeeping)
+    material_objs: list
+    texture_objs: list
+
+    def h2d_bytes(self):
+        return int(self.prims.nbytes + self.xforms.nbytes + self.materials.nbytes + self.textures.nbytes + self.camera.nbytes)
+
+
+def _compose(chain):
+    """Compose a translate / rotate-y chain (outermost first) into world = Ry*obj + off, in f64.
+    rotate-y object->world: (c*x + s*z, y, -s*x + c*z)  (geometry.scm:526-530)."""
+    c, s, off = 1.0, 0.0, (0.0, 0.0, 0.0)
+    for kind, prm in chain:        # A = current (outer), B = next (inner):  A∘B
+        if kind == g.TRANSLATE:
+            bc, bs, boff = 1.0, 0.0, prm
+        else:
+            bc, bs, boff = prm[1], prm[0], (0.0, 0.0, 0.0)
+        roff = (c * boff[0] + s * boff[2], boff[1], -s * boff[0] + c * boff[2])
+        off = (off[0] + roff[0], off[1] + roff[1], off[2] + roff[2])
+        c, s = c * bc - s * bs, s * bc + c * bs
+    return s, c, off
+
+
+def sky_kind(sky_function):
+    """Arbitrary sky lambdas cannot cross the FFI; the two shipped functions map to an enum."""
+    if sky_function is None:
+        return SKY_BLACK
+    if isinstance(sky_function, int):
+        return sky_function
+    name = getattr(sky_function, "__name__", "")
+    if name in ("sky_color", "sky-color"):
+        return SKY_GRADIENT
+    if name == "black":
+        return SKY_BLACK
+    raise ValueError("sky function must be scenes.sky_color or scenes.black (enum across the C-ABI)")
+
+
+def flatten_scene(scene):
+    prims, xforms, leaves = [], [], []
+    xform_ids = {}
+    mats, mat_ids, texs, tex_ids = [], {}, [], {}
+
+    def tex_id(tx):
+        if id(tx) in tex_ids:
+            return tex_ids[id(tx)]
+        even = odd = -1
+        if tx.kind == t.CHECKER:
+            even, odd = tex_id(tx.even), tex_id(tx.odd)
+        tex_ids[id(tx)] = len(texs)
+        texs.append((tx, even, odd))
+        return tex_ids[id(tx)]
+
+    def mat_id(m):
+        if m is None:
+            raise ValueError("primitive without material")
+        if id(m) not in mat_ids:
+            mat_ids[id(m)] = len(mats)
+            mats.append((m, tex_id(m.tex) if m.tex is not None else -1))
+        return mat_ids[id(m)]
+
+    def walk(obj, chain, flip):
+        if obj.kind == g.LIST:
+            for c in obj.children:
+                walk(c, chain, flip)
+        elif obj.kind == g.FLIP:
+            walk(obj.children[0], chain, flip ^ 1)
+        elif obj.kind in (g.TRANSLATE, g.ROTATE_Y):
+            walk(obj.children[0], chain + ((obj.kind, obj.params),), flip)
+        else:
+            xf = -1
+            if chain:
+                if chain not in xform_ids:
+                    xform_ids[chain] = len(xforms)
+                    xforms.append(_compose(chain))
+                xf = xform_ids[chain]
+            prims.append((obj.kind, flip, mat_id(obj.material), xf, obj.params))
+            leaves.append(obj)
+
+    for o in scene.obj_list:
+        walk(o, (), 0)
+
+    P = np.zeros(len(prims), dtype=PRIM_DTYPE)
+    for i, (kind, flip, m, xf, prm) in enumerate(prims):
+        P[i]["type"], P[i]["flags"], P[i]["material"], P[i]["xform"] = kind, flip, m, xf
+        P[i]["p"][:len(prm)] = prm
+    X = np.zeros(len(xforms), dtype=XFORM_DTYPE)
+    for i, (s, c, off) in enumerate(xforms):
+        X[i]["sin_t"], X[i]["cos_t"], X[i]["off"] = s, c, off
+    M = np.zeros(len(mats), dtype=MATERIAL_DTYPE)
+    for i, (m, tx) in enumerate(mats):
+        M[i]["kind"], M[i]["tex"], M[i]["param"] = m.kind, tx, m.param
+    T = np.zeros(len(texs), dtype=TEXTURE_DTYPE)
+    for i, (tx, even, odd) in enumerate(texs):
+        T[i]["kind"], T[i]["even"], T[i]["odd"], T[i]["scale"], T[i]["rgb"] = tx.kind, even, odd, tx.scale, tx.rgb
+    C = np.zeros(1, dtype=CAMERA_DTYPE)
+    if scene.camera is not None:
+        C.view("<f4")[:] = np.asarray(camera_to_floats(scene.camera), dtype=np.float32)
+    return FlatScene(P, X, M, T, C, sky_kind(scene.sky_function), leaves, [m for m, _ in mats], [tx for tx, _, _ in texs])

@@ -1,0 +1,149 @@
+"""The reference-facing render API: trace-all / save-as-ppm (main.scm:439-491) on top of libsrt.so."""
+import ctypes as C
+import numpy as np
+from . import ffi
+from .flatten import flatten_scene, FlatScene
+from .perlin import perlin_generate
+
+RAY_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("prim", "<i4"), ("material", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4"),
+                      ("p", "<f4", (3,)), ("n", "<f4", (3,))])
+BVH_NODE_DTYPE = np.dtype([("lmin", "<f4", (3,)), ("lmax", "<f4", (3,)), ("rmin", "<f4", (3,)), ("rmax", "<f4", (3,)),
+                           ("left", "<i4"), ("right", "<i4"), ("parent", "<i4"), ("sibling", "<i4")])
+assert RAY_DTYPE.itemsize == 28 and HIT_DTYPE.itemsize == 44 and BVH_NODE_DTYPE.itemsize == 64
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Renderer:
+    """Owns one committed scene on one GPU.  Replaces the in-process closure evaluation of
+    trace-all -> color -> g:hit / m:scatter (main.scm:100-121, 471-491)."""
+
+    def __init__(self, scene, device=0, perlin_seed=3):
+        self.lib = ffi.load()
+        ffi.check(self.lib.srt_init(int(device)), "srt_init")
+        self.flat = scene if isinstance(scene, FlatScene) else flatten_scene(scene)
+        self.perlin = perlin_generate(perlin_seed)
+        self.h = self.lib.srt_scene_create()
+        if not self.h:
+            raise ffi.SrtError("srt_scene_create failed")
+        self.commit()
+
+    def commit(self):
+        f, lib, h = self.flat, self.lib, self.h
+        ffi.check(lib.srt_scene_set_prims(h, _ptr(f.prims), len(f.prims)), "set_prims")
+        ffi.check(lib.srt_scene_set_xforms(h, _ptr(f.xforms), len(f.xforms)), "set_xforms")
+        ffi.check(lib.srt_scene_set_materials(h, _ptr(f.materials), len(f.materials)), "set_materials")
+        ffi.check(lib.srt_scene_set_textures(h, _ptr(f.textures), len(f.textures)), "set_textures")
+        rv, px, py, pz = self.perlin
+        self._rv32 = np.ascontiguousarray(rv, dtype=np.float32)
+        ffi.check(lib.srt_scene_set_perlin(h, _ptr(self._rv32), _ptr(px), _ptr(py), _ptr(pz)), "set_perlin")
+        ffi.check(lib.srt_scene_set_camera(h, _ptr(f.camera)), "set_camera")
+        ffi.check(lib.srt_scene_commit(h), "commit")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- LBVH inspection --------------------------------------------------------------------
+    def bvh_nodes(self):
+        n = self.lib.srt_bvh_node_count(self.h)
+        out = np.zeros(n, dtype=BVH_NODE_DTYPE)
+        ffi.check(self.lib.srt_bvh_readback(self.h, _ptr(out), n), "bvh_readback")
+        return out
+
+    def bvh_keys(self):
+        n = len(self.flat.prims)
+        keys, order = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.int32)
+        ffi.check(self.lib.srt_bvh_keys_readback(self.h, _ptr(keys), _ptr(order), n), "bvh_keys_readback")
+        return keys, order
+
+    def prim_bounds(self):
+        n = len(self.flat.prims)
+        out = np.zeros((n, 6), dtype=np.float32)
+        ffi.check(self.lib.srt_prim_bounds_readback(self.h, _ptr(out), n), "prim_bounds_readback")
+        return out
+
+    # -- parity hooks -----------------------------------------------------------------------
+    def trace_batch(self, rays, t_min=0.001, t_max=999999999999.0):
+        """rays: (n,7) float array [o d time] -> HIT_DTYPE array (prim = -1 on miss)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 7)
+        out = np.zeros(len(rays), dtype=HIT_DTYPE)
+        ffi.check(self.lib.srt_trace_batch(self.h, _ptr(rays), len(rays), t_min, t_max, _ptr(out)), "trace_batch")
+        return out
+
+    def eval_texture(self, tex, uvp, quirks=15):
+        uvp = np.ascontiguousarray(uvp, dtype=np.float32).reshape(-1, 5)
+        out = np.zeros((len(uvp), 3), dtype=np.float32)
+        ffi.check(self.lib.srt_eval_texture(self.h, tex, _ptr(uvp), len(uvp), quirks, _ptr(out)), "eval_texture")
+        return out
+
+    def eval_raygen(self, params, pixel, sample):
+        pixel = np.ascontiguousarray(pixel, dtype=np.int32)
+        sample = np.ascontiguousarray(sample, dtype=np.int32)
+        out = np.zeros((len(pixel), 7), dtype=np.float32)
+        ffi.check(self.lib.srt_eval_raygen(self.h, C.byref(params), len(pixel), _ptr(pixel), _ptr(sample), _ptr(out)), "eval_raygen")
+        return out
+
+    # -- rendering --------------------------------------------------------------------------
+    def params(self, width, height, spp_begin, spp_end, max_depth=50, seed=1, quirks=15, t_min=0.001, wave_spp=0, sky=None):
+        p = ffi.RenderParams()
+        p.width, p.height, p.spp_begin, p.spp_end = width, height, spp_begin, spp_end
+        p.max_depth, p.seed, p.quirks, p.t_min, p.wave_spp = max_depth, seed, quirks, t_min, wave_spp
+        p.sky = self.flat.sky if sky is None else sky
+        return p
+
+    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, rgb_sum=None, wave_spp=0):
+        """Adds samples [spp_begin, spp_begin+spp) into rgb_sum (H,W,3) float32 (row 0 = bottom).
+        Host buffers in and out (D2H inside the call)."""
+        if rgb_sum is None:
+            rgb_sum = np.zeros((height, width, 3), dtype=np.float32)
+        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp)
+        st = ffi.Stats()
+        ffi.check(self.lib.srt_render_host(self.h, C.byref(p), _ptr(rgb_sum), C.byref(st)), "render_host")
+        return rgb_sum, st
+
+    def render_device(self, d_ptr, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, wave_spp=0):
+        """Same, accumulating into a DEVICE buffer (e.g. a torch tensor's data_ptr())."""
+        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp)
+        st = ffi.Stats()
+        ffi.check(self.lib.srt_render_device(self.h, C.byref(p), C.c_void_p(int(d_ptr)), C.byref(st)), "render_device")
+        return st
+
+
+def correct_gamma_quantise(rgb_sum, spp):
+    """main.scm:123-124, 481-487 through the library's device resolve kernel."""
+    lib = ffi.load()
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    h, w = rgb_sum.shape[:2]
+    img = np.zeros((h, w, 3), dtype=np.uint8)
+    ffi.check(lib.srt_resolve_host(_ptr(rgb_sum), w, h, int(spp), _ptr(img)), "resolve_host")
+    return img
+
+
+def save_as_ppm(path, image):
+    """main.scm:439-450 (ASCII P3, header 'P3\\n W H\\n255\\n', rows top to bottom)."""
+    lib = ffi.load()
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    h, w = image.shape[:2]
+    ffi.check(lib.srt_save_ppm(str(path).encode(), _ptr(image), w, h), "save_ppm")
+
+
+def trace_all(scene, sample_count, width=200, height=200, max_depth=100, seed=1, quirks=15, device=0):
+    """(trace-all scene k) for k = 1..sample_count in one call (main.scm:471-491): returns the
+    running sum *raw-data* and the 8-bit *image*."""
+    r = Renderer(scene, device=device)
+    try:
+        rgb_sum, st = r.render(width, height, sample_count, max_depth=max_depth, seed=seed, quirks=quirks)
+    finally:
+        r.close()
+    return rgb_sum, correct_gamma_quantise(rgb_sum, sample_count), st

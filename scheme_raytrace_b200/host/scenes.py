@@ -1,0 +1,198 @@
+"""Scene scripts: the reference's scenes (main.scm:31-426) written against the mirrored
+constructor API, plus the five BASELINE.json configs as deterministic generators."""
+import numpy as np
+from . import vec as v
+from . import geometry as g
+from . import material as m
+from . import texture as t
+from . import bezier as b
+from . import camera as cam
+
+
+def sky_color(ray=None):        # main.scm:91-95 (evaluated on the device; this is the enum tag)
+    raise RuntimeError("sky functions are evaluated by the CUDA shade kernel")
+
+
+def black(ray=None):            # main.scm:97-98
+    raise RuntimeError("sky functions are evaluated by the CUDA shade kernel")
+
+
+def cornell_camera(size_x=200, size_y=200):      # main.scm:129-139
+    return cam.make_camera(v.vec3(278, 278, -800), v.vec3(278, 278, 0), v.vec3(0, 1, 0), 40, size_x / size_y, 0, 1, 0, 1)
+
+
+def default_camera(size_x=200, size_y=200):      # main.scm:141-153
+    return cam.make_camera(v.vec3(0, 5, 5), v.vec3(0, 0, 0), v.vec3(0, 1, 0), 40, size_x / size_y, 0, 1, 0, 1)
+
+
+def _checker():
+    return t.checker_texture(t.constant_texture(v.vec3(0.2, 0.3, 0.1)), t.constant_texture(v.vec3(0.9, 0.9, 0.9)))
+
+
+def test_scene_objects():                        # main.scm:155-172
+    return [
+        g.make_sphere(v.vec3(0, 0, -1), 0.5, m.make_lambertian(t.constant_texture(v.vec3(0.1, 0.2, 0.5)))),
+        g.make_sphere(v.vec3(0, -100.5, -1), 100, m.make_lambertian(_checker())),
+        g.make_sphere(v.vec3(1, 0, -1), 0.5, m.make_metal(t.constant_texture(v.vec3(0.8, 0.6, 0.2)), 0.3)),
+        g.make_sphere(v.vec3(-1, 0, -1), 0.5, m.make_dielectric(1.5)),
+        g.make_sphere(v.vec3(-1, 0, -1), -0.45, m.make_dielectric(1.5)),
+    ]
+
+
+def cfg1_weekend(size_x=200, size_y=100):
+    """configs[0]: main.scm test-scene with the 2:1 Weekend camera and sky-color (SURVEY §8d cfg1:
+    upstream's `black` sky renders an all-black image)."""
+    c = cam.make_camera(v.vec3(0, 0, 0), v.vec3(0, 0, -1), v.vec3(0, 1, 0), 90, size_x / size_y, 0, 1, 0, 1)
+    return g.make_scene(test_scene_objects(), c, sky_color)
+
+
+def random_scene(seed=2, lo=-11, hi=11, moving=False, checker_ground=False, big_spheres=True):
+    """main.scm:31-89 random-scene, generalised (upstream grid is [-5,10), moving lambertians,
+    checker ground).  Draw order follows the reference loop; `push!` prepends, so the final list
+    is in reverse creation order exactly like upstream."""
+    rnd = np.random.RandomState(seed).random_sample
+    obj_list = []
+    ground_tex = _checker() if checker_ground else t.constant_texture(v.vec3(0.5, 0.5, 0.5))
+    obj_list.insert(0, g.make_sphere(v.vec3(0, -1000, 0), 1000, m.make_lambertian(ground_tex)))
+    for a in range(lo, hi):
+        for bb in range(lo, hi):
+            choose_mat = rnd()
+            center = v.vec3(a + 0.9 * rnd(), 0.2, bb + 0.9 * rnd())
+            if v.length(v.diff(center, v.vec3(4, 0.2, 0))) > 0.9:
+                if choose_mat < 0.8:
+                    if moving:
+                        c1 = v.sum(center, v.vec3(0, 0.5 * rnd(), 0))
+                    alb = t.constant_texture(v.vec3(rnd() * rnd(), rnd() * rnd(), rnd() * rnd()))
+                    if moving:
+                        obj_list.insert(0, g.make_moving_sphere(center, c1, 0, 1, 0.2, m.make_lambertian(alb)))
+                    else:
+                        obj_list.insert(0, g.make_sphere(center, 0.2, m.make_lambertian(alb)))
+                elif choose_mat < 0.95:
+                    alb = t.constant_texture(v.vec3(0.5 * (1 + rnd()), 0.5 * (1 + rnd()), 0.5 * (1 + rnd())))
+                    obj_list.insert(0, g.make_sphere(center, 0.2, m.make_metal(alb, 0.5 * rnd())))
+                else:
+                    obj_list.insert(0, g.make_sphere(center, 0.2, m.make_dielectric(1.5)))
+    if big_spheres:
+        obj_list.insert(0, g.make_sphere(v.vec3(0, 1, 0), 1, m.make_dielectric(1.5)))
+        obj_list.insert(0, g.make_sphere(v.vec3(-4, 1, 0), 1, m.make_lambertian(t.constant_texture(v.vec3(0.4, 0.2, 0.1)))))
+        obj_list.insert(0, g.make_sphere(v.vec3(4, 1, 0), 1, m.make_metal(t.constant_texture(v.vec3(0.7, 0.6, 0.5)), 0)))
+    return obj_list
+
+
+def cfg2_random_spheres(size_x=1200, size_y=800, seed=2):
+    """configs[1]: Weekend final scene, static spheres, constant ground, ~488 primitives; book
+    camera (13,2,3)->origin, vfov 20, aperture 0.1, focus 10 (not in the reference)."""
+    c = cam.make_camera(v.vec3(13, 2, 3), v.vec3(0, 0, 0), v.vec3(0, 1, 0), 20, size_x / size_y, 0.1, 10, 0, 1)
+    return g.make_scene(random_scene(seed, -11, 11), c, sky_color)
+
+
+def cfg3_next_week(size_x=800, size_y=800, seed=3):
+    """configs[2]: random-scene in its reference form (moving spheres, checker ground,
+    main.scm:31-89) plus test-scene2's marble sphere, light sphere and light rect
+    (main.scm:316-328) and a noise-texture sphere."""
+    objs = random_scene(seed, -5, 10, moving=True, checker_ground=True, big_spheres=False)
+    per_tex = t.marble_texture(1)
+    light = m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))
+    extra = [
+        g.make_sphere(v.vec3(0, 2, 0), 2, m.make_lambertian(per_tex)),
+        g.make_sphere(v.vec3(0, 7, 0), 2, light),
+        g.make_xy_rect(3, 5, 1, 3, -2, light),
+        g.make_sphere(v.vec3(-4, 1, 0), 1, m.make_lambertian(t.noise_texture(4))),
+        g.make_sphere(v.vec3(4, 1, 0), 1, m.make_metal(t.constant_texture(v.vec3(0.7, 0.6, 0.5)), 0)),
+    ]
+    c = cam.make_camera(v.vec3(13, 2, 3), v.vec3(0, 1, 0), v.vec3(0, 1, 0), 30, size_x / size_y, 0.1, 10, 0, 1)
+    return g.make_scene(extra + objs, c, sky_color)
+
+
+def _cornell_walls():
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    white = m.make_lambertian(t.constant_texture(v.vec3(0.73, 0.73, 0.73)))
+    green = m.make_lambertian(t.constant_texture(v.vec3(0.12, 0.45, 0.15)))
+    light = m.make_diffuse_light(t.constant_texture(v.vec3(3, 3, 3)))
+    walls = [
+        g.flip_normals(g.make_yz_rect(0, 555, 0, 555, 555, green)),
+        g.make_yz_rect(0, 555, 0, 555, 0, red),
+        g.flip_normals(g.make_xz_rect(213, 343, 227, 332, 554, light)),
+        g.flip_normals(g.make_xz_rect(0, 555, 0, 555, 555, white)),
+        g.make_xz_rect(0, 555, 0, 555, 0, white),
+        g.flip_normals(g.make_xy_rect(0, 555, 0, 555, 555, white)),
+    ]
+    return walls, red, white, green, light
+
+
+def cfg4_cornell_box(size_x=1024, size_y=1024):
+    """configs[3]: main.scm:330-351 cornell-box (sky-color background, light (3,3,3): Q14)."""
+    walls, red, white, green, light = _cornell_walls()
+    objs = walls + [
+        g.translate(g.rotate_y(g.make_box(v.vec3(0, 0, 0), v.vec3(165, 165, 165), white), -18), v.vec3(130, 0, 65)),
+        g.translate(g.rotate_y(g.make_box(v.vec3(0, 0, 0), v.vec3(165, 330, 165), white), 15), v.vec3(265, 0, 295)),
+    ]
+    return g.make_scene(objs, cornell_camera(size_x, size_y), sky_color)
+
+
+def test_bezier(size_x=200, size_y=200):
+    """main.scm:237-277 test-bezier (3 curves + 6 spheres + checker ground)."""
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    green = m.make_lambertian(t.constant_texture(v.vec3(0.12, 0.45, 0.15)))
+    blue = m.make_lambertian(t.constant_texture(v.vec3(0.12, 0.15, 0.45)))
+    objs = [
+        g.make_sphere(v.vec3(0, -100.5, -1), 100, m.make_lambertian(_checker())),
+        g.make_bvh_node([
+            g.make_sphere(v.vec3(2, 0, 2), 0.5, red),
+            g.make_sphere(v.vec3(-2, 0, -2), 0.5, green),
+            g.make_sphere(v.vec3(-1, 0, -1), 0.1, blue),
+            g.make_sphere(v.vec3(-0.8, 1, 1), 0.1, blue),
+            g.make_sphere(v.vec3(0.8, -1, 1), 0.1, blue),
+            g.make_sphere(v.vec3(1, 0, -1), 0.1, blue),
+            b.make_bezier(v.vec3(-1, 0, -1), v.vec3(-0.8, 1, 1), v.vec3(0.8, -1, 1), v.vec3(1, 0, -1), 0.1, red),
+            b.make_bezier(v.vec3(-1, 0, 1), v.vec3(-0.8, 1, -1), v.vec3(0.8, -1, -1), v.vec3(1, 0, 1), 0.1, red),
+            b.make_bezier(v.vec3(-1, 0, 2), v.vec3(-0.8, 1, -2), v.vec3(0.8, -1, -2), v.vec3(1, 0, 2), 0.1, red),
+        ], 0, 0),
+    ]
+    return g.make_scene(objs, default_camera(size_x, size_y), sky_color)
+
+
+def cornell_bezier(size_x=200, size_y=200):
+    """main.scm:353-373 cornell-bezier."""
+    walls, red, white, green, light = _cornell_walls()
+    objs = walls + [b.make_bezier(v.vec3(130, 0, 65), v.vec3(150, 0, 190), v.vec3(130, 0, 190), v.vec3(265, 0, 295), 10, red)]
+    return g.make_scene(objs, cornell_camera(size_x, size_y), sky_color)
+
+
+def test_scene2(size_x=200, size_y=200):
+    """main.scm:316-328 test-scene2 (marble + lights, black sky)."""
+    per_tex = t.marble_texture(1)
+    light = m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))
+    objs = [
+        g.make_sphere(v.vec3(0, -1000, -1), 1000, m.make_lambertian(per_tex)),
+        g.make_sphere(v.vec3(0, 2, 0), 2, m.make_lambertian(per_tex)),
+        g.make_sphere(v.vec3(0, 7, 0), 2, light),
+        g.make_xy_rect(3, 5, 1, 3, -2, light),
+    ]
+    return g.make_scene(objs, default_camera(size_x, size_y), black)
+
+
+def line_upped_spheres(nx=10, ny=10, seed=7):
+    """main.scm:177-191 + 204-213 test-scene-non-bvh: the reference's own (commented) benchmark."""
+    rnd = np.random.RandomState(seed).random_sample
+    objs = []
+    for x in range(nx):
+        for y in range(ny):
+            objs.insert(0, g.make_sphere(v.vec3(x, 0, y), 0.5, m.make_lambertian(t.constant_texture(v.vec3(rnd(), rnd(), rnd())))))
+    return objs
+
+
+def test_scene_bvh(size_x=200, size_y=200):
+    """main.scm:215-235 test-scene-bvh / -bvh-sah (make-bvh-* are grouping hints here)."""
+    objs = [g.make_sphere(v.vec3(0, -100.5, -1), 100, m.make_lambertian(_checker())),
+            g.make_bvh_with_sah(line_upped_spheres(10, 10), 0, 0)]
+    return g.make_scene(objs, default_camera(size_x, size_y), sky_color)
+
+
+CONFIGS = {
+    "cfg1": dict(scene=cfg1_weekend, width=200, height=100, spp=16, max_depth=50, seed=1),
+    "cfg2": dict(scene=cfg2_random_spheres, width=1200, height=800, spp=500, max_depth=50, seed=2),
+    "cfg3": dict(scene=cfg3_next_week, width=800, height=800, spp=1000, max_depth=50, seed=3),
+    "cfg4": dict(scene=cfg4_cornell_box, width=1024, height=1024, spp=4096, max_depth=50, seed=4),
+    "cfg5": dict(scene=test_bezier, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
+}

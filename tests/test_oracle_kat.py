@@ -1,0 +1,182 @@
+"""Pins the CPU oracle against the known-answer vectors of SURVEY.md §8c (KAT1-10, derived from the
+reference sources; KAT1-6 are verifiable by hand) and the Random123 Philox vectors.  The reference
+itself ships no tests or golden vectors, so these are the only anchors ("parity unpinned")."""
+import numpy as np
+import pytest
+from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, vec as v, camera as cam, scenes
+
+MAXF = 999999999999.0
+LAMB = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
+
+
+def _scene(objs):
+    return g.make_scene(objs, scenes.default_camera(), scenes.sky_color)
+
+
+def test_philox_kat(orc):
+    # Random123 kat_vectors: philox4x32 10 rounds
+    assert list(orc.philox4x32_10([0, 0, 0, 0], [0, 0])) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert list(orc.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert list(orc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    u = orc.rng_block(1, 2, 3, 4, 5)
+    assert np.all((u > 0) & (u < 1))
+    assert np.all(u * 2 ** 24 - 0.5 == np.round(u * 2 ** 24 - 0.5))  # 24-bit grid, exact in fp32
+
+
+@pytest.mark.parametrize("d,t_exp", [((0, 0, -1), 0.5), ((0, 0, -2), 0.25)])
+def test_kat1_kat2_sphere(orc, d, t_exp):
+    S = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    r = S.trace_batch([[0, 0, 0, *d, 0]])
+    assert r["prim"][0] == 0 and r["t"][0] == t_exp
+    assert np.allclose(r["p"][0], (0, 0, -0.5)) and np.allclose(r["n"][0], (0, 0, 1))
+
+
+def test_kat3_from_centre(orc):
+    S = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    r = S.trace_batch([[0, 0, -1, 0, 1, 0, 0]])
+    assert r["t"][0] == 0.5 and np.allclose(r["p"][0], (0, 0.5, -1)) and np.allclose(r["n"][0], (0, 1, 0))
+
+
+def test_kat4_negative_radius(orc):
+    S = orc.OracleScene(_scene([g.make_sphere((-1, 0, -1), -0.45, LAMB)]))
+    r = S.trace_batch([[-1, 0, 0, 0, 0, -1, 0]])
+    assert abs(r["t"][0] - 0.55) < 1e-15 and np.allclose(r["p"][0], (-1, 0, -0.55)) and np.allclose(r["n"][0], (0, 0, -1))
+
+
+def test_kat5_cameras(orc):
+    c = cam.make_camera((278, 278, -800), (278, 278, 0), (0, 1, 0), 40, 1, 0, 1, 0, 1)
+    assert np.allclose(c[0], (278.3639702342662, 277.6360297657338, -799), rtol=0, atol=1e-12)
+    assert np.allclose(c[1], (-0.7279404685324047, 0, 0), atol=1e-15) and np.allclose(c[2], (0, 0.7279404685324047, 0), atol=1e-15)
+    assert np.allclose(c[4], (0, 0, -1)) and np.allclose(c[5], (-1, 0, 0)) and np.allclose(c[6], (0, 1, 0))
+    # the oracle's C++ restatement of make-camera agrees with the host mirror to the last bit
+    assert np.array_equal(orc.make_camera((278, 278, -800), (278, 278, 0), (0, 1, 0), 40, 1, 0, 1, 0, 1), np.asarray(cam.camera_to_floats(c)))
+    c2 = cam.make_camera((0, 5, 5), (0, 0, 0), (0, 1, 0), 40, 1, 0, 1, 0, 1)
+    assert np.allclose(c2[0], (-0.36397023426620234, 4.035527398013764, 4.55025903961314), atol=1e-14)
+    assert np.allclose(c2[2], (0, 0.5147316415993759, -0.5147316415993759), atol=1e-14)
+    assert np.array_equal(orc.make_camera((0, 5, 5), (0, 0, 0), (0, 1, 0), 40, 1, 0, 1, 0, 1), np.asarray(cam.camera_to_floats(c2)))
+    # centre rays (s = t = 0.5, zero lens offset)
+    S = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c, scenes.sky_color))
+    assert np.allclose(S.get_ray(0.5, 0.5, 0.0, 1, 0, 0)[3:6], (0, 0, 1), atol=1e-12)
+    S2 = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c2, scenes.sky_color))
+    assert np.allclose(S2.get_ray(0.5, 0.5, 0.0, 1, 0, 0)[3:6], (0, -0.7071067811865479, -0.7071067811865479), atol=1e-12)
+    # weekend camera of cfg1 == the dead <camera> class defaults (camera.scm:12-22)
+    c3 = cam.make_camera((0, 0, 0), (0, 0, -1), (0, 1, 0), 90, 2, 0, 1, 0, 1)
+    assert np.allclose(c3[0], (-2, -1, -1), atol=1e-12) and np.allclose(c3[1], (4, 0, 0), atol=1e-12) and np.allclose(c3[2], (0, 2, 0), atol=1e-12)
+
+
+def test_kat6_xz_rect(orc):
+    S = orc.OracleScene(_scene([g.make_xz_rect(213, 343, 227, 332, 554, LAMB)]))
+    r = S.trace_batch([[278, 0, 279.5, 0, 1, 0, 0]])
+    assert r["t"][0] == 554 and np.allclose(r["p"][0], (278, 554, 279.5)) and np.allclose(r["n"][0], (0, 1, 0))
+    assert np.allclose(r["uv"][0], (0.5, 0.5))
+
+
+BEZ = [-1, 0, -1, -0.8, 1, 1, 0.8, -1, 1, 1, 0, -1]
+
+
+def _curve(tt):
+    a, b, c, d = [np.array(BEZ[3 * i:3 * i + 3], float) for i in range(4)]
+    return a * (1 - tt) ** 3 + b * 3 * (1 - tt) ** 2 * tt + c * 3 * (1 - tt) * tt ** 2 + d * tt ** 3
+
+
+def test_kat7_bezier(orc):
+    o = np.array([0, 5, 5.0])
+    d = _curve(0.5) - o
+    d /= np.linalg.norm(d)
+    r = orc.bezier_hit(BEZ, 0.1, [*o, *d, 0])
+    assert r["hit"] and r["max_depth"] == 6 and r["converge_calls"] == 39
+    assert abs(r["t"] - 6.731228242402701) < 1e-12
+    assert np.allclose(r["p"], (0, -0.003282549631530, 0.497045705331623), atol=1e-12)
+    assert np.allclose(r["n"], (0, 0.7432941462471664, 0.6689647316224497), atol=1e-12)
+
+
+def test_kat8_bezier_unnormalised(orc):
+    r = orc.bezier_hit(BEZ, 0.1, [0, 5, 5, 0, -5, -4.5, 0])
+    assert r["hit"] and abs(r["t"] - 6.731228242402701) < 1e-12
+    assert np.allclose(r["p"], (0, -28.65614121201351, -25.290527090812155), atol=1e-10)   # Q9
+    assert np.allclose(r["n"], (0, 5, 4.5))
+
+
+def test_kat9_bezier_miss(orc):
+    r = orc.bezier_hit(BEZ, 0.1, [0, 5, 5, 0, -0.7071067811865479, -0.7071067811865479, 0])
+    assert not r["hit"] and r["max_depth"] == 6 and r["converge_calls"] == 9
+
+
+def test_kat10_bezier(orc):
+    o = np.array([0, 5, 5.0])
+    d = _curve(0.1) - o
+    d /= np.linalg.norm(d)
+    r = orc.bezier_hit(BEZ, 0.1, [*o, *d, 0])
+    assert r["hit"] and abs(r["t"] - 7.340737709682441) < 1e-10
+    assert np.allclose(r["p"], (-0.9039654664425595, 0.19918873061589348, -0.4791867748405565), atol=1e-10)
+
+
+def test_tie_rule_box_edge(orc):
+    """make-box faces are inclusive-type, later rect wins an equal-t tie."""
+    S = orc.OracleScene(_scene([g.make_box((0, 0, 0), (1, 1, 1), LAMB)]))
+    # ray into the exact edge shared by face 0 (xy @ z=1) and face 4 (yz @ x=1): both t = 1
+    r = S.trace_batch([[2, 0.5, 2, -1, 0, -1, 0]])
+    assert r["t"][0] == 1.0 and r["prim"][0] == 4
+    # sphere (strict) listed after a rect at the same t loses; listed before, the rect (inclusive) wins
+    S2 = orc.OracleScene(_scene([g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB), g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    assert S2.trace_batch([[0, 0, 0, 0, 0, -1, 0]])["prim"][0] == 0
+    S3 = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB), g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB)]))
+    assert S3.trace_batch([[0, 0, 0, 0, 0, -1, 0]])["prim"][0] == 1
+
+
+def test_instances_cornell_block(orc):
+    """translate(rotate-y(box)) (geometry.scm:465-543): a ray down onto the short block's top face."""
+    sc = scenes.cfg4_cornell_box(64, 64)
+    S = orc.OracleScene(sc)
+    # top face centre of the short block in world space
+    import math
+    s, c = math.sin(math.radians(-18)), math.cos(math.radians(-18))
+    px, pz = 82.5, 82.5
+    wx, wz = c * px + s * pz + 130, -s * px + c * pz + 65
+    r = S.trace_batch([[wx, 500, wz, 0, -1, 0, 0]])
+    assert r["prim"][0] == 8 and abs(r["t"][0] - 335) < 1e-9          # xz-rect @ y=165 is the 3rd box face -> id 6+2
+    assert np.allclose(r["n"][0], (0, 1, 0), atol=1e-12) and np.allclose(r["uv"][0], (0.5, 0.5), atol=1e-9)
+
+
+def test_aabb_quirk_q11(orc):
+    # per-axis independent slabs: a ray that misses a true box can still pass (looser than standard)
+    assert orc.aabb_hit((0, 0, 0), (1, 1, 1), [0.5, 0.5, -1, 0, 0, 1, 0], 0.001, MAXF)
+    assert not orc.aabb_hit((0, 0, 0), (1, 1, 1), [2, 0.5, -1, 0, 0, 1, 0], 0.001, MAXF)
+    assert orc.aabb_hit((0, 0, 0), (1, 1, 1), [-1, 2.5, 0.5, 1, -1, 0, 0], 0.001, MAXF)   # true slab test would miss
+
+
+def test_perlin_q4_and_textures(orc):
+    S = orc.OracleScene(scenes.test_scene2(32, 32))
+    p = np.random.RandomState(0).uniform(-5, 5, (64, 3))
+    n_ref, n_fix = S.noise(p, quirks=15), S.noise(p, quirks=0)
+    assert np.all(np.abs(n_ref) < 2) and not np.allclose(n_ref, n_fix)
+    tb = S.noise(p, quirks=15, turb=True)
+    assert np.all(tb >= 0)
+    # marble = 0.5*(1+sin(sc*z + 10*turb)) (texture.scm:30-34); texture 0 of test-scene2 is marble(1)
+    uvp = np.concatenate([np.zeros((64, 2)), p], axis=1)
+    assert np.allclose(S.tex_value(0, uvp)[:, 0], 0.5 * (1 + np.sin(p[:, 2] + 10 * tb)))
+
+
+def test_resolve_and_ppm(orc, tmp_path):
+    rgb = np.zeros((2, 3, 3))
+    rgb[0, 0] = (4.0, 1.0, 0.25)          # spp 4 -> (1, .25, .0625) -> sqrt -> (1, .5, .25)
+    rgb[1, 2] = (100.0, 0.0, 4.0)
+    img = orc.resolve(rgb, 4)
+    assert tuple(img[0, 0]) == (255, 127, 63) and tuple(img[1, 2]) == (255, 0, 255)
+    path = tmp_path / "test.ppm"
+    orc.save_ppm(path, img)
+    lines = path.read_text().split("\n")
+    assert lines[0] == "P3" and lines[1] == " 3 2" and lines[2] == "255"   # note the leading space (main.scm:442)
+    assert lines[3] == "0 0 0" and lines[5] == "255 0 255" and lines[6] == "255 127 63"   # top row first (y flipped)
+
+
+def test_render_cfg1_smoke(orc):
+    sc = scenes.cfg1_weekend(40, 20)
+    S = orc.OracleScene(sc)
+    a, nrays = S.render(40, 20, 4, max_depth=50, seed=1)
+    b, _ = S.render(40, 20, 4, max_depth=50, seed=1, nthreads=1)
+    assert np.array_equal(a, b)                     # counter-based RNG: thread-count independent
+    assert nrays > 40 * 20 * 4 and np.all(np.isfinite(a)) and a.min() >= 0
+    top = a[-1].mean(axis=0) / 4                    # sky gradient at the top rows is bluish
+    assert top[2] > top[0]

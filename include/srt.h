@@ -83,7 +83,7 @@ typedef struct {
   int32_t quirks;              /* SRT_Q* bits                                            */
   float t_min;                 /* main.scm:104: 0.001                                    */
   int32_t wave_spp;            /* samples per pixel per wavefront wave; 0 = auto         */
-  int32_t reserved[6];
+  int32_t reserved[6];         /* [0] = 1: time extend/shade launches separately (slower) */
 } SrtRenderParams;
 
 typedef struct {
@@ -95,6 +95,9 @@ typedef struct {
   int32_t waves;
   int32_t bvh_nodes, bvh_depth;
   uint64_t rays_per_bounce[8]; /* first 8 bounces                                        */
+  float ms_extend, ms_shade;   /* per-kernel device time, only when params.reserved[0]==1 */
+  int32_t extend_launches;     /* extend launches timed for ms_extend                    */
+  int32_t pad;
 } SrtStats;
 
 /* 64-byte node of the LBVH as the traversal kernel reads it; child < 0 is leaf ~child. */

@@ -1,0 +1,308 @@
+// lbvh.cu — GPU LBVH build: primitive bounds -> Morton keys -> LSD radix sort -> Karras radix
+// tree emit -> bottom-up refit.  Supersedes the reference's CPU builders make-bvh-node
+// (geometry.scm:226-260) and make-bvh-with-sah (geometry.scm:294-371); tree topology is not a
+// parity target, the build is instead bit-exact against the sequential host reference
+// oracle/lbvh_ref.cpp over the same AABBs (tests/test_lbvh.py).
+//
+// Algorithm specification (DESIGN.md "LBVH"); every fp32 op below is an explicitly rounded
+// intrinsic so that the host reference (compiled with -ffp-contract=off) produces the same bits:
+//   centroid = 0.5*(min+max); g = min(uint(q * 2^21), 2^21-1), q = (c - cmin)/(cmax - cmin)
+//   key = 63-bit Morton (x highest); stable sort; Karras 2012 with index tie-break for equal keys
+//   stored child boxes = union of primitive AABBs padded by S * 2^-21, S = max |coordinate|
+#include "srt_device.cuh"
+#include "srt_host.h"
+
+namespace {
+
+constexpr float BIG = 3.0e38f;
+
+// ---- 1. primitive bounds (geometry.scm bbox closures; instances get correct boxes, unlike Q7) ---
+__global__ void k_prim_bounds(DScene sc, float cam_t0, float cam_t1, float* __restrict__ aabb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sc.n_prims) return;
+  int4 hdr = sc.prim_hdr[i];
+  int type = hdr.x & 0xff;
+  float4 a = sc.prim_a[i];
+  float3 mn, mx;
+  if (type == SRT_PRIM_SPHERE) {                                   // geometry.scm:172-174
+    float r = fabsf(a.w);
+    mn = v3(a.x - r, a.y - r, a.z - r); mx = v3(a.x + r, a.y + r, a.z + r);
+  } else if (type == SRT_PRIM_MOVING_SPHERE) {                     // geometry.scm:209-214, over the shutter AND time 0 (Q6, Q13)
+    float4 b = sc.prim_b[i], c = sc.prim_c[i];
+    float r = fabsf(a.w);
+    float times[3] = {cam_t0, cam_t1, 0.0f};
+    mn = v3(BIG, BIG, BIG); mx = v3(-BIG, -BIG, -BIG);
+    for (int k = 0; k < 3; ++k) {
+      float3 cc = moving_center(a, b, c, times[k]);
+      mn = v3(fminf(mn.x, cc.x - r), fminf(mn.y, cc.y - r), fminf(mn.z, cc.z - r));
+      mx = v3(fmaxf(mx.x, cc.x + r), fmaxf(mx.y, cc.y + r), fmaxf(mx.z, cc.z + r));
+    }
+  } else if (type <= SRT_PRIM_YZ_RECT) {                           // geometry.scm:390-392, 409-411, 428-430
+    float k = sc.prim_b[i].x;
+    if (type == SRT_PRIM_XY_RECT) { mn = v3(a.x, a.z, k - 0.0001f); mx = v3(a.y, a.w, k + 0.0001f); }
+    else if (type == SRT_PRIM_XZ_RECT) { mn = v3(a.x, k - 0.0001f, a.z); mx = v3(a.y, k + 0.0001f, a.w); }
+    else { mn = v3(k - 0.0001f, a.x, a.z); mx = v3(k + 0.0001f, a.y, a.w); }
+  } else {                                                         // bezier.scm:88-98
+    float w1 = 0.5f * a.w;
+    float4 b = sc.prim_b[i], c = sc.prim_c[i], d = sc.prim_d[i];
+    mn = v3(fminf(fminf(a.x, b.x), fminf(c.x, d.x)) - w1, fminf(fminf(a.y, b.y), fminf(c.y, d.y)) - w1, fminf(fminf(a.z, b.z), fminf(c.z, d.z)) - w1);
+    mx = v3(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)) + w1, fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)) + w1, fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)) + w1);
+  }
+  if (hdr.z >= 0) {                                                // geometry.scm:479-480, 490-509 (8 corners)
+    Xf x = load_xf(sc, hdr.z);
+    float3 wmn = v3(BIG, BIG, BIG), wmx = v3(-BIG, -BIG, -BIG);
+    for (int c = 0; c < 8; ++c) {
+      float3 p = xf_point_to_world(x, v3((c & 1) ? mx.x : mn.x, (c & 2) ? mx.y : mn.y, (c & 4) ? mx.z : mn.z));
+      wmn = v3(fminf(wmn.x, p.x), fminf(wmn.y, p.y), fminf(wmn.z, p.z));
+      wmx = v3(fmaxf(wmx.x, p.x), fmaxf(wmx.y, p.y), fmaxf(wmx.z, p.z));
+    }
+    // the rotation is evaluated in fp32: widen by a relative epsilon so the box stays conservative
+    float e = 4e-7f * fmaxf(fmaxf(fabsf(wmn.x), fabsf(wmx.x)), fmaxf(fmaxf(fabsf(wmn.y), fabsf(wmx.y)), fmaxf(fabsf(wmn.z), fabsf(wmx.z))));
+    mn = v3(wmn.x - e, wmn.y - e, wmn.z - e); mx = v3(wmx.x + e, wmx.y + e, wmx.z + e);
+  }
+  float* o = aabb + 6 * (size_t)i;
+  o[0] = mn.x; o[1] = mn.y; o[2] = mn.z; o[3] = mx.x; o[4] = mx.y; o[5] = mx.z;
+}
+
+// ---- 2. centroid bounds + S (order-independent: min/max are exact) ------------------------------
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__global__ void k_bounds_init(int* b) { if (threadIdx.x < 3) b[threadIdx.x] = f2ord(BIG); else if (threadIdx.x < 6) b[threadIdx.x] = f2ord(-BIG); else if (threadIdx.x == 6) b[6] = f2ord(0.0f); }
+__global__ void k_bounds_reduce(int n, const float* __restrict__ aabb, int* __restrict__ b) {
+  float cmin[3] = {BIG, BIG, BIG}, cmax[3] = {-BIG, -BIG, -BIG}, S = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* q = aabb + 6 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float c = __fmul_rn(0.5f, __fadd_rn(q[k], q[3 + k]));
+      cmin[k] = fminf(cmin[k], c); cmax[k] = fmaxf(cmax[k], c);
+      S = fmaxf(S, fmaxf(fabsf(q[k]), fabsf(q[3 + k])));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o; o >>= 1) { cmin[k] = fminf(cmin[k], __shfl_xor_sync(0xffffffffu, cmin[k], o)); cmax[k] = fmaxf(cmax[k], __shfl_xor_sync(0xffffffffu, cmax[k], o)); }
+  }
+  for (int o = 16; o; o >>= 1) S = fmaxf(S, __shfl_xor_sync(0xffffffffu, S, o));
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 3; ++k) { atomicMin(&b[k], f2ord(cmin[k])); atomicMax(&b[3 + k], f2ord(cmax[k])); }
+    atomicMax(&b[6], f2ord(S));
+  }
+}
+
+// ---- 3. Morton keys ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long expand21(unsigned int v) {
+  unsigned long long x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__global__ void k_morton(int n, const float* __restrict__ aabb, const int* __restrict__ b, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = aabb + 6 * (size_t)i;
+  unsigned int g[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float cmin = ord2f(b[k]), cmax = ord2f(b[3 + k]);
+    float c = __fmul_rn(0.5f, __fadd_rn(q[k], q[3 + k]));
+    float ext = __fsub_rn(cmax, cmin);
+    float qq = ext > 0.0f ? __fdiv_rn(__fsub_rn(c, cmin), ext) : 0.0f;
+    float scv = __fmul_rn(qq, 2097152.0f);
+    unsigned int gi = (unsigned int)scv;
+    g[k] = gi < 2097151u ? gi : 2097151u;
+  }
+  keys[i] = (expand21(g[0]) << 2) | (expand21(g[1]) << 1) | expand21(g[2]);
+  vals[i] = i;
+}
+
+// ---- 4. stable LSD radix sort, 8-bit digits, 64-bit keys + 32-bit payload ------------------------
+constexpr int RS_BLOCK = 256;
+__global__ void k_rs_hist(const unsigned long long* __restrict__ keys, int n, int shift, int* __restrict__ hist, int nblk) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int i = blockIdx.x * RS_BLOCK + threadIdx.x;
+  if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 255ull)], 1);
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void k_rs_scan(int* __restrict__ hist, int total) {   // exclusive scan, single CTA of 1024
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < total; base += 1024) {
+    int idx = base + threadIdx.x;
+    int v = idx < total ? hist[idx] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+      wsum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int incl = x + ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0);
+    if (idx < total) hist[idx] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+}
+__global__ void k_rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ vin,
+                             unsigned long long* __restrict__ kout, int* __restrict__ vout, int n, int shift,
+                             const int* __restrict__ hist, int nblk) {
+  __shared__ int wc[RS_BLOCK / 32][256];
+  for (int j = threadIdx.x; j < (RS_BLOCK / 32) * 256; j += RS_BLOCK) (&wc[0][0])[j] = 0;
+  __syncthreads();
+  int i = blockIdx.x * RS_BLOCK + threadIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool active = i < n;
+  unsigned long long key = 0; int val = 0, d = 0, rank = 0;
+  unsigned int amask = __ballot_sync(0xffffffffu, active);
+  if (active) {
+    key = kin[i]; val = vin[i];
+    d = (int)((key >> shift) & 255ull);
+    unsigned int peers = __match_any_sync(amask, d);
+    rank = __popc(peers & ((1u << lane) - 1u));
+    if (rank == 0) wc[warp][d] = __popc(peers);
+  }
+  __syncthreads();
+  if (active) {
+    int off = 0;
+    for (int w = 0; w < warp; ++w) off += wc[w][d];
+    int pos = hist[d * nblk + blockIdx.x] + off + rank;
+    kout[pos] = key; vout[pos] = val;
+  }
+}
+
+// ---- 5. Karras 2012 radix tree ------------------------------------------------------------------
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a != b) return __clzll((long long)(a ^ b));
+  return 64 + __clz(i ^ j);
+}
+__global__ void k_karras(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ order,
+                         int4* __restrict__ links /* left right parent sibling per node */, int* __restrict__ leaf_parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s = 0, t = l;
+  do { t = (t + 1) >> 1; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int a = min(i, j), b = max(i, j);
+  int left = (a == gamma) ? ~order[gamma] : gamma;
+  int right = (b == gamma + 1) ? ~order[gamma + 1] : gamma + 1;
+  links[i].x = left; links[i].y = right;
+  if (left >= 0) { links[left].z = i; links[left].w = right; } else leaf_parent[gamma] = i;
+  if (right >= 0) { links[right].z = i; links[right].w = left; } else leaf_parent[gamma + 1] = i;
+  if (i == 0) { links[0].z = -1; links[0].w = -1; }
+}
+
+// ---- 6. bottom-up refit with atomic visit counters ----------------------------------------------
+// nbox[i] = unpadded box of internal node i (scratch); stored child boxes are padded on write.
+__global__ void k_refit(int n, const int* __restrict__ order, const float* __restrict__ aabb, const int4* __restrict__ links,
+                        const int* __restrict__ leaf_parent, const int* __restrict__ b, float* nbox, int* visit,
+                        float4* __restrict__ nodes, int* __restrict__ depth_out) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const float pad = __fmul_rn(ord2f(b[6]), 1.0f / 2097152.0f);
+  int node = leaf_parent[pos];
+  int depth = 0;   // internal ancestors of this leaf
+  {  // count the depth first (read-only walk), used for the stackless-trail bound
+    int p = node; while (p >= 0) { ++depth; p = links[p].z; }
+    atomicMax(depth_out, depth);
+  }
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&visit[node], 1) == 0) return;      // first arrival: the sibling subtree finishes this node
+    int4 lk = links[node];
+    float cb[2][6];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      int ch = c ? lk.y : lk.x;
+      if (ch < 0) { const float* q = aabb + 6 * (size_t)(~ch); for (int k = 0; k < 6; ++k) cb[c][k] = q[k]; }
+      else { const volatile float* q = nbox + 6 * (size_t)ch; for (int k = 0; k < 6; ++k) cb[c][k] = q[k]; }
+    }
+    float* o = nbox + 6 * (size_t)node;
+    for (int k = 0; k < 3; ++k) { o[k] = fminf(cb[0][k], cb[1][k]); o[3 + k] = fmaxf(cb[0][3 + k], cb[1][3 + k]); }
+    float l[6], r[6];
+    for (int k = 0; k < 3; ++k) {
+      l[k] = __fsub_rn(cb[0][k], pad); l[3 + k] = __fadd_rn(cb[0][3 + k], pad);
+      r[k] = __fsub_rn(cb[1][k], pad); r[3 + k] = __fadd_rn(cb[1][3 + k], pad);
+    }
+    nodes[4 * node + 0] = make_float4(l[0], l[1], l[2], l[3]);
+    nodes[4 * node + 1] = make_float4(l[4], l[5], r[0], r[1]);
+    nodes[4 * node + 2] = make_float4(r[2], r[3], r[4], r[5]);
+    nodes[4 * node + 3] = make_float4(__int_as_float(lk.x), __int_as_float(lk.y), __int_as_float(lk.z), __int_as_float(lk.w));
+    node = lk.z;
+  }
+}
+
+// n <= 1: a single node whose right box is empty.
+__global__ void k_single_node(int n, const float* __restrict__ aabb, const int* __restrict__ b, float4* __restrict__ nodes,
+                              unsigned long long* keys, int* order) {
+  if (threadIdx.x != 0) return;
+  float l[6] = {BIG, BIG, BIG, -BIG, -BIG, -BIG};
+  if (n == 1) {
+    const float pad = __fmul_rn(ord2f(b[6]), 1.0f / 2097152.0f);
+    for (int k = 0; k < 3; ++k) { l[k] = __fsub_rn(aabb[k], pad); l[3 + k] = __fadd_rn(aabb[3 + k], pad); }
+    order[0] = 0;
+  }
+  nodes[0] = make_float4(l[0], l[1], l[2], l[3]);
+  nodes[1] = make_float4(l[4], l[5], BIG, BIG);
+  nodes[2] = make_float4(BIG, -BIG, -BIG, -BIG);
+  nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), __int_as_float(-1), __int_as_float(-1));
+}
+
+}  // namespace
+
+// Builds the LBVH for sc (device arrays already uploaded).  All launches on `stream`.
+// Outputs: d_aabb[6n], d_keys[n] (sorted), d_order[n], d_nodes[4*max(n-1,1)]; returns launches.
+int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream) {
+  int n = sc.n_prims, launches = 0;
+  k_bounds_init<<<1, 32, 0, stream>>>(B.d_bounds); ++launches;
+  if (n > 0) {
+    k_prim_bounds<<<(n + 127) / 128, 128, 0, stream>>>(sc, cam_t0, cam_t1, B.d_aabb); ++launches;
+    int rb = min((n + 255) / 256, 1024);
+    k_bounds_reduce<<<rb, 256, 0, stream>>>(n, B.d_aabb, B.d_bounds); ++launches;
+  }
+  if (n <= 1) {
+    k_single_node<<<1, 32, 0, stream>>>(n, B.d_aabb, B.d_bounds, B.d_nodes, B.d_keys[0], B.d_order[0]); ++launches;
+    B.sorted = 0;
+    int one = n;   // depth = number of internal nodes on the path
+    cudaMemcpyAsync(B.d_depth, &one, sizeof(int), cudaMemcpyHostToDevice, stream);
+    return launches;
+  }
+  k_morton<<<(n + 255) / 256, 256, 0, stream>>>(n, B.d_aabb, B.d_bounds, B.d_keys[0], B.d_order[0]); ++launches;
+  int nblk = (n + RS_BLOCK - 1) / RS_BLOCK;
+  int cur = 0;
+  for (int pass = 0; pass < 8; ++pass) {
+    int shift = 8 * pass;
+    k_rs_hist<<<nblk, RS_BLOCK, 0, stream>>>(B.d_keys[cur], n, shift, B.d_hist, nblk);
+    k_rs_scan<<<1, 1024, 0, stream>>>(B.d_hist, 256 * nblk);
+    k_rs_scatter<<<nblk, RS_BLOCK, 0, stream>>>(B.d_keys[cur], B.d_order[cur], B.d_keys[cur ^ 1], B.d_order[cur ^ 1], n, shift, B.d_hist, nblk);
+    launches += 3; cur ^= 1;
+  }
+  B.sorted = cur;
+  cudaMemsetAsync(B.d_visit, 0, sizeof(int) * (size_t)(n - 1), stream);
+  cudaMemsetAsync(B.d_depth, 0, sizeof(int), stream);
+  k_karras<<<(n - 1 + 127) / 128, 128, 0, stream>>>(n, B.d_keys[cur], B.d_order[cur], B.d_links, B.d_leaf_parent); ++launches;
+  k_refit<<<(n + 127) / 128, 128, 0, stream>>>(n, B.d_order[cur], B.d_aabb, B.d_links, B.d_leaf_parent, B.d_bounds, B.d_nbox, B.d_visit, B.d_nodes, B.d_depth); ++launches;
+  return launches;
+}

@@ -1,0 +1,399 @@
+// srt_api.cu — the C-ABI of include/srt.h: scene tables -> device SoA, commit (H2D + LBVH build),
+// render / trace_batch entry points.  Host-side plumbing only; all arithmetic of the radiance loop
+// lives in the kernels (wavefront.cu, lbvh.cu).  No CPU fallback anywhere.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <string>
+#include "srt_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1, g_sm_count = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf; return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SRT_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) n = count ? count : 1;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct SrtScene {
+  std::vector<SrtPrim> prims; std::vector<SrtXform> xforms; std::vector<SrtMaterial> mats; std::vector<SrtTexture> texs;
+  float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
+  SrtCamera cam; bool has_cam = false;
+  bool committed = false;
+  // device tables
+  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
+  // LBVH
+  LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth;
+  DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
+  int n_nodes = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
+  // wavefront
+  WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit, w_L; DevBuf<int> w_counts; DevBuf<unsigned long long> w_totals;
+  DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host
+  DScene ds; DCamera dcam;
+};
+
+static void fill_dscene(SrtScene* s) {
+  DScene& d = s->ds;
+  d.n_prims = (int)s->prims.size(); d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
+  d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
+  d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
+  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p;
+}
+
+static int ensure_wave(SrtScene* s, size_t paths, int max_depth) {
+  WaveBuffers& W = s->wb;
+  if (paths > W.capacity) {
+    for (int g = 0; g < 2; ++g) { CK(s->w_ro[g].ensure(paths)); CK(s->w_rd[g].ensure(paths)); CK(s->w_st[g].ensure(paths)); }
+    CK(s->w_hit.ensure(paths)); CK(s->w_L.ensure(paths));
+    for (int g = 0; g < 2; ++g) { W.ray_o[g] = s->w_ro[g].p; W.ray_d[g] = s->w_rd[g].p; W.state[g] = s->w_st[g].p; }
+    W.hit = s->w_hit.p; W.path_L = s->w_L.p; W.capacity = paths;
+  }
+  if (max_depth + 2 > W.counts_cap) { CK(s->w_counts.ensure((size_t)max_depth + 2)); W.counts = s->w_counts.p; W.counts_cap = max_depth + 2; }
+  if (!W.totals) { CK(s->w_totals.ensure(16)); W.totals = s->w_totals.p; }
+  return 0;
+}
+
+static RenderLaunch make_launch(SrtScene* s, const SrtRenderParams* p) {
+  RenderLaunch L; L.sc = s->ds; L.cam = s->dcam; if (p) L.p = *p; else std::memset(&L.p, 0, sizeof(L.p));
+  L.sm_count = g_sm_count; L.extend_smem = srt_extend_smem_bytes(s->ds);
+  L.bvh_in_smem = L.extend_smem <= (size_t)200 * 1024;
+  return L;
+}
+
+extern "C" {
+
+const char* srt_last_error(void) { return g_err.c_str(); }
+
+int srt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+int srt_init(int device) {
+  int n = srt_device_count();
+  if (n <= 0) return fail(SRT_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(SRT_ERR_ARG, "device %d out of range (%d visible)", device, n);
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(SRT_ERR_NO_DEVICE, "device %d is sm_%d%d; libsrt is built for sm_100a only", device, prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  g_device = device; g_sm_count = prop.multiProcessorCount;
+  return 0;
+}
+void srt_shutdown(void) { g_device = -1; }
+
+SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); if (!s) g_err = "out of host memory"; return s; }
+
+void srt_scene_destroy(SrtScene* s) {
+  if (!s) return;
+  s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
+  s->d_ranvec.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
+  s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_visit.release(); s->d_depth.release();
+  s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
+  for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
+  s->w_hit.release(); s->w_L.release(); s->w_counts.release(); s->w_totals.release(); s->d_accum.release();
+  delete s;
+}
+
+int srt_scene_set_prims(SrtScene* s, const SrtPrim* p, int n) {
+  if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_prims: bad argument");
+  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_BEZIER) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
+  s->prims.assign(p, p + n); s->committed = false; return 0;
+}
+int srt_scene_set_xforms(SrtScene* s, const SrtXform* p, int n) {
+  if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_xforms: bad argument");
+  s->xforms.assign(p, p + n); s->committed = false; return 0;
+}
+int srt_scene_set_materials(SrtScene* s, const SrtMaterial* p, int n) {
+  if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_materials: bad argument");
+  s->mats.assign(p, p + n); s->committed = false; return 0;
+}
+int srt_scene_set_textures(SrtScene* s, const SrtTexture* p, int n) {
+  if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_textures: bad argument");
+  s->texs.assign(p, p + n); s->committed = false; return 0;
+}
+int srt_scene_set_perlin(SrtScene* s, const float* ranvec768, const int32_t* px, const int32_t* py, const int32_t* pz) {
+  if (!s || !ranvec768 || !px || !py || !pz) return fail(SRT_ERR_ARG, "set_perlin: bad argument");
+  std::memcpy(s->ranvec, ranvec768, sizeof(s->ranvec));
+  std::memcpy(s->perm[0], px, 1024); std::memcpy(s->perm[1], py, 1024); std::memcpy(s->perm[2], pz, 1024);
+  s->has_perlin = true; s->committed = false; return 0;
+}
+int srt_scene_set_camera(SrtScene* s, const SrtCamera* c) {
+  if (!s || !c) return fail(SRT_ERR_ARG, "set_camera: bad argument");
+  s->cam = *c; s->has_cam = true; s->committed = false; return 0;
+}
+
+int srt_scene_commit(SrtScene* s) {
+  if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
+  if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded");
+  const int n = (int)s->prims.size();
+  // validate indices (the kernels trust the tables)
+  for (int i = 0; i < n; ++i) {
+    const SrtPrim& p = s->prims[i];
+    if (p.material < 0 || p.material >= (int)s->mats.size()) return fail(SRT_ERR_ARG, "prim %d: material %d out of range", i, p.material);
+    if (p.xform >= (int)s->xforms.size()) return fail(SRT_ERR_ARG, "prim %d: xform %d out of range", i, p.xform);
+  }
+  for (size_t i = 0; i < s->mats.size(); ++i) {
+    const SrtMaterial& m = s->mats[i];
+    if (m.kind != SRT_MAT_DIELECTRIC && (m.tex < 0 || m.tex >= (int)s->texs.size())) return fail(SRT_ERR_ARG, "material %zu: texture %d out of range", i, m.tex);
+  }
+  for (size_t i = 0; i < s->texs.size(); ++i) {
+    const SrtTexture& t = s->texs[i];
+    if (t.kind == SRT_TEX_CHECKER && (t.even < 0 || t.odd < 0 || t.even >= (int)s->texs.size() || t.odd >= (int)s->texs.size()))
+      return fail(SRT_ERR_ARG, "texture %zu: checker children out of range", i);
+  }
+  cudaStream_t stream = 0;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, stream));
+  // ---- host SoA staging + H2D ---------------------------------------------------------------
+  std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
+  for (int i = 0; i < n; ++i) {
+    const SrtPrim& p = s->prims[i]; const float* q = p.p;
+    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, 0);
+    a[i] = b[i] = c[i] = d[i] = make_float4(0, 0, 0, 0);
+    switch (p.type) {
+      case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
+      case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
+      case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
+      default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
+    }
+  }
+  CK(s->d_hdr.ensure(n)); CK(s->d_a.ensure(n)); CK(s->d_b.ensure(n)); CK(s->d_c.ensure(n)); CK(s->d_d.ensure(n));
+  if (n) {
+    CK(cudaMemcpyAsync(s->d_hdr.p, hdr.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(s->d_a.p, a.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(s->d_b.p, b.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(s->d_c.p, c.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(s->d_d.p, d.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
+  }
+  size_t nx = s->xforms.size(), nm = s->mats.size(), nt = s->texs.size();
+  std::vector<float4> xf(2 * (nx ? nx : 1)), tx(2 * (nt ? nt : 1)); std::vector<int4> mt(nm ? nm : 1);
+  for (size_t i = 0; i < nx; ++i) { const SrtXform& x = s->xforms[i]; xf[2 * i] = make_float4(x.sin_t, x.cos_t, x.off[0], x.off[1]); xf[2 * i + 1] = make_float4(x.off[2], 0, 0, 0); }
+  for (size_t i = 0; i < nm; ++i) { const SrtMaterial& m = s->mats[i]; int pb; std::memcpy(&pb, &m.param, 4); mt[i] = make_int4(m.kind, m.tex, pb, 0); }
+  for (size_t i = 0; i < nt; ++i) {
+    const SrtTexture& t = s->texs[i]; float fk, fe, fo; std::memcpy(&fk, &t.kind, 4); std::memcpy(&fe, &t.even, 4); std::memcpy(&fo, &t.odd, 4);
+    tx[2 * i] = make_float4(fk, fe, fo, t.scale); tx[2 * i + 1] = make_float4(t.rgb[0], t.rgb[1], t.rgb[2], 0);
+  }
+  CK(s->d_xf.ensure(2 * nx)); CK(s->d_mats.ensure(nm)); CK(s->d_tex.ensure(2 * nt));
+  if (nx) CK(cudaMemcpyAsync(s->d_xf.p, xf.data(), sizeof(float4) * 2 * nx, cudaMemcpyHostToDevice, stream));
+  if (nm) CK(cudaMemcpyAsync(s->d_mats.p, mt.data(), sizeof(int4) * nm, cudaMemcpyHostToDevice, stream));
+  if (nt) CK(cudaMemcpyAsync(s->d_tex.p, tx.data(), sizeof(float4) * 2 * nt, cudaMemcpyHostToDevice, stream));
+  std::vector<float4> rv(256); std::vector<uint8_t> pm(768);
+  for (int i = 0; i < 256; ++i) rv[i] = s->has_perlin ? make_float4(s->ranvec[3 * i], s->ranvec[3 * i + 1], s->ranvec[3 * i + 2], 0) : make_float4(0, 0, 0, 0);
+  for (int k = 0; k < 3; ++k) for (int i = 0; i < 256; ++i) pm[256 * k + i] = s->has_perlin ? (uint8_t)(s->perm[k][i] & 255) : (uint8_t)i;
+  CK(s->d_ranvec.ensure(256)); CK(s->d_perm.ensure(768));
+  CK(cudaMemcpyAsync(s->d_ranvec.p, rv.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(s->d_perm.p, pm.data(), 768, cudaMemcpyHostToDevice, stream));
+  // camera (by value in kernel params)
+  if (s->has_cam) {
+    const SrtCamera& cm = s->cam; DCamera& dc = s->dcam;
+    dc.llc = make_float3(cm.llc[0], cm.llc[1], cm.llc[2]); dc.horiz = make_float3(cm.horiz[0], cm.horiz[1], cm.horiz[2]);
+    dc.vert = make_float3(cm.vert[0], cm.vert[1], cm.vert[2]); dc.origin = make_float3(cm.origin[0], cm.origin[1], cm.origin[2]);
+    dc.w = make_float3(cm.w[0], cm.w[1], cm.w[2]); dc.u = make_float3(cm.u[0], cm.u[1], cm.u[2]); dc.v = make_float3(cm.v[0], cm.v[1], cm.v[2]);
+    dc.lens_radius = cm.lens_radius; dc.time0 = cm.time0; dc.time1 = cm.time1;
+  } else std::memset(&s->dcam, 0, sizeof(s->dcam));
+  // ---- LBVH ------------------------------------------------------------------------------------
+  const int nint = n > 1 ? n - 1 : 1, nn = n ? n : 1;
+  CK(s->d_aabb.ensure(6 * (size_t)nn)); CK(s->d_bounds.ensure(8)); CK(s->d_keys0.ensure(nn)); CK(s->d_keys1.ensure(nn));
+  CK(s->d_order0.ensure(nn)); CK(s->d_order1.ensure(nn)); CK(s->d_hist.ensure(256 * (size_t)((nn + 255) / 256)));
+  CK(s->d_links.ensure(nint)); CK(s->d_leaf_parent.ensure(nn)); CK(s->d_nbox.ensure(6 * (size_t)nint)); CK(s->d_visit.ensure(nint));
+  CK(s->d_depth.ensure(1)); CK(s->d_nodes.ensure(4 * (size_t)nint));
+  LbvhBuffers& B = s->lb;
+  B.d_aabb = s->d_aabb.p; B.d_bounds = s->d_bounds.p; B.d_keys[0] = s->d_keys0.p; B.d_keys[1] = s->d_keys1.p;
+  B.d_order[0] = s->d_order0.p; B.d_order[1] = s->d_order1.p; B.d_hist = s->d_hist.p; B.d_links = s->d_links.p;
+  B.d_leaf_parent = s->d_leaf_parent.p; B.d_nbox = s->d_nbox.p; B.d_visit = s->d_visit.p; B.d_depth = s->d_depth.p; B.d_nodes = s->d_nodes.p;
+  s->n_nodes = nint;
+  fill_dscene(s);
+  s->commit_launches = srt_lbvh_build(s->ds, s->dcam.time0, s->dcam.time1, B, stream);
+  CK(cudaGetLastError());
+  int depth = 0;
+  CK(cudaMemcpyAsync(&depth, B.d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(e1, stream));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&s->ms_commit, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  s->bvh_depth = depth; s->ds.bvh_depth = depth;
+  if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level stackless trail", depth);
+  s->committed = true;
+  return 0;
+}
+
+int srt_bvh_node_count(SrtScene* s) { return (s && s->committed) ? s->n_nodes : 0; }
+int srt_bvh_readback(SrtScene* s, SrtBvhNode* nodes, int cap) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (cap < s->n_nodes || !nodes) return fail(SRT_ERR_ARG, "bvh_readback: capacity %d < %d nodes", cap, s->n_nodes);
+  CK(cudaMemcpy(nodes, s->d_nodes.p, sizeof(SrtBvhNode) * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  int n = (int)s->prims.size();
+  if (cap < n) return fail(SRT_ERR_ARG, "bvh_keys_readback: capacity too small");
+  if (n) {
+    CK(cudaMemcpy(keys, s->lb.d_keys[s->lb.sorted], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(order, s->lb.d_order[s->lb.sorted], sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+int srt_prim_bounds_readback(SrtScene* s, float* aabbs6, int cap) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  int n = (int)s->prims.size();
+  if (cap < n) return fail(SRT_ERR_ARG, "prim_bounds_readback: capacity too small");
+  if (n) CK(cudaMemcpy(aabbs6, s->d_aabb.p, sizeof(float) * 6 * (size_t)n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t_max, SrtHit* out) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (n < 0 || (n && (!rays || !out))) return fail(SRT_ERR_ARG, "trace_batch: bad argument");
+  if (n == 0) return 0;
+  if (int rc = ensure_wave(s, (size_t)n, 0)) return rc;
+  cudaStream_t stream = 0;
+  DevBuf<SrtRay> d_rays; DevBuf<SrtHit> d_out;
+  CK(d_rays.ensure(n)); CK(d_out.ensure(n));
+  CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(SrtRay) * (size_t)n, cudaMemcpyHostToDevice, stream));
+  RenderLaunch L = make_launch(s, nullptr);
+  srt_launch_upload_rays(d_rays.p, n, s->wb.ray_o[0], s->wb.ray_d[0], stream);
+  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, nullptr, n, t_min, t_max, stream);   // the renderer's extend kernel
+  srt_launch_complete_hits(s->ds, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, n, d_out.p, stream);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out.p, sizeof(SrtHit) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  d_rays.release(); d_out.release();
+  return 0;
+}
+
+static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (!p || !d_rgb_sum) return fail(SRT_ERR_ARG, "render: null argument");
+  if (p->width <= 0 || p->height <= 0 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4096)
+    return fail(SRT_ERR_ARG, "render: bad parameters (%dx%d, spp [%d,%d), depth %d)", p->width, p->height, p->spp_begin, p->spp_end, p->max_depth);
+  if (!s->has_cam) return fail(SRT_ERR_ARG, "render: no camera set");
+  const size_t npix = (size_t)p->width * p->height;
+  const int spp = p->spp_end - p->spp_begin;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (spp == 0) return 0;
+  // wave sizing: ~8M paths in flight (queues ~1 GB of the 180 GB HBM), at least one sample/pixel
+  int wave_spp = p->wave_spp > 0 ? p->wave_spp : (int)((size_t)(8u << 20) / npix);
+  if (wave_spp < 1) wave_spp = 1;
+  if (wave_spp > spp) wave_spp = spp;
+  if (npix * (size_t)wave_spp > (size_t)1 << 30) return fail(SRT_ERR_ARG, "render: wave of %zu paths too large", npix * (size_t)wave_spp);
+  if (int rc = ensure_wave(s, npix * (size_t)wave_spp, p->max_depth)) return rc;
+  cudaStream_t stream = 0;
+  RenderLaunch L = make_launch(s, p);
+  const bool profile = p->reserved[0] == 1;
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaMemsetAsync(s->wb.totals, 0, sizeof(unsigned long long) * 16, stream));
+  CK(cudaEventRecord(e0, stream));
+  int waves = 0, n_ext = 0; float ms_ext = 0.f, ms_shd = 0.f;
+  WaveBuffers W = s->wb; W.capacity = npix * (size_t)wave_spp;
+  int launches = srt_wavefront_render(L, W, d_rgb_sum, stream, &waves, profile, &ms_ext, &ms_shd, &n_ext);
+  CK(cudaEventRecord(e1, stream));
+  CK(cudaGetLastError());
+  unsigned long long totals[16];
+  CK(cudaMemcpyAsync(totals, s->wb.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaGetLastError());
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (stats) {
+    stats->rays = totals[0]; stats->paths = (uint64_t)npix * (uint64_t)spp; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
+    stats->kernel_launches = launches; stats->waves = waves; stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth;
+    for (int i = 0; i < 8; ++i) stats->rays_per_bounce[i] = totals[1 + i];
+    stats->ms_extend = ms_ext; stats->ms_shade = ms_shd; stats->extend_launches = n_ext;
+  }
+  return 0;
+}
+
+int srt_render_device(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) { return render_impl(s, p, d_rgb_sum, stats); }
+
+int srt_render_host(SrtScene* s, const SrtRenderParams* p, float* rgb_sum, SrtStats* stats) {
+  if (!s || !p || !rgb_sum) return fail(SRT_ERR_ARG, "render_host: null argument");
+  if (p->width <= 0 || p->height <= 0) return fail(SRT_ERR_ARG, "render_host: bad size");
+  size_t n3 = (size_t)p->width * p->height * 3;
+  CK(s->d_accum.ensure(n3));
+  CK(cudaMemcpyAsync(s->d_accum.p, rgb_sum, sizeof(float) * n3, cudaMemcpyHostToDevice, 0));   // running sum in (*raw-data*)
+  if (int rc = render_impl(s, p, s->d_accum.p, stats)) return rc;
+  CK(cudaMemcpy(rgb_sum, s->d_accum.p, sizeof(float) * n3, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int srt_resolve_device(const float* d_rgb_sum, int width, int height, int spp, uint8_t* d_image) {
+  if (!d_rgb_sum || !d_image || width <= 0 || height <= 0 || spp <= 0) return fail(SRT_ERR_ARG, "resolve: bad argument");
+  srt_launch_resolve(d_rgb_sum, width * height * 3, spp, d_image, 0);
+  CK(cudaGetLastError()); CK(cudaStreamSynchronize(0));
+  return 0;
+}
+int srt_resolve_host(const float* rgb_sum, int width, int height, int spp, uint8_t* image) {
+  if (!rgb_sum || !image || width <= 0 || height <= 0 || spp <= 0) return fail(SRT_ERR_ARG, "resolve: bad argument");
+  if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded (no CPU fallback)");
+  size_t n3 = (size_t)width * height * 3;
+  DevBuf<float> d_in; DevBuf<uint8_t> d_out;
+  CK(d_in.ensure(n3)); CK(d_out.ensure(n3));
+  CK(cudaMemcpy(d_in.p, rgb_sum, sizeof(float) * n3, cudaMemcpyHostToDevice));
+  int rc = srt_resolve_device(d_in.p, width, height, spp, d_out.p);
+  if (!rc) { cudaError_t e = cudaMemcpy(image, d_out.p, n3, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(SRT_ERR_CUDA, "resolve D2H: %s", cudaGetErrorString(e)); }
+  d_in.release(); d_out.release();
+  return rc;
+}
+
+// main.scm:439-450 save-as-ppm: ASCII P3, header "P3\n W H\n255\n" (space before W), rows from
+// y = H-1 down to 0, one "r g b\n" per pixel.
+int srt_save_ppm(const char* path, const uint8_t* image, int width, int height) {
+  if (!path || !image || width <= 0 || height <= 0) return fail(SRT_ERR_ARG, "save_ppm: bad argument");
+  FILE* f = std::fopen(path, "w");
+  if (!f) return fail(SRT_ERR_IO, "save_ppm: cannot open %s", path);
+  std::fprintf(f, "P3\n %d %d\n255\n", width, height);
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      size_t i = ((size_t)(height - y - 1) * width + x) * 3;
+      std::fprintf(f, "%d %d %d\n", image[i], image[i + 1], image[i + 2]);
+    }
+  std::fclose(f);
+  return 0;
+}
+
+int srt_eval_texture(SrtScene* s, int tex, const float* uvp5, int n, int quirks, float* rgb) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (tex < 0 || tex >= (int)s->texs.size() || n < 0 || (n && (!uvp5 || !rgb))) return fail(SRT_ERR_ARG, "eval_texture: bad argument");
+  if (n == 0) return 0;
+  DevBuf<float> d_in, d_out; CK(d_in.ensure(5 * (size_t)n)); CK(d_out.ensure(3 * (size_t)n));
+  CK(cudaMemcpy(d_in.p, uvp5, sizeof(float) * 5 * (size_t)n, cudaMemcpyHostToDevice));
+  srt_launch_eval_texture(s->ds, tex, d_in.p, n, quirks, d_out.p, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(rgb, d_out.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+  d_in.release(); d_out.release();
+  return 0;
+}
+int srt_eval_raygen(SrtScene* s, const SrtRenderParams* p, int n, const int32_t* pixel, const int32_t* sample, SrtRay* out) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (!p || n < 0 || (n && (!pixel || !sample || !out))) return fail(SRT_ERR_ARG, "eval_raygen: bad argument");
+  if (n == 0) return 0;
+  DevBuf<int> d_px, d_sm; DevBuf<SrtRay> d_out; CK(d_px.ensure(n)); CK(d_sm.ensure(n)); CK(d_out.ensure(n));
+  CK(cudaMemcpy(d_px.p, pixel, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_sm.p, sample, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  RenderLaunch L = make_launch(s, p);
+  srt_launch_eval_raygen(L, n, d_px.p, d_sm.p, d_out.p, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out.p, sizeof(SrtRay) * (size_t)n, cudaMemcpyDeviceToHost));
+  d_px.release(); d_sm.release(); d_out.release();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// srt_device.cuh — device-side building blocks of the radiance loop (fp32 register math).
+//
+// Each function cites the reference Scheme it replaces (paths under /root/reference).  The
+// reference computes in f64 on boxed f64vectors (vec.scm); here vec3 is three registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/srt.h"
+
+#define SRT_PI 3.14159265358979323846f
+#define SRT_MAX_FLOAT 999999999999.0f  // constant.scm:6
+
+// ------------------------------------------------------------------------------------------------
+// Device view of a committed scene ("primitive SoA, material and texture tables, Perlin tables").
+struct DScene {
+  int n_prims, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;
+  const int4* prim_hdr;     // x = type | flags << 8, y = material, z = xform, w = 0
+  const float4* prim_a;     // sphere: c.xyz r | rect: a0 a1 b0 b1 | bezier: A.xyz width
+  const float4* prim_b;     // moving: c1.xyz time0 | rect: k | bezier: B.xyz
+  const float4* prim_c;     // moving: time1 | bezier: C.xyz
+  const float4* prim_d;     // bezier: D.xyz
+  const float4* xf;         // 2 per xform: (sin cos off.x off.y) (off.z 0 0 0)
+  const float4* nodes;      // 4 per LBVH node == SrtBvhNode
+  const int4* mats;         // kind, tex, float_as_int(param), 0
+  const float4* tex;        // 2 per texture: (kind even odd scale as int bits / float) (r g b 0)
+  const float4* ranvec;     // 256 unit gradient vectors (perlin.scm:33)
+  const uint8_t* perm;      // 3 x 256: perm-x, perm-y, perm-z (perlin.scm:34-36)
+};
+
+struct DCamera { float3 llc, horiz, vert, origin, w, u, v; float lens_radius, time0, time1; };
+
+// ------------------------------------------------------------------------------------------------
+// vec.scm
+__device__ __forceinline__ float3 v3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }   // vec.scm:20
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }   // vec.scm:26
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }   // vec.scm:35
+__device__ __forceinline__ float3 operator*(float3 a, float k) { return v3(a.x * k, a.y * k, a.z * k); }          // vec.scm:41
+__device__ __forceinline__ float3 operator-(float3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }    // vec.scm:52
+__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }                                    // vec.scm:54
+__device__ __forceinline__ float3 unit(float3 a) { float k = 1.0f / length(a); return a * k; }                    // vec.scm:60
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {                                                      // vec.scm:64
+  return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float3 madd(float3 a, float k, float3 b) { return v3(fmaf(a.x, k, b.x), fmaf(a.y, k, b.y), fmaf(a.z, k, b.z)); }  // a*k + b
+__device__ __forceinline__ float3 xyz(float4 a) { return v3(a.x, a.y, a.z); }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, keyed by (pixel, seed), counter (sample, bounce, block, 0)  — replaces srfi-27
+// random-real.  uniform = ((x >> 8) + 0.5) * 2^-24 in (0,1).
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+struct RngAddr { uint32_t seed, pixel, sample, bounce; };
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float4 rng_block(const RngAddr& a, uint32_t block) {
+  uint4 r = philox4x32_10(a.sample, a.bounce, block, 0u, a.pixel, a.seed);
+  return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
+// util.scm:9-15 random-in-unit-sphere (iteration j draws block first+j)
+__device__ __forceinline__ float3 random_in_unit_sphere(const RngAddr& a, uint32_t first) {
+  for (uint32_t j = 0;; ++j) {
+    float4 u = rng_block(a, first + j);
+    float3 p = v3(2.0f * u.x - 1.0f, 2.0f * u.y - 1.0f, 2.0f * u.z - 1.0f);
+    if (dot(p, p) < 1.0f) return p;
+  }
+}
+// util.scm:17-23 random-in-unit-disk (two candidates per block)
+__device__ __forceinline__ float3 random_in_unit_disk(const RngAddr& a, uint32_t first) {
+  for (uint32_t j = 0;; ++j) {
+    float4 u = rng_block(a, first + j);
+    float3 p = v3(2.0f * u.x - 1.0f, 2.0f * u.y - 1.0f, 0.0f);
+    if (dot(p, p) < 1.0f) return p;
+    p = v3(2.0f * u.z - 1.0f, 2.0f * u.w - 1.0f, 0.0f);
+    if (dot(p, p) < 1.0f) return p;
+  }
+}
+// util.scm:37-44 random-cosine-direction (Q1: x,y scaled by 2)
+__device__ __forceinline__ float3 random_cosine_direction(float r1, float r2, int quirks) {
+  float z = sqrtf(1.0f - r2);
+  float s, c;
+  sincospif(2.0f * r1, &s, &c);                       // phi = 2*pi*r1
+  float k = (quirks & SRT_Q1_COSINE_X2) ? 2.0f : 1.0f;
+  float q = k * sqrtf(r2);
+  return v3(c * q, s * q, z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Instance transform (geometry.scm:465-543 translate / rotate-y, composed on the host).
+struct Xf { float s, c; float3 off; };
+__device__ __forceinline__ Xf load_xf(const DScene& sc, int id) {
+  float4 a = __ldg(&sc.xf[2 * id]), b = __ldg(&sc.xf[2 * id + 1]);
+  Xf x; x.s = a.x; x.c = a.y; x.off = v3(a.z, a.w, b.x); return x;
+}
+// world -> object (geometry.scm:467, 512-521)
+__device__ __forceinline__ float3 xf_point_to_obj(const Xf& x, float3 p) {
+  float3 q = p - x.off;
+  return v3(x.c * q.x - x.s * q.z, q.y, x.s * q.x + x.c * q.z);
+}
+__device__ __forceinline__ float3 xf_vec_to_obj(const Xf& x, float3 d) { return v3(x.c * d.x - x.s * d.z, d.y, x.s * d.x + x.c * d.z); }
+// object -> world (geometry.scm:473, 526-535)
+__device__ __forceinline__ float3 xf_vec_to_world(const Xf& x, float3 n) { return v3(x.c * n.x + x.s * n.z, n.y, -x.s * n.x + x.c * n.z); }
+__device__ __forceinline__ float3 xf_point_to_world(const Xf& x, float3 p) { return xf_vec_to_world(x, p) + x.off; }
+
+// ------------------------------------------------------------------------------------------------
+// Primitive intersectors.  All return the candidate t with only the LOWER bound applied; the
+// caller applies the upper bound / exact-tie rule against the current best.
+
+// geometry.scm:146-175 sphere.  Same roots as the reference's (-b -/+ sqrt(b^2 - a c))/a, but
+// the discriminant is formed from the perpendicular offset l = oc - (b/a) d, i.e.
+// disc/a = r^2 - |l|^2, which does not cancel catastrophically in fp32 for the r = 100/1000
+// ground spheres (main.scm:38,160,319).  Miss iff disc <= 0, like the reference.
+__device__ __forceinline__ bool isect_sphere(float3 c, float r, float3 o, float3 d, float inv_a, float tmin, float& t) {
+  float3 oc = o - c;
+  float b = dot(oc, d);
+  float s = b * inv_a;
+  float3 l = madd(d, -s, oc);
+  float dq = fmaf(r, r, -dot(l, l));
+  if (!(dq > 0.0f)) return false;
+  float h = sqrtf(dq * inv_a);
+  float t1 = -s - h;
+  if (t1 > tmin) { t = t1; return true; }     // (< t-min temp ...) strict
+  float t2 = h - s;
+  if (t2 > tmin) { t = t2; return true; }
+  return false;
+}
+// geometry.scm:178-182 moving-sphere centre at the ray's time
+__device__ __forceinline__ float3 moving_center(float4 a, float4 b, float4 c, float time) {
+  float3 c0 = xyz(a), c1 = xyz(b);
+  float f = (time - b.w) / (c.x - b.w);
+  return madd(c1 - c0, f, c0);
+}
+// geometry.scm:376-431 rects.  axis = thin axis; (ia, ib) in-plane axes in argument order.
+// Inclusive bounds (t < t-min rejects).  A NaN t (ray in the plane) is rejected.
+__device__ __forceinline__ float cmp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o, float3 d, float tmin, float& t, float& u, float& v) {
+  int axis = (type == SRT_PRIM_XY_RECT) ? 2 : (type == SRT_PRIM_XZ_RECT ? 1 : 0);
+  int ia = (type == SRT_PRIM_YZ_RECT) ? 1 : 0, ib = (type == SRT_PRIM_XY_RECT) ? 1 : 2;
+  float tt = __fdiv_rn(k - cmp3(o, axis), cmp3(d, axis));
+  if (!(tt >= tmin)) return false;                       // also rejects NaN
+  float pa = fmaf(tt, cmp3(d, ia), cmp3(o, ia));
+  float pb = fmaf(tt, cmp3(d, ib), cmp3(o, ib));
+  if (pa < a.x || pa > a.y || pb < a.z || pb > a.w) return false;
+  t = tt;
+  u = (pa - a.x) / (a.y - a.x);
+  v = (pb - a.z) / (a.w - a.z);
+  return true;
+}
+
+// bezier.scm — cubic Bezier curve with width; recursive subdivision with an explicit stack.
+struct Bez { float3 a, b, c, d; };
+__device__ __forceinline__ float3 bez_p(const Bez& c, float t) {                    // bezier.scm:67-77
+  float t2 = t * t, t3 = t2 * t, mt = 1.0f - t, mt2 = mt * mt, mt3 = mt2 * mt;
+  return c.a * mt3 + c.b * (3.0f * mt2 * t) + c.c * (3.0f * mt * t2) + c.d * t3;
+}
+__device__ __forceinline__ float3 idiv(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }   // bezier.scm:45
+__device__ __forceinline__ float3 bez_tan(const Bez& c, float t) {                  // bezier.scm:106-117
+  float3 ca = c.b * 3.0f + c.d + c.c * -3.0f + c.a * -1.0f;
+  float3 cb = (c.a + c.b * -2.0f + c.c) * 3.0f;
+  float3 cc = (c.b - c.a) * 3.0f;
+  return unit(ca * (3.0f * t * t) + cb * (2.0f * t) + cc);
+}
+__device__ __forceinline__ float dot2d(float3 a, float3 b) { return a.x * b.x + a.y * b.y; }
+#define SRT_BEZ_MAX_DEPTH 20
+// bezier.scm:176-214 hit + :121-175 converge.  tbest plays the role of t-max (closest so far).
+static __device__ __noinline__ bool isect_bezier(float4 pa, float4 pb, float4 pc, float4 pd, float3 o, float3 dir, float tmin, float tbest, float& tout) {
+  float width = pa.w, width1 = width * 0.5f, width2 = width1 * width1, eps = width / 20.0f;
+  // get-projection-mat bezier.scm:13-43 (row-vector convention, swizzle (x,y,z)->(x,-z,y))
+  float3 ud = unit(dir);
+  float lx = ud.x, ly = -ud.z, lz = ud.y;
+  float dd = sqrtf(lx * lx + lz * lz);
+  float R[3][3];
+  if (dd == 0.0f) {
+    float ang = (ly >= 0.0f) ? -0.5f * SRT_PI : 0.5f * SRT_PI;
+    float ca = cosf(ang), sa = sinf(ang);
+    R[0][0] = 1; R[0][1] = 0; R[0][2] = 0; R[1][0] = 0; R[1][1] = ca; R[1][2] = -sa; R[2][0] = 0; R[2][1] = sa; R[2][2] = ca;
+  } else {
+    R[0][0] = lz / dd; R[0][1] = (-lx * ly) / dd; R[0][2] = lx;
+    R[1][0] = 0.0f;    R[1][1] = dd;              R[1][2] = ly;
+    R[2][0] = -lx / dd; R[2][1] = (-ly * lz) / dd; R[2][2] = lz;
+  }
+  float3 so = v3(o.x, -o.z, o.y);
+  auto xform = [&](float4 q) {                        // bezier.scm:49-55 transform
+    float3 s = v3(q.x, -q.z, q.y) - so;
+    return v3(s.x * R[0][0] + s.y * R[1][0] + s.z * R[2][0], s.x * R[0][1] + s.y * R[1][1] + s.z * R[2][1],
+              s.x * R[0][2] + s.y * R[1][2] + s.z * R[2][2]);
+  };
+  Bez cur; cur.a = xform(pa); cur.b = xform(pb); cur.c = xform(pc); cur.d = xform(pd);
+  float l0 = fmaxf(fmaxf(fabsf(cur.a.x - 2.0f * cur.b.x + cur.c.x), fabsf(cur.a.y - 2.0f * cur.b.y + cur.c.y)),
+                   fmaxf(fabsf(cur.b.x - 2.0f * cur.c.x + cur.d.x), fabsf(cur.b.y - 2.0f * cur.c.y + cur.d.y)));
+  int max_depth = 0;                                   // bezier.scm:179-192
+  if (l0 > 0.0f) max_depth = (int)ceilf(logf((1.41421356237f * 4.0f * 3.0f * l0) / (8.0f * eps)) * (1.0f / 1.38629436112f));
+  if (max_depth > SRT_BEZ_MAX_DEPTH) max_depth = SRT_BEZ_MAX_DEPTH;
+  // depth-first over the binary subdivision tree; the stack keeps the pending right halves
+  Bez stk[SRT_BEZ_MAX_DEPTH + 1]; float sv0[SRT_BEZ_MAX_DEPTH + 1], svn[SRT_BEZ_MAX_DEPTH + 1]; int sdepth[SRT_BEZ_MAX_DEPTH + 1];
+  int sp = 0; float v0 = 0.0f, vn = 1.0f; int depth = max_depth;
+  const float t = tbest;                               // both halves see the same incoming t (let*-values)
+  bool any = false; float tmin_found = tbest;
+  for (;;) {
+    bool descend = false;
+    // bbox reject bezier.scm:126-129 (bbox = cps -/+ width1)
+    float bminx = fminf(fminf(cur.a.x, cur.b.x), fminf(cur.c.x, cur.d.x)) - width1, bmaxx = fmaxf(fmaxf(cur.a.x, cur.b.x), fmaxf(cur.c.x, cur.d.x)) + width1;
+    float bminy = fminf(fminf(cur.a.y, cur.b.y), fminf(cur.c.y, cur.d.y)) - width1, bmaxy = fmaxf(fmaxf(cur.a.y, cur.b.y), fmaxf(cur.c.y, cur.d.y)) + width1;
+    float bminz = fminf(fminf(cur.a.z, cur.b.z), fminf(cur.c.z, cur.d.z)) - width1, bmaxz = fmaxf(fmaxf(cur.a.z, cur.b.z), fmaxf(cur.c.z, cur.d.z)) + width1;
+    if (!(bminz >= t || bmaxz <= 0.000001f || bminx >= width1 || bmaxx <= -width1 || bminy >= width1 || bmaxy <= -width1)) {
+      if (depth < 0) {                                 // leaf bezier.scm:130-166
+        float3 dirv = cur.d - cur.a;
+        float3 dp0 = bez_tan(cur, 0.0f);
+        if (dot2d(dirv, dp0) < 0.0f) dp0 = -dp0;
+        if (!(dot2d(dp0, -cur.a) < 0.0f)) {
+          float3 dpn = bez_tan(cur, 1.0f);
+          if (dot2d(dirv, dpn) < 0.0f) dpn = -dpn;
+          if (!(dot2d(dpn, cur.d) < 0.0f)) {
+            float w = dirv.x * dirv.x + dirv.y * dirv.y;
+            if (w != 0.0f) {
+              w = (cur.a.x * dirv.x + cur.a.y * dirv.y) / (-w);
+              w = fminf(fmaxf(w, 0.0f), 1.0f);
+              float v = v0 * (1.0f - w) + vn * w;
+              float3 p = bez_p(cur, v);                // Q8: sub-curve at the global parameter
+              if (!((p.x * p.x + p.y * p.y) >= width2 || p.z <= 0.0001f || t < p.z)) {
+                any = true; if (p.z < tmin_found) tmin_found = p.z;
+              }
+            }
+          }
+        }
+      } else {
+        descend = true;
+      }
+    }
+    if (descend) {                                     // split at 0.5 bezier.scm:78-87, left first
+      float3 sp_ = bez_p(cur, 0.5f);
+      float3 nbc = idiv(cur.b, cur.c, 0.5f), lb = idiv(cur.a, cur.b, 0.5f), lc = idiv(lb, nbc, 0.5f);
+      float3 rc = idiv(cur.c, cur.d, 0.5f), rb = idiv(nbc, rc, 0.5f);
+      float vm = (v0 + vn) / 2.0f;
+      stk[sp].a = sp_; stk[sp].b = rb; stk[sp].c = rc; stk[sp].d = cur.d; sv0[sp] = vm; svn[sp] = vn; sdepth[sp] = depth - 1; ++sp;
+      cur.b = lb; cur.c = lc; cur.d = sp_; vn = vm; depth -= 1;
+    } else {
+      if (sp == 0) break;
+      --sp; cur = stk[sp]; v0 = sv0[sp]; vn = svn[sp]; depth = sdepth[sp];
+    }
+  }
+  if (any && tmin < tmin_found) { tout = tmin_found; return true; }   // (and hit? (< t-min t))
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact-tie rule: the order-independent restatement of hit-obj-list's
+// sequential "later object replaces the best iff t < best (sphere-type) or t <= best (rect-type,
+// curve)".  ids are positions in the reference's flattened object list.
+__device__ __forceinline__ bool prim_inclusive(int type) { return type >= SRT_PRIM_XY_RECT; }
+__device__ __forceinline__ bool accept_hit(float t, int id, bool incl, float best_t, int best_id, bool best_incl) {
+  if (t < best_t) return true;
+  if (!(t == best_t)) return false;
+  if (id > best_id) return incl;
+  if (id < best_id) return !best_incl;
+  return false;
+}
+
+struct Hit { float t; int prim; float u, v; bool incl; };
+
+// One leaf primitive against the ray (world space in, candidate merged into `h`).
+template <class PrimSrc>
+__device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin, Hit& h) {
+  int4 hdr = ps.hdr(id);
+  int type = hdr.x & 0xff;
+  float4 a = ps.a(id);
+  float t = 0.f, u = 0.f, v = 0.f; bool ok = false;
+  if (type == SRT_PRIM_SPHERE) {
+    ok = isect_sphere(xyz(a), a.w, o, d, inv_a, tmin, t);
+  } else if (type == SRT_PRIM_MOVING_SPHERE) {
+    float4 b = __ldg(&sc.prim_b[id]), c = __ldg(&sc.prim_c[id]);
+    ok = isect_sphere(moving_center(a, b, c, time), a.w, o, d, inv_a, tmin, t);
+  } else if (type <= SRT_PRIM_YZ_RECT) {
+    float k = __ldg(&sc.prim_b[id]).x;
+    float3 oo = o, dd = d;
+    if (hdr.z >= 0) { Xf x = load_xf(sc, hdr.z); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
+    ok = isect_rect(type, a, k, oo, dd, tmin, t, u, v);
+  } else if (type == SRT_PRIM_BEZIER) {
+    ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
+  }
+  bool incl = prim_inclusive(type);
+  if (ok && accept_hit(t, id, incl, h.t, h.prim, h.incl)) { h.t = t; h.prim = id; h.u = u; h.v = v; h.incl = incl; }
+}
+
+// Hit-record completion: p and normal in world space (ray.scm:27 make-hit-record fields).
+// geometry.scm:158-160 (sphere), :386-387 (rects), :438 (flip), :473/:526-535 (instances),
+// bezier.scm:209-211 (Q9: p along the raw direction, normal = -dir).
+__device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t, float3 o, float3 d, float time, float3& p, float3& n, int& material) {
+  int4 hdr = __ldg(&sc.prim_hdr[prim]);
+  int type = hdr.x & 0xff;
+  material = hdr.y;
+  float4 a = __ldg(&sc.prim_a[prim]);
+  if (type <= SRT_PRIM_MOVING_SPHERE) {
+    float3 c = xyz(a);
+    if (type == SRT_PRIM_MOVING_SPHERE) c = moving_center(a, __ldg(&sc.prim_b[prim]), __ldg(&sc.prim_c[prim]), time);
+    p = madd(d, t, o);
+    n = (p - c) * (1.0f / a.w);
+  } else if (type <= SRT_PRIM_YZ_RECT) {
+    n = v3(type == SRT_PRIM_YZ_RECT ? 1.f : 0.f, type == SRT_PRIM_XZ_RECT ? 1.f : 0.f, type == SRT_PRIM_XY_RECT ? 1.f : 0.f);
+    if (hdr.z >= 0) {
+      Xf x = load_xf(sc, hdr.z);
+      float3 po = madd(xf_vec_to_obj(x, d), t, xf_point_to_obj(x, o));
+      p = xf_point_to_world(x, po);
+      n = xf_vec_to_world(x, n);
+    } else {
+      p = madd(d, t, o);
+    }
+  } else {
+    p = madd(d, t, o);
+    n = -d;
+  }
+  if ((hdr.x >> 8) & SRT_PRIM_FLAG_FLIP) n = -n;
+}
+// geometry.scm:138-144 get-sphere-uv (Q5) — only the parity hook needs it (dead in shading).
+__device__ __forceinline__ void sphere_uv(float3 p, float& u, float& v) {
+  float phi = atan2f(p.z, p.z), theta = asinf(p.y);
+  u = 1.0f - (phi + SRT_PI) / (2.0f * SRT_PI);
+  v = (theta + 0.5f * SRT_PI) / SRT_PI;
+}
+
+// ------------------------------------------------------------------------------------------------
+// perlin.scm:51-103 / texture.scm:9-34
+__device__ __forceinline__ float perlin_noise(const DScene& sc, float3 p, int quirks) {
+  float fi = floorf(p.x), fj = floorf(p.y), fk = floorf(p.z);
+  float u = p.x - fi, v = p.y - fj, w = p.z - fk;
+  int i = (int)fi, j = (int)fj, k = (int)fk;
+  float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+  const bool alias = quirks & SRT_Q4_PERLIN_ALIAS;   // Q4 perlin.scm:76: c[i][j][k] = grad(i+1, j+1, k+dk)
+  float acc = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        int ei = alias ? 1 : a, ej = alias ? 1 : b;
+        int idx = __ldg(&sc.perm[(i + ei) & 255]) ^ __ldg(&sc.perm[256 + ((j + ej) & 255)]) ^ __ldg(&sc.perm[512 + ((k + c) & 255)]);
+        float3 g = xyz(__ldg(&sc.ranvec[idx]));
+        float wa = a ? uu : 1.0f - uu, wb = b ? vv : 1.0f - vv, wc = c ? ww : 1.0f - ww;
+        acc += wa * wb * wc * dot(v3(u - a, v - b, w - c), g);
+      }
+  return acc;
+}
+__device__ __forceinline__ float perlin_turb(const DScene& sc, float3 p, int quirks) {   // perlin.scm:92-103, depth 7
+  float acc = 0.0f, weight = 1.0f;
+  for (int d = 0; d < 7; ++d) { acc = fmaf(weight, perlin_noise(sc, p, quirks), acc); p = p * 2.0f; weight *= 0.5f; }
+  return fabsf(acc);
+}
+__device__ __forceinline__ float3 tex_value(const DScene& sc, int tex, float u, float v, float3 p, int quirks) {
+  for (int guard = 0; guard < 64; ++guard) {
+    float4 t0 = __ldg(&sc.tex[2 * tex]);
+    int kind = __float_as_int(t0.x);
+    if (kind == SRT_TEX_CONSTANT) return xyz(__ldg(&sc.tex[2 * tex + 1]));                    // texture.scm:12
+    if (kind == SRT_TEX_CHECKER) {                                                           // texture.scm:16-23
+      float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
+      tex = (sines < 0.0f) ? __float_as_int(t0.z) : __float_as_int(t0.y);
+      continue;
+    }
+    if (kind == SRT_TEX_NOISE) { float n = perlin_noise(sc, p * t0.w, quirks); return v3(n, n, n); }   // texture.scm:25
+    float s = 0.5f * (1.0f + sinf(fmaf(t0.w, p.z, 10.0f * perlin_turb(sc, p, quirks))));                // texture.scm:30
+    return v3(s, s, s);
+  }
+  return v3(0.f, 0.f, 0.f);
+}
+
+// main.scm:91-98 sky functions
+__device__ __forceinline__ float3 sky_value(int sky, float3 d) {
+  if (sky == SRT_SKY_BLACK) return v3(0.f, 0.f, 0.f);
+  float3 ud = unit(d);
+  float t = 0.5f * (1.0f + ud.y);
+  return v3(1.f, 1.f, 1.f) * (1.0f - t) + v3(0.5f, 0.7f, 1.0f) * t;
+}
+
+// camera.scm:80-92 get-ray.  Draw slots (bounce 0): block 0 = [xi_u, xi_v, xi_time, -], lens
+// disk rejection from block 1 (skipped when lens-radius == 0: the offset is exactly zero).
+__device__ __forceinline__ void get_ray(const DCamera& cam, float s, float t, float xi_time, const RngAddr& addr, float3& o, float3& d, float& time) {
+  float3 rd = v3(0.f, 0.f, 0.f);
+  if (cam.lens_radius != 0.0f) rd = random_in_unit_disk(addr, 1) * cam.lens_radius;
+  float3 offset = cam.u * rd.x + cam.v * rd.y;
+  time = cam.time0 + xi_time * (cam.time1 - cam.time0);
+  o = cam.origin + offset;
+  d = cam.llc + cam.horiz * s + cam.vert * t - cam.origin - offset;
+}
+
+// ------------------------------------------------------------------------------------------------
+// material.scm — scatter.  Returns true when the path continues; `weight` multiplies throughput.
+__device__ __forceinline__ float3 reflect(float3 v, float3 n) { return v - n * (2.0f * dot(v, n)); }   // material.scm:41
+__device__ __forceinline__ float schlick(float cosine, float ref_idx) {                                 // material.scm:69
+  float r0 = (1.0f - ref_idx) / (1.0f + ref_idx); r0 = r0 * r0;
+  float m = 1.0f - cosine, m2 = m * m;
+  return r0 + (1.0f - r0) * (m2 * m2 * m);
+}
+struct Scatter { float3 dir; float3 weight; float3 emitted; bool valid; };
+
+__device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float3 d_in, float3 p, float3 n, float u, float v,
+                                           const RngAddr& addr, int quirks) {
+  Scatter r; r.valid = false; r.emitted = v3(0.f, 0.f, 0.f); r.weight = v3(1.f, 1.f, 1.f); r.dir = v3(0.f, 1.f, 0.f);
+  int4 m = __ldg(&sc.mats[material]);
+  float param = __int_as_float(m.z);
+  switch (m.x) {
+    case SRT_MAT_LAMBERTIAN: {                                   // material.scm:24-39 + onb.scm:8-16
+      float len_n = length(n);
+      float3 w = n * (1.0f / len_n);
+      float3 a = (fabsf(w.x) > 0.9f) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+      float3 vv = unit(cross(w, a));
+      float3 uu = cross(w, vv);
+      float4 xi = rng_block(addr, 0);
+      float3 rc = random_cosine_direction(xi.x, xi.y, quirks);
+      float3 target = uu * rc.x + vv * rc.y + w * rc.z;
+      r.dir = unit(target);
+      float pdf_cos = dot(w, r.dir);                              // pdf  = (w . dir)/pi
+      float spdf_cos = fmaxf(0.0f, dot(n, r.dir));                // spdf = max(0, n . dir)/pi   (material.scm:33-36)
+      float3 atten = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks);   // (t:value albedo 0 0 p)
+      r.weight = atten * spdf_cos * (1.0f / pdf_cos);             // main.scm:113-118
+      r.valid = true;
+      break;
+    }
+    case SRT_MAT_METAL: {                                        // material.scm:45-57 (specular: weight = albedo)
+      float3 refl = reflect(unit(d_in), n);
+      float3 f = random_in_unit_sphere(addr, 0);
+      r.dir = refl + f * param;
+      r.valid = dot(r.dir, n) > 0.0f;
+      r.weight = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks);
+      break;
+    }
+    case SRT_MAT_DIELECTRIC: {                                   // material.scm:76-101 (Q10)
+      float ref_idx = param;
+      float3 din = (quirks & SRT_Q10_DIELECTRIC_UNNORM) ? d_in : unit(d_in);
+      float3 refl = reflect(din, n);
+      float dd = dot(din, n);
+      float3 outward = (dd > 0.0f) ? -n : n;
+      float ni_over_nt = (dd > 0.0f) ? ref_idx : 1.0f / ref_idx;
+      float len_d = length(din);
+      float cosine = (dd > 0.0f) ? (dd * ref_idx) / len_d : (-dd) / len_d;
+      float3 uv_ = din * (1.0f / len_d);                          // refract material.scm:59-67
+      float dt = dot(uv_, outward);
+      float disc = 1.0f - ni_over_nt * ni_over_nt * (1.0f - dt * dt);
+      float reflect_prob = 1.0f; float3 refr = refl;
+      if (disc > 0.0f) {
+        float3 vv = (quirks & SRT_Q10_DIELECTRIC_UNNORM) ? din : uv_;
+        refr = (vv - outward * dt) * ni_over_nt - outward * sqrtf(disc);
+        reflect_prob = schlick(cosine, ref_idx);
+      }
+      float4 xi = rng_block(addr, 0);
+      r.dir = (xi.x < reflect_prob) ? refl : refr;
+      r.valid = true;
+      break;
+    }
+    case SRT_MAT_DIFFUSE_LIGHT: {                                // material.scm:103-111
+      if (dot(n, d_in) < 0.0f) r.emitted = tex_value(sc, m.y, u, v, p, quirks);
+      break;
+    }
+    case SRT_MAT_ISOTROPIC: {                                    // absent upstream; book semantics
+      r.dir = random_in_unit_sphere(addr, 0);
+      r.weight = tex_value(sc, m.y, u, v, p, quirks);
+      r.valid = true;
+      break;
+    }
+  }
+  return r;
+}

@@ -1,0 +1,53 @@
+// srt_host.h — internal host-side declarations shared by lbvh.cu, wavefront.cu and srt_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "srt_device.cuh"
+
+struct LbvhBuffers {
+  float* d_aabb = nullptr;                 // 6 per primitive
+  int* d_bounds = nullptr;                 // 7 ordered-int floats: cmin[3] cmax[3] S
+  unsigned long long* d_keys[2] = {nullptr, nullptr};
+  int* d_order[2] = {nullptr, nullptr};
+  int* d_hist = nullptr;                   // 256 * nblk
+  int4* d_links = nullptr;                 // n-1
+  int* d_leaf_parent = nullptr;            // n
+  float* d_nbox = nullptr;                 // 6 * (n-1)
+  int* d_visit = nullptr;                  // n-1
+  int* d_depth = nullptr;
+  float4* d_nodes = nullptr;               // 4 * max(n-1, 1)
+  int sorted = 0;                          // which of d_keys/d_order holds the sorted result
+};
+
+int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
+
+// Wavefront queues (SoA, 16-byte vectorised).  Two generations (ping-pong) of the ray/state
+// arrays: shade reads generation g and writes the compacted survivors into generation g^1.
+struct WaveBuffers {
+  size_t capacity = 0;                     // paths
+  float4* ray_o[2] = {nullptr, nullptr};   // o.xyz, time
+  float4* ray_d[2] = {nullptr, nullptr};   // d.xyz, -
+  float4* state[2] = {nullptr, nullptr};   // throughput.rgb, path id (int bits)
+  float4* hit = nullptr;                   // t, prim (int bits), u, v
+  float4* path_L = nullptr;                // radiance per path (rgb, -)
+  int* counts = nullptr;                   // live-queue length per bounce [max_depth + 2]
+  int counts_cap = 0;
+  unsigned long long* totals = nullptr;    // [0] rays, [1..8] rays per bounce 0..7
+};
+
+struct RenderLaunch {
+  DScene sc; DCamera cam; SrtRenderParams p;
+  int sm_count; bool bvh_in_smem; size_t extend_smem;
+};
+
+// returns number of kernel launches; d_rgb_sum accumulates W*H*3 floats
+int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream,
+                         int* waves_out, bool profile, float* ms_extend, float* ms_shade, int* n_extend);
+int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
+                      float tmin, float tmax, cudaStream_t stream);
+int srt_launch_complete_hits(const DScene& sc, const float4* ray_o, const float4* ray_d, const float4* hit, int n, SrtHit* d_out, cudaStream_t stream);
+int srt_launch_upload_rays(const SrtRay* d_rays, int n, float4* ray_o, float4* ray_d, cudaStream_t stream);
+int srt_launch_resolve(const float* d_rgb_sum, int n3, int spp, uint8_t* d_image, cudaStream_t stream);
+int srt_launch_eval_texture(const DScene& sc, int tex, const float* d_uvp5, int n, int quirks, float* d_rgb, cudaStream_t stream);
+int srt_launch_eval_raygen(const RenderLaunch& L, int n, const int* d_pixel, const int* d_sample, SrtRay* d_out, cudaStream_t stream);
+size_t srt_extend_smem_bytes(const DScene& sc);

@@ -15,7 +15,8 @@ class RenderParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("ms_total", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("waves", C.c_int32), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32),
-                ("rays_per_bounce", C.c_uint64 * 8)]
+                ("rays_per_bounce", C.c_uint64 * 8), ("ms_extend", C.c_float), ("ms_shade", C.c_float),
+                ("extend_launches", C.c_int32), ("pad", C.c_int32)]
 
 
 # every symbol include/srt.h declares (tests check the library exports all of them)

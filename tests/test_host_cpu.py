@@ -1,0 +1,102 @@
+"""CPU-side checks (-m "not gpu"): host logic, LBVH host reference, C-ABI library loads and
+exports every symbol of include/srt.h (no compute without a GPU)."""
+import re
+import os
+import numpy as np
+import pytest
+import scheme_raytrace_b200 as srt
+from scheme_raytrace_b200.host import ffi, flatten, scenes, geometry as g, material as m, texture as t
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "srt.h")).read()
+    declared = set(re.findall(r"\b(srt_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(ffi.SYMBOLS), declared ^ set(ffi.SYMBOLS)
+    lib = ffi.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = ffi.load()
+    if lib.srt_device_count() > 0:
+        pytest.skip("GPU present")
+    assert lib.srt_init(0) == -1 and b"no CPU fallback" in lib.srt_last_error()
+    with pytest.raises(ffi.SrtError):
+        srt.Renderer(scenes.cfg1_weekend(8, 8))
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    assert C.sizeof(ffi.RenderParams) == 64 and C.sizeof(ffi.Stats) == 120
+    assert flatten.PRIM_DTYPE.itemsize == 80 and flatten.CAMERA_DTYPE.itemsize == 96
+
+
+def test_flatten_order_and_instances():
+    f = srt.flatten_scene(scenes.cfg4_cornell_box(32, 32))
+    assert len(f.prims) == 18 and len(f.xforms) == 2
+    assert list(f.prims["type"][:6]) == [4, 4, 3, 3, 3, 2] and list(f.prims["flags"][:6]) == [1, 0, 1, 1, 0, 1]
+    # make-box face order geometry.scm:446-457: xy@z1, flip xy@z0, xz@y1, flip xz@y0, yz@x1, flip yz@x0
+    assert list(f.prims["type"][6:12]) == [2, 2, 3, 3, 4, 4] and list(f.prims["flags"][6:12]) == [0, 1, 0, 1, 0, 1]
+    assert np.allclose(f.xforms[0]["off"], (130, 0, 65)) and np.isclose(f.xforms[0]["sin_t"], np.sin(np.radians(-18)))
+    # nested chain composes: translate(rotate-y(translate(x)))
+    LAMB = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
+    o = g.translate(g.rotate_y(g.translate(g.make_xy_rect(0, 1, 0, 1, 0, LAMB), (1, 0, 0)), 90), (0, 0, 5))
+    f2 = srt.flatten_scene(g.make_scene([o], scenes.default_camera(), scenes.black))
+    # rotate-y(90): (x,y,z) -> (z, y, -x); inner offset (1,0,0) -> (0,0,-1); plus (0,0,5)
+    assert np.allclose(f2.xforms[0]["off"], (0, 0, 4), atol=1e-6) and np.isclose(f2.xforms[0]["sin_t"], 1.0)
+    assert f2.sky == flatten.SKY_BLACK
+
+
+def test_random_scene_is_deterministic_and_reference_shaped():
+    a = srt.flatten_scene(scenes.cfg2_random_spheres())
+    b = srt.flatten_scene(scenes.cfg2_random_spheres())
+    assert a.prims.tobytes() == b.prims.tobytes() and 450 <= len(a.prims) <= 500
+    # push! prepends: the three big spheres come first, the ground last (main.scm:36-88)
+    assert a.prims[0]["p"][3] == 1.0 and a.prims[-1]["p"][3] == 1000.0
+    c3 = srt.flatten_scene(scenes.cfg3_next_week())
+    assert set(c3.prims["type"]) == {0, 1, 2} and {0, 1, 2, 3} <= set(c3.textures["kind"])
+
+
+def test_lbvh_host_reference_properties(orc):
+    rs = np.random.RandomState(1)
+    for n in (1, 2, 3, 17, 257, 1000):
+        c = rs.uniform(-10, 10, (n, 3)).astype(np.float32)
+        if n == 257:
+            c[100:160] = c[100]                      # duplicate centroids -> equal Morton keys
+        r = rs.uniform(0.01, 1, (n, 1)).astype(np.float32)
+        aabb = np.concatenate([c - r, c + r], axis=1)
+        keys, order, nodes = orc.lbvh_build(aabb)
+        assert np.all(keys[:-1] <= keys[1:]) and sorted(order.tolist()) == list(range(n))
+        eq = keys[:-1] == keys[1:]
+        assert np.all(order[:-1][eq] < order[1:][eq])          # stable
+        if n == 1:
+            assert len(nodes) == 1 and nodes[0]["left"] == ~0
+            continue
+        assert len(nodes) == n - 1
+        leaves = [~x for x in list(nodes["left"]) + list(nodes["right"]) if x < 0]
+        assert sorted(leaves) == list(range(n))                # every primitive exactly once
+        # each child box contains the boxes below it
+        def box_of(ch):
+            if ch < 0:
+                return aabb[~ch, :3], aabb[~ch, 3:]
+            nd = nodes[ch]
+            return np.minimum(nd["lmin"], nd["rmin"]), np.maximum(nd["lmax"], nd["rmax"])
+        for i, nd in enumerate(nodes):
+            for side, ch in (("l", nd["left"]), ("r", nd["right"])):
+                lo, hi = box_of(ch)
+                assert np.all(nd[side + "min"] <= lo) and np.all(nd[side + "max"] >= hi)
+                if ch >= 0:
+                    assert nodes[ch]["parent"] == i and nodes[ch]["sibling"] == (nd["right"] if side == "l" else nd["left"])
+        assert nodes[0]["parent"] == -1 and orc.lbvh_depth(nodes) <= 64
+
+
+def test_morton_expand_bits(orc):
+    # key of a 2-primitive set: the centroid at cmax gets all-ones on that axis
+    aabb = np.array([[0, 0, 0, 0, 0, 0], [1, 2, 4, 1, 2, 4]], np.float32)
+    keys, order, _ = orc.lbvh_build(aabb)
+    assert keys[0] == 0 and keys[1] == (1 << 63) - 1 and list(order) == [0, 1]

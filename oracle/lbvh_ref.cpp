@@ -101,7 +101,7 @@ int orc_lbvh_build(int n, const float* aabbs, uint64_t* keys_sorted, int32_t* or
     Node64& nd = nodes[0];
     leaf_box(0, nd.lmin, nd.lmax);
     for (int k = 0; k < 3; ++k) { nd.lmin[k] = nd.lmin[k] - pad; nd.lmax[k] = nd.lmax[k] + pad; }
-    set_empty(nd.rmin, nd.rmax);
+    for (int k = 0; k < 3; ++k) { nd.rmin[k] = nd.lmin[k]; nd.rmax[k] = nd.lmax[k]; }   // same leaf, same box on both sides
     nd.left = nd.right = ~ord[0]; nd.parent = nd.sibling = -1; return 1;
   }
   // 4. Karras emit

@@ -254,7 +254,7 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
   }
 }
 
-// n <= 1: a single node whose right box is empty.
+// n <= 1: a single node.
 __global__ void k_single_node(int n, const float* __restrict__ aabb, const int* __restrict__ b, float4* __restrict__ nodes,
                               unsigned long long* keys, int* order) {
   if (threadIdx.x != 0) return;
@@ -264,9 +264,11 @@ __global__ void k_single_node(int n, const float* __restrict__ aabb, const int* 
     for (int k = 0; k < 3; ++k) { l[k] = __fsub_rn(aabb[k], pad); l[3 + k] = __fadd_rn(aabb[3 + k], pad); }
     order[0] = 0;
   }
+  // both children reference the same leaf with the same box (an inverted "empty" box would not
+  // be empty under a min/max slab test); n == 0 is never traversed
   nodes[0] = make_float4(l[0], l[1], l[2], l[3]);
-  nodes[1] = make_float4(l[4], l[5], BIG, BIG);
-  nodes[2] = make_float4(BIG, -BIG, -BIG, -BIG);
+  nodes[1] = make_float4(l[4], l[5], l[0], l[1]);
+  nodes[2] = make_float4(l[2], l[3], l[4], l[5]);
   nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), __int_as_float(-1), __int_as_float(-1));
 }
 

@@ -116,21 +116,26 @@ __device__ __forceinline__ float3 xf_point_to_world(const Xf& x, float3 p) { ret
 // Primitive intersectors.  All return the candidate t with only the LOWER bound applied; the
 // caller applies the upper bound / exact-tie rule against the current best.
 
-// geometry.scm:146-175 sphere.  Same roots as the reference's (-b -/+ sqrt(b^2 - a c))/a, but
-// the discriminant is formed from the perpendicular offset l = oc - (b/a) d, i.e.
-// disc/a = r^2 - |l|^2, which does not cancel catastrophically in fp32 for the r = 100/1000
-// ground spheres (main.scm:38,160,319).  Miss iff disc <= 0, like the reference.
+// geometry.scm:146-175 sphere.  The reference evaluates oc, a, b, c and the discriminant
+// b^2 - a*c in f64.  For the r = 100/1000 ground spheres (main.scm:38,160,319) those terms cancel
+// catastrophically in fp32 (t off by 1e-2 relative for origins near the surface), so exactly
+// these terms are evaluated in FP64 here — B200 issues DFMA at half the FFMA rate, and sphere
+// tests are a small share of the extend kernel — with the reference's own formula; the square
+// root and the two roots are then finished in fp32 in the cancellation-free form
+// q = -(b + sign(b) sqrt(disc)), roots {q/a, c/q}.  Miss iff disc <= 0, like the reference.
 __device__ __forceinline__ bool isect_sphere(float3 c, float r, float3 o, float3 d, float inv_a, float tmin, float& t) {
-  float3 oc = o - c;
-  float b = dot(oc, d);
-  float s = b * inv_a;
-  float3 l = madd(d, -s, oc);
-  float dq = fmaf(r, r, -dot(l, l));
-  if (!(dq > 0.0f)) return false;
-  float h = sqrtf(dq * inv_a);
-  float t1 = -s - h;
-  if (t1 > tmin) { t = t1; return true; }     // (< t-min temp ...) strict
-  float t2 = h - s;
+  double ocx = (double)o.x - (double)c.x, ocy = (double)o.y - (double)c.y, ocz = (double)o.z - (double)c.z;
+  double dx = d.x, dy = d.y, dz = d.z;
+  double a = dx * dx + dy * dy + dz * dz;
+  double b = ocx * dx + ocy * dy + ocz * dz;
+  double cc = ocx * ocx + ocy * ocy + ocz * ocz - (double)r * (double)r;
+  double disc = b * b - a * cc;
+  if (!(disc > 0.0)) return false;
+  float bf = (float)b, ccf = (float)cc;
+  float q = -(bf + copysignf(sqrtf((float)disc), bf));
+  float ta = q * inv_a, tb = ccf / q;            // the two roots (-b -/+ sqrt(disc))/a in some order
+  float t1 = fminf(ta, tb), t2 = fmaxf(ta, tb);
+  if (t1 > tmin) { t = t1; return true; }        // (< t-min temp ...) strict
   if (t2 > tmin) { t = t2; return true; }
   return false;
 }
@@ -143,10 +148,12 @@ __device__ __forceinline__ float3 moving_center(float4 a, float4 b, float4 c, fl
 // geometry.scm:376-431 rects.  axis = thin axis; (ia, ib) in-plane axes in argument order.
 // Inclusive bounds (t < t-min rejects).  A NaN t (ray in the plane) is rejected.
 __device__ __forceinline__ float cmp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
-__device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o, float3 d, float tmin, float& t, float& u, float& v) {
+__device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o, float3 d, float tmin, float num_axis, bool have_num,
+                                           float& t, float& u, float& v) {
   int axis = (type == SRT_PRIM_XY_RECT) ? 2 : (type == SRT_PRIM_XZ_RECT ? 1 : 0);
   int ia = (type == SRT_PRIM_YZ_RECT) ? 1 : 0, ib = (type == SRT_PRIM_XY_RECT) ? 1 : 2;
-  float tt = __fdiv_rn(k - cmp3(o, axis), cmp3(d, axis));
+  float num = have_num ? num_axis : k - cmp3(o, axis);     // (- k (v:z (origin ray))) etc.
+  float tt = __fdiv_rn(num, cmp3(d, axis));
   if (!(tt >= tmin)) return false;                       // also rejects NaN
   float pa = fmaf(tt, cmp3(d, ia), cmp3(o, ia));
   float pb = fmaf(tt, cmp3(d, ib), cmp3(o, ib));
@@ -155,6 +162,15 @@ __device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o
   u = (pa - a.x) / (a.y - a.x);
   v = (pb - a.z) / (a.w - a.z);
   return true;
+}
+// k - (object-space origin)[axis] for an instanced rect, with the rotate-y / translate of the
+// origin (geometry.scm:467, 512-516) carried in FP64: at Cornell coordinates (~555) the fp32
+// rotation loses ~6e-5 absolute, i.e. > 1e-4 relative on t for origins within ~0.5 of a face.
+__device__ __forceinline__ float rect_num_f64(const Xf& x, int type, float k, float3 o) {
+  double qx = (double)o.x - (double)x.off.x, qz = (double)o.z - (double)x.off.z;
+  if (type == SRT_PRIM_XY_RECT) return (float)((double)k - ((double)x.s * qx + (double)x.c * qz));
+  if (type == SRT_PRIM_YZ_RECT) return (float)((double)k - ((double)x.c * qx - (double)x.s * qz));
+  return k - (o.y - x.off.y);
 }
 
 // bezier.scm — cubic Bezier curve with width; recursive subdivision with an explicit stack.
@@ -282,9 +298,9 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     ok = isect_sphere(moving_center(a, b, c, time), a.w, o, d, inv_a, tmin, t);
   } else if (type <= SRT_PRIM_YZ_RECT) {
     float k = __ldg(&sc.prim_b[id]).x;
-    float3 oo = o, dd = d;
-    if (hdr.z >= 0) { Xf x = load_xf(sc, hdr.z); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
-    ok = isect_rect(type, a, k, oo, dd, tmin, t, u, v);
+    float3 oo = o, dd = d; float num = 0.f; bool have_num = false;
+    if (hdr.z >= 0) { Xf x = load_xf(sc, hdr.z); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); num = rect_num_f64(x, type, k, o); have_num = true; }
+    ok = isect_rect(type, a, k, oo, dd, tmin, num, have_num, t, u, v);
   } else if (type == SRT_PRIM_BEZIER) {
     ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
   }

@@ -62,7 +62,11 @@ __device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restri
                                         float3 o, float3 d, float time, float tmin, float tmax) {
   Hit h; h.t = tmax; h.prim = -1; h.u = 0.f; h.v = 0.f; h.incl = false;
   if (sc.n_prims == 0) return h;
-  const float3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  // reciprocal direction; (near-)zero components become +-1e18 instead of +-inf so that the FMA
+  // slab form below never produces inf - inf (boxes are padded, see lbvh.cu, so the sign of
+  // (b - o) * 1e18 is exact for every ray that can reach a primitive inside the box)
+  const float3 inv = v3(fabsf(d.x) > 1e-18f ? 1.0f / d.x : copysignf(1e18f, d.x), fabsf(d.y) > 1e-18f ? 1.0f / d.y : copysignf(1e18f, d.y),
+                        fabsf(d.z) > 1e-18f ? 1.0f / d.z : copysignf(1e18f, d.z));
   const float3 oi = v3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
   const float inv_a = 1.0f / dot(d, d);
   int node = 0;
@@ -71,8 +75,7 @@ __device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restri
     float4 n0, n1, n2, n3;
     if (SMEM) { n0 = nodes[4 * node]; n1 = nodes[4 * node + 1]; n2 = nodes[4 * node + 2]; n3 = nodes[4 * node + 3]; }
     else { n0 = __ldg(&nodes[4 * node]); n1 = __ldg(&nodes[4 * node + 1]); n2 = __ldg(&nodes[4 * node + 2]); n3 = __ldg(&nodes[4 * node + 3]); }
-    // slabs, FMA form t = b*inv - o*inv.  NaNs (0*inf) are dropped by fminf/fmaxf, which only
-    // ever widens the interval (conservative).  Boxes are padded at build time (lbvh.cu).
+    // slabs, FMA form t = b*inv - o*inv (6 FFMA per box).  Boxes are padded at build time (lbvh.cu).
     float lx0 = fmaf(n0.x, inv.x, -oi.x), lx1 = fmaf(n0.w, inv.x, -oi.x);
     float ly0 = fmaf(n0.y, inv.y, -oi.y), ly1 = fmaf(n1.x, inv.y, -oi.y);
     float lz0 = fmaf(n0.z, inv.z, -oi.z), lz1 = fmaf(n1.y, inv.z, -oi.z);

@@ -48,13 +48,13 @@ def interest_bounds(flat, clip=30.0):
 
 
 def compare(gpu, orc, orc32, second_t, rel=1e-4):
-    """Parity verdict of one batch.  Near-ties (|t2 - t1| < 1e-5 * t1 in the f64 oracle) and rays on
+    """Parity verdict of one batch.  Near-ties (0 < |t2 - t1| < 1e-5 * t1 in the f64 oracle) and rays on
     which the reference algorithm itself flips under fp32 rounding (f32 oracle != f64 oracle) are
     filtered and counted; on every other ray the primitive id must match exactly and t / normal /
     uv must agree within `rel` relative error."""
     n = len(gpu)
     t1 = orc["t"]
-    near_tie = (orc["prim"] >= 0) & (np.abs(second_t - t1) < 1e-5 * np.abs(t1))
+    near_tie = (orc["prim"] >= 0) & (np.abs(second_t - t1) < 1e-5 * np.abs(t1)) & (second_t != t1)   # exact ties are kept: the tie rule decides them
     unstable = orc32["prim"] != orc["prim"]
     keep = ~(near_tie | unstable)
     id_ok = gpu["prim"] == orc["prim"]

@@ -82,7 +82,7 @@ typedef struct {
   uint32_t seed;               /* Philox key word 1                                      */
   int32_t quirks;              /* SRT_Q* bits                                            */
   float t_min;                 /* main.scm:104: 0.001                                    */
-  int32_t wave_spp;            /* samples per pixel per wavefront wave; 0 = auto         */
+  int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (~8M paths) */
   int32_t reserved[6];         /* [0] = 1: time extend/shade launches separately (slower) */
 } SrtRenderParams;
 
@@ -92,9 +92,9 @@ typedef struct {
   float ms_total;              /* device time, first ray-gen launch .. accumulation done */
   float ms_commit;             /* last commit: H2D + LBVH build                          */
   int32_t kernel_launches;     /* kernels launched by this call                          */
-  int32_t waves;
+  int32_t waves;               /* extend/shade/regen iterations of the streaming wavefront */
   int32_t bvh_nodes, bvh_depth;
-  uint64_t rays_per_bounce[8]; /* first 8 bounces                                        */
+  uint64_t rays_per_bounce[8]; /* reserved (not tracked by the streaming wavefront)      */
   float ms_extend, ms_shade;   /* per-kernel device time, only when params.reserved[0]==1 */
   int32_t extend_launches;     /* extend launches timed for ms_extend                    */
   int32_t pad;

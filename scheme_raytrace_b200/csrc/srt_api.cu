@@ -46,7 +46,8 @@ struct SrtScene {
   DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
   int n_nodes = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
   // wavefront
-  WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit, w_L; DevBuf<int> w_counts; DevBuf<unsigned long long> w_totals;
+  WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
+  void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host
   DScene ds; DCamera dcam;
 };
@@ -59,16 +60,21 @@ static void fill_dscene(SrtScene* s) {
   d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p;
 }
 
-static int ensure_wave(SrtScene* s, size_t paths, int max_depth) {
+static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
   WaveBuffers& W = s->wb;
   if (paths > W.capacity) {
     for (int g = 0; g < 2; ++g) { CK(s->w_ro[g].ensure(paths)); CK(s->w_rd[g].ensure(paths)); CK(s->w_st[g].ensure(paths)); }
-    CK(s->w_hit.ensure(paths)); CK(s->w_L.ensure(paths));
+    CK(s->w_hit.ensure(paths));
     for (int g = 0; g < 2; ++g) { W.ray_o[g] = s->w_ro[g].p; W.ray_d[g] = s->w_rd[g].p; W.state[g] = s->w_st[g].p; }
-    W.hit = s->w_hit.p; W.path_L = s->w_L.p; W.capacity = paths;
+    W.hit = s->w_hit.p; W.capacity = paths;
   }
-  if (max_depth + 2 > W.counts_cap) { CK(s->w_counts.ensure((size_t)max_depth + 2)); W.counts = s->w_counts.p; W.counts_cap = max_depth + 2; }
-  if (!W.totals) { CK(s->w_totals.ensure(16)); W.totals = s->w_totals.p; }
+  if (npix) { CK(s->w_accum.ensure(3 * npix)); W.accum64 = s->w_accum.p; }
+  if (!W.ctrl) { CK(s->w_ctrl.ensure(srt_wave_ctrl_bytes())); W.ctrl = s->w_ctrl.p; }
+  if (!s->h_ctrl) {
+    CK(cudaMallocHost(&s->h_ctrl, 2 * srt_wave_ctrl_bytes()));
+    CK(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
+    W.h_ctrl = s->h_ctrl; W.poll_events = s->poll_ev;
+  }
   return 0;
 }
 
@@ -76,6 +82,7 @@ static RenderLaunch make_launch(SrtScene* s, const SrtRenderParams* p) {
   RenderLaunch L; L.sc = s->ds; L.cam = s->dcam; if (p) L.p = *p; else std::memset(&L.p, 0, sizeof(L.p));
   L.sm_count = g_sm_count; L.extend_smem = srt_extend_smem_bytes(s->ds);
   L.bvh_in_smem = L.extend_smem <= (size_t)200 * 1024;
+  L.prim_mask = 0; for (const SrtPrim& q : s->prims) L.prim_mask |= 1 << q.type;
   return L;
 }
 
@@ -106,7 +113,9 @@ void srt_scene_destroy(SrtScene* s) {
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
   for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
-  s->w_hit.release(); s->w_L.release(); s->w_counts.release(); s->w_totals.release(); s->d_accum.release();
+  s->w_hit.release(); s->w_accum.release(); s->w_ctrl.release(); s->d_accum.release();
+  if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+  for (int i = 0; i < 2; ++i) if (s->poll_ev[i]) cudaEventDestroy(s->poll_ev[i]);
   delete s;
 }
 
@@ -288,35 +297,30 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
   const int spp = p->spp_end - p->spp_begin;
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (spp == 0) return 0;
-  // wave sizing: ~8M paths in flight (queues ~1 GB of the 180 GB HBM), at least one sample/pixel
-  int wave_spp = p->wave_spp > 0 ? p->wave_spp : (int)((size_t)(8u << 20) / npix);
-  if (wave_spp < 1) wave_spp = 1;
-  if (wave_spp > spp) wave_spp = spp;
-  if (npix * (size_t)wave_spp > (size_t)1 << 30) return fail(SRT_ERR_ARG, "render: wave of %zu paths too large", npix * (size_t)wave_spp);
-  if (int rc = ensure_wave(s, npix * (size_t)wave_spp, p->max_depth)) return rc;
+  if (p->max_depth > 4095 || p->spp_end > (1 << 20)) return fail(SRT_ERR_ARG, "render: max_depth <= 4095 and spp_end <= 2^20 (packed path state)");
+  // queue sizing: ~8M paths in flight (ray/hit queues ~1.7 GB of the 180 GB HBM), never more than the job
+  size_t total = npix * (size_t)spp;
+  size_t cap = p->wave_spp > 0 ? npix * (size_t)p->wave_spp : (size_t)(8u << 20);
+  if (cap > total) cap = total;
+  if (cap > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: queue of %zu paths too large", cap);
+  if (int rc = ensure_wave(s, cap, npix)) return rc;
   cudaStream_t stream = 0;
   RenderLaunch L = make_launch(s, p);
   const bool profile = p->reserved[0] == 1;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  CK(cudaMemsetAsync(s->wb.totals, 0, sizeof(unsigned long long) * 16, stream));
   CK(cudaEventRecord(e0, stream));
-  int waves = 0, n_ext = 0; float ms_ext = 0.f, ms_shd = 0.f;
-  WaveBuffers W = s->wb; W.capacity = npix * (size_t)wave_spp;
-  int launches = srt_wavefront_render(L, W, d_rgb_sum, stream, &waves, profile, &ms_ext, &ms_shd, &n_ext);
+  WaveBuffers W = s->wb; W.capacity = cap;
+  SrtStats st; std::memset(&st, 0, sizeof(st));
+  srt_wavefront_render(L, W, d_rgb_sum, stream, &st, profile);
   CK(cudaEventRecord(e1, stream));
-  CK(cudaGetLastError());
-  unsigned long long totals[16];
-  CK(cudaMemcpyAsync(totals, s->wb.totals, sizeof(totals), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventSynchronize(e1));
-  CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (stats) {
-    stats->rays = totals[0]; stats->paths = (uint64_t)npix * (uint64_t)spp; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
-    stats->kernel_launches = launches; stats->waves = waves; stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth;
-    for (int i = 0; i < 8; ++i) stats->rays_per_bounce[i] = totals[1 + i];
-    stats->ms_extend = ms_ext; stats->ms_shade = ms_shd; stats->extend_launches = n_ext;
+    *stats = st;
+    stats->paths = (uint64_t)total; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
+    stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth;
   }
   return 0;
 }

@@ -148,12 +148,11 @@ __device__ __forceinline__ float3 moving_center(float4 a, float4 b, float4 c, fl
 // geometry.scm:376-431 rects.  axis = thin axis; (ia, ib) in-plane axes in argument order.
 // Inclusive bounds (t < t-min rejects).  A NaN t (ray in the plane) is rejected.
 __device__ __forceinline__ float cmp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
-__device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o, float3 d, float tmin, float num_axis, bool have_num,
+__device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o, float3 d, float tmin, float t_inst, bool have_t,
                                            float& t, float& u, float& v) {
   int axis = (type == SRT_PRIM_XY_RECT) ? 2 : (type == SRT_PRIM_XZ_RECT ? 1 : 0);
   int ia = (type == SRT_PRIM_YZ_RECT) ? 1 : 0, ib = (type == SRT_PRIM_XY_RECT) ? 1 : 2;
-  float num = have_num ? num_axis : k - cmp3(o, axis);     // (- k (v:z (origin ray))) etc.
-  float tt = __fdiv_rn(num, cmp3(d, axis));
+  float tt = have_t ? t_inst : __fdiv_rn(k - cmp3(o, axis), cmp3(d, axis));     // (/ (- k (v:z (origin ray))) (v:z (dir ray)))
   if (!(tt >= tmin)) return false;                       // also rejects NaN
   float pa = fmaf(tt, cmp3(d, ia), cmp3(o, ia));
   float pb = fmaf(tt, cmp3(d, ib), cmp3(o, ib));
@@ -163,14 +162,17 @@ __device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o
   v = (pb - a.z) / (a.w - a.z);
   return true;
 }
-// k - (object-space origin)[axis] for an instanced rect, with the rotate-y / translate of the
-// origin (geometry.scm:467, 512-516) carried in FP64: at Cornell coordinates (~555) the fp32
-// rotation loses ~6e-5 absolute, i.e. > 1e-4 relative on t for origins within ~0.5 of a face.
-__device__ __forceinline__ float rect_num_f64(const Xf& x, int type, float k, float3 o) {
+// t = (k - o'[axis]) / d'[axis] for an instanced rect, with the rotate-y / translate of origin and
+// direction (geometry.scm:467, 512-521) carried in FP64: at Cornell coordinates (~555) the fp32
+// rotation loses ~6e-5 absolute in o' (> 1e-4 relative on t for origins within ~0.5 of a face)
+// and cancels in d' for rays grazing a rotated face.
+__device__ __forceinline__ float rect_t_f64(const Xf& x, int type, float k, float3 o, float3 d) {
+  if (type == SRT_PRIM_XZ_RECT) return __fdiv_rn(k - (o.y - x.off.y), d.y);
   double qx = (double)o.x - (double)x.off.x, qz = (double)o.z - (double)x.off.z;
-  if (type == SRT_PRIM_XY_RECT) return (float)((double)k - ((double)x.s * qx + (double)x.c * qz));
-  if (type == SRT_PRIM_YZ_RECT) return (float)((double)k - ((double)x.c * qx - (double)x.s * qz));
-  return k - (o.y - x.off.y);
+  double num, den;
+  if (type == SRT_PRIM_XY_RECT) { num = (double)k - ((double)x.s * qx + (double)x.c * qz); den = (double)x.s * (double)d.x + (double)x.c * (double)d.z; }
+  else { num = (double)k - ((double)x.c * qx - (double)x.s * qz); den = (double)x.c * (double)d.x - (double)x.s * (double)d.z; }
+  return __fdiv_rn((float)num, (float)den);
 }
 
 // bezier.scm — cubic Bezier curve with width; recursive subdivision with an explicit stack.
@@ -284,24 +286,30 @@ __device__ __forceinline__ bool accept_hit(float t, int id, bool incl, float bes
 
 struct Hit { float t; int prim; float u, v; bool incl; };
 
-// One leaf primitive against the ray (world space in, candidate merged into `h`).
-template <class PrimSrc>
+// One leaf primitive against the ray (world space in, candidate merged into `h`).  MASK is the
+// set of primitive kinds present in the scene (bit = SRT_PRIM_*): the extend kernel is compiled
+// per mask so that e.g. sphere-only scenes carry no rect / instance / Bezier code or registers.
+#define SRT_MASK_ALL 0x3f
+template <int MASK, class PrimSrc>
 __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin, Hit& h) {
-  int4 hdr = ps.hdr(id);
-  int type = hdr.x & 0xff;
+  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20;
+  constexpr bool SINGLE_KIND = (MASK & (MASK - 1)) == 0;
   float4 a = ps.a(id);
+  int type, xform = -1;
+  if (SINGLE_KIND && !HAS_RECT) type = HAS_SPHERE ? SRT_PRIM_SPHERE : (HAS_MOVING ? SRT_PRIM_MOVING_SPHERE : SRT_PRIM_BEZIER);
+  else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; }
   float t = 0.f, u = 0.f, v = 0.f; bool ok = false;
-  if (type == SRT_PRIM_SPHERE) {
+  if (HAS_SPHERE && type == SRT_PRIM_SPHERE) {
     ok = isect_sphere(xyz(a), a.w, o, d, inv_a, tmin, t);
-  } else if (type == SRT_PRIM_MOVING_SPHERE) {
+  } else if (HAS_MOVING && type == SRT_PRIM_MOVING_SPHERE) {
     float4 b = __ldg(&sc.prim_b[id]), c = __ldg(&sc.prim_c[id]);
     ok = isect_sphere(moving_center(a, b, c, time), a.w, o, d, inv_a, tmin, t);
-  } else if (type <= SRT_PRIM_YZ_RECT) {
+  } else if (HAS_RECT && type <= SRT_PRIM_YZ_RECT) {
     float k = __ldg(&sc.prim_b[id]).x;
-    float3 oo = o, dd = d; float num = 0.f; bool have_num = false;
-    if (hdr.z >= 0) { Xf x = load_xf(sc, hdr.z); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); num = rect_num_f64(x, type, k, o); have_num = true; }
-    ok = isect_rect(type, a, k, oo, dd, tmin, num, have_num, t, u, v);
-  } else if (type == SRT_PRIM_BEZIER) {
+    float3 oo = o, dd = d; float ti = 0.f; bool have_t = false;
+    if (xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); ti = rect_t_f64(x, type, k, o, d); have_t = true; }
+    ok = isect_rect(type, a, k, oo, dd, tmin, ti, have_t, t, u, v);
+  } else if (HAS_BEZIER && type == SRT_PRIM_BEZIER) {
     ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
   }
   bool incl = prim_inclusive(type);

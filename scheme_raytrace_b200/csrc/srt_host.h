@@ -22,27 +22,29 @@ struct LbvhBuffers {
 int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
 
 // Wavefront queues (SoA, 16-byte vectorised).  Two generations (ping-pong) of the ray/state
-// arrays: shade reads generation g and writes the compacted survivors into generation g^1.
+// arrays: shade reads generation g and writes the compacted survivors into generation g^1, regen
+// appends fresh camera paths behind them.
 struct WaveBuffers {
-  size_t capacity = 0;                     // paths
+  size_t capacity = 0;                     // paths in flight
   float4* ray_o[2] = {nullptr, nullptr};   // o.xyz, time
-  float4* ray_d[2] = {nullptr, nullptr};   // d.xyz, -
-  float4* state[2] = {nullptr, nullptr};   // throughput.rgb, path id (int bits)
+  float4* ray_d[2] = {nullptr, nullptr};   // d.xyz, (sample << 12 | depth) as int bits
+  float4* state[2] = {nullptr, nullptr};   // throughput.rgb, pixel (int bits)
   float4* hit = nullptr;                   // t, prim (int bits), u, v
-  float4* path_L = nullptr;                // radiance per path (rgb, -)
-  int* counts = nullptr;                   // live-queue length per bounce [max_depth + 2]
-  int counts_cap = 0;
-  unsigned long long* totals = nullptr;    // [0] rays, [1..8] rays per bounce 0..7
+  unsigned long long* accum64 = nullptr;   // W*H*3 fixed-point (2^-36) radiance sums
+  void* ctrl = nullptr;                    // WaveCtrl (device)
+  void* h_ctrl = nullptr;                  // 2 x WaveCtrl (pinned host)
+  void* poll_events = nullptr;             // 2 x cudaEvent_t
 };
 
 struct RenderLaunch {
   DScene sc; DCamera cam; SrtRenderParams p;
   int sm_count; bool bvh_in_smem; size_t extend_smem;
+  int prim_mask;                            // bit k set = primitive kind k present (extend kernel variant)
 };
 
 // returns number of kernel launches; d_rgb_sum accumulates W*H*3 floats
-int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream,
-                         int* waves_out, bool profile, float* ms_extend, float* ms_shade, int* n_extend);
+int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile);
+size_t srt_wave_ctrl_bytes();
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, cudaStream_t stream);
 int srt_launch_complete_hits(const DScene& sc, const float4* ray_o, const float4* ray_d, const float4* hit, int n, SrtHit* d_out, cudaStream_t stream);

@@ -1,17 +1,17 @@
 // wavefront.cu — the per-sample radiance loop as a wavefront path tracer.
 //
 // Replaces trace-all -> get-ray -> color -> g:hit / m:scatter / m:emitted (main.scm:100-121,
-// 471-491; camera.scm:80-92; geometry.scm:14-15; material.scm:15-22).  Stages per wave of
-// W*H*wave_spp paths:
-//   k_raygen     camera rays (Philox bounce slot 0)
-//   k_extend     closest hit: stackless LBVH traversal (bit-trail, near child first), the whole
-//                node array + primitive headers staged in shared memory
-//   k_shade      hit-record completion, material scatter / emitted, sky on miss; survivors are
-//                compacted (warp ballot + one atomic per CTA) into the other queue generation
-//   k_accumulate per-pixel sum of the wave's path radiances into the running sum (*raw-data*)
-// The recursive estimator `color` is run in its iterative form L = sum_k (prod_{j<k} w_j) e_k;
-// in the reference every emission event (light, sky, depth cut) ends the path, so each path
-// writes its radiance exactly once.
+// 471-491; camera.scm:80-92; geometry.scm:14-15; material.scm:15-22).  STREAMING wavefront: one
+// queue of up to `capacity` paths is kept full; every iteration runs
+//   k_extend  closest hit: stackless LBVH traversal (bit-trail, near child first), the whole
+//             node array + primitive headers staged in shared memory
+//   k_shade   hit-record completion, material scatter / emitted, sky on miss; terminated paths add
+//             their radiance into a 64-bit fixed-point accumulator; survivors are compacted
+//             (warp ballot + one atomic per CTA) into the other queue generation
+//   k_regen   fresh camera paths (Philox bounce slot 0) are appended behind the survivors
+// so the long thin tail of deep paths (depth <= max_depth) is paid once per frame, not once per
+// batch of samples.  The recursive estimator `color` is run in its iterative form
+// L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
 #include "srt_device.cuh"
 #include "srt_host.h"
 
@@ -21,23 +21,64 @@ constexpr int EXT_THREADS = 256;
 constexpr int SHD_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------
-// ray generation: path id -> (pixel, sample); main.scm:476-478 + camera.scm:80-92
-__global__ void __launch_bounds__(256) k_raygen(DCamera cam, SrtRenderParams p, int npaths, int npix, int sample_base,
-                                                 float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ state,
-                                                 float4* __restrict__ path_L) {
-  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < npaths; id += gridDim.x * blockDim.x) {
-    int sl = id / npix, pixel = id - sl * npix;
+// Queue control block (device memory).  Fields are double-buffered by queue generation /
+// iteration parity so that no kernel reads a field another CTA of the same launch writes.
+//   qcount[g]     live length of queue generation g (read by extend / shade)
+//   survivors[g]  compaction cursor: shade(g^1) atomically appends survivors into generation g
+//   next_path[k]  first camera path not yet generated, as seen by the regen of parity k
+struct WaveCtrl {
+  int qcount[2]; int survivors[2];
+  unsigned long long next_path[2];
+  unsigned long long total_paths;
+  unsigned long long rays;          // sum of qcount over iterations = closest-hit queries
+  unsigned long long iterations;
+};
+#define SRT_ACC_SCALE 68719476736.0f   // 2^36: radiance accumulates in 64-bit fixed point
+
+__device__ __forceinline__ void accumulate_fixed(unsigned long long* __restrict__ acc, int pixel, float3 L) {
+  // order-independent (integer) accumulation: the image is bit-identical for any scheduling,
+  // queue size or sample-range split.  main.scm:480 running sum.
+  if (L.x != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 0], (unsigned long long)__float2ll_rn(L.x * SRT_ACC_SCALE));
+  if (L.y != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 1], (unsigned long long)__float2ll_rn(L.y * SRT_ACC_SCALE));
+  if (L.z != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 2], (unsigned long long)__float2ll_rn(L.z * SRT_ACC_SCALE));
+}
+
+// ------------------------------------------------------------------------------------------------
+// regen: tops queue generation g up with fresh camera paths (main.scm:476-478 + camera.scm:80-92).
+// Path id -> (pixel, sample) with consecutive ids on consecutive pixels, so the appended block of
+// primary rays is coherent.  Path state: ray_o = (o, time), ray_d = (d, sample << 12 | depth),
+// state = (throughput, pixel).
+__global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, int npix, int capacity, int g, int parity,
+                                                float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ state,
+                                                WaveCtrl* __restrict__ ctrl) {
+  const int surv = ctrl->survivors[g];
+  const unsigned long long next = ctrl->next_path[parity], total = ctrl->total_paths;
+  unsigned long long room = (unsigned long long)(capacity - surv), left = total - next;
+  const int n_new = (int)(room < left ? room : left);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
+    unsigned long long id = next + (unsigned long long)j;
+    unsigned int sl = (unsigned int)(id / (unsigned long long)npix);
+    int pixel = (int)(id - (unsigned long long)sl * (unsigned long long)npix);
     int y = pixel / p.width, x = pixel - y * p.width;
-    RngAddr addr{p.seed, (uint32_t)pixel, (uint32_t)(sample_base + sl), 0u};
+    unsigned int sample = (unsigned int)p.spp_begin + sl;
+    RngAddr addr{p.seed, (uint32_t)pixel, sample, 0u};
     float4 xi = rng_block(addr, 0);
     float u = ((float)x + xi.x) / (float)p.width;       // y = 0 is the bottom row
     float v = ((float)y + xi.y) / (float)p.height;
     float3 o, d; float time;
     get_ray(cam, u, v, xi.z, addr, o, d, time);
-    ray_o[id] = make_float4(o.x, o.y, o.z, time);
-    ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
-    state[id] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(id));
-    path_L[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int slot = surv + j;
+    ray_o[slot] = make_float4(o.x, o.y, o.z, time);
+    ray_d[slot] = make_float4(d.x, d.y, d.z, __int_as_float((int)(sample << 12)));
+    state[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(pixel));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int q = surv + n_new;
+    ctrl->qcount[g] = q;
+    ctrl->next_path[parity ^ 1] = next + (unsigned long long)n_new;
+    ctrl->survivors[g ^ 1] = 0;          // cursor of the generation the next shade appends into
+    ctrl->rays += (unsigned long long)q;
+    ctrl->iterations += q ? 1ull : 0ull;
   }
 }
 
@@ -57,7 +98,7 @@ struct PrimGlobal {
   __device__ __forceinline__ float4 a(int i) const { return __ldg(&pa[i]); }
 };
 
-template <bool SMEM, class PrimSrc>
+template <bool SMEM, int MASK, class PrimSrc>
 __device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
                                         float3 o, float3 d, float time, float tmin, float tmax) {
   Hit h; h.t = tmax; h.prim = -1; h.u = 0.f; h.v = 0.f; h.incl = false;
@@ -93,7 +134,7 @@ __device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restri
     if (hl && left < 0) { pend0 = ~left; hl = false; }
     if (hr && right < 0) { if (pend0 < 0) pend0 = ~right; else pend1 = ~right; hr = false; }
     while (pend0 >= 0) {
-      intersect_prim(sc, ps, pend0, o, d, time, inv_a, tmin, h);
+      intersect_prim<MASK>(sc, ps, pend0, o, d, time, inv_a, tmin, h);
       pend0 = pend1; pend1 = -1;
     }
     if (hl | hr) {
@@ -116,8 +157,8 @@ __device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restri
   return h;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(EXT_THREADS, 2)
+template <bool SMEM, int MASK>
+__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x20) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
          const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax) {
   extern __shared__ float4 smem[];
@@ -137,61 +178,59 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     PrimShared ps{sh, sa};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
       float4 o4 = ray_o[i], d4 = ray_d[i];
-      Hit h = traverse<true>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
+      Hit h = traverse<true, MASK>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
       hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
     }
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
       float4 o4 = ray_o[i], d4 = ray_d[i];
-      Hit h = traverse<false>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
+      Hit h = traverse<false, MASK>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
       hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// shade: one bounce of `color` (main.scm:100-121) for every live path + compaction.
+// shade: one bounce of `color` (main.scm:100-121) for every live path + compaction of survivors
+// into the other queue generation (warp ballot -> per-warp count -> one atomic per CTA).
 __global__ void __launch_bounds__(SHD_THREADS)
-k_shade(DScene sc, SrtRenderParams p, int depth, int npix, int sample_base,
+k_shade(DScene sc, SrtRenderParams p, int g,
         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
         float4* __restrict__ ray_o_next, float4* __restrict__ ray_d_next, float4* __restrict__ state_next,
-        float4* __restrict__ path_L, const int* __restrict__ count_ptr, int* __restrict__ next_count) {
+        unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {
   __shared__ int s_warp[SHD_THREADS / 32];
   __shared__ int s_base;
-  const int count = *count_ptr;
+  const int count = ctrl->qcount[g];
+  int* next_count = &ctrl->survivors[g ^ 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {   // block-uniform trip count
     int i = base + threadIdx.x;
     bool alive = false;
-    float3 no = v3(0, 0, 0), nd = v3(0, 0, 0), thr = v3(0, 0, 0); float ntime = 0.f; int id = 0;
+    float3 no = v3(0, 0, 0), nd = v3(0, 0, 0), thr = v3(0, 0, 0); float ntime = 0.f; int pixel = 0, sd = 0;
     if (i < count) {
       float4 h4 = hit[i], o4 = ray_o[i], d4 = ray_d[i], s4 = state[i];
       int prim = __float_as_int(h4.y);
-      thr = xyz(s4); id = __float_as_int(s4.w);
+      thr = xyz(s4); pixel = __float_as_int(s4.w); sd = __float_as_int(d4.w);
+      const int depth = sd & 0xfff; const unsigned int sample = (unsigned int)sd >> 12;
       float3 o = xyz(o4), d = xyz(d4);
       if (prim < 0) {                                              // main.scm:120 sky
-        float3 L = thr * sky_value(p.sky, d);
-        path_L[id] = make_float4(L.x, L.y, L.z, 0.f);
+        accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d));
       } else {
         float3 pt, n; int material;
         complete_hit(sc, prim, h4.x, o, d, o4.w, pt, n, material);
-        int sl = id / npix, pixel = id - sl * npix;
-        RngAddr addr{p.seed, (uint32_t)pixel, (uint32_t)(sample_base + sl), (uint32_t)(depth + 1)};
+        RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
         Scatter s = scatter(sc, material, d, pt, n, h4.z, h4.w, addr, p.quirks);
-        if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f) {   // main.scm:113/119 emitted
-          float3 L = thr * s.emitted;
-          path_L[id] = make_float4(L.x, L.y, L.z, 0.f);
-        }
+        if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
+          accumulate_fixed(accum, pixel, thr * s.emitted);
         if (s.valid && depth < p.max_depth) {                      // main.scm:112
           alive = true;
           thr = thr * s.weight;
-          no = pt; nd = s.dir;
+          no = pt; nd = s.dir; sd += 1;
           ntime = (p.quirks & SRT_Q6_SCATTER_TIME0) ? 0.0f : o4.w;   // Q6: make-ray forces time 0
         }
       }
     }
-    // compaction: warp ballot -> per-warp count -> one atomic per CTA
     unsigned ballot = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
@@ -205,30 +244,21 @@ k_shade(DScene sc, SrtRenderParams p, int depth, int npix, int sample_base,
     if (alive) {
       int pos = s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
       ray_o_next[pos] = make_float4(no.x, no.y, no.z, ntime);
-      ray_d_next[pos] = make_float4(nd.x, nd.y, nd.z, 0.f);
-      state_next[pos] = make_float4(thr.x, thr.y, thr.z, __int_as_float(id));
+      ray_d_next[pos] = make_float4(nd.x, nd.y, nd.z, __int_as_float(sd));
+      state_next[pos] = make_float4(thr.x, thr.y, thr.z, __int_as_float(pixel));
     }
     __syncthreads();
   }
 }
 
-// main.scm:480 running sum: rgb_sum[pixel] += sum over the wave's samples, in sample order
-__global__ void k_accumulate(int npix, int wave_spp, const float4* __restrict__ path_L, float* __restrict__ rgb_sum) {
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
-    float r = 0.f, g = 0.f, b = 0.f;
-    for (int s = 0; s < wave_spp; ++s) { float4 L = path_L[(size_t)s * npix + pix]; r += L.x; g += L.y; b += L.z; }
-    rgb_sum[3 * (size_t)pix] += r; rgb_sum[3 * (size_t)pix + 1] += g; rgb_sum[3 * (size_t)pix + 2] += b;
-  }
+// end of render: rgb_sum += fixed-point accumulator (main.scm:480 running sum, *raw-data*)
+__global__ void k_accum_to_float(int n3, const unsigned long long* __restrict__ accum, float* __restrict__ rgb_sum) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x)
+    rgb_sum[i] += (float)((double)(long long)accum[i] * (1.0 / 68719476736.0));
 }
-
-__global__ void k_wave_begin(int* counts, int ncounts, int npaths) {
-  for (int i = threadIdx.x; i < ncounts; i += blockDim.x) counts[i] = (i == 0) ? npaths : 0;
-}
-__global__ void k_wave_end(const int* counts, int ncounts, unsigned long long* totals) {
-  unsigned long long s = 0;
-  for (int i = threadIdx.x; i < ncounts; i += blockDim.x) { s += (unsigned long long)counts[i]; if (i < 8) atomicAdd(&totals[1 + i], (unsigned long long)counts[i]); }
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&totals[0], s);
+__global__ void k_ctrl_init(WaveCtrl* ctrl, unsigned long long total_paths) {
+  ctrl->qcount[0] = ctrl->qcount[1] = 0; ctrl->survivors[0] = ctrl->survivors[1] = 0;
+  ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull;
 }
 
 // main.scm:123-124, 481-487: correct-gamma (sqrt) + floor(255.99 * min(1, c)); negative sums
@@ -289,73 +319,100 @@ __global__ void k_eval_raygen(DCamera cam, SrtRenderParams p, int n, const int* 
 // =================================================================================================
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
-static int extend_grid(const RenderLaunch& L, int* blocks_per_sm_out) {
-  // persistent grid: SM count x resident CTAs per SM (queried, depends on the staged-BVH size)
-  static int cached_bps[2] = {0, 0}; static size_t cached_smem = ~(size_t)0;
-  int which = L.bvh_in_smem ? 1 : 0;
-  if (!cached_bps[which] || (which && cached_smem != L.extend_smem)) {
-    int bps = 0;
-    if (which) {
-      cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.extend_smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_extend<true>, EXT_THREADS, L.extend_smem);
-      cached_smem = L.extend_smem;
-    } else {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_extend<false>, EXT_THREADS, 0);
-    }
-    cached_bps[which] = bps < 1 ? 1 : bps;
+// Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
+typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, float, float);
+struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
+static ExtendVariant g_variants[2][4];
+
+static int variant_of(int mask) {
+  if ((mask & ~0x01) == 0) return 0;
+  if ((mask & ~0x03) == 0) return 1;
+  if ((mask & 0x20) == 0) return 2;
+  return 3;
+}
+static ExtendFn variant_fn(bool smem, int v) {
+  switch (v) {
+    case 0: return smem ? k_extend<true, 0x01> : k_extend<false, 0x01>;
+    case 1: return smem ? k_extend<true, 0x03> : k_extend<false, 0x03>;
+    case 2: return smem ? k_extend<true, 0x1f> : k_extend<false, 0x1f>;
+    default: return smem ? k_extend<true, SRT_MASK_ALL> : k_extend<false, SRT_MASK_ALL>;
   }
-  if (blocks_per_sm_out) *blocks_per_sm_out = cached_bps[which];
-  return L.sm_count * cached_bps[which];
+}
+// persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
+static const ExtendVariant& extend_variant(const RenderLaunch& L) {
+  int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
+  ExtendVariant& e = g_variants[which][v];
+  size_t smem = which ? L.extend_smem : 0;
+  if (!e.fn || e.smem != smem) {
+    e.fn = variant_fn(which, v); e.smem = smem;
+    if (which) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, EXT_THREADS, smem);
+    e.bps = bps < 1 ? 1 : bps;
+  }
+  return e;
 }
 
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, cudaStream_t stream) {
-  int grid = extend_grid(L, nullptr);
-  if (L.bvh_in_smem) {
-    k_extend<true><<<grid, EXT_THREADS, L.extend_smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
-  } else {
-    k_extend<false><<<grid, EXT_THREADS, 0, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
-  }
+  const ExtendVariant& e = extend_variant(L);
+  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
   return 1;
 }
 
-int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream,
-                         int* waves_out, bool profile, float* ms_extend, float* ms_shade, int* n_extend) {
+size_t srt_wave_ctrl_bytes() { return sizeof(WaveCtrl); }
+
+// The streaming wavefront: iterate extend -> shade -> regen until every camera path of the sample
+// range has been generated and the queue has drained.  The host enqueues iterations in batches
+// and polls the control block (pinned copy) one batch behind, so the GPU never waits on the host.
+int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile) {
   const SrtRenderParams& p = L.p;
   const int npix = p.width * p.height;
-  const int spp = p.spp_end - p.spp_begin;
-  int wave_spp = (int)(W.capacity / (size_t)npix);
-  if (wave_spp > spp) wave_spp = spp;
-  int launches = 0, waves = 0;
-  const int ncounts = p.max_depth + 2;
-  const int shade_grid = L.sm_count * 8;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  float acc_ext = 0.f, acc_shd = 0.f; int next_launches = 0;
-  if (profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
-  for (int s0 = p.spp_begin; s0 < p.spp_end; s0 += wave_spp, ++waves) {
-    int ws = (p.spp_end - s0 < wave_spp) ? (p.spp_end - s0) : wave_spp;
-    int npaths = npix * ws;
-    k_wave_begin<<<1, 128, 0, stream>>>(W.counts, ncounts, npaths); ++launches;
-    k_raygen<<<L.sm_count * 8, 256, 0, stream>>>(L.cam, p, npaths, npix, s0, W.ray_o[0], W.ray_d[0], W.state[0], W.path_L); ++launches;
-    int g = 0;
-    for (int depth = 0; depth <= p.max_depth; ++depth) {
+  const unsigned long long total = (unsigned long long)npix * (unsigned long long)(p.spp_end - p.spp_begin);
+  const int cap = (int)W.capacity;
+  WaveCtrl* ctrl = (WaveCtrl*)W.ctrl;
+  int launches = 0;
+  const int shade_grid = L.sm_count * 8, regen_grid = L.sm_count * 8;
+  cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream);
+  k_ctrl_init<<<1, 1, 0, stream>>>(ctrl, total); ++launches;
+  k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, p, npix, cap, 0, 0, W.ray_o[0], W.ray_d[0], W.state[0], ctrl); ++launches;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  float acc_ext = 0.f, acc_shd = 0.f; int n_ext = 0;
+  if (profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
+  const int BATCH = 8;
+  WaveCtrl* h = (WaveCtrl*)W.h_ctrl;            // pinned, 2 slots
+  cudaEvent_t* ev = (cudaEvent_t*)W.poll_events;
+  int g = 0, parity = 1, batch = 0;
+  bool done = false;
+  while (!done) {
+    for (int k = 0; k < BATCH; ++k) {
       if (profile) cudaEventRecord(e0, stream);
-      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, W.counts + depth, 0, p.t_min, SRT_MAX_FLOAT, stream);
-      if (profile) { cudaEventRecord(e1, stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); acc_ext += ms; ++next_launches; cudaEventRecord(e0, stream); }
-      k_shade<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, depth, npix, s0, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
-                                                       W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.path_L, W.counts + depth, W.counts + depth + 1);
-      ++launches;
-      if (profile) { cudaEventRecord(e1, stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); acc_shd += ms; }
-      g ^= 1;
+      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, stream);
+      if (profile) cudaEventRecord(e1, stream);
+      k_shade<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
+                                                       W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
+      if (profile) { cudaEventRecord(e2, stream); cudaEventSynchronize(e2); float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); acc_ext += a; acc_shd += b; ++n_ext; }
+      k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, p, npix, cap, g ^ 1, parity, W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], ctrl);
+      launches += 2;
+      g ^= 1; parity ^= 1;
     }
-    k_accumulate<<<L.sm_count * 4, 256, 0, stream>>>(npix, ws, W.path_L, d_rgb_sum); ++launches;
-    k_wave_end<<<1, 128, 0, stream>>>(W.counts, ncounts, W.totals); ++launches;
+    cudaMemcpyAsync(&h[batch & 1], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
+    cudaEventRecord(ev[batch & 1], stream);
+    if (batch >= 1) {                             // look at the PREVIOUS batch while this one runs
+      cudaEventSynchronize(ev[(batch - 1) & 1]);
+      const WaveCtrl& c = h[(batch - 1) & 1];
+      if (c.qcount[0] == 0 && c.qcount[1] == 0 && c.next_path[0] >= total && c.next_path[1] >= total) done = true;
+    }
+    ++batch;
   }
-  if (profile) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
-  if (waves_out) *waves_out = waves;
-  if (ms_extend) *ms_extend = acc_ext;
-  if (ms_shade) *ms_shade = acc_shd;
-  if (n_extend) *n_extend = next_launches;
+  k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches;
+  cudaMemcpyAsync(&h[0], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
+  cudaStreamSynchronize(stream);
+  if (profile) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
+  if (stats) {
+    stats->rays = h[0].rays; stats->waves = (int)h[0].iterations; stats->kernel_launches = launches;
+    stats->ms_extend = acc_ext; stats->ms_shade = acc_shd; stats->extend_launches = n_ext;
+  }
   return launches;
 }
 

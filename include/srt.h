@@ -100,8 +100,9 @@ typedef struct {
   int32_t pad;
 } SrtStats;
 
-/* 64-byte node of the LBVH as the traversal kernel reads it; child < 0 is leaf ~child. */
-typedef struct { float lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, parent, sibling; } SrtBvhNode;
+/* 64-byte node of the LBVH as the traversal kernel reads it: the two child boxes as centre and
+ * padded half extent; child < 0 is leaf ~child. */
+typedef struct { float lc[3], le[3], rc[3], re[3]; int32_t left, right, parent, sibling; } SrtBvhNode;
 
 /* ray / hit records of the parity hook (replaces (g:hit scene r t-min t-max), geometry.scm:14) */
 typedef struct { float o[3], d[3], time; } SrtRay;

@@ -12,7 +12,8 @@
 //   2. 21-bit grid coordinate per axis, 63-bit Morton key (x highest)
 //   3. stable sort by key (ties keep primitive order)
 //   4. Karras 2012 radix-tree emit with delta(i,j) = clz64(ki^kj), or 64+clz32(i^j) for equal keys
-//   5. child boxes = union of primitive AABBs, padded by S*2^-21 (S = largest |coordinate|)
+//   5. child boxes = union of primitive AABBs, stored as centre 0.5*(min+max) and half extent
+//      0.5*(max-min) + S*2^-21 (S = largest |coordinate|)
 // Compile with -ffp-contract=off (see Makefile) so every fp32 op is separately rounded, matching
 // the __f*_rn intrinsics of the device code.
 #include <cstdint>
@@ -25,7 +26,7 @@
 namespace {
 
 struct Node64 {   // == SrtBvhNode in include/srt.h (64 bytes)
-  float lmin[3], lmax[3], rmin[3], rmax[3];
+  float lc[3], le[3], rc[3], re[3];   // child boxes as centre / padded half extent
   int32_t left, right, parent, sibling;
 };
 
@@ -62,7 +63,7 @@ int orc_lbvh_build(int n, const float* aabbs, uint64_t* keys_sorted, int32_t* or
   const float BIG = 3.0e38f;
   auto set_empty = [&](float* mn, float* mx) { for (int k = 0; k < 3; ++k) { mn[k] = BIG; mx[k] = -BIG; } };
   if (n <= 0) {
-    Node64& nd = nodes[0]; set_empty(nd.lmin, nd.lmax); set_empty(nd.rmin, nd.rmax);
+    Node64& nd = nodes[0]; for (int k = 0; k < 3; ++k) nd.lc[k] = nd.le[k] = nd.rc[k] = nd.re[k] = 0.f;
     nd.left = nd.right = ~0; nd.parent = nd.sibling = -1; return 1;
   }
   // 1. centroids + bounds, S
@@ -99,9 +100,9 @@ int orc_lbvh_build(int n, const float* aabbs, uint64_t* keys_sorted, int32_t* or
   };
   if (n == 1) {
     Node64& nd = nodes[0];
-    leaf_box(0, nd.lmin, nd.lmax);
-    for (int k = 0; k < 3; ++k) { nd.lmin[k] = nd.lmin[k] - pad; nd.lmax[k] = nd.lmax[k] + pad; }
-    for (int k = 0; k < 3; ++k) { nd.rmin[k] = nd.lmin[k]; nd.rmax[k] = nd.lmax[k]; }   // same leaf, same box on both sides
+    float mn[3], mx[3]; leaf_box(0, mn, mx);
+    for (int k = 0; k < 3; ++k) { nd.lc[k] = 0.5f * (mn[k] + mx[k]); nd.le[k] = 0.5f * (mx[k] - mn[k]) + pad; }
+    for (int k = 0; k < 3; ++k) { nd.rc[k] = nd.lc[k]; nd.re[k] = nd.le[k]; }   // same leaf, same box on both sides
     nd.left = nd.right = ~ord[0]; nd.parent = nd.sibling = -1; return 1;
   }
   // 4. Karras emit
@@ -133,13 +134,13 @@ int orc_lbvh_build(int n, const float* aabbs, uint64_t* keys_sorted, int32_t* or
   }
   // 5. boxes: unpadded union per node range [lo,hi] of sorted leaves, then pad on store.
   //    (min/max are exact, so any evaluation order gives identical bits.)
-  auto range_box = [&](int a, int b, float* mn, float* mx) {
-    set_empty(mn, mx);
+  auto range_box = [&](int a, int b, float* cen, float* ext) {
+    float mn[3], mx[3]; set_empty(mn, mx);
     for (int p = a; p <= b; ++p) {
       float lm[3], lx[3]; leaf_box(p, lm, lx);
       for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], lm[k]); mx[k] = std::max(mx[k], lx[k]); }
     }
-    for (int k = 0; k < 3; ++k) { mn[k] = mn[k] - pad; mx[k] = mx[k] + pad; }
+    for (int k = 0; k < 3; ++k) { cen[k] = 0.5f * (mn[k] + mx[k]); ext[k] = 0.5f * (mx[k] - mn[k]) + pad; }
   };
   // position of a leaf in sorted order is needed for leaf children: recover from gamma again
   for (int i = 0; i < nint; ++i) {
@@ -147,8 +148,8 @@ int orc_lbvh_build(int n, const float* aabbs, uint64_t* keys_sorted, int32_t* or
     // the split position gamma: left covers [lo, gamma], right covers [gamma+1, hi]
     int gamma;
     if (L >= 0) gamma = hi[L]; else if (R >= 0) gamma = lo[R] - 1; else gamma = lo[i];
-    range_box(lo[i], gamma, nodes[i].lmin, nodes[i].lmax);
-    range_box(gamma + 1, hi[i], nodes[i].rmin, nodes[i].rmax);
+    range_box(lo[i], gamma, nodes[i].lc, nodes[i].le);
+    range_box(gamma + 1, hi[i], nodes[i].rc, nodes[i].re);
   }
   return nint;
 }

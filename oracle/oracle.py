@@ -66,7 +66,9 @@ def _d(seq):
 
 class OracleScene:
     """Builds the oracle's node tree from the host object tree (scheme_raytrace_b200.host.geometry),
-    mirroring the reference's closure nesting one to one."""
+    mirroring the reference's closure nesting one to one.  Every scene parameter is first rounded
+    to fp32 — the precision of the C-ABI tables — so the f64 oracle and the GPU evaluate the SAME
+    scene (like the fixed ray batches, which are generated in fp32 and widened)."""
 
     def __init__(self, scene, perlin=None, flat=None):
         from scheme_raytrace_b200.host import geometry as g
@@ -89,11 +91,11 @@ class OracleScene:
         self.lib.orc_set_root(self.h, root)
         self.n_leaves = self._leaf
         if scene.camera is not None:
-            cam = _d(camera_to_floats(scene.camera))
+            cam = _d(np.asarray(camera_to_floats(scene.camera), dtype=np.float32))
             self.lib.orc_set_camera(self.h, _p(cam))
         self.lib.orc_set_sky(self.h, sky_kind(scene.sky_function))
         rv, px, py, pz = perlin if perlin is not None else perlin_generate(3)
-        rv = _d(rv)
+        rv = _d(np.asarray(rv, dtype=np.float32))
         self.lib.orc_set_perlin(self.h, _p(rv), _p(px), _p(py), _p(pz))
 
     def _add_tex(self, tx, t):
@@ -102,7 +104,8 @@ class OracleScene:
         even = odd = -1
         if tx.kind == t.CHECKER:
             even, odd = self._add_tex(tx.even, t), self._add_tex(tx.odd, t)
-        i = self.lib.orc_add_texture(self.h, tx.kind, tx.rgb[0], tx.rgb[1], tx.rgb[2], tx.scale, even, odd)
+        r, g_, b, sc = (float(np.float32(x)) for x in (tx.rgb[0], tx.rgb[1], tx.rgb[2], tx.scale))
+        i = self.lib.orc_add_texture(self.h, tx.kind, r, g_, b, sc, even, odd)
         self._tex[id(tx)] = i
         return i
 
@@ -111,11 +114,11 @@ class OracleScene:
             return -1
         if id(m) not in self._mat:
             tx = self._tex[id(m.tex)] if m.tex is not None else -1
-            self._mat[id(m)] = self.lib.orc_add_material(self.h, m.kind, tx, m.param)
+            self._mat[id(m)] = self.lib.orc_add_material(self.h, m.kind, tx, float(np.float32(m.param)))
         return self._mat[id(m)]
 
     def _node(self, kind, material, leaf, params, children):
-        prm = _d(list(params) if len(params) else [0.0])
+        prm = _d(np.asarray(list(params) if len(params) else [0.0], dtype=np.float32))
         ch = np.ascontiguousarray(children if len(children) else [0], dtype=np.int32)
         return self.lib.orc_add_node(self.h, kind, material, leaf, _p(prm), len(params), _p(ch), len(children))
 
@@ -240,7 +243,7 @@ def save_ppm(path, image):
     return load().orc_save_ppm(str(path).encode(), _p(image), w, h)
 
 
-NODE64 = np.dtype([("lmin", "<f4", (3,)), ("lmax", "<f4", (3,)), ("rmin", "<f4", (3,)), ("rmax", "<f4", (3,)),
+NODE64 = np.dtype([("lc", "<f4", (3,)), ("le", "<f4", (3,)), ("rc", "<f4", (3,)), ("re", "<f4", (3,)),
                    ("left", "<i4"), ("right", "<i4"), ("parent", "<i4"), ("sibling", "<i4")])
 
 

@@ -8,7 +8,9 @@
 // intrinsic so that the host reference (compiled with -ffp-contract=off) produces the same bits:
 //   centroid = 0.5*(min+max); g = min(uint(q * 2^21), 2^21-1), q = (c - cmin)/(cmax - cmin)
 //   key = 63-bit Morton (x highest); stable sort; Karras 2012 with index tie-break for equal keys
-//   stored child boxes = union of primitive AABBs padded by S * 2^-21, S = max |coordinate|
+//   stored child boxes = union of primitive AABBs as centre c = 0.5*(min+max) and half extent
+//   e = 0.5*(max-min) + S * 2^-21 (S = max |coordinate|; the pad covers fp32 rounding in c, e and in
+//   the traversal's FMA slab test)
 #include "srt_device.cuh"
 #include "srt_host.h"
 
@@ -241,10 +243,10 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
     }
     float* o = nbox + 6 * (size_t)node;
     for (int k = 0; k < 3; ++k) { o[k] = fminf(cb[0][k], cb[1][k]); o[3 + k] = fmaxf(cb[0][3 + k], cb[1][3 + k]); }
-    float l[6], r[6];
+    float l[6], r[6];   // centre (0..2), padded half extent (3..5)
     for (int k = 0; k < 3; ++k) {
-      l[k] = __fsub_rn(cb[0][k], pad); l[3 + k] = __fadd_rn(cb[0][3 + k], pad);
-      r[k] = __fsub_rn(cb[1][k], pad); r[3 + k] = __fadd_rn(cb[1][3 + k], pad);
+      l[k] = __fmul_rn(0.5f, __fadd_rn(cb[0][k], cb[0][3 + k])); l[3 + k] = __fadd_rn(__fmul_rn(0.5f, __fsub_rn(cb[0][3 + k], cb[0][k])), pad);
+      r[k] = __fmul_rn(0.5f, __fadd_rn(cb[1][k], cb[1][3 + k])); r[3 + k] = __fadd_rn(__fmul_rn(0.5f, __fsub_rn(cb[1][3 + k], cb[1][k])), pad);
     }
     nodes[4 * node + 0] = make_float4(l[0], l[1], l[2], l[3]);
     nodes[4 * node + 1] = make_float4(l[4], l[5], r[0], r[1]);
@@ -258,14 +260,13 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
 __global__ void k_single_node(int n, const float* __restrict__ aabb, const int* __restrict__ b, float4* __restrict__ nodes,
                               unsigned long long* keys, int* order) {
   if (threadIdx.x != 0) return;
-  float l[6] = {BIG, BIG, BIG, -BIG, -BIG, -BIG};
+  float l[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (n == 1) {
     const float pad = __fmul_rn(ord2f(b[6]), 1.0f / 2097152.0f);
-    for (int k = 0; k < 3; ++k) { l[k] = __fsub_rn(aabb[k], pad); l[3 + k] = __fadd_rn(aabb[3 + k], pad); }
+    for (int k = 0; k < 3; ++k) { l[k] = __fmul_rn(0.5f, __fadd_rn(aabb[k], aabb[3 + k])); l[3 + k] = __fadd_rn(__fmul_rn(0.5f, __fsub_rn(aabb[3 + k], aabb[k])), pad); }
     order[0] = 0;
   }
-  // both children reference the same leaf with the same box (an inverted "empty" box would not
-  // be empty under a min/max slab test); n == 0 is never traversed
+  // both children reference the same leaf with the same box; n == 0 is never traversed
   nodes[0] = make_float4(l[0], l[1], l[2], l[3]);
   nodes[1] = make_float4(l[4], l[5], l[0], l[1]);
   nodes[2] = make_float4(l[2], l[3], l[4], l[5]);

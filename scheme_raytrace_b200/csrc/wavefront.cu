@@ -13,6 +13,7 @@
 // batch of samples.  The recursive estimator `color` is run in its iterative form
 // L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
 #include "srt_device.cuh"
+#include <cstdlib>
 #include "srt_host.h"
 
 namespace {
@@ -32,6 +33,7 @@ struct WaveCtrl {
   unsigned long long total_paths;
   unsigned long long rays;          // sum of qcount over iterations = closest-hit queries
   unsigned long long iterations;
+  int cursor; int pad;              // ray-chunk cursor of the persistent extend warps (reset by regen)
 };
 #define SRT_ACC_SCALE 68719476736.0f   // 2^36: radiance accumulates in 64-bit fixed point
 
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
     ctrl->qcount[g] = q;
     ctrl->next_path[parity ^ 1] = next + (unsigned long long)n_new;
     ctrl->survivors[g ^ 1] = 0;          // cursor of the generation the next shade appends into
+    ctrl->cursor = 0;
     ctrl->rays += (unsigned long long)q;
     ctrl->iterations += q ? 1ull : 0ull;
   }
@@ -98,73 +101,160 @@ struct PrimGlobal {
   __device__ __forceinline__ float4 a(int i) const { return __ldg(&pa[i]); }
 };
 
-template <bool SMEM, int MASK, class PrimSrc>
-__device__ __forceinline__ Hit traverse(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
-                                        float3 o, float3 d, float time, float tmin, float tmax) {
-  Hit h; h.t = tmax; h.prim = -1; h.u = 0.f; h.v = 0.f; h.incl = false;
-  if (sc.n_prims == 0) return h;
+// Per-lane traversal state of the persistent extend kernel.
+struct Trav {
+  float3 o, d, inv, oi, ainv; float time, inv_a;
+  Hit h; int node; unsigned long long trail; int ray;
+  unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
+};
+__device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float tmax, int ray) {
+  T.o = xyz(o4); T.d = xyz(d4); T.time = o4.w; T.ray = ray;
   // reciprocal direction; (near-)zero components become +-1e18 instead of +-inf so that the FMA
-  // slab form below never produces inf - inf (boxes are padded, see lbvh.cu, so the sign of
+  // slab form never produces inf - inf (boxes are padded, see lbvh.cu, so the sign of
   // (b - o) * 1e18 is exact for every ray that can reach a primitive inside the box)
-  const float3 inv = v3(fabsf(d.x) > 1e-18f ? 1.0f / d.x : copysignf(1e18f, d.x), fabsf(d.y) > 1e-18f ? 1.0f / d.y : copysignf(1e18f, d.y),
-                        fabsf(d.z) > 1e-18f ? 1.0f / d.z : copysignf(1e18f, d.z));
-  const float3 oi = v3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-  const float inv_a = 1.0f / dot(d, d);
-  int node = 0;
-  unsigned long long trail = 0ull;
-  for (;;) {
-    float4 n0, n1, n2, n3;
-    if (SMEM) { n0 = nodes[4 * node]; n1 = nodes[4 * node + 1]; n2 = nodes[4 * node + 2]; n3 = nodes[4 * node + 3]; }
-    else { n0 = __ldg(&nodes[4 * node]); n1 = __ldg(&nodes[4 * node + 1]); n2 = __ldg(&nodes[4 * node + 2]); n3 = __ldg(&nodes[4 * node + 3]); }
-    // slabs, FMA form t = b*inv - o*inv (6 FFMA per box).  Boxes are padded at build time (lbvh.cu).
-    float lx0 = fmaf(n0.x, inv.x, -oi.x), lx1 = fmaf(n0.w, inv.x, -oi.x);
-    float ly0 = fmaf(n0.y, inv.y, -oi.y), ly1 = fmaf(n1.x, inv.y, -oi.y);
-    float lz0 = fmaf(n0.z, inv.z, -oi.z), lz1 = fmaf(n1.y, inv.z, -oi.z);
-    float rx0 = fmaf(n1.z, inv.x, -oi.x), rx1 = fmaf(n2.y, inv.x, -oi.x);
-    float ry0 = fmaf(n1.w, inv.y, -oi.y), ry1 = fmaf(n2.z, inv.y, -oi.y);
-    float rz0 = fmaf(n2.x, inv.z, -oi.z), rz1 = fmaf(n2.w, inv.z, -oi.z);
-    float lt0 = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
-    float lt1 = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), h.t));
-    float rt0 = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
-    float rt1 = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), h.t));
-    bool hl = lt0 <= lt1, hr = rt0 <= rt1;
-    int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
-    // leaves are intersected right away (one primitive per leaf)
-    int pend0 = -1, pend1 = -1;
-    if (hl && left < 0) { pend0 = ~left; hl = false; }
-    if (hr && right < 0) { if (pend0 < 0) pend0 = ~right; else pend1 = ~right; hr = false; }
-    while (pend0 >= 0) {
-      intersect_prim<MASK>(sc, ps, pend0, o, d, time, inv_a, tmin, h);
-      pend0 = pend1; pend1 = -1;
-    }
-    if (hl | hr) {
-      bool both = hl & hr;
-      node = (both ? (lt0 <= rt0) : hl) ? left : right;     // near child first
-      trail = (trail << 1) | (both ? 1ull : 0ull);
-      continue;
-    }
-    if (trail == 0ull) break;
-    int up = __ffsll((long long)trail) - 1;
-    trail >>= up;
-    int par = __float_as_int(n3.z), sib = __float_as_int(n3.w);
-    for (int k = 0; k < up; ++k) {
-      float4 m = SMEM ? nodes[4 * par + 3] : __ldg(&nodes[4 * par + 3]);
-      par = __float_as_int(m.z); sib = __float_as_int(m.w);
-    }
-    node = sib;
-    trail ^= 1ull;
-  }
-  return h;
+  T.inv = v3(fabsf(T.d.x) > 1e-18f ? 1.0f / T.d.x : copysignf(1e18f, T.d.x), fabsf(T.d.y) > 1e-18f ? 1.0f / T.d.y : copysignf(1e18f, T.d.y),
+             fabsf(T.d.z) > 1e-18f ? 1.0f / T.d.z : copysignf(1e18f, T.d.z));
+  T.oi = v3(T.o.x * T.inv.x, T.o.y * T.inv.y, T.o.z * T.inv.z);
+  T.ainv = v3(fabsf(T.inv.x), fabsf(T.inv.y), fabsf(T.inv.z));
+  T.inv_a = 1.0f / dot(T.d, T.d);
+  T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
+  T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0;
 }
 
-template <bool SMEM, int MASK>
+// One node step: slab-test both children, stash hit leaf children in (pend0, pend1), descend into
+// the near internal child or backtrack.  Returns false when the traversal is finished.
+//
+// Slab test on centre / half-extent boxes: t_c = c*inv - o*inv, t_near/far = t_c -/+ e*|inv| —
+// 9 FFMA + 4 min/max per box (the min/max-heavy 6 FFMA + 10 FMNMX form saturates the ALU pipe while
+// the FMA pipe idles).
+//
+// Backtracking is stackless in the sense of Barringer & Akenine-Moller: the bit trail says at
+// which level above a far child is still pending, parent links lead there and the sibling link
+// enters it.  Because that climb is a serial chain of dependent loads executed by few lanes, the
+// 8 most recent far children are additionally cached in two 64-bit registers (16-bit ids,
+// CACHE = true when the tree has < 65536 nodes); the climb only runs when the cache has overflowed.
+template <bool SMEM, bool CACHE>
+__device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, float tmin, int& pend0, int& pend1) {
+  const int node = T.node;
+  float4 n0, n1, n2, n3;
+  if (SMEM) { n0 = nodes[4 * node]; n1 = nodes[4 * node + 1]; n2 = nodes[4 * node + 2]; n3 = nodes[4 * node + 3]; }
+  else { n0 = __ldg(&nodes[4 * node]); n1 = __ldg(&nodes[4 * node + 1]); n2 = __ldg(&nodes[4 * node + 2]); n3 = __ldg(&nodes[4 * node + 3]); }
+  const float3 inv = T.inv, oi = T.oi, ai = T.ainv;
+  // left: c = (n0.x n0.y n0.z) e = (n0.w n1.x n1.y); right: c = (n1.z n1.w n2.x) e = (n2.y n2.z n2.w)
+  float lcx = fmaf(n0.x, inv.x, -oi.x), lcy = fmaf(n0.y, inv.y, -oi.y), lcz = fmaf(n0.z, inv.z, -oi.z);
+  float rcx = fmaf(n1.z, inv.x, -oi.x), rcy = fmaf(n1.w, inv.y, -oi.y), rcz = fmaf(n2.x, inv.z, -oi.z);
+  float lt0 = fmaxf(fmaxf(fmaf(-n0.w, ai.x, lcx), fmaf(-n1.x, ai.y, lcy)), fmaxf(fmaf(-n1.y, ai.z, lcz), tmin));
+  float lt1 = fminf(fminf(fmaf(n0.w, ai.x, lcx), fmaf(n1.x, ai.y, lcy)), fminf(fmaf(n1.y, ai.z, lcz), T.h.t));
+  float rt0 = fmaxf(fmaxf(fmaf(-n2.y, ai.x, rcx), fmaf(-n2.z, ai.y, rcy)), fmaxf(fmaf(-n2.w, ai.z, rcz), tmin));
+  float rt1 = fminf(fminf(fmaf(n2.y, ai.x, rcx), fmaf(n2.z, ai.y, rcy)), fminf(fmaf(n2.w, ai.z, rcz), T.h.t));
+  bool hl = lt0 <= lt1, hr = rt0 <= rt1;
+  int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+  if (hl && left < 0) { pend0 = ~left; hl = false; }
+  if (hr && right < 0) { if (pend0 < 0) pend0 = ~right; else pend1 = ~right; hr = false; }
+  if (hl | hr) {
+    bool both = hl & hr;
+    bool go_left = both ? (lt0 <= rt0) : hl;                  // near child first
+    T.node = go_left ? left : right;
+    T.trail = (T.trail << 1) | (both ? 1ull : 0ull);
+    if (CACHE && both) {
+      unsigned long long far_id = (unsigned long long)(unsigned)(go_left ? right : left);
+      T.s1 = (T.s1 << 16) | (T.s0 >> 48);
+      T.s0 = (T.s0 << 16) | far_id;
+      T.nstk = min(T.nstk + 1, 8);
+    }
+    return true;
+  }
+  if (T.trail == 0ull) return false;
+  int up = __ffsll((long long)T.trail) - 1;                   // levels up to the pending far child
+  T.trail = (T.trail >> up) ^ 1ull;
+  if (CACHE && T.nstk > 0) {
+    T.node = (int)(T.s0 & 0xffffull);
+    T.s0 = (T.s0 >> 16) | (T.s1 << 48);
+    T.s1 >>= 16;
+    T.nstk -= 1;
+    return true;
+  }
+  int par = __float_as_int(n3.z), sib = __float_as_int(n3.w);
+  for (int k = 0; k < up; ++k) {
+    float4 m = SMEM ? nodes[4 * par + 3] : __ldg(&nodes[4 * par + 3]);
+    par = __float_as_int(m.z); sib = __float_as_int(m.w);
+  }
+  T.node = sib;
+  return true;
+}
+
+// Persistent warps with dynamic ray fetch: a warp pulls chunks of EXT_CHUNK rays from a global
+// cursor and refills idle lanes as soon as EXT_REFILL of them have finished, so short rays do
+// not idle behind the longest ray of the warp.  Inside, a while-while loop: every lane walks
+// nodes until it has found a leaf (or finished), then the leaf primitives are intersected
+// together (fewer lanes idle than with an interleaved if-if step).
+constexpr int EXT_CHUNK = 128;
+
+template <bool SMEM, int MASK, int MODE, class PrimSrc>
+__device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
+                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
+                                            int count, int* __restrict__ cursor, float tmin, float tmax, int refill) {
+  constexpr bool DYN = MODE & 1, WW = MODE & 2, CACHE = MODE & 4;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (sc.n_prims == 0) {   // empty scene: every ray misses
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
+    return;
+  }
+  Trav T; T.ray = -1; T.node = 0; T.trail = 0ull;
+  if (!DYN) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      trav_init(T, ray_o[i], ray_d[i], tmax, i);
+      bool more = true;
+      while (more) {
+        int pend0 = -1, pend1 = -1;
+        if (WW) { while (more && pend0 < 0) more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1); }
+        else more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+        while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1; }
+      }
+      hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
+    }
+    return;
+  }
+  int w_cur = 0, w_end = 0; bool exhausted = false;
+  bool busy = false;
+  for (;;) {
+    unsigned idle = __ballot_sync(full, !busy);
+    if (idle == full || (!exhausted && __popc(idle) >= refill)) {
+      if (w_cur >= w_end && !exhausted) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, EXT_CHUNK);
+        base = __shfl_sync(full, base, 0);
+        w_cur = base; w_end = min(base + EXT_CHUNK, count);
+        if (base >= count) { exhausted = true; w_cur = w_end = 0; }
+      }
+      if (!busy) {
+        int idx = w_cur + __popc(idle & ((1u << lane) - 1u));
+        if (idx < w_end) { trav_init(T, ray_o[idx], ray_d[idx], tmax, idx); busy = true; }
+      }
+      w_cur = min(w_cur + __popc(idle), w_end);
+      if (exhausted && !__any_sync(full, busy)) break;
+    }
+    if (busy) {
+      int pend0 = -1, pend1 = -1; bool more = true;
+      if (WW) { while (more && pend0 < 0) more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1); }
+      else more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+      while (pend0 >= 0) {
+        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h);
+        pend0 = pend1; pend1 = -1;
+      }
+      if (!more) { hit[T.ray] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v); busy = false; }
+    }
+  }
+}
+
+template <bool SMEM, int MASK, int MODE>
 __global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x20) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-         const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax) {
+         const int* __restrict__ count_ptr, int count_fixed, int* __restrict__ cursor, float tmin, float tmax, int refill) {
   extern __shared__ float4 smem[];
   const int count = count_ptr ? *count_ptr : count_fixed;
   if (count == 0) return;
-  const float4* nodes = sc.nodes;
   if (SMEM) {
     // stage the whole LBVH + primitive headers ("shared-memory staging of BVH top levels":
     // for the <= few-thousand-primitive scenes of the reference the top levels are all levels)
@@ -174,20 +264,11 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     float4* sa = smem + nn + np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
-    nodes = smem;
     PrimShared ps{sh, sa};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-      float4 o4 = ray_o[i], d4 = ray_d[i];
-      Hit h = traverse<true, MASK>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
-      hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-    }
+    extend_loop<true, MASK, MODE>(sc, smem, ps, ray_o, ray_d, hit, count, cursor, tmin, tmax, refill);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-      float4 o4 = ray_o[i], d4 = ray_d[i];
-      Hit h = traverse<false, MASK>(sc, nodes, ps, xyz(o4), xyz(d4), o4.w, tmin, tmax);
-      hit[i] = make_float4(h.t, __int_as_float(h.prim), h.u, h.v);
-    }
+    extend_loop<false, MASK, MODE>(sc, sc.nodes, ps, ray_o, ray_d, hit, count, cursor, tmin, tmax, refill);
   }
 }
 
@@ -258,7 +339,7 @@ __global__ void k_accum_to_float(int n3, const unsigned long long* __restrict__ 
 }
 __global__ void k_ctrl_init(WaveCtrl* ctrl, unsigned long long total_paths) {
   ctrl->qcount[0] = ctrl->qcount[1] = 0; ctrl->survivors[0] = ctrl->survivors[1] = 0;
-  ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull;
+  ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull; ctrl->cursor = 0;
 }
 
 // main.scm:123-124, 481-487: correct-gamma (sqrt) + floor(255.99 * min(1, c)); negative sums
@@ -320,9 +401,10 @@ __global__ void k_eval_raygen(DCamera cam, SrtRenderParams p, int n, const int* 
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
 // Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
-typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, float, float);
+typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, int*, float, float, int);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
-static ExtendVariant g_variants[2][4];
+static ExtendVariant g_variants[2][4][8];
+static int g_ext_mode = -1, g_ext_refill = 8;
 
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
@@ -330,21 +412,34 @@ static int variant_of(int mask) {
   if ((mask & 0x20) == 0) return 2;
   return 3;
 }
-static ExtendFn variant_fn(bool smem, int v) {
+template <bool SMEM, int MODE> static ExtendFn variant_fn_m(int v) {
   switch (v) {
-    case 0: return smem ? k_extend<true, 0x01> : k_extend<false, 0x01>;
-    case 1: return smem ? k_extend<true, 0x03> : k_extend<false, 0x03>;
-    case 2: return smem ? k_extend<true, 0x1f> : k_extend<false, 0x1f>;
-    default: return smem ? k_extend<true, SRT_MASK_ALL> : k_extend<false, SRT_MASK_ALL>;
+    case 0: return k_extend<SMEM, 0x01, MODE>;
+    case 1: return k_extend<SMEM, 0x03, MODE>;
+    case 2: return k_extend<SMEM, 0x1f, MODE>;
+    default: return k_extend<SMEM, SRT_MASK_ALL, MODE>;
+  }
+}
+static ExtendFn variant_fn(bool smem, int v, int mode) {
+  switch (mode) {
+    case 0: return smem ? variant_fn_m<true, 0>(v) : variant_fn_m<false, 0>(v);
+    case 1: return smem ? variant_fn_m<true, 1>(v) : variant_fn_m<false, 1>(v);
+    case 4: return smem ? variant_fn_m<true, 4>(v) : variant_fn_m<false, 4>(v);
+    default: return smem ? variant_fn_m<true, 5>(v) : variant_fn_m<false, 5>(v);
   }
 }
 // persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
 static const ExtendVariant& extend_variant(const RenderLaunch& L) {
+  if (g_ext_mode < 0) {   // mode: bit0 = dynamic ray fetch, bit2 = far-child register cache (tuning knobs, default 4)
+    const char* e = getenv("SRT_EXT_MODE"); g_ext_mode = e ? atoi(e) & 5 : 4;
+    const char* r = getenv("SRT_EXT_REFILL"); if (r) g_ext_refill = atoi(r);
+  }
   int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
-  ExtendVariant& e = g_variants[which][v];
+  int mode = g_ext_mode; if (L.sc.n_nodes >= 65536) mode &= ~4;      // 16-bit ids in the far-child cache
+  ExtendVariant& e = g_variants[which][v][mode];
   size_t smem = which ? L.extend_smem : 0;
   if (!e.fn || e.smem != smem) {
-    e.fn = variant_fn(which, v); e.smem = smem;
+    e.fn = variant_fn(which, v, mode); e.smem = smem;
     if (which) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, EXT_THREADS, smem);
@@ -353,12 +448,14 @@ static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   return e;
 }
 
+// `cursor` = device int the persistent warps pull ray chunks from; must be 0 at launch.
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
-                      float tmin, float tmax, cudaStream_t stream) {
+                      int* cursor, float tmin, float tmax, cudaStream_t stream) {
   const ExtendVariant& e = extend_variant(L);
-  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
+  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, cursor, tmin, tmax, g_ext_refill);
   return 1;
 }
+int* srt_ctrl_cursor(void* ctrl) { return &((WaveCtrl*)ctrl)->cursor; }
 
 size_t srt_wave_ctrl_bytes() { return sizeof(WaveCtrl); }
 
@@ -387,7 +484,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   while (!done) {
     for (int k = 0; k < BATCH; ++k) {
       if (profile) cudaEventRecord(e0, stream);
-      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, stream);
+      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, &ctrl->cursor, p.t_min, SRT_MAX_FLOAT, stream);
       if (profile) cudaEventRecord(e1, stream);
       k_shade<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
                                                        W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);

@@ -8,7 +8,7 @@ from .perlin import perlin_generate
 RAY_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("time", "<f4")])
 HIT_DTYPE = np.dtype([("prim", "<i4"), ("material", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4"),
                       ("p", "<f4", (3,)), ("n", "<f4", (3,))])
-BVH_NODE_DTYPE = np.dtype([("lmin", "<f4", (3,)), ("lmax", "<f4", (3,)), ("rmin", "<f4", (3,)), ("rmax", "<f4", (3,)),
+BVH_NODE_DTYPE = np.dtype([("lc", "<f4", (3,)), ("le", "<f4", (3,)), ("rc", "<f4", (3,)), ("re", "<f4", (3,)),
                            ("left", "<i4"), ("right", "<i4"), ("parent", "<i4"), ("sibling", "<i4")])
 assert RAY_DTYPE.itemsize == 28 and HIT_DTYPE.itemsize == 44 and BVH_NODE_DTYPE.itemsize == 64
 

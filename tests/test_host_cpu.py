@@ -80,16 +80,21 @@ def test_lbvh_host_reference_properties(orc):
         assert len(nodes) == n - 1
         leaves = [~x for x in list(nodes["left"]) + list(nodes["right"]) if x < 0]
         assert sorted(leaves) == list(range(n))                # every primitive exactly once
-        # each child box contains the boxes below it
+        # each stored child box (centre / padded half extent) contains every primitive AABB below it
+        import functools
+
+        @functools.lru_cache(maxsize=None)
         def box_of(ch):
             if ch < 0:
-                return aabb[~ch, :3], aabb[~ch, 3:]
+                return tuple(aabb[~ch, :3].astype(np.float64)), tuple(aabb[~ch, 3:].astype(np.float64))
             nd = nodes[ch]
-            return np.minimum(nd["lmin"], nd["rmin"]), np.maximum(nd["lmax"], nd["rmax"])
+            (llo, lhi), (rlo, rhi) = box_of(int(nd["left"])), box_of(int(nd["right"]))
+            return tuple(np.minimum(llo, rlo)), tuple(np.maximum(lhi, rhi))
         for i, nd in enumerate(nodes):
-            for side, ch in (("l", nd["left"]), ("r", nd["right"])):
+            for side, ch in (("l", int(nd["left"])), ("r", int(nd["right"]))):
                 lo, hi = box_of(ch)
-                assert np.all(nd[side + "min"] <= lo) and np.all(nd[side + "max"] >= hi)
+                c, e = nd[side + "c"].astype(np.float64), nd[side + "e"].astype(np.float64)
+                assert np.all(c - e <= lo) and np.all(c + e >= hi)
                 if ch >= 0:
                     assert nodes[ch]["parent"] == i and nodes[ch]["sibling"] == (nd["right"] if side == "l" else nd["left"])
         assert nodes[0]["parent"] == -1 and orc.lbvh_depth(nodes) <= 64

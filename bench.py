@@ -166,7 +166,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H, SPP, D, SEED = cfg["width"], cfg["height"], cfg["spp"], cfg["max_depth"], cfg["seed"]
-    s_begin, s_end = rank * SPP // world, (rank + 1) * SPP // world      # sample-range sharding
+    from scheme_raytrace_b200.host import sharding
+    s_begin, s_end = sharding.sample_range(rank, world, SPP)            # sample-range sharding
     scene = cfg["scene"](W, H)
     flat = srt.flatten_scene(scene)
     r = srt.Renderer(flat, device=local)
@@ -182,8 +183,7 @@ def main():
         """value: scene resident in HBM, accumulate into the device buffer, one NCCL reduce."""
         accum.zero_()
         st = r.render_device(accum.data_ptr(), W, H, s_end - s_begin, max_depth=D, seed=SEED, spp_begin=s_begin)
-        if dist is not None:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        sharding.reduce_accumulators(accum, dist)
         return st
 
     def step_e2e():
@@ -191,8 +191,7 @@ def main():
         r.commit()
         accum.zero_()
         st = r.render_device(accum.data_ptr(), W, H, s_end - s_begin, max_depth=D, seed=SEED, spp_begin=s_begin)
-        if dist is not None:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        sharding.reduce_accumulators(accum, dist)
         if rank == 0:
             host_img.copy_(accum, non_blocking=True)
         torch.cuda.synchronize()

@@ -70,13 +70,14 @@ class OracleScene:
     to fp32 — the precision of the C-ABI tables — so the f64 oracle and the GPU evaluate the SAME
     scene (like the fixed ray batches, which are generated in fp32 and widened)."""
 
-    def __init__(self, scene, perlin=None, flat=None):
+    def __init__(self, scene, perlin=None, flat=None, quantise=True):
         from scheme_raytrace_b200.host import geometry as g
         from scheme_raytrace_b200.host import texture as t
         from scheme_raytrace_b200.host.camera import camera_to_floats
         from scheme_raytrace_b200.host.flatten import flatten_scene, sky_kind
         from scheme_raytrace_b200.host.perlin import perlin_generate
         self.lib = load()
+        self._q = (lambda a: np.asarray(a, dtype=np.float32)) if quantise else (lambda a: np.asarray(a, dtype=np.float64))
         self.h = self.lib.orc_create()
         self.flat = flat if flat is not None else flatten_scene(scene)
         self._tex, self._mat = {}, {}
@@ -91,11 +92,11 @@ class OracleScene:
         self.lib.orc_set_root(self.h, root)
         self.n_leaves = self._leaf
         if scene.camera is not None:
-            cam = _d(np.asarray(camera_to_floats(scene.camera), dtype=np.float32))
+            cam = _d(self._q(camera_to_floats(scene.camera)))
             self.lib.orc_set_camera(self.h, _p(cam))
         self.lib.orc_set_sky(self.h, sky_kind(scene.sky_function))
         rv, px, py, pz = perlin if perlin is not None else perlin_generate(3)
-        rv = _d(np.asarray(rv, dtype=np.float32))
+        rv = _d(self._q(rv))
         self.lib.orc_set_perlin(self.h, _p(rv), _p(px), _p(py), _p(pz))
 
     def _add_tex(self, tx, t):
@@ -104,7 +105,7 @@ class OracleScene:
         even = odd = -1
         if tx.kind == t.CHECKER:
             even, odd = self._add_tex(tx.even, t), self._add_tex(tx.odd, t)
-        r, g_, b, sc = (float(np.float32(x)) for x in (tx.rgb[0], tx.rgb[1], tx.rgb[2], tx.scale))
+        r, g_, b, sc = (float(x) for x in self._q([tx.rgb[0], tx.rgb[1], tx.rgb[2], tx.scale]))
         i = self.lib.orc_add_texture(self.h, tx.kind, r, g_, b, sc, even, odd)
         self._tex[id(tx)] = i
         return i
@@ -114,11 +115,11 @@ class OracleScene:
             return -1
         if id(m) not in self._mat:
             tx = self._tex[id(m.tex)] if m.tex is not None else -1
-            self._mat[id(m)] = self.lib.orc_add_material(self.h, m.kind, tx, float(np.float32(m.param)))
+            self._mat[id(m)] = self.lib.orc_add_material(self.h, m.kind, tx, float(self._q([m.param])[0]))
         return self._mat[id(m)]
 
     def _node(self, kind, material, leaf, params, children):
-        prm = _d(np.asarray(list(params) if len(params) else [0.0], dtype=np.float32))
+        prm = _d(self._q(list(params) if len(params) else [0.0]))
         ch = np.ascontiguousarray(children if len(children) else [0], dtype=np.int32)
         return self.lib.orc_add_node(self.h, kind, material, leaf, _p(prm), len(params), _p(ch), len(children))
 

@@ -26,20 +26,20 @@ def test_philox_kat(orc):
 
 @pytest.mark.parametrize("d,t_exp", [((0, 0, -1), 0.5), ((0, 0, -2), 0.25)])
 def test_kat1_kat2_sphere(orc, d, t_exp):
-    S = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    S = orc.OracleScene(quantise=False, scene=_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
     r = S.trace_batch([[0, 0, 0, *d, 0]])
     assert r["prim"][0] == 0 and r["t"][0] == t_exp
     assert np.allclose(r["p"][0], (0, 0, -0.5)) and np.allclose(r["n"][0], (0, 0, 1))
 
 
 def test_kat3_from_centre(orc):
-    S = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    S = orc.OracleScene(quantise=False, scene=_scene([g.make_sphere((0, 0, -1), 0.5, LAMB)]))
     r = S.trace_batch([[0, 0, -1, 0, 1, 0, 0]])
     assert r["t"][0] == 0.5 and np.allclose(r["p"][0], (0, 0.5, -1)) and np.allclose(r["n"][0], (0, 1, 0))
 
 
 def test_kat4_negative_radius(orc):
-    S = orc.OracleScene(_scene([g.make_sphere((-1, 0, -1), -0.45, LAMB)]))
+    S = orc.OracleScene(quantise=False, scene=_scene([g.make_sphere((-1, 0, -1), -0.45, LAMB)]))
     r = S.trace_batch([[-1, 0, 0, 0, 0, -1, 0]])
     assert abs(r["t"][0] - 0.55) < 1e-15 and np.allclose(r["p"][0], (-1, 0, -0.55)) and np.allclose(r["n"][0], (0, 0, -1))
 
@@ -56,9 +56,9 @@ def test_kat5_cameras(orc):
     assert np.allclose(c2[2], (0, 0.5147316415993759, -0.5147316415993759), atol=1e-14)
     assert np.array_equal(orc.make_camera((0, 5, 5), (0, 0, 0), (0, 1, 0), 40, 1, 0, 1, 0, 1), np.asarray(cam.camera_to_floats(c2)))
     # centre rays (s = t = 0.5, zero lens offset)
-    S = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c, scenes.sky_color))
+    S = orc.OracleScene(quantise=False, scene=g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c, scenes.sky_color))
     assert np.allclose(S.get_ray(0.5, 0.5, 0.0, 1, 0, 0)[3:6], (0, 0, 1), atol=1e-12)
-    S2 = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c2, scenes.sky_color))
+    S2 = orc.OracleScene(quantise=False, scene=g.make_scene([g.make_sphere((0, 0, 0), 1, LAMB)], c2, scenes.sky_color))
     assert np.allclose(S2.get_ray(0.5, 0.5, 0.0, 1, 0, 0)[3:6], (0, -0.7071067811865479, -0.7071067811865479), atol=1e-12)
     # weekend camera of cfg1 == the dead <camera> class defaults (camera.scm:12-22)
     c3 = cam.make_camera((0, 0, 0), (0, 0, -1), (0, 1, 0), 90, 2, 0, 1, 0, 1)
@@ -66,7 +66,7 @@ def test_kat5_cameras(orc):
 
 
 def test_kat6_xz_rect(orc):
-    S = orc.OracleScene(_scene([g.make_xz_rect(213, 343, 227, 332, 554, LAMB)]))
+    S = orc.OracleScene(quantise=False, scene=_scene([g.make_xz_rect(213, 343, 227, 332, 554, LAMB)]))
     r = S.trace_batch([[278, 0, 279.5, 0, 1, 0, 0]])
     assert r["t"][0] == 554 and np.allclose(r["p"][0], (278, 554, 279.5)) and np.allclose(r["n"][0], (0, 1, 0))
     assert np.allclose(r["uv"][0], (0.5, 0.5))
@@ -114,21 +114,21 @@ def test_kat10_bezier(orc):
 
 def test_tie_rule_box_edge(orc):
     """make-box faces are inclusive-type, later rect wins an equal-t tie."""
-    S = orc.OracleScene(_scene([g.make_box((0, 0, 0), (1, 1, 1), LAMB)]))
+    S = orc.OracleScene(quantise=False, scene=_scene([g.make_box((0, 0, 0), (1, 1, 1), LAMB)]))
     # ray into the exact edge shared by face 0 (xy @ z=1) and face 4 (yz @ x=1): both t = 1
     r = S.trace_batch([[2, 0.5, 2, -1, 0, -1, 0]])
     assert r["t"][0] == 1.0 and r["prim"][0] == 4
     # sphere (strict) listed after a rect at the same t loses; listed before, the rect (inclusive) wins
-    S2 = orc.OracleScene(_scene([g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB), g.make_sphere((0, 0, -1), 0.5, LAMB)]))
+    S2 = orc.OracleScene(quantise=False, scene=_scene([g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB), g.make_sphere((0, 0, -1), 0.5, LAMB)]))
     assert S2.trace_batch([[0, 0, 0, 0, 0, -1, 0]])["prim"][0] == 0
-    S3 = orc.OracleScene(_scene([g.make_sphere((0, 0, -1), 0.5, LAMB), g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB)]))
+    S3 = orc.OracleScene(quantise=False, scene=_scene([g.make_sphere((0, 0, -1), 0.5, LAMB), g.make_xy_rect(-1, 1, -1, 1, -0.5, LAMB)]))
     assert S3.trace_batch([[0, 0, 0, 0, 0, -1, 0]])["prim"][0] == 1
 
 
 def test_instances_cornell_block(orc):
     """translate(rotate-y(box)) (geometry.scm:465-543): a ray down onto the short block's top face."""
     sc = scenes.cfg4_cornell_box(64, 64)
-    S = orc.OracleScene(sc)
+    S = orc.OracleScene(quantise=False, scene=sc)
     # top face centre of the short block in world space
     import math
     s, c = math.sin(math.radians(-18)), math.cos(math.radians(-18))
@@ -147,7 +147,7 @@ def test_aabb_quirk_q11(orc):
 
 
 def test_perlin_q4_and_textures(orc):
-    S = orc.OracleScene(scenes.test_scene2(32, 32))
+    S = orc.OracleScene(quantise=False, scene=scenes.test_scene2(32, 32))
     p = np.random.RandomState(0).uniform(-5, 5, (64, 3))
     n_ref, n_fix = S.noise(p, quirks=15), S.noise(p, quirks=0)
     assert np.all(np.abs(n_ref) < 2) and not np.allclose(n_ref, n_fix)

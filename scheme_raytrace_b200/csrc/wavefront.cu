@@ -106,6 +106,9 @@ struct Trav {
   float3 o, d, inv, oi, ainv; float time, inv_a;
   Hit h; int node; unsigned long long trail; int ray;
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
+#ifdef SRT_COUNT_STEPS
+  int nsteps, ntests, nmiss;                // instrumented build only (tools/step_stats.py)
+#endif
 };
 __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float tmax, int ray) {
   T.o = xyz(o4); T.d = xyz(d4); T.time = o4.w; T.ray = ray;
@@ -119,6 +122,9 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
   T.inv_a = 1.0f / dot(T.d, T.d);
   T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
   T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0;
+#ifdef SRT_COUNT_STEPS
+  T.nsteps = 0; T.ntests = 0; T.nmiss = 0;
+#endif
 }
 
 // One node step: slab-test both children, stash hit leaf children in (pend0, pend1), descend into
@@ -136,6 +142,9 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
 template <bool SMEM, bool CACHE>
 __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, float tmin, int& pend0, int& pend1) {
   const int node = T.node;
+#ifdef SRT_COUNT_STEPS
+  T.nsteps++;
+#endif
   float4 n0, n1, n2, n3;
   if (SMEM) { n0 = nodes[4 * node]; n1 = nodes[4 * node + 1]; n2 = nodes[4 * node + 2]; n3 = nodes[4 * node + 3]; }
   else { n0 = __ldg(&nodes[4 * node]); n1 = __ldg(&nodes[4 * node + 1]); n2 = __ldg(&nodes[4 * node + 2]); n3 = __ldg(&nodes[4 * node + 3]); }
@@ -210,8 +219,15 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
         int pend0 = -1, pend1 = -1;
         if (WW) { while (more && pend0 < 0) more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1); }
         else more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
-        while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1; }
+        while (pend0 >= 0) {
+#ifdef SRT_COUNT_STEPS
+          T.ntests++;
+#endif
+          intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1; }
       }
+#ifdef SRT_COUNT_STEPS
+      T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
+#endif
       hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
     }
     return;
@@ -366,12 +382,19 @@ __global__ void k_complete_hits(DScene sc, const float4* __restrict__ ray_o, con
   float4 h4 = hit[i], o4 = ray_o[i], d4 = ray_d[i];
   SrtHit r; r.prim = __float_as_int(h4.y); r.material = -1; r.t = 0.f; r.u = r.v = 0.f;
   r.p[0] = r.p[1] = r.p[2] = 0.f; r.n[0] = r.n[1] = r.n[2] = 0.f;
+#ifdef SRT_COUNT_STEPS
+  r.u = h4.z; r.v = h4.w;
+#endif
   if (r.prim >= 0) {
     float3 p, nn; int m;
     complete_hit(sc, r.prim, h4.x, xyz(o4), xyz(d4), o4.w, p, nn, m);
     r.t = h4.x; r.u = h4.z; r.v = h4.w; r.material = m;
     int type = sc.prim_hdr[r.prim].x & 0xff;
+#ifndef SRT_COUNT_STEPS
     if (type <= SRT_PRIM_MOVING_SPHERE) sphere_uv(p, r.u, r.v);     // Q5 (dead in shading)
+#else
+    (void)type;
+#endif
     r.p[0] = p.x; r.p[1] = p.y; r.p[2] = p.z; r.n[0] = nn.x; r.n[1] = nn.y; r.n[2] = nn.z;
   }
   out[i] = r;

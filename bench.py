@@ -25,6 +25,13 @@ sys.path.insert(0, ROOT)
 
 B_PER_RAY_LOOP = 160      # ray w+r 2x32 + ray re-read by shade 32 ... = 160 B per ray-bounce (whole loop)
 B_PER_RAY_EXTEND = 48     # the extend kernel's part: ray read 32 B + hit record write 16 B
+# FP32 work model: flops/ray = 27*N_box + 3 + sum F_type*N_type + F_shade, with the
+# per-ray counts MEASURED by the instrumented build (tools/step_stats.py, profiles/r1_step_stats.txt):
+# node steps per ray (2 box tests each), primitive tests per ray, dominant primitive cost, shade cost.
+FP32_MODEL = {  # workload: (node steps/ray, prim tests/ray, flops per prim test, shade flops/ray)
+    "cfg1": (3.0, 2.5, 35, 110), "cfg2": (12.0, 1.7, 35, 100), "cfg3": (12.0, 1.9, 45, 160),
+    "cfg4": (8.0, 1.3, 42, 100), "cfg5": (9.0, 2.0, 1500, 100),
+}
 
 
 def read_peaks():
@@ -255,6 +262,16 @@ def main():
                 "loop_hbm_gbs": B_PER_RAY_LOOP * value * 1e6 / 1e9,
                 "note": "scenes fit in shared memory, so the HBM fraction is small by construction (SURVEY §8d); "
                         "the binding resource is fp32 issue + latency under divergence"}
+    ns, nt, fp, fs = FP32_MODEL.get(args.workload, FP32_MODEL["cfg2"])
+    flops_per_ray = 27 * 2 * ns + 3 + fp * nt + fs
+    tfl = C.c_float(0.0)
+    ffi.check(r.lib.srt_measure_fp32_peak(C.byref(tfl)), "fp32 peak")
+    ext_rays_s = pst.rays / (ext_ms * 1e-3) if ext_ms > 0 else 0.0
+    roofline["fp32"] = {"flops_per_ray": flops_per_ray, "model": {"node_steps": ns, "prim_tests": nt, "prim_flops": fp, "shade_flops": fs},
+                        "achieved_tflops_loop": value * 1e6 * flops_per_ray / 1e12,
+                        "achieved_tflops_extend": ext_rays_s * (flops_per_ray - fs) / 1e12,
+                        "peak_tflops": float(tfl.value), "peak_kind": "measured FFMA microbenchmark (srt_measure_fp32_peak)",
+                        "frac_loop": value * 1e6 * flops_per_ray / 1e12 / max(float(tfl.value), 1e-9)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_oracle_rate(cfg, args.workload)

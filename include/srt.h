@@ -74,6 +74,10 @@ enum { SRT_SKY_GRADIENT = 0 /* main.scm:91 sky-color */, SRT_SKY_BLACK = 1 /* ma
 #define SRT_Q10_DIELECTRIC_UNNORM 8 /* material.scm:59-67 */
 #define SRT_QUIRKS_REFERENCE 15
 
+/* radiance estimator: the reference's `color` (main.scm:100-121, cosine sampling only), or the
+ * Rest-of-Life mixture(hittable(lights), cosine) pdf (pdf.scm:18-41; hittable part unpinned) */
+enum { SRT_EST_REFERENCE = 0, SRT_EST_MIXTURE = 1 };
+
 typedef struct {
   int32_t width, height;       /* main.scm:126-127 *size-x* *size-y*                     */
   int32_t spp_begin, spp_end;  /* sample range [begin,end) rendered by this call         */
@@ -83,7 +87,8 @@ typedef struct {
   int32_t quirks;              /* SRT_Q* bits                                            */
   float t_min;                 /* main.scm:104: 0.001                                    */
   int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (~8M paths) */
-  int32_t reserved[6];         /* [0] = 1: time extend/shade launches separately (slower) */
+  int32_t estimator;           /* SRT_EST_*                                              */
+  int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately (slower) */
 } SrtRenderParams;
 
 typedef struct {
@@ -114,6 +119,7 @@ int srt_device_count(void);
 int srt_init(int device);                         /* selects the device; fails without sm_100  */
 const char* srt_last_error(void);
 void srt_shutdown(void);
+int srt_measure_fp32_peak(float* tflops);         /* FFMA microbenchmark: the FP32 roofline denominator */
 
 SrtScene* srt_scene_create(void);
 void srt_scene_destroy(SrtScene*);
@@ -123,6 +129,7 @@ int srt_scene_set_materials(SrtScene*, const SrtMaterial*, int n);
 int srt_scene_set_textures(SrtScene*, const SrtTexture*, int n);
 int srt_scene_set_perlin(SrtScene*, const float* ranvec768, const int32_t* perm_x, const int32_t* perm_y, const int32_t* perm_z);
 int srt_scene_set_camera(SrtScene*, const SrtCamera*);
+int srt_scene_set_lights(SrtScene*, const int32_t* prim_ids, int n);   /* shapes sampled by the hittable pdf */
 int srt_scene_commit(SrtScene*);                  /* H2D + GPU LBVH build                      */
 
 /* LBVH inspection (bit-exact check against the host reference build) */

@@ -47,7 +47,8 @@ def load():
         lib.orc_get_ray.argtypes = [vp, dbl, dbl, dbl, u32, u32, u32, vp]
         lib.orc_sky.argtypes = [vp, vp, vp]
         lib.orc_onb_cosine.argtypes = [vp, dbl, dbl, i32, vp]
-        lib.orc_render.argtypes = [vp, i32, i32, i32, i32, i32, u32, i32, i32, i32, vp, vp]
+        lib.orc_render.argtypes = [vp, i32, i32, i32, i32, i32, u32, i32, i32, i32, vp, vp, i32]
+        lib.orc_set_lights.argtypes = [vp, vp, i32]
         lib.orc_resolve.argtypes = [vp, i32, i32, i32, vp]
         lib.orc_save_ppm.argtypes = [C.c_char_p, vp, i32, i32]
         lib.orc_lbvh_build.argtypes = [i32, vp, vp, vp, vp]
@@ -165,14 +166,20 @@ class OracleScene:
             out[idx] = np.where(r["prim"] >= 0, r["t"], np.inf)
         return out
 
-    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, nthreads=0, precision=64, rgb_sum=None):
+    def set_lights(self, prim_ids):
+        ids = np.ascontiguousarray(prim_ids, dtype=np.int32)
+        rc = self.lib.orc_set_lights(self.h, _p(ids), len(ids))
+        if rc != 0:
+            raise ValueError(f"orc_set_lights failed ({rc})")
+
+    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, nthreads=0, precision=64, rgb_sum=None, estimator=0):
         if rgb_sum is None:
             rgb_sum = np.zeros((height, width, 3), dtype=np.float64)
         if nthreads <= 0:
             nthreads = os.cpu_count() or 1
         nrays = C.c_uint64(0)
         self.lib.orc_render(self.h, width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, nthreads, precision,
-                            _p(rgb_sum), C.byref(nrays))
+                            _p(rgb_sum), C.byref(nrays), estimator)
         return rgb_sum, int(nrays.value)
 
     def tex_value(self, tex, uvp, quirks=15):

@@ -61,6 +61,8 @@ struct Scene {
   int sky = SKY_GRADIENT;
   double ranvec[256 * 3]; int perm_x[256], perm_y[256], perm_z[256];   // perlin.scm:33-36
   int exclude_leaf = -1;   // test hook: skip one leaf (second-best-hit query)
+  std::vector<int> lights; // node ids of the light shapes sampled by the hittable pdf (S7)
+  std::vector<int> leaf_node;   // leaf id -> node id
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,13 +102,14 @@ static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], u
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 // Draw-slot specification (DESIGN.md "RNG"): key = (pixel_index, seed); counter = (sample, bounce,
-// block, 0); uniform = ((x >> 8) + 0.5) * 2^-24, which lies strictly inside (0,1) like srfi-27's
-// random-real and is exactly representable in both f32 and f64.
+// block, 0); uniform = ((x >> 9) + 0.5) * 2^-23, a 23-bit grid that lies strictly inside (0,1) like
+// srfi-27's random-real and is exactly representable in both f32 and f64 (a 24-bit grid is not:
+// its top point rounds to 1.0 in fp32).
 struct RngAddr { uint32_t seed, pixel, sample, bounce; };
 template <class T> static inline void rng_block(const RngAddr& a, uint32_t block, T u[4]) {
   uint32_t ctr[4] = {a.sample, a.bounce, block, 0u}, key[2] = {a.pixel, a.seed}, o[4];
   philox4x32_10(ctr, key, o);
-  for (int i = 0; i < 4; ++i) u[i] = T(((double)(o[i] >> 8) + 0.5) * (1.0 / 16777216.0));
+  for (int i = 0; i < 4; ++i) u[i] = T(((double)(o[i] >> 9) + 0.5) * (1.0 / 8388608.0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -133,6 +136,14 @@ template <class T> static V3<T> random_cosine_direction(T r1, T r2, int quirks) 
   T k = (quirks & Q1_COSINE_X2) ? T(2) : T(1);                                                    // Q1: util.scm:42-43
   T x = std::cos(phi) * k * std::sqrt(r2);
   T y = std::sin(phi) * k * std::sqrt(r2);
+  return mk<T>(x, y, z);
+}
+
+template <class T> static V3<T> random_to_sphere(T radius, T distance_sq, T r1, T r2) {             // util.scm:46-54
+  T z = T(1) + r2 * (std::sqrt(T(1) - (radius * radius) / distance_sq) - T(1));
+  T phi = T(2) * T(PI) * r1;
+  T x = std::cos(phi) * std::sqrt(T(1) - z * z);
+  T y = std::sin(phi) * std::sqrt(T(1) - z * z);
   return mk<T>(x, y, z);
 }
 
@@ -482,7 +493,52 @@ template <class T> static V3<T> sky_value(const Scene& sc, const Ray<T>& r) {
   return add(scale(mk<T>(1, 1, 1), T(1) - t), scale(mk<T>(T(0.5), T(0.7), T(1.0)), t));
 }
 
-struct RenderCtx { int max_depth; int quirks; uint32_t seed; std::atomic<uint64_t>* nrays; };
+// ---------------------------------------------------------------------------------------------
+// pdf.scm.  make-cosine-pdf (:18-26) and make-mixture-pdf (:34-41) are pinned by source;
+// make-hitable-pdf (:28-32) delegates to g:pdf-value / g:random, which do NOT exist upstream
+//  — PARITY UNPINNED; the per-shape pdf-value / random below follow "Ray Tracing:
+// The Rest of Your Life" (rect: dist^2 / (|cos| area); sphere: 1 / (2 pi (1 - cos_theta_max)),
+// random = onb.local(random-to-sphere), util.scm:46-54).  Lights must be un-instanced rects or
+// spheres.
+template <class T> static T cosine_pdf_value(V3<T> w_unit, V3<T> direction) {                    // pdf.scm:19-23
+  T cosine = dot(unit(direction), w_unit);
+  return cosine > T(0) ? cosine / T(PI) : T(0);
+}
+template <class T> static T light_pdf_value(const Scene& sc, int node, V3<T> o, V3<T> v) {
+  const Node& nd = sc.nodes[node];
+  Ray<T> r{o, v, T(0)}; HitRec<T> rec;
+  if (nd.kind == N_SPHERE) {
+    if (!hit_sphere_at(ld3<T>(nd.p), T(nd.p[3]), nd.material, nd.leaf_id, r, T(0.001), T(MAX_FLOAT), rec)) return T(0);
+    V3<T> dc = sub(ld3<T>(nd.p), o);
+    T cos_theta_max = std::sqrt(T(1) - T(nd.p[3]) * T(nd.p[3]) / dot(dc, dc));
+    return T(1) / (T(2) * T(PI) * (T(1) - cos_theta_max));
+  }
+  int axis = nd.kind == N_XY_RECT ? 2 : (nd.kind == N_XZ_RECT ? 1 : 0);
+  if (!hit_rect(nd, axis, r, T(0.001), T(MAX_FLOAT), rec)) return T(0);
+  T area = (T(nd.p[1]) - T(nd.p[0])) * (T(nd.p[3]) - T(nd.p[2]));
+  T dist2 = rec.t * rec.t * dot(v, v);
+  T cosine = std::fabs(cmp(v, axis)) / length(v);
+  return dist2 / (cosine * area);
+}
+template <class T> static V3<T> light_random(const Scene& sc, int node, V3<T> o, T xa, T xb) {
+  const Node& nd = sc.nodes[node];
+  if (nd.kind == N_SPHERE) {
+    V3<T> dc = sub(ld3<T>(nd.p), o);
+    Onb<T> uvw = make_onb_from_w(dc);
+    return onb_local(uvw, random_to_sphere<T>(T(nd.p[3]), dot(dc, dc), xa, xb));
+  }
+  T a = T(nd.p[0]) + xa * (T(nd.p[1]) - T(nd.p[0])), b = T(nd.p[2]) + xb * (T(nd.p[3]) - T(nd.p[2])), k = T(nd.p[4]);
+  V3<T> pt = nd.kind == N_XY_RECT ? mk<T>(a, b, k) : (nd.kind == N_XZ_RECT ? mk<T>(a, k, b) : mk<T>(k, a, b));
+  return sub(pt, o);
+}
+template <class T> static T lights_pdf_value(const Scene& sc, V3<T> o, V3<T> v) {   // hittable_list::pdf_value: plain average
+  T sum = 0;
+  for (size_t j = 0; j < sc.lights.size(); ++j) sum += light_pdf_value<T>(sc, sc.lights[j], o, v);
+  return sum / T(sc.lights.size());
+}
+
+enum Estimator { EST_REFERENCE = 0, EST_MIXTURE = 1 };
+struct RenderCtx { int max_depth; int quirks; uint32_t seed; std::atomic<uint64_t>* nrays; int estimator; };
 
 // main.scm:100-121 — recursive radiance estimator.  RNG: scatter at depth k draws from bounce k+1.
 template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int depth, RngAddr addr, const RenderCtx& cx, uint64_t& nrays) {
@@ -496,6 +552,26 @@ template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int dept
     case M_LAMBERTIAN: {                                            // material.scm:24-39
       Onb<T> uvw = make_onb_from_w(rec.n);
       T u4[4]; rng_block<T>(addr, 0, u4);
+      if (cx.estimator == EST_MIXTURE && !sc.lights.empty()) {
+        // Rest-of-Life estimator: mixture(hittable(lights), cosine) — pdf.scm:34-41.  Draw slots:
+        // block 0 = (r1, r2, xi_choice, xi_light), block 1 = (xa, xb).
+        T v4[4]; rng_block<T>(addr, 1, v4);
+        V3<T> dir;
+        if (u4[2] < T(0.5)) {                                       // (generate p0): hittable pdf
+          int li = std::min((int)(u4[3] * T(sc.lights.size())), (int)sc.lights.size() - 1);
+          dir = light_random<T>(sc, sc.lights[li], rec.p, v4[0], v4[1]);
+        } else {
+          dir = onb_local(uvw, random_cosine_direction<T>(u4[0], u4[1], cx.quirks));   // (generate p1): cosine pdf
+        }
+        Ray<T> scattered{rec.p, dir, time0};
+        T pdf_val = T(0.5) * lights_pdf_value<T>(sc, rec.p, dir) + T(0.5) * cosine_pdf_value<T>(uvw.w, dir);
+        T cosine = dot(rec.n, unit(dir)); if (cosine < T(0)) cosine = 0;
+        T spdf = cosine / T(PI);
+        V3<T> atten = tex_value<T>(sc, m.tex, T(0), T(0), rec.p, cx.quirks);
+        if (depth < cx.max_depth && spdf > T(0) && pdf_val > T(0))  // zero-weight paths end here (0 * color = 0)
+          return scale(mul(scale(atten, spdf), color(sc, scattered, depth + 1, addr, cx, nrays)), T(1) / pdf_val);
+        return mk<T>(0, 0, 0);
+      }
       V3<T> target = onb_local(uvw, random_cosine_direction<T>(u4[0], u4[1], cx.quirks));
       Ray<T> scattered{rec.p, unit(target), time0};
       V3<T> atten = tex_value<T>(sc, m.tex, T(0), T(0), rec.p, cx.quirks);
@@ -581,10 +657,10 @@ template <class T> static V3<T> sample_pixel(const Scene& sc, int x, int y, int 
 }
 
 template <class T> static void render(const Scene& sc, int w, int h, int spp_begin, int spp_end, int max_depth, uint32_t seed,
-                                      int quirks, int nthreads, double* rgb_sum, uint64_t* nrays_out) {
+                                      int quirks, int nthreads, double* rgb_sum, uint64_t* nrays_out, int estimator) {
   std::atomic<int> next_row{0};
   std::atomic<uint64_t> total{0};
-  RenderCtx cx{max_depth, quirks, seed, &total};
+  RenderCtx cx{max_depth, quirks, seed, &total, estimator};
   auto work = [&]() {
     uint64_t nr = 0;
     for (;;) {
@@ -631,7 +707,18 @@ int orc_add_node(void* h, int kind, int material, int leaf_id, const double* par
   for (int i = 0; i < nparams && i < 16; ++i) n.p[i] = params[i];
   n.child_begin = (int)s->children.size(); n.child_count = nchildren;
   for (int i = 0; i < nchildren; ++i) s->children.push_back(children[i]);
-  s->nodes.push_back(n); return (int)s->nodes.size() - 1; }
+  s->nodes.push_back(n);
+  if (leaf_id >= 0) { if ((int)s->leaf_node.size() <= leaf_id) s->leaf_node.resize(leaf_id + 1, -1); s->leaf_node[leaf_id] = (int)s->nodes.size() - 1; }
+  return (int)s->nodes.size() - 1; }
+// lights by LEAF id (== primitive id of the flattened scene); only un-instanced spheres / rects
+int orc_set_lights(void* h, const int* leaf_ids, int n) {
+  Scene* s = (Scene*)h; s->lights.clear();
+  for (int i = 0; i < n; ++i) {
+    int lf = leaf_ids[i]; if (lf < 0 || lf >= (int)s->leaf_node.size() || s->leaf_node[lf] < 0) return -1;
+    int k = s->nodes[s->leaf_node[lf]].kind; if (k != N_SPHERE && k != N_XY_RECT && k != N_XZ_RECT && k != N_YZ_RECT) return -2;
+    s->lights.push_back(s->leaf_node[lf]);
+  }
+  return 0; }
 void orc_set_root(void* h, int node) { ((Scene*)h)->root = node; }
 void orc_set_camera(void* h, const double* cam24) { std::memcpy(((Scene*)h)->cam, cam24, 24 * sizeof(double)); }
 void orc_set_sky(void* h, int kind) { ((Scene*)h)->sky = kind; }
@@ -726,10 +813,10 @@ void orc_onb_cosine(const double* n3, double r1, double r2, int quirks, double* 
 
 // Render: accumulates samples [spp_begin, spp_end) into rgb_sum (w*h*3 doubles, y=0 bottom row).
 int orc_render(void* h, int w, int hh, int spp_begin, int spp_end, int max_depth, uint32_t seed, int quirks,
-               int nthreads, int precision, double* rgb_sum, uint64_t* nrays) {
+               int nthreads, int precision, double* rgb_sum, uint64_t* nrays, int estimator) {
   Scene* s = (Scene*)h;
-  if (precision == 32) render<float>(*s, w, hh, spp_begin, spp_end, max_depth, seed, quirks, nthreads, rgb_sum, nrays);
-  else render<double>(*s, w, hh, spp_begin, spp_end, max_depth, seed, quirks, nthreads, rgb_sum, nrays);
+  if (precision == 32) render<float>(*s, w, hh, spp_begin, spp_end, max_depth, seed, quirks, nthreads, rgb_sum, nrays, estimator);
+  else render<double>(*s, w, hh, spp_begin, spp_end, max_depth, seed, quirks, nthreads, rgb_sum, nrays, estimator);
   return 0;
 }
 

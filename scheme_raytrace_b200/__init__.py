@@ -6,7 +6,7 @@ reference's scene-construction API (geometry.scm, material.scm, texture.scm, cam
 bezier.scm) and flattens scenes into the POD tables the C-ABI takes.  There is no CPU fallback:
 rendering without the CUDA library fails loudly.
 """
-from .host import vec, constant, texture, material, geometry, bezier, camera, perlin, points  # noqa: F401
+from .host import vec, constant, texture, material, geometry, bezier, camera, perlin, points, pdf  # noqa: F401
 from .host.flatten import flatten_scene, FlatScene  # noqa: F401
 from .host.render import Renderer, trace_all, save_as_ppm, correct_gamma_quantise  # noqa: F401
 from .host import scenes  # noqa: F401

@@ -38,6 +38,7 @@ struct SrtScene {
   std::vector<SrtPrim> prims; std::vector<SrtXform> xforms; std::vector<SrtMaterial> mats; std::vector<SrtTexture> texs;
   float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
   SrtCamera cam; bool has_cam = false;
+  std::vector<int32_t> lights; DevBuf<int> d_lights;
   bool committed = false;
   // device tables
   DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
@@ -57,7 +58,7 @@ static void fill_dscene(SrtScene* s) {
   d.n_prims = (int)s->prims.size(); d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
-  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p;
+  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size();
 }
 
 static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
@@ -104,12 +105,20 @@ int srt_init(int device) {
 }
 void srt_shutdown(void) { g_device = -1; }
 
+int srt_measure_fp32_peak(float* tflops) {
+  if (!tflops) return fail(SRT_ERR_ARG, "measure_fp32_peak: null argument");
+  if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded");
+  *tflops = srt_measure_fma_tflops(g_sm_count, 0);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); if (!s) g_err = "out of host memory"; return s; }
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
   s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
-  s->d_ranvec.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
+  s->d_ranvec.release(); s->d_lights.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
   for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
@@ -147,6 +156,11 @@ int srt_scene_set_camera(SrtScene* s, const SrtCamera* c) {
   s->cam = *c; s->has_cam = true; s->committed = false; return 0;
 }
 
+int srt_scene_set_lights(SrtScene* s, const int32_t* prim_ids, int n) {
+  if (!s || n < 0 || (n && !prim_ids)) return fail(SRT_ERR_ARG, "set_lights: bad argument");
+  s->lights.assign(prim_ids, prim_ids + n); s->committed = false; return 0;
+}
+
 int srt_scene_commit(SrtScene* s) {
   if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
   if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded");
@@ -166,9 +180,17 @@ int srt_scene_commit(SrtScene* s) {
     if (t.kind == SRT_TEX_CHECKER && (t.even < 0 || t.odd < 0 || t.even >= (int)s->texs.size() || t.odd >= (int)s->texs.size()))
       return fail(SRT_ERR_ARG, "texture %zu: checker children out of range", i);
   }
+  for (size_t i = 0; i < s->lights.size(); ++i) {
+    int id = s->lights[i];
+    if (id < 0 || id >= n) return fail(SRT_ERR_ARG, "light %zu: primitive %d out of range", i, id);
+    const SrtPrim& p = s->prims[id];
+    if (p.xform >= 0 || p.type == SRT_PRIM_MOVING_SPHERE || p.type == SRT_PRIM_BEZIER) return fail(SRT_ERR_ARG, "light %zu: only un-instanced spheres and rects can be sampled", i);
+  }
   cudaStream_t stream = 0;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, stream));
+  CK(s->d_lights.ensure(s->lights.size()));
+  if (!s->lights.empty()) CK(cudaMemcpyAsync(s->d_lights.p, s->lights.data(), sizeof(int) * s->lights.size(), cudaMemcpyHostToDevice, stream));
   // ---- host SoA staging + H2D ---------------------------------------------------------------
   std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
   for (int i = 0; i < n; ++i) {

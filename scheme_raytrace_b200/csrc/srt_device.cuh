@@ -25,6 +25,8 @@ struct DScene {
   const float4* tex;        // 2 per texture: (kind even odd scale as int bits / float) (r g b 0)
   const float4* ranvec;     // 256 unit gradient vectors (perlin.scm:33)
   const uint8_t* perm;      // 3 x 256: perm-x, perm-y, perm-z (perlin.scm:34-36)
+  const int* lights;        // primitive ids sampled by the hittable pdf (pdf.scm:28-32)
+  int n_lights;
 };
 
 struct DCamera { float3 llc, horiz, vert, origin, w, u, v; float lens_radius, time0, time1; };
@@ -48,7 +50,10 @@ __device__ __forceinline__ float3 xyz(float4 a) { return v3(a.x, a.y, a.z); }
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10, keyed by (pixel, seed), counter (sample, bounce, block, 0)  — replaces srfi-27
-// random-real.  uniform = ((x >> 8) + 0.5) * 2^-24 in (0,1).
+// random-real.  uniform = ((x >> 9) + 0.5) * 2^-23: a 23-bit grid whose every point (including
+// the +0.5) is exactly representable in fp32, strictly inside (0,1) like srfi-27's random-real.
+// (A 24-bit grid is NOT: 16777215.5f rounds to 2^24, i.e. u = 1.0, and sqrt(1 - r2) = 0 then
+// turns the lambertian weight into 0 * inf.)
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -61,7 +66,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 struct RngAddr { uint32_t seed, pixel, sample, bounce; };
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 __device__ __forceinline__ float4 rng_block(const RngAddr& a, uint32_t block) {
   uint4 r = philox4x32_10(a.sample, a.bounce, block, 0u, a.pixel, a.seed);
   return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
@@ -417,6 +422,57 @@ __device__ __forceinline__ void get_ray(const DCamera& cam, float s, float t, fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// pdf.scm — importance sampling.  make-cosine-pdf (:18-26) and make-mixture-pdf (:34-41) follow
+// the source; make-hitable-pdf (:28-32) calls g:pdf-value / g:random which do not exist upstream,
+// so the per-shape functions follow "The Rest of Your Life" (PARITY UNPINNED, validated against
+// the oracle's identical definition).  Lights are un-instanced rects or spheres.
+__device__ __forceinline__ float3 random_to_sphere(float radius, float distance_sq, float r1, float r2) {   // util.scm:46-54
+  float z = 1.0f + r2 * (sqrtf(1.0f - (radius * radius) / distance_sq) - 1.0f);
+  float s, c; sincospif(2.0f * r1, &s, &c);
+  float q = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  return v3(c * q, s * q, z);
+}
+__device__ __forceinline__ float light_pdf_value(const DScene& sc, int prim, float3 o, float3 v) {
+  int type = __ldg(&sc.prim_hdr[prim]).x & 0xff;
+  float4 a = __ldg(&sc.prim_a[prim]);
+  float t, uu, vv;
+  if (type == SRT_PRIM_SPHERE) {
+    if (!isect_sphere(xyz(a), a.w, o, v, 1.0f / dot(v, v), 0.001f, t) || !(t < SRT_MAX_FLOAT)) return 0.0f;
+    float3 dc = xyz(a) - o;
+    float cos_theta_max = sqrtf(1.0f - a.w * a.w / dot(dc, dc));
+    return 1.0f / (2.0f * SRT_PI * (1.0f - cos_theta_max));
+  }
+  float k = __ldg(&sc.prim_b[prim]).x;
+  if (!isect_rect(type, a, k, o, v, 0.001f, 0.f, false, t, uu, vv) || !(t <= SRT_MAX_FLOAT)) return 0.0f;
+  int axis = (type == SRT_PRIM_XY_RECT) ? 2 : (type == SRT_PRIM_XZ_RECT ? 1 : 0);
+  float area = (a.y - a.x) * (a.w - a.z);
+  float dist2 = t * t * dot(v, v);
+  float cosine = fabsf(cmp3(v, axis)) / length(v);
+  return dist2 / (cosine * area);
+}
+__device__ __forceinline__ float3 light_random(const DScene& sc, int prim, float3 o, float xa, float xb) {
+  int type = __ldg(&sc.prim_hdr[prim]).x & 0xff;
+  float4 a = __ldg(&sc.prim_a[prim]);
+  if (type == SRT_PRIM_SPHERE) {
+    float3 dc = xyz(a) - o;
+    float3 w = unit(dc);
+    float3 ax = (fabsf(w.x) > 0.9f) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
+    float3 vv = unit(cross(w, ax)), uu = cross(w, vv);
+    float3 r = random_to_sphere(a.w, dot(dc, dc), xa, xb);
+    return uu * r.x + vv * r.y + w * r.z;
+  }
+  float k = __ldg(&sc.prim_b[prim]).x;
+  float pa = a.x + xa * (a.y - a.x), pb = a.z + xb * (a.w - a.z);
+  float3 pt = type == SRT_PRIM_XY_RECT ? v3(pa, pb, k) : (type == SRT_PRIM_XZ_RECT ? v3(pa, k, pb) : v3(k, pa, pb));
+  return pt - o;
+}
+__device__ __forceinline__ float lights_pdf_value(const DScene& sc, float3 o, float3 v) {   // plain average over the lights
+  float sum = 0.0f;
+  for (int j = 0; j < sc.n_lights; ++j) sum += light_pdf_value(sc, __ldg(&sc.lights[j]), o, v);
+  return sum / (float)sc.n_lights;
+}
+
+// ------------------------------------------------------------------------------------------------
 // material.scm — scatter.  Returns true when the path continues; `weight` multiplies throughput.
 __device__ __forceinline__ float3 reflect(float3 v, float3 n) { return v - n * (2.0f * dot(v, n)); }   // material.scm:41
 __device__ __forceinline__ float schlick(float cosine, float ref_idx) {                                 // material.scm:69
@@ -426,6 +482,7 @@ __device__ __forceinline__ float schlick(float cosine, float ref_idx) {         
 }
 struct Scatter { float3 dir; float3 weight; float3 emitted; bool valid; };
 
+template <int EST>
 __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float3 d_in, float3 p, float3 n, float u, float v,
                                            const RngAddr& addr, int quirks) {
   Scatter r; r.valid = false; r.emitted = v3(0.f, 0.f, 0.f); r.weight = v3(1.f, 1.f, 1.f); r.dir = v3(0.f, 1.f, 0.f);
@@ -440,6 +497,24 @@ __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float
       float3 uu = cross(w, vv);
       float4 xi = rng_block(addr, 0);
       float3 rc = random_cosine_direction(xi.x, xi.y, quirks);
+      if (EST == SRT_EST_MIXTURE && sc.n_lights > 0) {
+        // mixture(hittable(lights), cosine) pdf.scm:34-41; block 0 = (r1, r2, xi_choice, xi_light), block 1 = (xa, xb)
+        float4 xj = rng_block(addr, 1);
+        float3 dir;
+        if (xi.z < 0.5f) {
+          int li = min((int)(xi.w * (float)sc.n_lights), sc.n_lights - 1);
+          dir = light_random(sc, __ldg(&sc.lights[li]), p, xj.x, xj.y);
+        } else {
+          dir = uu * rc.x + vv * rc.y + w * rc.z;
+        }
+        float cosw = dot(unit(dir), w);
+        float pdf_val = 0.5f * lights_pdf_value(sc, p, dir) + 0.5f * (cosw > 0.0f ? cosw / SRT_PI : 0.0f);
+        float spdf = fmaxf(0.0f, dot(n, unit(dir))) / SRT_PI;
+        r.dir = dir;
+        r.valid = spdf > 0.0f && pdf_val > 0.0f;             // zero-weight paths end here
+        if (r.valid) r.weight = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks) * spdf * (1.0f / pdf_val);
+        break;
+      }
       float3 target = uu * rc.x + vv * rc.y + w * rc.z;
       r.dir = unit(target);
       float pdf_cos = dot(w, r.dir);                              // pdf  = (w . dir)/pi

@@ -54,3 +54,4 @@ int srt_launch_resolve(const float* d_rgb_sum, int n3, int spp, uint8_t* d_image
 int srt_launch_eval_texture(const DScene& sc, int tex, const float* d_uvp5, int n, int quirks, float* d_rgb, cudaStream_t stream);
 int srt_launch_eval_raygen(const RenderLaunch& L, int n, const int* d_pixel, const int* d_sample, SrtRay* d_out, cudaStream_t stream);
 size_t srt_extend_smem_bytes(const DScene& sc);
+float srt_measure_fma_tflops(int sm_count, cudaStream_t stream);

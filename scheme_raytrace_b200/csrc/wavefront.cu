@@ -291,6 +291,7 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
 // ------------------------------------------------------------------------------------------------
 // shade: one bounce of `color` (main.scm:100-121) for every live path + compaction of survivors
 // into the other queue generation (warp ballot -> per-warp count -> one atomic per CTA).
+template <int EST>
 __global__ void __launch_bounds__(SHD_THREADS)
 k_shade(DScene sc, SrtRenderParams p, int g,
         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
@@ -317,7 +318,7 @@ k_shade(DScene sc, SrtRenderParams p, int g,
         float3 pt, n; int material;
         complete_hit(sc, prim, h4.x, o, d, o4.w, pt, n, material);
         RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
-        Scatter s = scatter(sc, material, d, pt, n, h4.z, h4.w, addr, p.quirks);
+        Scatter s = scatter<EST>(sc, material, d, pt, n, h4.z, h4.w, addr, p.quirks);
         if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
           accumulate_fixed(accum, pixel, thr * s.emitted);
         if (s.valid && depth < p.max_depth) {                      // main.scm:112
@@ -418,7 +419,41 @@ __global__ void k_eval_raygen(DCamera cam, SrtRenderParams p, int n, const int* 
   out[i] = r;
 }
 
+// FP32 roofline denominator: dependent-chain-free FFMA loop, 8 accumulators per thread.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 }  // namespace
+
+// Measures sustained FFMA throughput (TFLOP/s, 2 flops per FFMA) on the current device.
+float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
+  const int grid = sm_count * 8, iters = 4096;
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(float) * (size_t)grid * 256) != cudaSuccess) return 0.f;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_fma_peak<<<grid, 256, 0, stream>>>(d, 64, 0.999f, 0.001f);            // warm-up
+  float best = 0.f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, stream);
+    k_fma_peak<<<grid, 256, 0, stream>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * 256.0;
+    float tf = (float)(flops / (ms * 1e-3) / 1e12);
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return best;
+}
 
 // =================================================================================================
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
@@ -509,7 +544,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
       if (profile) cudaEventRecord(e0, stream);
       launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, &ctrl->cursor, p.t_min, SRT_MAX_FLOAT, stream);
       if (profile) cudaEventRecord(e1, stream);
-      k_shade<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
+      (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
                                                        W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
       if (profile) { cudaEventRecord(e2, stream); cudaEventSynchronize(e2); float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); acc_ext += a; acc_shd += b; ++n_ext; }
       k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, p, npix, cap, g ^ 1, parity, W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], ctrl);

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libsrt.so")
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_begin", C.c_int32), ("spp_end", C.c_int32),
                 ("max_depth", C.c_int32), ("sky", C.c_int32), ("seed", C.c_uint32), ("quirks", C.c_int32),
-                ("t_min", C.c_float), ("wave_spp", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("t_min", C.c_float), ("wave_spp", C.c_int32), ("estimator", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -21,9 +21,9 @@ class Stats(C.Structure):
 
 # every symbol include/srt.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "srt_device_count", "srt_init", "srt_last_error", "srt_shutdown", "srt_scene_create", "srt_scene_destroy",
+    "srt_device_count", "srt_init", "srt_last_error", "srt_shutdown", "srt_measure_fp32_peak", "srt_scene_create", "srt_scene_destroy",
     "srt_scene_set_prims", "srt_scene_set_xforms", "srt_scene_set_materials", "srt_scene_set_textures",
-    "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
+    "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_set_lights", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
     "srt_bvh_keys_readback", "srt_prim_bounds_readback", "srt_trace_batch", "srt_render_host", "srt_render_device",
     "srt_resolve_device", "srt_resolve_host", "srt_save_ppm", "srt_eval_texture", "srt_eval_raygen",
 ]
@@ -44,12 +44,14 @@ def load():
     lib.srt_device_count.restype = i32
     lib.srt_init.argtypes = [i32]
     lib.srt_last_error.restype = C.c_char_p
+    lib.srt_measure_fp32_peak.argtypes = [C.POINTER(C.c_float)]
     lib.srt_scene_create.restype = vp
     lib.srt_scene_destroy.argtypes = [vp]
     for name in ("srt_scene_set_prims", "srt_scene_set_xforms", "srt_scene_set_materials", "srt_scene_set_textures"):
         getattr(lib, name).argtypes = [vp, vp, i32]
     lib.srt_scene_set_perlin.argtypes = [vp, vp, vp, vp, vp]
     lib.srt_scene_set_camera.argtypes = [vp, vp]
+    lib.srt_scene_set_lights.argtypes = [vp, vp, i32]
     lib.srt_scene_commit.argtypes = [vp]
     lib.srt_bvh_node_count.argtypes = [vp]
     lib.srt_bvh_readback.argtypes = [vp, vp, i32]

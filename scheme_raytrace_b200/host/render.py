@@ -21,11 +21,12 @@ class Renderer:
     """Owns one committed scene on one GPU.  Replaces the in-process closure evaluation of
     trace-all -> color -> g:hit / m:scatter (main.scm:100-121, 471-491)."""
 
-    def __init__(self, scene, device=0, perlin_seed=3):
+    def __init__(self, scene, device=0, perlin_seed=3, lights=()):
         self.lib = ffi.load()
         ffi.check(self.lib.srt_init(int(device)), "srt_init")
         self.flat = scene if isinstance(scene, FlatScene) else flatten_scene(scene)
         self.perlin = perlin_generate(perlin_seed)
+        self.lights = np.ascontiguousarray(list(lights), dtype=np.int32)   # primitive ids for the hittable pdf (make-hitable-pdf)
         self.h = self.lib.srt_scene_create()
         if not self.h:
             raise ffi.SrtError("srt_scene_create failed")
@@ -41,6 +42,7 @@ class Renderer:
         self._rv32 = np.ascontiguousarray(rv, dtype=np.float32)
         ffi.check(lib.srt_scene_set_perlin(h, _ptr(self._rv32), _ptr(px), _ptr(py), _ptr(pz)), "set_perlin")
         ffi.check(lib.srt_scene_set_camera(h, _ptr(f.camera)), "set_camera")
+        ffi.check(lib.srt_scene_set_lights(h, _ptr(self.lights), len(self.lights)), "set_lights")
         ffi.check(lib.srt_scene_commit(h), "commit")
 
     def close(self):
@@ -95,26 +97,27 @@ class Renderer:
         return out
 
     # -- rendering --------------------------------------------------------------------------
-    def params(self, width, height, spp_begin, spp_end, max_depth=50, seed=1, quirks=15, t_min=0.001, wave_spp=0, sky=None):
+    def params(self, width, height, spp_begin, spp_end, max_depth=50, seed=1, quirks=15, t_min=0.001, wave_spp=0, sky=None, estimator=0):
         p = ffi.RenderParams()
         p.width, p.height, p.spp_begin, p.spp_end = width, height, spp_begin, spp_end
         p.max_depth, p.seed, p.quirks, p.t_min, p.wave_spp = max_depth, seed, quirks, t_min, wave_spp
         p.sky = self.flat.sky if sky is None else sky
+        p.estimator = estimator
         return p
 
-    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, rgb_sum=None, wave_spp=0):
+    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, rgb_sum=None, wave_spp=0, estimator=0):
         """Adds samples [spp_begin, spp_begin+spp) into rgb_sum (H,W,3) float32 (row 0 = bottom).
         Host buffers in and out (D2H inside the call)."""
         if rgb_sum is None:
             rgb_sum = np.zeros((height, width, 3), dtype=np.float32)
-        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp)
+        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp, estimator=estimator)
         st = ffi.Stats()
         ffi.check(self.lib.srt_render_host(self.h, C.byref(p), _ptr(rgb_sum), C.byref(st)), "render_host")
         return rgb_sum, st
 
-    def render_device(self, d_ptr, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, wave_spp=0):
+    def render_device(self, d_ptr, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, wave_spp=0, estimator=0):
         """Same, accumulating into a DEVICE buffer (e.g. a torch tensor's data_ptr())."""
-        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp)
+        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp, estimator=estimator)
         st = ffi.Stats()
         ffi.check(self.lib.srt_render_device(self.h, C.byref(p), C.c_void_p(int(d_ptr)), C.byref(st)), "render_device")
         return st

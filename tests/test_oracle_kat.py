@@ -21,7 +21,9 @@ def test_philox_kat(orc):
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
     u = orc.rng_block(1, 2, 3, 4, 5)
     assert np.all((u > 0) & (u < 1))
-    assert np.all(u * 2 ** 24 - 0.5 == np.round(u * 2 ** 24 - 0.5))  # 24-bit grid, exact in fp32
+    assert np.all(u * 2 ** 23 - 0.5 == np.round(u * 2 ** 23 - 0.5))  # 23-bit grid
+    top = (2 ** 23 - 1 + 0.5) / 2 ** 23                               # largest uniform: exact in fp32 and < 1
+    assert np.float32(top) == top and np.float32(top) < 1.0 and np.float32((2 ** 24 - 0.5) / 2 ** 24) == 1.0
 
 
 @pytest.mark.parametrize("d,t_exp", [((0, 0, -1), 0.5), ((0, 0, -2), 0.25)])

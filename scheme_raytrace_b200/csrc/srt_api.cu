@@ -300,8 +300,7 @@ int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t
   CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(SrtRay) * (size_t)n, cudaMemcpyHostToDevice, stream));
   RenderLaunch L = make_launch(s, nullptr);
   srt_launch_upload_rays(d_rays.p, n, s->wb.ray_o[0], s->wb.ray_d[0], stream);
-  CK(cudaMemsetAsync(srt_ctrl_cursor(s->wb.ctrl), 0, sizeof(int), stream));
-  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, nullptr, n, srt_ctrl_cursor(s->wb.ctrl), t_min, t_max, stream);   // the renderer's extend kernel
+  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, nullptr, n, t_min, t_max, stream);   // the renderer's extend kernel
   srt_launch_complete_hits(s->ds, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, n, d_out.p, stream);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out.p, sizeof(SrtHit) * (size_t)n, cudaMemcpyDeviceToHost, stream));

@@ -13,7 +13,6 @@
 // batch of samples.  The recursive estimator `color` is run in its iterative form
 // L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
 #include "srt_device.cuh"
-#include <cstdlib>
 #include "srt_host.h"
 
 namespace {
@@ -33,7 +32,6 @@ struct WaveCtrl {
   unsigned long long total_paths;
   unsigned long long rays;          // sum of qcount over iterations = closest-hit queries
   unsigned long long iterations;
-  int cursor; int pad;              // ray-chunk cursor of the persistent extend warps (reset by regen)
 };
 #define SRT_ACC_SCALE 68719476736.0f   // 2^36: radiance accumulates in 64-bit fixed point
 
@@ -79,7 +77,6 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
     ctrl->qcount[g] = q;
     ctrl->next_path[parity ^ 1] = next + (unsigned long long)n_new;
     ctrl->survivors[g ^ 1] = 0;          // cursor of the generation the next shade appends into
-    ctrl->cursor = 0;
     ctrl->rays += (unsigned long long)q;
     ctrl->iterations += q ? 1ull : 0ull;
   }
@@ -192,82 +189,41 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   return true;
 }
 
-// Persistent warps with dynamic ray fetch: a warp pulls chunks of EXT_CHUNK rays from a global
-// cursor and refills idle lanes as soon as EXT_REFILL of them have finished, so short rays do
-// not idle behind the longest ray of the warp.  Inside, a while-while loop: every lane walks
-// nodes until it has found a leaf (or finished), then the leaf primitives are intersected
-// together (fewer lanes idle than with an interleaved if-if step).
-constexpr int EXT_CHUNK = 128;
-
-template <bool SMEM, int MASK, int MODE, class PrimSrc>
+// One ray per lane, 32 consecutive rays per warp (static assignment: dynamic ray fetch and a
+// while-while loop were both measured slower at 32 resident warps/SM, see profiles/README.md).
+template <bool SMEM, int MASK, bool CACHE, class PrimSrc>
 __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
                                             const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-                                            int count, int* __restrict__ cursor, float tmin, float tmax, int refill) {
-  constexpr bool DYN = MODE & 1, WW = MODE & 2, CACHE = MODE & 4;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+                                            int count, float tmin, float tmax) {
   if (sc.n_prims == 0) {   // empty scene: every ray misses
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
     return;
   }
-  Trav T; T.ray = -1; T.node = 0; T.trail = 0ull;
-  if (!DYN) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-      trav_init(T, ray_o[i], ray_d[i], tmax, i);
-      bool more = true;
-      while (more) {
-        int pend0 = -1, pend1 = -1;
-        if (WW) { while (more && pend0 < 0) more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1); }
-        else more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
-        while (pend0 >= 0) {
-#ifdef SRT_COUNT_STEPS
-          T.ntests++;
-#endif
-          intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1; }
-      }
-#ifdef SRT_COUNT_STEPS
-      T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
-#endif
-      hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
-    }
-    return;
-  }
-  int w_cur = 0, w_end = 0; bool exhausted = false;
-  bool busy = false;
-  for (;;) {
-    unsigned idle = __ballot_sync(full, !busy);
-    if (idle == full || (!exhausted && __popc(idle) >= refill)) {
-      if (w_cur >= w_end && !exhausted) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, EXT_CHUNK);
-        base = __shfl_sync(full, base, 0);
-        w_cur = base; w_end = min(base + EXT_CHUNK, count);
-        if (base >= count) { exhausted = true; w_cur = w_end = 0; }
-      }
-      if (!busy) {
-        int idx = w_cur + __popc(idle & ((1u << lane) - 1u));
-        if (idx < w_end) { trav_init(T, ray_o[idx], ray_d[idx], tmax, idx); busy = true; }
-      }
-      w_cur = min(w_cur + __popc(idle), w_end);
-      if (exhausted && !__any_sync(full, busy)) break;
-    }
-    if (busy) {
-      int pend0 = -1, pend1 = -1; bool more = true;
-      if (WW) { while (more && pend0 < 0) more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1); }
-      else more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+  Trav T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    trav_init(T, ray_o[i], ray_d[i], tmax, i);
+    bool more = true;
+    while (more) {
+      int pend0 = -1, pend1 = -1;
+      more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
       while (pend0 >= 0) {
-        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h);
-        pend0 = pend1; pend1 = -1;
+#ifdef SRT_COUNT_STEPS
+        T.ntests++;
+#endif
+        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1;
       }
-      if (!more) { hit[T.ray] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v); busy = false; }
     }
+#ifdef SRT_COUNT_STEPS
+    T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
+#endif
+    hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
   }
 }
 
-template <bool SMEM, int MASK, int MODE>
+template <bool SMEM, int MASK, bool CACHE>
 __global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x20) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-         const int* __restrict__ count_ptr, int count_fixed, int* __restrict__ cursor, float tmin, float tmax, int refill) {
+         const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax) {
   extern __shared__ float4 smem[];
   const int count = count_ptr ? *count_ptr : count_fixed;
   if (count == 0) return;
@@ -281,10 +237,10 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
     PrimShared ps{sh, sa};
-    extend_loop<true, MASK, MODE>(sc, smem, ps, ray_o, ray_d, hit, count, cursor, tmin, tmax, refill);
+    extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, hit, count, tmin, tmax);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    extend_loop<false, MASK, MODE>(sc, sc.nodes, ps, ray_o, ray_d, hit, count, cursor, tmin, tmax, refill);
+    extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, hit, count, tmin, tmax);
   }
 }
 
@@ -356,7 +312,7 @@ __global__ void k_accum_to_float(int n3, const unsigned long long* __restrict__ 
 }
 __global__ void k_ctrl_init(WaveCtrl* ctrl, unsigned long long total_paths) {
   ctrl->qcount[0] = ctrl->qcount[1] = 0; ctrl->survivors[0] = ctrl->survivors[1] = 0;
-  ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull; ctrl->cursor = 0;
+  ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull;
 }
 
 // main.scm:123-124, 481-487: correct-gamma (sqrt) + floor(255.99 * min(1, c)); negative sums
@@ -459,10 +415,9 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
 // Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
-typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, int*, float, float, int);
+typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, float, float);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
-static ExtendVariant g_variants[2][4][8];
-static int g_ext_mode = -1, g_ext_refill = 8;
+static ExtendVariant g_variants[2][4][2];
 
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
@@ -470,34 +425,26 @@ static int variant_of(int mask) {
   if ((mask & 0x20) == 0) return 2;
   return 3;
 }
-template <bool SMEM, int MODE> static ExtendFn variant_fn_m(int v) {
+template <bool SMEM, bool CACHE> static ExtendFn variant_fn_m(int v) {
   switch (v) {
-    case 0: return k_extend<SMEM, 0x01, MODE>;
-    case 1: return k_extend<SMEM, 0x03, MODE>;
-    case 2: return k_extend<SMEM, 0x1f, MODE>;
-    default: return k_extend<SMEM, SRT_MASK_ALL, MODE>;
+    case 0: return k_extend<SMEM, 0x01, CACHE>;
+    case 1: return k_extend<SMEM, 0x03, CACHE>;
+    case 2: return k_extend<SMEM, 0x1f, CACHE>;
+    default: return k_extend<SMEM, SRT_MASK_ALL, CACHE>;
   }
 }
-static ExtendFn variant_fn(bool smem, int v, int mode) {
-  switch (mode) {
-    case 0: return smem ? variant_fn_m<true, 0>(v) : variant_fn_m<false, 0>(v);
-    case 1: return smem ? variant_fn_m<true, 1>(v) : variant_fn_m<false, 1>(v);
-    case 4: return smem ? variant_fn_m<true, 4>(v) : variant_fn_m<false, 4>(v);
-    default: return smem ? variant_fn_m<true, 5>(v) : variant_fn_m<false, 5>(v);
-  }
+static ExtendFn variant_fn(bool smem, int v, bool cache) {
+  if (cache) return smem ? variant_fn_m<true, true>(v) : variant_fn_m<false, true>(v);
+  return smem ? variant_fn_m<true, false>(v) : variant_fn_m<false, false>(v);
 }
 // persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
 static const ExtendVariant& extend_variant(const RenderLaunch& L) {
-  if (g_ext_mode < 0) {   // mode: bit0 = dynamic ray fetch, bit2 = far-child register cache (tuning knobs, default 4)
-    const char* e = getenv("SRT_EXT_MODE"); g_ext_mode = e ? atoi(e) & 5 : 4;
-    const char* r = getenv("SRT_EXT_REFILL"); if (r) g_ext_refill = atoi(r);
-  }
   int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
-  int mode = g_ext_mode; if (L.sc.n_nodes >= 65536) mode &= ~4;      // 16-bit ids in the far-child cache
-  ExtendVariant& e = g_variants[which][v][mode];
+  int cache = L.sc.n_nodes < 65536 ? 1 : 0;          // 16-bit node ids in the far-child register cache
+  ExtendVariant& e = g_variants[which][v][cache];
   size_t smem = which ? L.extend_smem : 0;
   if (!e.fn || e.smem != smem) {
-    e.fn = variant_fn(which, v, mode); e.smem = smem;
+    e.fn = variant_fn(which, v, cache); e.smem = smem;
     if (which) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, EXT_THREADS, smem);
@@ -506,14 +453,12 @@ static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   return e;
 }
 
-// `cursor` = device int the persistent warps pull ray chunks from; must be 0 at launch.
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
-                      int* cursor, float tmin, float tmax, cudaStream_t stream) {
+                      float tmin, float tmax, cudaStream_t stream) {
   const ExtendVariant& e = extend_variant(L);
-  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, cursor, tmin, tmax, g_ext_refill);
+  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
   return 1;
 }
-int* srt_ctrl_cursor(void* ctrl) { return &((WaveCtrl*)ctrl)->cursor; }
 
 size_t srt_wave_ctrl_bytes() { return sizeof(WaveCtrl); }
 
@@ -542,7 +487,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   while (!done) {
     for (int k = 0; k < BATCH; ++k) {
       if (profile) cudaEventRecord(e0, stream);
-      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, &ctrl->cursor, p.t_min, SRT_MAX_FLOAT, stream);
+      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, stream);
       if (profile) cudaEventRecord(e1, stream);
       (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
                                                        W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);

@@ -32,9 +32,12 @@ enum {
   SRT_PRIM_XY_RECT = 2,       /* geometry.scm:376 make-xy-rect        p = x0 x1 y0 y1 k                    */
   SRT_PRIM_XZ_RECT = 3,       /* geometry.scm:395 make-xz-rect        p = x0 x1 z0 z1 k                    */
   SRT_PRIM_YZ_RECT = 4,       /* geometry.scm:414 make-yz-rect        p = y0 y1 z0 z1 k                    */
-  SRT_PRIM_BEZIER = 5         /* bezier.scm:61   make-bezier          p = a.xyz b.xyz c.xyz d.xyz width    */
+  SRT_PRIM_BEZIER = 5,        /* bezier.scm:61   make-bezier          p = a.xyz b.xyz c.xyz d.xyz width    */
+  SRT_PRIM_CONSTANT_MEDIUM = 6 /* geometry.scm:545 make-constant-medium p = density, first boundary prim, #boundary prims */
 };
 #define SRT_PRIM_FLAG_FLIP 1  /* geometry.scm:433 flip-normals (parity of the flips above the leaf)        */
+#define SRT_PRIM_FLAG_BOUNDARY 2 /* boundary shape of a constant medium: not a scene surface, not in the LBVH;
+                                  * boundary primitives must form a suffix of the primitive array */
 
 /* One flattened leaf primitive.  Position in the array = primitive id = position in the
  * reference's flattened top-level object list (box faces in make-box order, geometry.scm:446-457);

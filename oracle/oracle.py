@@ -124,13 +124,13 @@ class OracleScene:
         ch = np.ascontiguousarray(children if len(children) else [0], dtype=np.int32)
         return self.lib.orc_add_node(self.h, kind, material, leaf, _p(prm), len(params), _p(ch), len(children))
 
-    def _add(self, obj, g):
-        children = [self._add(c, g) for c in obj.children]
-        mat = self._add_mat(obj.material)
+    def _add(self, obj, g, boundary=False):
         leaf = -1
-        if obj.kind in g.LEAF_KINDS:
+        if obj.kind in g.LEAF_KINDS and not boundary:      # boundary shapes of a medium are not scene primitives
             leaf = self._leaf
             self._leaf += 1
+        children = [self._add(c, g, boundary or obj.kind == g.CONSTANT_MEDIUM) for c in obj.children]
+        mat = self._add_mat(obj.material)
         return self._node(obj.kind, mat, leaf, obj.params, children)
 
     def close(self):

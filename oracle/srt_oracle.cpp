@@ -39,7 +39,7 @@ static const double MAX_FLOAT = 999999999999.0;
 static const double PI = 3.141592653589793;  // math.const pi
 
 enum NodeKind { N_SPHERE = 0, N_MOVING_SPHERE = 1, N_XY_RECT = 2, N_XZ_RECT = 3, N_YZ_RECT = 4,
-                N_BEZIER = 5, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
+                N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
 enum MatKind { M_LAMBERTIAN = 0, M_METAL = 1, M_DIELECTRIC = 2, M_DIFFUSE_LIGHT = 3, M_ISOTROPIC = 4 };
 enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3 };
 enum SkyKind { SKY_GRADIENT = 0, SKY_BLACK = 1 };
@@ -413,39 +413,63 @@ template <class T> static bool hit_bezier(const Node& nd, const Ray<T>& r, T tmi
 
 // ---------------------------------------------------------------------------------------------
 // geometry.scm:14-15 — (hit obj r t-min t-max), dispatch over the object kinds.
-template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec) {
+template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec, const RngAddr* rng = nullptr) {
   const Node& nd = sc.nodes[id];
   switch (nd.kind) {
     case N_LIST: {                                         // geometry.scm:33-50 hit-obj-list
       bool any = false; T closest = tmax; HitRec<T> tmp;
       for (int i = 0; i < nd.child_count; ++i) {
-        if (hit_node(sc, sc.children[nd.child_begin + i], r, tmin, closest, tmp)) { any = true; closest = tmp.t; rec = tmp; }
+        if (hit_node(sc, sc.children[nd.child_begin + i], r, tmin, closest, tmp, rng)) { any = true; closest = tmp.t; rec = tmp; }
       }
       return any;
     }
     case N_SPHERE:
-      if (nd.leaf_id == sc.exclude_leaf) return false;
+      if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false;
       return hit_sphere_at(ld3<T>(nd.p), T(nd.p[3]), nd.material, nd.leaf_id, r, tmin, tmax, rec);
     case N_MOVING_SPHERE: {                                // geometry.scm:178-184
-      if (nd.leaf_id == sc.exclude_leaf) return false;
+      if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false;
       V3<T> c0 = ld3<T>(nd.p), c1 = ld3<T>(nd.p + 4);
       T time0 = T(nd.p[7]), time1 = T(nd.p[8]);
       V3<T> cc = add(c0, scale(sub(c1, c0), (r.time - time0) / (time1 - time0)));
       return hit_sphere_at(cc, T(nd.p[3]), nd.material, nd.leaf_id, r, tmin, tmax, rec);
     }
-    case N_XY_RECT: if (nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 2, r, tmin, tmax, rec);
-    case N_XZ_RECT: if (nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 1, r, tmin, tmax, rec);
-    case N_YZ_RECT: if (nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 0, r, tmin, tmax, rec);
-    case N_BEZIER: if (nd.leaf_id == sc.exclude_leaf) return false; return hit_bezier(nd, r, tmin, tmax, rec, (BezStats*)nullptr);
+    case N_XY_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 2, r, tmin, tmax, rec);
+    case N_XZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 1, r, tmin, tmax, rec);
+    case N_YZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 0, r, tmin, tmax, rec);
+    case N_BEZIER: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_bezier(nd, r, tmin, tmax, rec, (BezStats*)nullptr);
+    case N_CONSTANT_MEDIUM: {                              // geometry.scm:545-578
+      // phase function = lambertian (isotropic is commented out upstream, geometry.scm:546).
+      // The free-flight draw replaces (random-real) by block 16 + leaf id of the ray's
+      // (pixel, sample, bounce) Philox stream, so the result does not depend on visit order.
+      if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false;
+      int obj = sc.children[nd.child_begin];
+      HitRec<T> rec1, rec2;
+      if (!hit_node(sc, obj, r, T(-MAX_FLOAT), T(MAX_FLOAT), rec1)) return false;
+      if (!hit_node(sc, obj, r, rec1.t + T(0.0001), T(MAX_FLOAT), rec2)) return false;
+      T t1 = (rec1.t < tmin) ? tmin : rec1.t;
+      T t2 = (rec2.t > tmax) ? tmax : rec2.t;
+      if (t1 >= t2) return false;
+      if (t1 < T(0)) t1 = 0;
+      T len = length(r.d);
+      T distance_inside = (t2 - t1) * len;
+      T xi = T(0.5);
+      if (rng) { T u4[4]; rng_block<T>(*rng, 16u + (uint32_t)nd.leaf_id, u4); xi = u4[0]; }
+      T hit_distance = (-(T(1) / T(nd.p[0]))) * std::log(xi);
+      if (!(hit_distance < distance_inside)) return false;
+      T nt = t1 + hit_distance / len;
+      rec.t = nt; rec.p = point_at(r, nt); rec.n = mk<T>(1, 0, 0);
+      rec.mat = nd.material; rec.leaf = nd.leaf_id; rec.u = 0; rec.v = 0;
+      return true;
+    }
     case N_FLIP: {                                         // geometry.scm:433-442
-      if (!hit_node(sc, sc.children[nd.child_begin], r, tmin, tmax, rec)) return false;
+      if (!hit_node(sc, sc.children[nd.child_begin], r, tmin, tmax, rec, rng)) return false;
       rec.n = scale(rec.n, T(-1));
       return true;
     }
     case N_TRANSLATE: {                                    // geometry.scm:465-481
       V3<T> off = ld3<T>(nd.p);
       Ray<T> moved{sub(r.o, off), r.d, r.time};
-      if (!hit_node(sc, sc.children[nd.child_begin], moved, tmin, tmax, rec)) return false;
+      if (!hit_node(sc, sc.children[nd.child_begin], moved, tmin, tmax, rec, rng)) return false;
       rec.p = add(rec.p, off);
       return true;
     }
@@ -454,7 +478,7 @@ template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r
       Ray<T> rot{mk<T>(c * r.o.x - s * r.o.z, r.o.y, s * r.o.x + c * r.o.z),
                  mk<T>(c * r.d.x - s * r.d.z, r.d.y, s * r.d.x + c * r.d.z), r.time};
       int ch = sc.children[nd.child_begin];
-      if (!hit_node(sc, ch, rot, tmin, tmax, rec)) return false;
+      if (!hit_node(sc, ch, rot, tmin, tmax, rec, rng)) return false;
       V3<T> p = mk<T>(c * rec.p.x + s * rec.p.z, rec.p.y, (-s) * rec.p.x + c * rec.p.z);
       V3<T> n = mk<T>(c * rec.n.x + s * rec.n.z, rec.n.y, (-s) * rec.n.x + c * rec.n.z);
       rec.p = p; rec.n = n;
@@ -544,9 +568,9 @@ struct RenderCtx { int max_depth; int quirks; uint32_t seed; std::atomic<uint64_
 template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int depth, RngAddr addr, const RenderCtx& cx, uint64_t& nrays) {
   HitRec<T> rec;
   nrays++;
-  if (!hit_node(sc, sc.root, r, T(0.001), T(MAX_FLOAT), rec)) return sky_value(sc, r);
-  const Mat& m = sc.mat[rec.mat];
   addr.bounce = (uint32_t)depth + 1;
+  if (!hit_node(sc, sc.root, r, T(0.001), T(MAX_FLOAT), rec, &addr)) return sky_value(sc, r);
+  const Mat& m = sc.mat[rec.mat];
   T time0 = (cx.quirks & Q6_SCATTER_TIME0) ? T(0) : r.time;         // Q6: make-ray forces time 0
   switch (m.kind) {
     case M_LAMBERTIAN: {                                            // material.scm:24-39
@@ -756,11 +780,13 @@ int orc_trace_batch(void* h, int n, const double* rays, double tmin, double tmax
     bool hit; double rt = 0, rp[3] = {0, 0, 0}, rn[3] = {0, 0, 0}, ru = 0, rv = 0; int rl = -1, rm = -1;
     if (precision == 32) {
       Ray<float> r{ld3<float>(q), ld3<float>(q + 3), (float)q[6]}; HitRec<float> rec;
-      hit = hit_node<float>(*s, s->root, r, (float)tmin, (float)tmax, rec);
+      RngAddr ra{0u, (uint32_t)i, 0u, 1u};
+      hit = hit_node<float>(*s, s->root, r, (float)tmin, (float)tmax, rec, &ra);
       if (hit) { rt = rec.t; rp[0] = rec.p.x; rp[1] = rec.p.y; rp[2] = rec.p.z; rn[0] = rec.n.x; rn[1] = rec.n.y; rn[2] = rec.n.z; ru = rec.u; rv = rec.v; rl = rec.leaf; rm = rec.mat; }
     } else {
       Ray<double> r{ld3<double>(q), ld3<double>(q + 3), q[6]}; HitRec<double> rec;
-      hit = hit_node<double>(*s, s->root, r, tmin, tmax, rec);
+      RngAddr ra{0u, (uint32_t)i, 0u, 1u};
+      hit = hit_node<double>(*s, s->root, r, tmin, tmax, rec, &ra);
       if (hit) { rt = rec.t; rp[0] = rec.p.x; rp[1] = rec.p.y; rp[2] = rec.p.z; rn[0] = rec.n.x; rn[1] = rec.n.y; rn[2] = rec.n.z; ru = rec.u; rv = rec.v; rl = rec.leaf; rm = rec.mat; }
     }
     leaf[i] = hit ? rl : -1; t[i] = rt;

@@ -19,13 +19,10 @@ namespace {
 constexpr float BIG = 3.0e38f;
 
 // ---- 1. primitive bounds (geometry.scm bbox closures; instances get correct boxes, unlike Q7) ---
-__global__ void k_prim_bounds(DScene sc, float cam_t0, float cam_t1, float* __restrict__ aabb) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sc.n_prims) return;
+__device__ void prim_box(const DScene& sc, int i, float cam_t0, float cam_t1, float3& mn, float3& mx) {
   int4 hdr = sc.prim_hdr[i];
   int type = hdr.x & 0xff;
   float4 a = sc.prim_a[i];
-  float3 mn, mx;
   if (type == SRT_PRIM_SPHERE) {                                   // geometry.scm:172-174
     float r = fabsf(a.w);
     mn = v3(a.x - r, a.y - r, a.z - r); mx = v3(a.x + r, a.y + r, a.z + r);
@@ -62,6 +59,19 @@ __global__ void k_prim_bounds(DScene sc, float cam_t0, float cam_t1, float* __re
     float e = 4e-7f * fmaxf(fmaxf(fabsf(wmn.x), fabsf(wmx.x)), fmaxf(fmaxf(fabsf(wmn.y), fabsf(wmx.y)), fmaxf(fabsf(wmn.z), fabsf(wmx.z))));
     mn = v3(wmn.x - e, wmn.y - e, wmn.z - e); mx = v3(wmx.x + e, wmx.y + e, wmx.z + e);
   }
+}
+__global__ void k_prim_bounds(DScene sc, float cam_t0, float cam_t1, float* __restrict__ aabb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sc.n_surf) return;
+  float3 mn, mx;
+  if ((sc.prim_hdr[i].x & 0xff) == SRT_PRIM_CONSTANT_MEDIUM) {     // geometry.scm:576-577: the boundary's box
+    float4 a = sc.prim_a[i];
+    mn = v3(BIG, BIG, BIG); mx = v3(-BIG, -BIG, -BIG);
+    for (int j = (int)a.y; j < (int)a.y + (int)a.z; ++j) {
+      float3 bm, bx; prim_box(sc, j, cam_t0, cam_t1, bm, bx);
+      mn = v3(fminf(mn.x, bm.x), fminf(mn.y, bm.y), fminf(mn.z, bm.z)); mx = v3(fmaxf(mx.x, bx.x), fmaxf(mx.y, bx.y), fmaxf(mx.z, bx.z));
+    }
+  } else prim_box(sc, i, cam_t0, cam_t1, mn, mx);
   float* o = aabb + 6 * (size_t)i;
   o[0] = mn.x; o[1] = mn.y; o[2] = mn.z; o[3] = mx.x; o[4] = mx.y; o[5] = mx.z;
 }
@@ -278,7 +288,7 @@ __global__ void k_single_node(int n, const float* __restrict__ aabb, const int* 
 // Builds the LBVH for sc (device arrays already uploaded).  All launches on `stream`.
 // Outputs: d_aabb[6n], d_keys[n] (sorted), d_order[n], d_nodes[4*max(n-1,1)]; returns launches.
 int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream) {
-  int n = sc.n_prims, launches = 0;
+  int n = sc.n_surf, launches = 0;
   k_bounds_init<<<1, 32, 0, stream>>>(B.d_bounds); ++launches;
   if (n > 0) {
     k_prim_bounds<<<(n + 127) / 128, 128, 0, stream>>>(sc, cam_t0, cam_t1, B.d_aabb); ++launches;

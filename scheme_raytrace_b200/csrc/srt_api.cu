@@ -45,7 +45,7 @@ struct SrtScene {
   // LBVH
   LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth;
   DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
-  int n_nodes = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
+  int n_nodes = 0, n_surf = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
   // wavefront
   WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
   void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
@@ -55,7 +55,7 @@ struct SrtScene {
 
 static void fill_dscene(SrtScene* s) {
   DScene& d = s->ds;
-  d.n_prims = (int)s->prims.size(); d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
+  d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
   d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size();
@@ -130,7 +130,7 @@ void srt_scene_destroy(SrtScene* s) {
 
 int srt_scene_set_prims(SrtScene* s, const SrtPrim* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_prims: bad argument");
-  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_BEZIER) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
+  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_CONSTANT_MEDIUM) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
   s->prims.assign(p, p + n); s->committed = false; return 0;
 }
 int srt_scene_set_xforms(SrtScene* s, const SrtXform* p, int n) {
@@ -171,6 +171,20 @@ int srt_scene_commit(SrtScene* s) {
     if (p.material < 0 || p.material >= (int)s->mats.size()) return fail(SRT_ERR_ARG, "prim %d: material %d out of range", i, p.material);
     if (p.xform >= (int)s->xforms.size()) return fail(SRT_ERR_ARG, "prim %d: xform %d out of range", i, p.xform);
   }
+  // surfaces first, medium boundaries (SRT_PRIM_FLAG_BOUNDARY) as a suffix
+  int ns = 0; while (ns < n && !(s->prims[ns].flags & SRT_PRIM_FLAG_BOUNDARY)) ++ns;
+  for (int i = ns; i < n; ++i) {
+    const SrtPrim& p = s->prims[i];
+    if (!(p.flags & SRT_PRIM_FLAG_BOUNDARY)) return fail(SRT_ERR_ARG, "prim %d: boundary primitives must form a suffix", i);
+    if (p.type != SRT_PRIM_SPHERE && (p.type < SRT_PRIM_XY_RECT || p.type > SRT_PRIM_YZ_RECT)) return fail(SRT_ERR_ARG, "prim %d: a medium boundary must be a sphere or rect", i);
+  }
+  for (int i = 0; i < ns; ++i) {
+    const SrtPrim& p = s->prims[i];
+    if (p.type != SRT_PRIM_CONSTANT_MEDIUM) continue;
+    int first = (int)p.p[1], cnt = (int)p.p[2];
+    if (!(p.p[0] > 0.f) || first < ns || cnt < 1 || first + cnt > n) return fail(SRT_ERR_ARG, "prim %d: bad constant-medium parameters", i);
+  }
+  s->n_surf = ns;
   for (size_t i = 0; i < s->mats.size(); ++i) {
     const SrtMaterial& m = s->mats[i];
     if (m.kind != SRT_MAT_DIELECTRIC && (m.tex < 0 || m.tex >= (int)s->texs.size())) return fail(SRT_ERR_ARG, "material %zu: texture %d out of range", i, m.tex);
@@ -200,6 +214,7 @@ int srt_scene_commit(SrtScene* s) {
     switch (p.type) {
       case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
       case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
+      case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
       case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
       default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
     }
@@ -239,7 +254,7 @@ int srt_scene_commit(SrtScene* s) {
     dc.lens_radius = cm.lens_radius; dc.time0 = cm.time0; dc.time1 = cm.time1;
   } else std::memset(&s->dcam, 0, sizeof(s->dcam));
   // ---- LBVH ------------------------------------------------------------------------------------
-  const int nint = n > 1 ? n - 1 : 1, nn = n ? n : 1;
+  const int nint = ns > 1 ? ns - 1 : 1, nn = n ? n : 1;
   CK(s->d_aabb.ensure(6 * (size_t)nn)); CK(s->d_bounds.ensure(8)); CK(s->d_keys0.ensure(nn)); CK(s->d_keys1.ensure(nn));
   CK(s->d_order0.ensure(nn)); CK(s->d_order1.ensure(nn)); CK(s->d_hist.ensure(256 * (size_t)((nn + 255) / 256)));
   CK(s->d_links.ensure(nint)); CK(s->d_leaf_parent.ensure(nn)); CK(s->d_nbox.ensure(6 * (size_t)nint)); CK(s->d_visit.ensure(nint));
@@ -273,7 +288,7 @@ int srt_bvh_readback(SrtScene* s, SrtBvhNode* nodes, int cap) {
 }
 int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
-  int n = (int)s->prims.size();
+  int n = s->n_surf;
   if (cap < n) return fail(SRT_ERR_ARG, "bvh_keys_readback: capacity too small");
   if (n) {
     CK(cudaMemcpy(keys, s->lb.d_keys[s->lb.sorted], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
@@ -283,7 +298,7 @@ int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) 
 }
 int srt_prim_bounds_readback(SrtScene* s, float* aabbs6, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
-  int n = (int)s->prims.size();
+  int n = s->n_surf;
   if (cap < n) return fail(SRT_ERR_ARG, "prim_bounds_readback: capacity too small");
   if (n) CK(cudaMemcpy(aabbs6, s->d_aabb.p, sizeof(float) * 6 * (size_t)n, cudaMemcpyDeviceToHost));
   return 0;
@@ -300,7 +315,7 @@ int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t
   CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(SrtRay) * (size_t)n, cudaMemcpyHostToDevice, stream));
   RenderLaunch L = make_launch(s, nullptr);
   srt_launch_upload_rays(d_rays.p, n, s->wb.ray_o[0], s->wb.ray_d[0], stream);
-  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, nullptr, n, t_min, t_max, stream);   // the renderer's extend kernel
+  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], nullptr, s->wb.hit, nullptr, n, t_min, t_max, 0u, stream);   // the renderer's extend kernel
   srt_launch_complete_hits(s->ds, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, n, d_out.p, stream);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out.p, sizeof(SrtHit) * (size_t)n, cudaMemcpyDeviceToHost, stream));

@@ -13,7 +13,7 @@
 // ------------------------------------------------------------------------------------------------
 // Device view of a committed scene ("primitive SoA, material and texture tables, Perlin tables").
 struct DScene {
-  int n_prims, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;
+  int n_prims, n_surf, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;   // n_surf = scene surfaces (LBVH leaves); the rest are medium boundaries
   const int4* prim_hdr;     // x = type | flags << 8, y = material, z = xform, w = 0
   const float4* prim_a;     // sphere: c.xyz r | rect: a0 a1 b0 b1 | bezier: A.xyz width
   const float4* prim_b;     // moving: c1.xyz time0 | rect: k | bezier: B.xyz
@@ -280,7 +280,7 @@ static __device__ __noinline__ bool isect_bezier(float4 pa, float4 pb, float4 pc
 // Exact-tie rule: the order-independent restatement of hit-obj-list's
 // sequential "later object replaces the best iff t < best (sphere-type) or t <= best (rect-type,
 // curve)".  ids are positions in the reference's flattened object list.
-__device__ __forceinline__ bool prim_inclusive(int type) { return type >= SRT_PRIM_XY_RECT; }
+__device__ __forceinline__ bool prim_inclusive(int type) { return type >= SRT_PRIM_XY_RECT && type <= SRT_PRIM_BEZIER; }
 __device__ __forceinline__ bool accept_hit(float t, int id, bool incl, float best_t, int best_id, bool best_incl) {
   if (t < best_t) return true;
   if (!(t == best_t)) return false;
@@ -294,10 +294,11 @@ struct Hit { float t; int prim; float u, v; bool incl; };
 // One leaf primitive against the ray (world space in, candidate merged into `h`).  MASK is the
 // set of primitive kinds present in the scene (bit = SRT_PRIM_*): the extend kernel is compiled
 // per mask so that e.g. sphere-only scenes carry no rect / instance / Bezier code or registers.
-#define SRT_MASK_ALL 0x3f
+#define SRT_MASK_ALL 0x7f
 template <int MASK, class PrimSrc>
-__device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin, Hit& h) {
-  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20;
+__device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin,
+                                               const RngAddr& ra, Hit& h) {
+  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40;
   constexpr bool SINGLE_KIND = (MASK & (MASK - 1)) == 0;
   float4 a = ps.a(id);
   int type, xform = -1;
@@ -316,6 +317,26 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     ok = isect_rect(type, a, k, oo, dd, tmin, ti, have_t, t, u, v);
   } else if (HAS_BEZIER && type == SRT_PRIM_BEZIER) {
     ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
+  } else if (HAS_MEDIUM && type == SRT_PRIM_CONSTANT_MEDIUM) {
+    // geometry.scm:545-578.  Two closest-hit queries on the boundary shapes, then the free flight
+    // -log(xi)/density.  The reference clamps the exit to t-max = closest-so-far; accepting
+    // nt < exit here and nt < best in accept_hit below is the same condition, order-independent.
+    // xi = block (16 + id) of the ray's (pixel, sample, bounce) stream (upstream: (random-real)).
+    const int first = (int)a.y, cnt = (int)a.z;
+    Hit h1; h1.t = SRT_MAX_FLOAT; h1.prim = -1; h1.u = h1.v = 0.f; h1.incl = false;
+    for (int j = first; j < first + cnt; ++j) intersect_prim<MASK & 0x1d>(sc, ps, j, o, d, time, inv_a, -SRT_MAX_FLOAT, ra, h1);
+    if (h1.prim >= 0) {
+      Hit h2; h2.t = SRT_MAX_FLOAT; h2.prim = -1; h2.u = h2.v = 0.f; h2.incl = false;
+      for (int j = first; j < first + cnt; ++j) intersect_prim<MASK & 0x1d>(sc, ps, j, o, d, time, inv_a, h1.t + 0.0001f, ra, h2);
+      if (h2.prim >= 0) {
+        float t1 = fmaxf(fmaxf(h1.t, tmin), 0.0f);
+        float len = length(d);
+        float xi = rng_block(ra, 16u + (uint32_t)id).x;
+        float hit_distance = -(1.0f / a.x) * logf(xi);
+        float nt = t1 + hit_distance / len;
+        if (t1 < h2.t && hit_distance < (h2.t - t1) * len) { t = nt; ok = true; }
+      }
+    }
   }
   bool incl = prim_inclusive(type);
   if (ok && accept_hit(t, id, incl, h.t, h.prim, h.incl)) { h.t = t; h.prim = id; h.u = u; h.v = v; h.incl = incl; }
@@ -344,6 +365,9 @@ __device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t
     } else {
       p = madd(d, t, o);
     }
+  } else if (type == SRT_PRIM_CONSTANT_MEDIUM) {      // geometry.scm:567-571: normal (1,0,0), phase-function material
+    p = madd(d, t, o);
+    n = v3(1.f, 0.f, 0.f);
   } else {
     p = madd(d, t, o);
     n = -d;

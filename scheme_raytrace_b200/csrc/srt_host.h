@@ -45,8 +45,8 @@ struct RenderLaunch {
 // returns number of kernel launches; d_rgb_sum accumulates W*H*3 floats
 int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile);
 size_t srt_wave_ctrl_bytes();
-int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
-                      float tmin, float tmax, cudaStream_t stream);
+int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
+                      float tmin, float tmax, uint32_t seed, cudaStream_t stream);
 int srt_launch_complete_hits(const DScene& sc, const float4* ray_o, const float4* ray_d, const float4* hit, int n, SrtHit* d_out, cudaStream_t stream);
 int srt_launch_upload_rays(const SrtRay* d_rays, int n, float4* ray_o, float4* ray_d, cudaStream_t stream);
 int srt_launch_resolve(const float* d_rgb_sum, int n3, int spp, uint8_t* d_image, cudaStream_t stream);

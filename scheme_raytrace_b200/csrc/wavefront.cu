@@ -102,6 +102,7 @@ struct PrimGlobal {
 struct Trav {
   float3 o, d, inv, oi, ainv; float time, inv_a;
   Hit h; int node; unsigned long long trail; int ray;
+  RngAddr ra;                                // only read by constant-medium primitives
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
 #ifdef SRT_COUNT_STEPS
   int nsteps, ntests, nmiss;                // instrumented build only (tools/step_stats.py)
@@ -193,15 +194,21 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
 // while-while loop were both measured slower at 32 resident warps/SM, see profiles/README.md).
 template <bool SMEM, int MASK, bool CACHE, class PrimSrc>
 __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
-                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-                                            int count, float tmin, float tmax) {
-  if (sc.n_prims == 0) {   // empty scene: every ray misses
+                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
+                                            float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed) {
+  if (sc.n_surf == 0) {   // empty scene: every ray misses
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
     return;
   }
   Trav T;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    trav_init(T, ray_o[i], ray_d[i], tmax, i);
+    const float4 d4 = ray_d[i];
+    trav_init(T, ray_o[i], d4, tmax, i);
+    if (MASK & 0x40) {   // Philox address of this ray: (pixel, sample, bounce = depth + 1)
+      const int sd = __float_as_int(d4.w);
+      T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
+      T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
+    }
     bool more = true;
     while (more) {
       int pend0 = -1, pend1 = -1;
@@ -210,7 +217,7 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
 #ifdef SRT_COUNT_STEPS
         T.ntests++;
 #endif
-        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.h); pend0 = pend1; pend1 = -1;
+        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h); pend0 = pend1; pend1 = -1;
       }
     }
 #ifdef SRT_COUNT_STEPS
@@ -221,9 +228,9 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
 }
 
 template <bool SMEM, int MASK, bool CACHE>
-__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x20) ? 2 : ((MASK & 0x1c) ? 3 : 4))
-k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit,
-         const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax) {
+__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x60) ? 2 : ((MASK & 0x1c) ? 3 : 4))
+k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
+         float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
   extern __shared__ float4 smem[];
   const int count = count_ptr ? *count_ptr : count_fixed;
   if (count == 0) return;
@@ -237,10 +244,10 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
     PrimShared ps{sh, sa};
-    extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, hit, count, tmin, tmax);
+    extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, hit, count, tmin, tmax);
+    extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   }
 }
 
@@ -415,14 +422,14 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
 // Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
-typedef void (*ExtendFn)(DScene, const float4*, const float4*, float4*, const int*, int, float, float);
+typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
 static ExtendVariant g_variants[2][4][2];
 
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
   if ((mask & ~0x03) == 0) return 1;
-  if ((mask & 0x20) == 0) return 2;
+  if ((mask & 0x60) == 0) return 2;
   return 3;
 }
 template <bool SMEM, bool CACHE> static ExtendFn variant_fn_m(int v) {
@@ -453,10 +460,10 @@ static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   return e;
 }
 
-int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, float4* hit, const int* d_count, int count,
-                      float tmin, float tmax, cudaStream_t stream) {
+int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
+                      float tmin, float tmax, uint32_t seed, cudaStream_t stream) {
   const ExtendVariant& e = extend_variant(L);
-  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, hit, d_count, count, tmin, tmax);
+  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, state, hit, d_count, count, tmin, tmax, seed);
   return 1;
 }
 
@@ -487,7 +494,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   while (!done) {
     for (int k = 0; k < BATCH; ++k) {
       if (profile) cudaEventRecord(e0, stream);
-      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, stream);
+      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.state[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, p.seed, stream);
       if (profile) cudaEventRecord(e1, stream);
       (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
                                                        W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);

@@ -71,6 +71,7 @@ def sky_kind(sky_function):
 
 def flatten_scene(scene):
     prims, xforms, leaves = [], [], []
+    boundary = []          # boundary primitives of constant media: appended after the surface primitives
     xform_ids = {}
     mats, mat_ids, texs, tex_ids = [], {}, [], {}
 
@@ -92,14 +93,27 @@ def flatten_scene(scene):
             mats.append((m, tex_id(m.tex) if m.tex is not None else -1))
         return mat_ids[id(m)]
 
-    def walk(obj, chain, flip):
+    def walk(obj, chain, flip, out=None, out_leaves=None):
+        out = prims if out is None else out
+        out_leaves = leaves if out_leaves is None else out_leaves
         if obj.kind == g.LIST:
             for c in obj.children:
-                walk(c, chain, flip)
+                walk(c, chain, flip, out, out_leaves)
+        elif obj.kind == g.CONSTANT_MEDIUM:
+            if out is not prims:
+                raise ValueError("a constant medium cannot bound another constant medium")
+            mine = []
+            walk(obj.children[0], chain, 0, mine, [])          # boundary shapes (geometry.scm:549-553)
+            for b in mine:
+                if b[0] not in (g.SPHERE, g.XY_RECT, g.XZ_RECT, g.YZ_RECT):
+                    raise ValueError("constant-medium boundaries must be spheres / rects / boxes")
+            prims.append((g.CONSTANT_MEDIUM, 0, mat_id(obj.material), -1, [obj.params[0], ("boundary", len(boundary)), len(mine)]))
+            boundary.extend((k, fl | 2, mat_id(obj.material), xf, prm) for (k, fl, _m, xf, prm) in mine)
+            leaves.append(obj)
         elif obj.kind == g.FLIP:
-            walk(obj.children[0], chain, flip ^ 1)
+            walk(obj.children[0], chain, flip ^ 1, out, out_leaves)
         elif obj.kind in (g.TRANSLATE, g.ROTATE_Y):
-            walk(obj.children[0], chain + ((obj.kind, obj.params),), flip)
+            walk(obj.children[0], chain + ((obj.kind, obj.params),), flip, out, out_leaves)
         else:
             xf = -1
             if chain:
@@ -107,15 +121,18 @@ def flatten_scene(scene):
                     xform_ids[chain] = len(xforms)
                     xforms.append(_compose(chain))
                 xf = xform_ids[chain]
-            prims.append((obj.kind, flip, mat_id(obj.material), xf, obj.params))
-            leaves.append(obj)
+            out.append((obj.kind, flip, mat_id(obj.material), xf, obj.params))
+            out_leaves.append(obj)
 
     for o in scene.obj_list:
         walk(o, (), 0)
 
-    P = np.zeros(len(prims), dtype=PRIM_DTYPE)
-    for i, (kind, flip, m, xf, prm) in enumerate(prims):
+    n_surface = len(prims)
+    allp = prims + boundary                  # boundary primitives (flag 2) form a suffix, outside the LBVH
+    P = np.zeros(len(allp), dtype=PRIM_DTYPE)
+    for i, (kind, flip, m, xf, prm) in enumerate(allp):
         P[i]["type"], P[i]["flags"], P[i]["material"], P[i]["xform"] = kind, flip, m, xf
+        prm = [n_surface + q[1] if isinstance(q, tuple) else q for q in prm]
         P[i]["p"][:len(prm)] = prm
     X = np.zeros(len(xforms), dtype=XFORM_DTYPE)
     for i, (s, c, off) in enumerate(xforms):

@@ -11,9 +11,9 @@ from dataclasses import dataclass, field
 from typing import Any, List, Optional, Tuple
 
 # node kinds (leaf kinds equal the SRT_PRIM_* codes of include/srt.h)
-SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER = 0, 1, 2, 3, 4, 5
+SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM = 0, 1, 2, 3, 4, 5, 6
 FLIP, LIST, TRANSLATE, ROTATE_Y = 16, 17, 18, 19
-LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER)
+LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM)
 
 
 @dataclass(eq=False)
@@ -96,8 +96,11 @@ def make_bvh_with_sah(obj_list, time0=0, time1=0):             # geometry.scm:29
     return Obj(LIST, None, (), list(obj_list))
 
 
-def make_constant_medium(obj, density, a):                     # geometry.scm:545
-    raise NotImplementedError("constant medium is a SURVEY.md §8f 'next' row (needs RNG inside traversal)")
+def make_constant_medium(obj, density, a):                     # geometry.scm:545-578
+    """Volume bounded by `obj` (any object tree); phase function = lambertian(a) exactly like
+    upstream (make-isotropic is commented out at geometry.scm:546)."""
+    from .material import make_lambertian
+    return Obj(CONSTANT_MEDIUM, make_lambertian(a), (float(density),), [obj])
 
 
 def make_klein(center, material):                              # geometry.scm:644

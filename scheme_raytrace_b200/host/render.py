@@ -64,13 +64,13 @@ class Renderer:
         return out
 
     def bvh_keys(self):
-        n = len(self.flat.prims)
+        n = int(np.sum((self.flat.prims["flags"] & 2) == 0))
         keys, order = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.int32)
         ffi.check(self.lib.srt_bvh_keys_readback(self.h, _ptr(keys), _ptr(order), n), "bvh_keys_readback")
         return keys, order
 
     def prim_bounds(self):
-        n = len(self.flat.prims)
+        n = int(np.sum((self.flat.prims["flags"] & 2) == 0))
         out = np.zeros((n, 6), dtype=np.float32)
         ffi.check(self.lib.srt_prim_bounds_readback(self.h, _ptr(out), n), "prim_bounds_readback")
         return out

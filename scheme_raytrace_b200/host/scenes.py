@@ -130,6 +130,28 @@ def cfg4_cornell_box(size_x=1024, size_y=1024):
     return g.make_scene(objs, cornell_camera(size_x, size_y), sky_color)
 
 
+def cornell_smoke(size_x=200, size_y=200):
+    """main.scm:375-398 cornell-smoke: two constant media bounded by the rotated boxes, big light,
+    black sky."""
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    white = m.make_lambertian(t.constant_texture(v.vec3(0.73, 0.73, 0.73)))
+    green = m.make_lambertian(t.constant_texture(v.vec3(0.12, 0.45, 0.15)))
+    light = m.make_diffuse_light(t.constant_texture(v.vec3(3, 3, 3)))
+    b1 = g.translate(g.rotate_y(g.make_box(v.vec3(0, 0, 0), v.vec3(165, 165, 165), white), -18), v.vec3(130, 0, 65))
+    b2 = g.translate(g.rotate_y(g.make_box(v.vec3(0, 0, 0), v.vec3(165, 330, 165), white), 15), v.vec3(265, 0, 295))
+    objs = [
+        g.flip_normals(g.make_yz_rect(0, 555, 0, 555, 555, green)),
+        g.make_yz_rect(0, 555, 0, 555, 0, red),
+        g.flip_normals(g.make_xz_rect(113, 443, 127, 432, 554, light)),
+        g.flip_normals(g.make_xz_rect(0, 555, 0, 555, 555, white)),
+        g.make_xz_rect(0, 555, 0, 555, 0, white),
+        g.flip_normals(g.make_xy_rect(0, 555, 0, 555, 555, white)),
+        g.make_constant_medium(b1, 0.01, t.constant_texture(v.vec3(1, 1, 1))),
+        g.make_constant_medium(b2, 0.01, t.constant_texture(v.vec3(0, 0, 0))),
+    ]
+    return g.make_scene(objs, cornell_camera(size_x, size_y), black)
+
+
 def test_bezier(size_x=200, size_y=200):
     """main.scm:237-277 test-bezier (3 curves + 6 spheres + checker ground)."""
     red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))

@@ -28,6 +28,8 @@ def interest_bounds(flat, clip=30.0):
     pts = []
     for p in flat.prims:
         q = p["p"]
+        if p["type"] == 6 or (p["flags"] & 2 and p["xform"] >= 0):
+            continue            # media / instanced boundary shapes: covered by the other primitives' extent
         if p["type"] in (0, 1):
             pts.append(q[0:3]);
         elif p["type"] == 2:

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 SMALL = {"cfg1": (scenes.cfg1_weekend, 200, 100), "cfg2": (scenes.cfg2_random_spheres, 120, 80),
          "cfg3": (scenes.cfg3_next_week, 80, 80), "cfg4": (scenes.cfg4_cornell_box, 64, 64),
          "bezier": (scenes.test_bezier, 64, 64), "cornell_bezier": (scenes.cornell_bezier, 64, 64),
-         "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64)}
+         "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64),
+         "smoke": (scenes.cornell_smoke, 64, 64)}
 
 
 @pytest.fixture(scope="module", params=list(SMALL))
@@ -152,7 +153,7 @@ def test_raygen_parity(orc):
     r.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke"])
 def test_image_same_stream(name, orc):
     """Image parity under IDENTICAL Philox streams: GPU fp32 vs oracle f64 follow the same paths
     except where rounding flips a decision, so the per-pixel linear difference is tiny for almost

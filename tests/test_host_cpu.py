@@ -105,3 +105,11 @@ def test_morton_expand_bits(orc):
     aabb = np.array([[0, 0, 0, 0, 0, 0], [1, 2, 4, 1, 2, 4]], np.float32)
     keys, order, _ = orc.lbvh_build(aabb)
     assert keys[0] == 0 and keys[1] == (1 << 63) - 1 and list(order) == [0, 1]
+
+
+def test_flatten_constant_medium():
+    f = srt.flatten_scene(scenes.cornell_smoke(32, 32))
+    assert len(f.prims) == 20 and list(f.prims["type"][6:8]) == [6, 6]
+    assert np.all((f.prims["flags"][:8] & 2) == 0) and np.all((f.prims["flags"][8:] & 2) == 2)     # boundaries form a suffix
+    assert tuple(f.prims[6]["p"][:3]) == (np.float32(0.01), 8.0, 6.0) and tuple(f.prims[7]["p"][1:3]) == (14.0, 6.0)
+    assert f.materials[f.prims[6]["material"]]["kind"] == 0        # phase function = lambertian (geometry.scm:546)

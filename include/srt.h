@@ -33,7 +33,10 @@ enum {
   SRT_PRIM_XZ_RECT = 3,       /* geometry.scm:395 make-xz-rect        p = x0 x1 z0 z1 k                    */
   SRT_PRIM_YZ_RECT = 4,       /* geometry.scm:414 make-yz-rect        p = y0 y1 z0 z1 k                    */
   SRT_PRIM_BEZIER = 5,        /* bezier.scm:61   make-bezier          p = a.xyz b.xyz c.xyz d.xyz width    */
-  SRT_PRIM_CONSTANT_MEDIUM = 6 /* geometry.scm:545 make-constant-medium p = density, first boundary prim, #boundary prims */
+  SRT_PRIM_CONSTANT_MEDIUM = 6, /* geometry.scm:545 make-constant-medium p = density, first boundary prim, #boundary prims */
+  SRT_PRIM_PATCH = 7          /* bicubic Bezier (sub-)patch (north-star extension, absent upstream):
+                               * p = index into the patch table, u0, v0, size of this sub-patch in its parent's
+                               * (u,v) domain; the host pre-splits each patch 2 levels into 16 of these */
 };
 #define SRT_PRIM_FLAG_FLIP 1  /* geometry.scm:433 flip-normals (parity of the flips above the leaf)        */
 #define SRT_PRIM_FLAG_BOUNDARY 2 /* boundary shape of a constant medium: not a scene surface, not in the LBVH;
@@ -47,7 +50,8 @@ typedef struct {
   int32_t flags;     /* SRT_PRIM_FLAG_*       */
   int32_t material;  /* index into materials  */
   int32_t xform;     /* index into xforms, -1 = none */
-  float p[16];
+  float p[16];       /* p[15]: logical primitive id + 1 reported by srt_trace_batch (0 = array position);
+                      * the 16 sub-patches of one patch share their parent's logical id */
 } SrtPrim;
 
 /* Rigid instance transform = the composition of a translate / rotate-y chain
@@ -128,6 +132,7 @@ SrtScene* srt_scene_create(void);
 void srt_scene_destroy(SrtScene*);
 int srt_scene_set_prims(SrtScene*, const SrtPrim*, int n);
 int srt_scene_set_xforms(SrtScene*, const SrtXform*, int n);
+int srt_scene_set_patches(SrtScene*, const float* cp48, int n);      /* n x 16 control points (xyz), P[i][j] at 3*(4i+j) */
 int srt_scene_set_materials(SrtScene*, const SrtMaterial*, int n);
 int srt_scene_set_textures(SrtScene*, const SrtTexture*, int n);
 int srt_scene_set_perlin(SrtScene*, const float* ranvec768, const int32_t* perm_x, const int32_t* perm_y, const int32_t* perm_z);

@@ -32,6 +32,7 @@ def load():
         lib.orc_add_material.argtypes = [vp, i32, i32, dbl]
         lib.orc_add_node.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32]
         lib.orc_set_root.argtypes = [vp, i32]
+        lib.orc_add_patch.argtypes = [vp, vp]
         lib.orc_set_camera.argtypes = [vp, vp]
         lib.orc_set_sky.argtypes = [vp, i32]
         lib.orc_set_perlin.argtypes = [vp, vp, vp, vp, vp]
@@ -131,7 +132,17 @@ class OracleScene:
             self._leaf += 1
         children = [self._add(c, g, boundary or obj.kind == g.CONSTANT_MEDIUM) for c in obj.children]
         mat = self._add_mat(obj.material)
-        return self._node(obj.kind, mat, leaf, obj.params, children)
+        params = obj.params
+        if obj.kind == g.PATCH:                            # control net goes to the patch table
+            cp = _d(self._q(obj.params))
+            params = (float(self.lib.orc_add_patch(self.h, _p(cp))),)
+            return self._node_raw(obj.kind, mat, leaf, params, children)
+        return self._node(obj.kind, mat, leaf, params, children)
+
+    def _node_raw(self, kind, material, leaf, params, children):
+        prm = _d(list(params))
+        ch = np.ascontiguousarray(children if len(children) else [0], dtype=np.int32)
+        return self.lib.orc_add_node(self.h, kind, material, leaf, _p(prm), len(params), _p(ch), len(children))
 
     def close(self):
         if self.h:

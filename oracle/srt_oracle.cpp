@@ -39,7 +39,7 @@ static const double MAX_FLOAT = 999999999999.0;
 static const double PI = 3.141592653589793;  // math.const pi
 
 enum NodeKind { N_SPHERE = 0, N_MOVING_SPHERE = 1, N_XY_RECT = 2, N_XZ_RECT = 3, N_YZ_RECT = 4,
-                N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
+                N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_PATCH = 7, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
 enum MatKind { M_LAMBERTIAN = 0, M_METAL = 1, M_DIELECTRIC = 2, M_DIFFUSE_LIGHT = 3, M_ISOTROPIC = 4 };
 enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3 };
 enum SkyKind { SKY_GRADIENT = 0, SKY_BLACK = 1 };
@@ -63,6 +63,7 @@ struct Scene {
   int exclude_leaf = -1;   // test hook: skip one leaf (second-best-hit query)
   std::vector<int> lights; // node ids of the light shapes sampled by the hittable pdf (S7)
   std::vector<int> leaf_node;   // leaf id -> node id
+  std::vector<double> patches;  // 48 doubles per bicubic patch: P[i][j], i along u, j along v
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -412,6 +413,90 @@ template <class T> static bool hit_bezier(const Node& nd, const Ray<T>& r, T tmi
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bicubic Bezier PATCH — north-star extension, ABSENT from the reference (which only has the
+// curve above): PARITY UNPINNED.  Specification shared with the CUDA path (DESIGN.md "Patches"):
+//   1. control net projected into ray space with bezier.scm's projection (ray = +z axis)
+//   2. fixed-depth (2) quadtree subdivision by de Casteljau at 0.5 (u then v); a cell is culled
+//      when the hull of its net misses the z axis or the (tmin, tbest) range
+//   3. Newton on (S.x, S.y) = 0 from the cell centre, <= 8 iterations; accepted inside the cell
+//      (+-1e-3); t = S.z / |d| (true parameter along the raw direction), strict both sides
+//   4. normal = Su x Sv at the global (u, v) in world space, flipped to face the ray
+template <class T> struct Net { V3<T> q[4][4]; };
+template <class T> static void bern(T s, T b[4], T db[4]) {
+  T m = T(1) - s;
+  b[0] = m * m * m; b[1] = T(3) * s * m * m; b[2] = T(3) * s * s * m; b[3] = s * s * s;
+  db[0] = T(-3) * m * m; db[1] = T(3) * m * m - T(6) * s * m; db[2] = T(6) * s * m - T(3) * s * s; db[3] = T(3) * s * s;
+}
+template <class T> static void patch_eval(const Net<T>& N, T s, T t, V3<T>& S, V3<T>& Su, V3<T>& Sv) {
+  T bs[4], dbs[4], bt[4], dbt[4]; bern(s, bs, dbs); bern(t, bt, dbt);
+  S = Su = Sv = mk<T>(0, 0, 0);
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+    S = add(S, scale(N.q[i][j], bs[i] * bt[j]));
+    Su = add(Su, scale(N.q[i][j], dbs[i] * bt[j]));
+    Sv = add(Sv, scale(N.q[i][j], bs[i] * dbt[j]));
+  }
+}
+template <class T> static void cubic_split(const V3<T> c[4], V3<T> l[4], V3<T> r[4]) {   // de Casteljau at 0.5
+  V3<T> ab = scale(add(c[0], c[1]), T(0.5)), bc = scale(add(c[1], c[2]), T(0.5)), cd = scale(add(c[2], c[3]), T(0.5));
+  V3<T> abc = scale(add(ab, bc), T(0.5)), bcd = scale(add(bc, cd), T(0.5)), m = scale(add(abc, bcd), T(0.5));
+  l[0] = c[0]; l[1] = ab; l[2] = abc; l[3] = m; r[0] = m; r[1] = bcd; r[2] = cd; r[3] = c[3];
+}
+template <class T> static void net_split_u(const Net<T>& N, Net<T>& lo, Net<T>& hi) {
+  for (int j = 0; j < 4; ++j) { V3<T> c[4] = {N.q[0][j], N.q[1][j], N.q[2][j], N.q[3][j]}, l[4], r[4]; cubic_split(c, l, r);
+    for (int i = 0; i < 4; ++i) { lo.q[i][j] = l[i]; hi.q[i][j] = r[i]; } }
+}
+template <class T> static void net_split_v(const Net<T>& N, Net<T>& lo, Net<T>& hi) {
+  for (int i = 0; i < 4; ++i) { V3<T> l[4], r[4]; cubic_split(N.q[i], l, r);
+    for (int j = 0; j < 4; ++j) { lo.q[i][j] = l[j]; hi.q[i][j] = r[j]; } }
+}
+template <class T> static bool net_cull(const Net<T>& N, T zmin, T zmax) {
+  T mnx = N.q[0][0].x, mxx = mnx, mny = N.q[0][0].y, mxy = mny, mnz = N.q[0][0].z, mxz = mnz;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { const V3<T>& q = N.q[i][j];
+    mnx = std::min(mnx, q.x); mxx = std::max(mxx, q.x); mny = std::min(mny, q.y); mxy = std::max(mxy, q.y); mnz = std::min(mnz, q.z); mxz = std::max(mxz, q.z); }
+  return mnx > T(0) || mxx < T(0) || mny > T(0) || mxy < T(0) || mxz < zmin || mnz > zmax;
+}
+template <class T> static void patch_recurse(const Net<T>& N, int depth, T u0, T v0, T size, T zmin, T& zbest, T& ub, T& vb, bool& any) {
+  if (net_cull(N, zmin, zbest)) return;
+  if (depth == 0) {
+    T s = T(0.5), t = T(0.5); bool conv = false; V3<T> S, Su, Sv;
+    for (int it = 0; it < 8; ++it) {
+      patch_eval(N, s, t, S, Su, Sv);
+      T det = Su.x * Sv.y - Sv.x * Su.y;
+      if (!(std::fabs(det) > T(1e-30))) break;
+      T ds = (-S.x * Sv.y + S.y * Sv.x) / det, dt = (-Su.x * S.y + Su.y * S.x) / det;
+      s += ds; t += dt;
+      if (!(std::fabs(s) < T(4)) || !(std::fabs(t) < T(4))) break;
+      if (std::max(std::fabs(ds), std::fabs(dt)) < T(1e-5)) { conv = true; break; }
+    }
+    if (!conv || s < T(-1e-3) || s > T(1) + T(1e-3) || t < T(-1e-3) || t > T(1) + T(1e-3)) return;
+    s = std::min(std::max(s, T(0)), T(1)); t = std::min(std::max(t, T(0)), T(1));
+    patch_eval(N, s, t, S, Su, Sv);
+    if (S.z > zmin && S.z < zbest) { zbest = S.z; ub = u0 + s * size; vb = v0 + t * size; any = true; }
+    return;
+  }
+  Net<T> lo, hi, a, b; net_split_u(N, lo, hi);
+  T h = size * T(0.5);
+  net_split_v(lo, a, b); patch_recurse(a, depth - 1, u0, v0, h, zmin, zbest, ub, vb, any); patch_recurse(b, depth - 1, u0, v0 + h, h, zmin, zbest, ub, vb, any);
+  net_split_v(hi, a, b); patch_recurse(a, depth - 1, u0 + h, v0, h, zmin, zbest, ub, vb, any); patch_recurse(b, depth - 1, u0 + h, v0 + h, h, zmin, zbest, ub, vb, any);
+}
+template <class T> static bool hit_patch(const Scene& sc, const Node& nd, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec) {
+  const double* cp = &sc.patches[48 * (size_t)nd.p[0]];
+  T M[4][4]; projection_mat(r, M);
+  Net<T> N, W;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { W.q[i][j] = ld3<T>(cp + 3 * (4 * i + j)); N.q[i][j] = bez_transform_pt(W.q[i][j], M); }
+  T len = length(r.d);
+  T zbest = tmax * len, ub = 0, vb = 0; bool any = false;
+  patch_recurse<T>(N, 2, T(0), T(0), T(1), tmin * len, zbest, ub, vb, any);
+  if (!any) return false;
+  rec.t = zbest / len; rec.p = point_at(r, rec.t);
+  V3<T> S, Su, Sv; patch_eval(W, ub, vb, S, Su, Sv);
+  V3<T> n = unit(cross(Su, Sv));
+  if (dot(n, r.d) > T(0)) n = scale(n, T(-1));
+  rec.n = n; rec.mat = nd.material; rec.leaf = nd.leaf_id; rec.u = ub; rec.v = vb;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // geometry.scm:14-15 — (hit obj r t-min t-max), dispatch over the object kinds.
 template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec, const RngAddr* rng = nullptr) {
   const Node& nd = sc.nodes[id];
@@ -437,6 +522,7 @@ template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r
     case N_XZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 1, r, tmin, tmax, rec);
     case N_YZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 0, r, tmin, tmax, rec);
     case N_BEZIER: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_bezier(nd, r, tmin, tmax, rec, (BezStats*)nullptr);
+    case N_PATCH: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_patch(sc, nd, r, tmin, tmax, rec);
     case N_CONSTANT_MEDIUM: {                              // geometry.scm:545-578
       // phase function = lambertian (isotropic is commented out upstream, geometry.scm:546).
       // The free-flight draw replaces (random-real) by block 16 + leaf id of the ray's
@@ -743,6 +829,7 @@ int orc_set_lights(void* h, const int* leaf_ids, int n) {
     s->lights.push_back(s->leaf_node[lf]);
   }
   return 0; }
+int orc_add_patch(void* h, const double* cp48) { Scene* s = (Scene*)h; s->patches.insert(s->patches.end(), cp48, cp48 + 48); return (int)(s->patches.size() / 48) - 1; }
 void orc_set_root(void* h, int node) { ((Scene*)h)->root = node; }
 void orc_set_camera(void* h, const double* cam24) { std::memcpy(((Scene*)h)->cam, cam24, 24 * sizeof(double)); }
 void orc_set_sky(void* h, int kind) { ((Scene*)h)->sky = kind; }

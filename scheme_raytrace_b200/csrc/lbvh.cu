@@ -41,6 +41,10 @@ __device__ void prim_box(const DScene& sc, int i, float cam_t0, float cam_t1, fl
     if (type == SRT_PRIM_XY_RECT) { mn = v3(a.x, a.z, k - 0.0001f); mx = v3(a.y, a.w, k + 0.0001f); }
     else if (type == SRT_PRIM_XZ_RECT) { mn = v3(a.x, k - 0.0001f, a.z); mx = v3(a.y, k + 0.0001f, a.w); }
     else { mn = v3(k - 0.0001f, a.x, a.z); mx = v3(k + 0.0001f, a.y, a.w); }
+  } else if (type == SRT_PRIM_PATCH) {                             // convex hull of the 4x4 control net
+    const float4* cp = sc.patch_cp + 16 * hdr.w;
+    mn = v3(BIG, BIG, BIG); mx = v3(-BIG, -BIG, -BIG);
+    for (int k = 0; k < 16; ++k) { float4 q = cp[k]; mn = v3(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z)); mx = v3(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z)); }
   } else {                                                         // bezier.scm:88-98
     float w1 = 0.5f * a.w;
     float4 b = sc.prim_b[i], c = sc.prim_c[i], d = sc.prim_d[i];

@@ -39,6 +39,7 @@ struct SrtScene {
   float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
   SrtCamera cam; bool has_cam = false;
   std::vector<int32_t> lights; DevBuf<int> d_lights;
+  std::vector<float> patches; DevBuf<float4> d_patches; DevBuf<int> d_logical;
   bool committed = false;
   // device tables
   DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
@@ -58,7 +59,7 @@ static void fill_dscene(SrtScene* s) {
   d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
-  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size();
+  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
 }
 
 static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
@@ -118,7 +119,7 @@ SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
   s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
-  s->d_ranvec.release(); s->d_lights.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
+  s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
   for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
@@ -130,7 +131,7 @@ void srt_scene_destroy(SrtScene* s) {
 
 int srt_scene_set_prims(SrtScene* s, const SrtPrim* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_prims: bad argument");
-  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_CONSTANT_MEDIUM) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
+  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_PATCH) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
   s->prims.assign(p, p + n); s->committed = false; return 0;
 }
 int srt_scene_set_xforms(SrtScene* s, const SrtXform* p, int n) {
@@ -156,6 +157,11 @@ int srt_scene_set_camera(SrtScene* s, const SrtCamera* c) {
   s->cam = *c; s->has_cam = true; s->committed = false; return 0;
 }
 
+int srt_scene_set_patches(SrtScene* s, const float* cp48, int n) {
+  if (!s || n < 0 || (n && !cp48)) return fail(SRT_ERR_ARG, "set_patches: bad argument");
+  s->patches.assign(cp48, cp48 + 48 * (size_t)n); s->committed = false; return 0;
+}
+
 int srt_scene_set_lights(SrtScene* s, const int32_t* prim_ids, int n) {
   if (!s || n < 0 || (n && !prim_ids)) return fail(SRT_ERR_ARG, "set_lights: bad argument");
   s->lights.assign(prim_ids, prim_ids + n); s->committed = false; return 0;
@@ -170,6 +176,7 @@ int srt_scene_commit(SrtScene* s) {
     const SrtPrim& p = s->prims[i];
     if (p.material < 0 || p.material >= (int)s->mats.size()) return fail(SRT_ERR_ARG, "prim %d: material %d out of range", i, p.material);
     if (p.xform >= (int)s->xforms.size()) return fail(SRT_ERR_ARG, "prim %d: xform %d out of range", i, p.xform);
+    if (p.type == SRT_PRIM_PATCH && ((int)p.p[0] < 0 || (size_t)p.p[0] >= s->patches.size() / 48 || p.xform >= 0)) return fail(SRT_ERR_ARG, "prim %d: bad patch index / instanced patch", i);
   }
   // surfaces first, medium boundaries (SRT_PRIM_FLAG_BOUNDARY) as a suffix
   int ns = 0; while (ns < n && !(s->prims[ns].flags & SRT_PRIM_FLAG_BOUNDARY)) ++ns;
@@ -203,21 +210,35 @@ int srt_scene_commit(SrtScene* s) {
   cudaStream_t stream = 0;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, stream));
+  {
+    size_t np16 = s->patches.size() / 3;
+    std::vector<float4> pc(np16 ? np16 : 1);
+    for (size_t k = 0; k < np16; ++k) pc[k] = make_float4(s->patches[3 * k], s->patches[3 * k + 1], s->patches[3 * k + 2], 0.f);
+    CK(s->d_patches.ensure(np16));
+    if (np16) CK(cudaMemcpy(s->d_patches.p, pc.data(), sizeof(float4) * np16, cudaMemcpyHostToDevice));
+  }
   CK(s->d_lights.ensure(s->lights.size()));
   if (!s->lights.empty()) CK(cudaMemcpyAsync(s->d_lights.p, s->lights.data(), sizeof(int) * s->lights.size(), cudaMemcpyHostToDevice, stream));
   // ---- host SoA staging + H2D ---------------------------------------------------------------
   std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
   for (int i = 0; i < n; ++i) {
     const SrtPrim& p = s->prims[i]; const float* q = p.p;
-    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, 0);
+    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, p.type == SRT_PRIM_PATCH ? (int)q[0] : 0);
     a[i] = b[i] = c[i] = d[i] = make_float4(0, 0, 0, 0);
     switch (p.type) {
       case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
       case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
       case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
+      case SRT_PRIM_PATCH: a[i] = make_float4(q[0], 0, 0, 0); b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0); break;
       case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
       default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
     }
+  }
+  {
+    std::vector<int> logical(n ? n : 1);
+    for (int i = 0; i < n; ++i) logical[i] = s->prims[i].p[15] > 0.f ? (int)s->prims[i].p[15] - 1 : i;   // p[15] = logical id + 1, 0 = array index
+    CK(s->d_logical.ensure(n));
+    if (n) CK(cudaMemcpy(s->d_logical.p, logical.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
   }
   CK(s->d_hdr.ensure(n)); CK(s->d_a.ensure(n)); CK(s->d_b.ensure(n)); CK(s->d_c.ensure(n)); CK(s->d_d.ensure(n));
   if (n) {

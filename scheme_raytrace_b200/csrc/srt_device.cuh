@@ -25,6 +25,8 @@ struct DScene {
   const float4* tex;        // 2 per texture: (kind even odd scale as int bits / float) (r g b 0)
   const float4* ranvec;     // 256 unit gradient vectors (perlin.scm:33)
   const uint8_t* perm;      // 3 x 256: perm-x, perm-y, perm-z (perlin.scm:34-36)
+  const float4* patch_cp;   // 16 control points per (sub-)patch (north-star extension)
+  const int* prim_logical;  // logical primitive id reported by the parity hook (sub-patches share their parent's)
   const int* lights;        // primitive ids sampled by the hittable pdf (pdf.scm:28-32)
   int n_lights;
 };
@@ -277,6 +279,106 @@ static __device__ __noinline__ bool isect_bezier(float4 pa, float4 pb, float4 pc
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bicubic Bezier PATCH (north-star extension; the reference only has the curve).  Same
+// specification as the oracle (DESIGN.md "Patches"): ray-space projection of bezier.scm, depth-2
+// quadtree subdivision by de Casteljau (done once on the host: 16 leaves per patch), hull culling,
+// Newton on (S.x, S.y) = 0 from each leaf's centre, t = S.z / |d|.
+struct Net { float3 q[4][4]; };
+__device__ __forceinline__ void bern(float s, float b[4], float db[4]) {
+  float m = 1.0f - s;
+  b[0] = m * m * m; b[1] = 3.0f * s * m * m; b[2] = 3.0f * s * s * m; b[3] = s * s * s;
+  db[0] = -3.0f * m * m; db[1] = 3.0f * m * m - 6.0f * s * m; db[2] = 6.0f * s * m - 3.0f * s * s; db[3] = 3.0f * s * s;
+}
+__device__ __forceinline__ void patch_eval(const Net& N, float s, float t, float3& S, float3& Su, float3& Sv) {
+  float bs[4], dbs[4], bt[4], dbt[4]; bern(s, bs, dbs); bern(t, bt, dbt);
+  S = Su = Sv = v3(0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      S = S + N.q[i][j] * (bs[i] * bt[j]); Su = Su + N.q[i][j] * (dbs[i] * bt[j]); Sv = Sv + N.q[i][j] * (bs[i] * dbt[j]);
+    }
+}
+__device__ __forceinline__ void cubic_split(const float3 c0, const float3 c1, const float3 c2, const float3 c3, float3 l[4], float3 r[4]) {
+  float3 ab = (c0 + c1) * 0.5f, bc = (c1 + c2) * 0.5f, cd = (c2 + c3) * 0.5f;
+  float3 abc = (ab + bc) * 0.5f, bcd = (bc + cd) * 0.5f, m = (abc + bcd) * 0.5f;
+  l[0] = c0; l[1] = ab; l[2] = abc; l[3] = m; r[0] = m; r[1] = bcd; r[2] = cd; r[3] = c3;
+}
+__device__ __forceinline__ bool net_cull(const Net& N, float zmin, float zmax) {
+  float mnx = N.q[0][0].x, mxx = mnx, mny = N.q[0][0].y, mxy = mny, mnz = N.q[0][0].z, mxz = mnz;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float3 q = N.q[i][j];
+      mnx = fminf(mnx, q.x); mxx = fmaxf(mxx, q.x); mny = fminf(mny, q.y); mxy = fmaxf(mxy, q.y); mnz = fminf(mnz, q.z); mxz = fmaxf(mxz, q.z); }
+  return mnx > 0.f || mxx < 0.f || mny > 0.f || mxy < 0.f || mxz < zmin || mnz > zmax;
+}
+// One LEAF sub-patch: the host pre-splits every patch SRT_PATCH_LEVELS = 2 levels (16 leaves,
+// separate LBVH leaves, so the BVH does the subdivision culling with cheap box tests); here only
+// hull cull + Newton from the leaf's centre, with the projected net held in registers (no local
+// memory: the smem-staged BVH leaves almost no L1).  dom = (u0, v0, size) of the leaf in the
+// parent patch's domain; u/v out are GLOBAL.
+static __device__ __noinline__ bool isect_patch(const float4* __restrict__ cp, float4 dom, float3 o, float3 dir, float tmin, float tbest,
+                                                float& tout, float& uout, float& vout) {
+  // ray-space projection (bezier.scm:13-55)
+  float3 ud = unit(dir);
+  float lx = ud.x, ly = -ud.z, lz = ud.y;
+  float dd = sqrtf(lx * lx + lz * lz);
+  float R00, R01, R02, R10, R11, R12, R20, R21, R22;
+  if (dd == 0.0f) {
+    float ang = (ly >= 0.0f) ? -0.5f * SRT_PI : 0.5f * SRT_PI;
+    float ca = cosf(ang), sa = sinf(ang);
+    R00 = 1; R01 = 0; R02 = 0; R10 = 0; R11 = ca; R12 = -sa; R20 = 0; R21 = sa; R22 = ca;
+  } else {
+    R00 = lz / dd; R01 = (-lx * ly) / dd; R02 = lx;
+    R10 = 0.0f;    R11 = dd;              R12 = ly;
+    R20 = -lx / dd; R21 = (-ly * lz) / dd; R22 = lz;
+  }
+  const float3 so = v3(o.x, -o.z, o.y);
+  float X[16], Y[16], Z[16];
+  float mnx = 3e38f, mxx = -3e38f, mny = 3e38f, mxy = -3e38f, mnz = 3e38f, mxz = -3e38f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float4 q = __ldg(&cp[k]);
+    float3 s = v3(q.x, -q.z, q.y) - so;
+    X[k] = s.x * R00 + s.y * R10 + s.z * R20; Y[k] = s.x * R01 + s.y * R11 + s.z * R21; Z[k] = s.x * R02 + s.y * R12 + s.z * R22;
+    mnx = fminf(mnx, X[k]); mxx = fmaxf(mxx, X[k]); mny = fminf(mny, Y[k]); mxy = fmaxf(mxy, Y[k]); mnz = fminf(mnz, Z[k]); mxz = fmaxf(mxz, Z[k]);
+  }
+  const float len = length(dir);
+  const float zmin = tmin * len, zmax = tbest * len;
+  if (mnx > 0.f || mxx < 0.f || mny > 0.f || mxy < 0.f || mxz < zmin || mnz > zmax) return false;   // hull misses the ray
+  float s = 0.5f, t = 0.5f; bool conv = false;
+  float bs[4], dbs[4], bt[4], dbt[4];
+  for (int it = 0; it < 8; ++it) {
+    bern(s, bs, dbs); bern(t, bt, dbt);
+    float Sx = 0.f, Sy = 0.f, Sux = 0.f, Suy = 0.f, Svx = 0.f, Svy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float rx = X[4 * i] * bt[0] + X[4 * i + 1] * bt[1] + X[4 * i + 2] * bt[2] + X[4 * i + 3] * bt[3];
+      float ry = Y[4 * i] * bt[0] + Y[4 * i + 1] * bt[1] + Y[4 * i + 2] * bt[2] + Y[4 * i + 3] * bt[3];
+      float dx = X[4 * i] * dbt[0] + X[4 * i + 1] * dbt[1] + X[4 * i + 2] * dbt[2] + X[4 * i + 3] * dbt[3];
+      float dy = Y[4 * i] * dbt[0] + Y[4 * i + 1] * dbt[1] + Y[4 * i + 2] * dbt[2] + Y[4 * i + 3] * dbt[3];
+      Sx = fmaf(bs[i], rx, Sx); Sy = fmaf(bs[i], ry, Sy); Sux = fmaf(dbs[i], rx, Sux); Suy = fmaf(dbs[i], ry, Suy); Svx = fmaf(bs[i], dx, Svx); Svy = fmaf(bs[i], dy, Svy);
+    }
+    float det = Sux * Svy - Svx * Suy;
+    if (!(fabsf(det) > 1e-30f)) break;
+    float ds = (-Sx * Svy + Sy * Svx) / det, dt = (-Sux * Sy + Suy * Sx) / det;
+    s += ds; t += dt;
+    if (!(fabsf(s) < 4.0f) || !(fabsf(t) < 4.0f)) break;
+    if (fmaxf(fabsf(ds), fabsf(dt)) < 1e-5f) { conv = true; break; }
+  }
+  if (!conv || s < -1e-3f || s > 1.0f + 1e-3f || t < -1e-3f || t > 1.0f + 1e-3f) return false;
+  s = fminf(fmaxf(s, 0.f), 1.f); t = fminf(fmaxf(t, 0.f), 1.f);
+  bern(s, bs, dbs); bern(t, bt, dbt);
+  float Sz = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) Sz = fmaf(bs[i], Z[4 * i] * bt[0] + Z[4 * i + 1] * bt[1] + Z[4 * i + 2] * bt[2] + Z[4 * i + 3] * bt[3], Sz);
+  if (!(Sz > zmin && Sz < zmax)) return false;
+  tout = Sz / len; uout = dom.x + s * dom.z; vout = dom.y + t * dom.z;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exact-tie rule: the order-independent restatement of hit-obj-list's
 // sequential "later object replaces the best iff t < best (sphere-type) or t <= best (rect-type,
 // curve)".  ids are positions in the reference's flattened object list.
@@ -294,16 +396,16 @@ struct Hit { float t; int prim; float u, v; bool incl; };
 // One leaf primitive against the ray (world space in, candidate merged into `h`).  MASK is the
 // set of primitive kinds present in the scene (bit = SRT_PRIM_*): the extend kernel is compiled
 // per mask so that e.g. sphere-only scenes carry no rect / instance / Bezier code or registers.
-#define SRT_MASK_ALL 0x7f
+#define SRT_MASK_ALL 0xff
 template <int MASK, class PrimSrc>
 __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin,
                                                const RngAddr& ra, Hit& h) {
-  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40;
+  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40, HAS_PATCH = MASK & 0x80;
   constexpr bool SINGLE_KIND = (MASK & (MASK - 1)) == 0;
   float4 a = ps.a(id);
-  int type, xform = -1;
-  if (SINGLE_KIND && !HAS_RECT) type = HAS_SPHERE ? SRT_PRIM_SPHERE : (HAS_MOVING ? SRT_PRIM_MOVING_SPHERE : SRT_PRIM_BEZIER);
-  else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; }
+  int type, xform = -1, aux = 0;
+  if (SINGLE_KIND && (MASK & 0x23)) type = HAS_SPHERE ? SRT_PRIM_SPHERE : (HAS_MOVING ? SRT_PRIM_MOVING_SPHERE : SRT_PRIM_BEZIER);
+  else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; aux = hdr.w; }
   float t = 0.f, u = 0.f, v = 0.f; bool ok = false;
   if (HAS_SPHERE && type == SRT_PRIM_SPHERE) {
     ok = isect_sphere(xyz(a), a.w, o, d, inv_a, tmin, t);
@@ -317,6 +419,8 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     ok = isect_rect(type, a, k, oo, dd, tmin, ti, have_t, t, u, v);
   } else if (HAS_BEZIER && type == SRT_PRIM_BEZIER) {
     ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
+  } else if (HAS_PATCH && type == SRT_PRIM_PATCH) {
+    ok = isect_patch(sc.patch_cp + 16 * aux, __ldg(&sc.prim_b[id]), o, d, tmin, h.t, t, u, v);
   } else if (HAS_MEDIUM && type == SRT_PRIM_CONSTANT_MEDIUM) {
     // geometry.scm:545-578.  Two closest-hit queries on the boundary shapes, then the free flight
     // -log(xi)/density.  The reference clamps the exit to t-max = closest-so-far; accepting
@@ -338,14 +442,34 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
       }
     }
   }
+  (void)aux;
   bool incl = prim_inclusive(type);
   if (ok && accept_hit(t, id, incl, h.t, h.prim, h.incl)) { h.t = t; h.prim = id; h.u = u; h.v = v; h.incl = incl; }
+}
+
+// world-space normal of a (sub-)patch at the global (u, v): Su x Sv accumulated row by row so
+// that the shade kernel never holds the 4x4 net in registers
+__device__ __forceinline__ float3 patch_normal(const float4* __restrict__ cp, float4 dom, float hu, float hv, float3 d) {
+  const float s = (hu - dom.x) / dom.z, t = (hv - dom.y) / dom.z;
+  float bt[4], dbt[4]; bern(t, bt, dbt);
+  const float m = 1.0f - s;
+  float3 Su = v3(0.f, 0.f, 0.f), Sv = v3(0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const float bi = i == 0 ? m * m * m : (i == 1 ? 3.0f * s * m * m : (i == 2 ? 3.0f * s * s * m : s * s * s));
+    const float dbi = i == 0 ? -3.0f * m * m : (i == 1 ? 3.0f * m * m - 6.0f * s * m : (i == 2 ? 6.0f * s * m - 3.0f * s * s : 3.0f * s * s));
+    const float3 q0 = xyz(__ldg(&cp[4 * i])), q1 = xyz(__ldg(&cp[4 * i + 1])), q2 = xyz(__ldg(&cp[4 * i + 2])), q3 = xyz(__ldg(&cp[4 * i + 3]));
+    Su = Su + (q0 * bt[0] + q1 * bt[1] + q2 * bt[2] + q3 * bt[3]) * dbi;
+    Sv = Sv + (q0 * dbt[0] + q1 * dbt[1] + q2 * dbt[2] + q3 * dbt[3]) * bi;
+  }
+  float3 n = unit(cross(Su, Sv));
+  return dot(n, d) > 0.0f ? -n : n;
 }
 
 // Hit-record completion: p and normal in world space (ray.scm:27 make-hit-record fields).
 // geometry.scm:158-160 (sphere), :386-387 (rects), :438 (flip), :473/:526-535 (instances),
 // bezier.scm:209-211 (Q9: p along the raw direction, normal = -dir).
-__device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t, float3 o, float3 d, float time, float3& p, float3& n, int& material) {
+__device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t, float hu, float hv, float3 o, float3 d, float time, float3& p, float3& n, int& material) {
   int4 hdr = __ldg(&sc.prim_hdr[prim]);
   int type = hdr.x & 0xff;
   material = hdr.y;
@@ -365,6 +489,9 @@ __device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t
     } else {
       p = madd(d, t, o);
     }
+  } else if (type == SRT_PRIM_PATCH) {                // normal = Su x Sv at (u, v), facing the ray
+    p = madd(d, t, o);
+    n = patch_normal(sc.patch_cp + 16 * hdr.w, __ldg(&sc.prim_b[prim]), hu, hv, d);
   } else if (type == SRT_PRIM_CONSTANT_MEDIUM) {      // geometry.scm:567-571: normal (1,0,0), phase-function material
     p = madd(d, t, o);
     n = v3(1.f, 0.f, 0.f);

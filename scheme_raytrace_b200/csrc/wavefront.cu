@@ -227,8 +227,76 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
   }
 }
 
+// Variant for scenes with EXPENSIVE primitives (Bezier curve / patch, constant medium: thousands of
+// instructions per test).  Interleaving such a test with traversal serialises it lane by lane
+// (each lane reaches its leaf in a different iteration).  Here a lane that reaches an expensive
+// leaf PARKS; a warp vote runs the test block only when >= EXT_PARK_VOTE lanes are parked or no
+// lane can make progress otherwise, so the block executes with many active lanes ("deferred
+// candidate queue", one or two entries per lane, in registers).  Cheap primitives (spheres,
+// rects) are still intersected immediately.
+constexpr int EXT_PARK_VOTE = 12;
+template <bool SMEM, int MASK, bool CACHE, class PrimSrc>
+__device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
+                                                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
+                                                     float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (sc.n_surf == 0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
+    return;
+  }
+  Trav T;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < count; base += gridDim.x * blockDim.x) {   // warp-uniform
+    const int i = base + lane;
+    bool more = i < count;
+    const float4 d4 = more ? ray_d[i] : make_float4(1.f, 1.f, 1.f, 0.f);
+    trav_init(T, more ? ray_o[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4, tmax, i);
+    {
+      const int sd = __float_as_int(d4.w);
+      T.ra.seed = seed; T.ra.pixel = (state && more) ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
+      T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
+    }
+    int park0 = -1, park1 = -1;
+    for (;;) {
+      const bool parked = park0 >= 0;
+      const unsigned pm = __ballot_sync(full, parked);
+      const unsigned rm = __ballot_sync(full, more && !parked);
+      if ((pm | rm) == 0u) break;
+      if (__popc(pm) >= EXT_PARK_VOTE || rm == 0u) {
+        if (parked) {
+#ifdef SRT_COUNT_STEPS
+          T.ntests++;
+#endif
+          intersect_prim<MASK>(sc, ps, park0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+          park0 = park1; park1 = -1;
+        }
+        continue;
+      }
+      if (more && !parked) {
+        int pend0 = -1, pend1 = -1;
+        more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+        while (pend0 >= 0) {
+          const int type = ps.hdr(pend0).x & 0xff;
+          if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
+          else {
+#ifdef SRT_COUNT_STEPS
+            T.ntests++;
+#endif
+            intersect_prim<MASK & 0x1f>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+          }
+          pend0 = pend1; pend1 = -1;
+        }
+      }
+    }
+#ifdef SRT_COUNT_STEPS
+    T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
+#endif
+    if (i < count) hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
+  }
+}
+
 template <bool SMEM, int MASK, bool CACHE>
-__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x60) ? 2 : ((MASK & 0x1c) ? 3 : 4))
+__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0xe0) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
          float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
   extern __shared__ float4 smem[];
@@ -244,10 +312,12 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
     PrimShared ps{sh, sa};
-    extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    if (MASK & 0xe0) extend_loop_deferred<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    else extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    if (MASK & 0xe0) extend_loop_deferred<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    else extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   }
 }
 
@@ -279,7 +349,7 @@ k_shade(DScene sc, SrtRenderParams p, int g,
         accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d));
       } else {
         float3 pt, n; int material;
-        complete_hit(sc, prim, h4.x, o, d, o4.w, pt, n, material);
+        complete_hit(sc, prim, h4.x, h4.z, h4.w, o, d, o4.w, pt, n, material);
         RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
         Scatter s = scatter<EST>(sc, material, d, pt, n, h4.z, h4.w, addr, p.quirks);
         if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
@@ -351,7 +421,7 @@ __global__ void k_complete_hits(DScene sc, const float4* __restrict__ ray_o, con
 #endif
   if (r.prim >= 0) {
     float3 p, nn; int m;
-    complete_hit(sc, r.prim, h4.x, xyz(o4), xyz(d4), o4.w, p, nn, m);
+    complete_hit(sc, r.prim, h4.x, h4.z, h4.w, xyz(o4), xyz(d4), o4.w, p, nn, m);
     r.t = h4.x; r.u = h4.z; r.v = h4.w; r.material = m;
     int type = sc.prim_hdr[r.prim].x & 0xff;
 #ifndef SRT_COUNT_STEPS
@@ -360,6 +430,7 @@ __global__ void k_complete_hits(DScene sc, const float4* __restrict__ ray_o, con
     (void)type;
 #endif
     r.p[0] = p.x; r.p[1] = p.y; r.p[2] = p.z; r.n[0] = nn.x; r.n[1] = nn.y; r.n[2] = nn.z;
+    r.prim = sc.prim_logical[r.prim];
   }
   out[i] = r;
 }
@@ -429,7 +500,7 @@ static ExtendVariant g_variants[2][4][2];
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
   if ((mask & ~0x03) == 0) return 1;
-  if ((mask & 0x60) == 0) return 2;
+  if ((mask & 0xe0) == 0) return 2;
   return 3;
 }
 template <bool SMEM, bool CACHE> static ExtendFn variant_fn_m(int v) {

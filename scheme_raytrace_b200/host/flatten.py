@@ -22,11 +22,38 @@ assert PRIM_DTYPE.itemsize == 80 and XFORM_DTYPE.itemsize == 20 and MATERIAL_DTY
 assert TEXTURE_DTYPE.itemsize == 32 and CAMERA_DTYPE.itemsize == 96
 
 SKY_GRADIENT, SKY_BLACK = 0, 1
+PATCH_HOST_LEVELS = 2          # each bicubic patch becomes 4**2 = 16 sub-patch primitives (separate LBVH leaves)
+
+
+def _split_cubic(c):
+    ab, bc, cd = 0.5 * (c[0] + c[1]), 0.5 * (c[1] + c[2]), 0.5 * (c[2] + c[3])
+    abc, bcd = 0.5 * (ab + bc), 0.5 * (bc + cd)
+    m_ = 0.5 * (abc + bcd)
+    return np.stack([c[0], ab, abc, m_]), np.stack([m_, bcd, cd, c[3]])
+
+
+def split_patch(net, u0=0.0, v0=0.0, size=1.0, levels=PATCH_HOST_LEVELS):
+    """de Casteljau split at 0.5 in u then v, `levels` times: [(net(4,4,3), u0, v0, size), ...]."""
+    if levels == 0:
+        return [(net, u0, v0, size)]
+    lo, hi = np.zeros_like(net), np.zeros_like(net)
+    for j in range(4):
+        lo[:, j], hi[:, j] = _split_cubic(net[:, j])
+    out, h = [], size * 0.5
+    for half, (du, sub) in enumerate(((0.0, lo), (h, hi))):
+        a, b = np.zeros_like(net), np.zeros_like(net)
+        for i in range(4):
+            a[i], b[i] = _split_cubic(sub[i])
+        out += split_patch(a, u0 + du, v0, h, levels - 1) + split_patch(b, u0 + du, v0 + h, h, levels - 1)
+    return out
 
 
 @dataclass
 class FlatScene:
     prims: np.ndarray
+    patches: np.ndarray     # (n_sub_patches, 48) float32 control nets of the pre-split bicubic patches
+    logical: np.ndarray     # array position -> logical primitive id (== oracle leaf id)
+    first_of_logical: np.ndarray   # logical id -> first array position
     xforms: np.ndarray
     materials: np.ndarray
     textures: np.ndarray
@@ -37,7 +64,7 @@ class FlatScene:
     texture_objs: list
 
     def h2d_bytes(self):
-        return int(self.prims.nbytes + self.xforms.nbytes + self.materials.nbytes + self.textures.nbytes + self.camera.nbytes)
+        return int(self.prims.nbytes + self.patches.nbytes + self.xforms.nbytes + self.materials.nbytes + self.textures.nbytes + self.camera.nbytes)
 
 
 def _compose(chain):
@@ -71,6 +98,7 @@ def sky_kind(sky_function):
 
 def flatten_scene(scene):
     prims, xforms, leaves = [], [], []
+    patches = []
     boundary = []          # boundary primitives of constant media: appended after the surface primitives
     xform_ids = {}
     mats, mat_ids, texs, tex_ids = [], {}, [], {}
@@ -107,8 +135,8 @@ def flatten_scene(scene):
             for b in mine:
                 if b[0] not in (g.SPHERE, g.XY_RECT, g.XZ_RECT, g.YZ_RECT):
                     raise ValueError("constant-medium boundaries must be spheres / rects / boxes")
-            prims.append((g.CONSTANT_MEDIUM, 0, mat_id(obj.material), -1, [obj.params[0], ("boundary", len(boundary)), len(mine)]))
-            boundary.extend((k, fl | 2, mat_id(obj.material), xf, prm) for (k, fl, _m, xf, prm) in mine)
+            prims.append((g.CONSTANT_MEDIUM, 0, mat_id(obj.material), -1, [obj.params[0], ("boundary", len(boundary)), len(mine)], len(leaves)))
+            boundary.extend((k, fl | 2, mat_id(obj.material), xf, prm, -1) for (k, fl, _m, xf, prm, _l) in mine)
             leaves.append(obj)
         elif obj.kind == g.FLIP:
             walk(obj.children[0], chain, flip ^ 1, out, out_leaves)
@@ -121,7 +149,16 @@ def flatten_scene(scene):
                     xform_ids[chain] = len(xforms)
                     xforms.append(_compose(chain))
                 xf = xform_ids[chain]
-            out.append((obj.kind, flip, mat_id(obj.material), xf, obj.params))
+            if obj.kind == g.PATCH:
+                if xf >= 0:
+                    raise ValueError("bicubic patches cannot be instanced (transform the control net instead)")
+                net = np.asarray(obj.params, dtype=np.float64).reshape(4, 4, 3)
+                for sub, su0, sv0, ssize in split_patch(net):       # 16 sub-patches share one logical id
+                    patches.append(sub.reshape(48))
+                    out.append((obj.kind, flip, mat_id(obj.material), xf, (len(patches) - 1, su0, sv0, ssize), len(out_leaves)))
+                out_leaves.append(obj)
+                return
+            out.append((obj.kind, flip, mat_id(obj.material), xf, obj.params, len(out_leaves)))
             out_leaves.append(obj)
 
     for o in scene.obj_list:
@@ -130,10 +167,16 @@ def flatten_scene(scene):
     n_surface = len(prims)
     allp = prims + boundary                  # boundary primitives (flag 2) form a suffix, outside the LBVH
     P = np.zeros(len(allp), dtype=PRIM_DTYPE)
-    for i, (kind, flip, m, xf, prm) in enumerate(allp):
+    logical = np.zeros(len(allp), dtype=np.int32)
+    for i, (kind, flip, m, xf, prm, lid) in enumerate(allp):
         P[i]["type"], P[i]["flags"], P[i]["material"], P[i]["xform"] = kind, flip, m, xf
         prm = [n_surface + q[1] if isinstance(q, tuple) else q for q in prm]
         P[i]["p"][:len(prm)] = prm
+        logical[i] = lid if lid >= 0 else len(leaves) + (i - n_surface)
+        P[i]["p"][15] = logical[i] + 1
+    first_of_logical = np.full(int(logical.max()) + 1 if len(logical) else 0, -1, dtype=np.int32)
+    for i in range(len(allp) - 1, -1, -1):
+        first_of_logical[logical[i]] = i
     X = np.zeros(len(xforms), dtype=XFORM_DTYPE)
     for i, (s, c, off) in enumerate(xforms):
         X[i]["sin_t"], X[i]["cos_t"], X[i]["off"] = s, c, off
@@ -146,4 +189,5 @@ def flatten_scene(scene):
     C = np.zeros(1, dtype=CAMERA_DTYPE)
     if scene.camera is not None:
         C.view("<f4")[:] = np.asarray(camera_to_floats(scene.camera), dtype=np.float32)
-    return FlatScene(P, X, M, T, C, sky_kind(scene.sky_function), leaves, [m for m, _ in mats], [tx for tx, _, _ in texs])
+    PT = np.asarray(patches, dtype=np.float32).reshape(-1, 48)
+    return FlatScene(P, PT, logical, first_of_logical, X, M, T, C, sky_kind(scene.sky_function), leaves, [m for m, _ in mats], [tx for tx, _, _ in texs])

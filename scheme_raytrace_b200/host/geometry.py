@@ -11,9 +11,9 @@ from dataclasses import dataclass, field
 from typing import Any, List, Optional, Tuple
 
 # node kinds (leaf kinds equal the SRT_PRIM_* codes of include/srt.h)
-SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM = 0, 1, 2, 3, 4, 5, 6
+SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH = 0, 1, 2, 3, 4, 5, 6, 7
 FLIP, LIST, TRANSLATE, ROTATE_Y = 16, 17, 18, 19
-LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM)
+LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH)
 
 
 @dataclass(eq=False)

@@ -36,6 +36,7 @@ class Renderer:
         f, lib, h = self.flat, self.lib, self.h
         ffi.check(lib.srt_scene_set_prims(h, _ptr(f.prims), len(f.prims)), "set_prims")
         ffi.check(lib.srt_scene_set_xforms(h, _ptr(f.xforms), len(f.xforms)), "set_xforms")
+        ffi.check(lib.srt_scene_set_patches(h, _ptr(f.patches), len(f.patches)), "set_patches")
         ffi.check(lib.srt_scene_set_materials(h, _ptr(f.materials), len(f.materials)), "set_materials")
         ffi.check(lib.srt_scene_set_textures(h, _ptr(f.textures), len(f.textures)), "set_textures")
         rv, px, py, pz = self.perlin

@@ -181,6 +181,54 @@ def cornell_bezier(size_x=200, size_y=200):
     return g.make_scene(objs, cornell_camera(size_x, size_y), sky_color)
 
 
+_K = 0.5522847498307936      # cubic Bezier circle constant
+
+# Profile curves (radius, height) of the rotationally symmetric parts of the Utah teapot (rim,
+# upper body, lower body, lid knob, lid, bottom).  Handle and spout are NOT included: their
+# control nets cannot be reproduced from memory and there is no network (SURVEY §7 "hard parts").
+TEAPOT_PROFILES = [
+    [(1.4, 2.25), (1.3375, 2.38125), (1.4375, 2.38125), (1.5, 2.25)],
+    [(1.5, 2.25), (1.75, 1.725), (2.0, 1.2), (2.0, 0.75)],
+    [(2.0, 0.75), (2.0, 0.3), (1.5, 0.075), (1.5, 0.0)],
+    [(0.0, 3.15), (0.8, 3.15), (0.0, 2.7), (0.2, 2.55)],
+    [(0.2, 2.55), (0.4, 2.4), (1.3, 2.4), (1.3, 2.25)],
+    [(1.5, 0.0), (1.5, -0.075), (1.425, -0.15), (0.0, -0.15)],
+]
+
+
+def revolve_profile(profile, material, center=(0.0, 0.0, 0.0), scale=1.0):
+    """Four bicubic patches = one cubic profile curve revolved about the y axis."""
+    quads = [((1, 0), (1, _K), (_K, 1), (0, 1)), ((0, 1), (-_K, 1), (-1, _K), (-1, 0)),
+             ((-1, 0), (-1, -_K), (-_K, -1), (0, -1)), ((0, -1), (_K, -1), (1, -_K), (1, 0))]
+    out = []
+    for q in quads:
+        cp = [[(center[0] + scale * r * cx, center[1] + scale * y, center[2] + scale * r * cz) for (cx, cz) in q] for (r, y) in profile]
+        out.append(b.make_bezier_patch(cp, material))
+    return out
+
+
+def teapot_patches(material, center=(0.0, 0.0, 0.0), scale=1.0):
+    return [pt for prof in TEAPOT_PROFILES for pt in revolve_profile(prof, material, center, scale)]
+
+
+def cfg5_patches(size_x=3840, size_y=2160):
+    """configs[4]: bicubic Bezier-patch scene — the rotationally symmetric 24 patches of the Utah
+    teapot (body, lid, bottom) in three materials' worth of copies on a checker ground, plus the
+    reference's three Bezier curves (main.scm:259-273).  Patches are a north-star extension
+    (absent upstream): parity vs the oracle's identical definition only."""
+    white = m.make_lambertian(t.constant_texture(v.vec3(0.73, 0.73, 0.73)))
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    gold = m.make_metal(t.constant_texture(v.vec3(0.8, 0.6, 0.2)), 0.1)
+    objs = [g.make_sphere(v.vec3(0, -1000, 0), 1000, m.make_lambertian(_checker()))]
+    objs += teapot_patches(white, (0.0, 0.15, 0.0), 1.0)
+    objs += teapot_patches(gold, (-4.5, 0.1, -1.0), 0.66)
+    objs += teapot_patches(red, (4.2, 0.1, 1.0), 0.66)
+    objs += [b.make_bezier(v.vec3(-3, 0.3, 3), v.vec3(-1, 2.0, 2.5), v.vec3(1, -1.0, 3.5), v.vec3(3, 0.3, 3), 0.1, red),
+             g.make_sphere(v.vec3(0, 4.2, 0), 0.5, m.make_dielectric(1.5))]
+    c = cam.make_camera(v.vec3(0, 5, 11), v.vec3(0, 1.3, 0), v.vec3(0, 1, 0), 35, size_x / size_y, 0, 1, 0, 1)
+    return g.make_scene(objs, c, sky_color)
+
+
 def test_scene2(size_x=200, size_y=200):
     """main.scm:316-328 test-scene2 (marble + lights, black sky)."""
     per_tex = t.marble_texture(1)
@@ -216,5 +264,6 @@ CONFIGS = {
     "cfg2": dict(scene=cfg2_random_spheres, width=1200, height=800, spp=500, max_depth=50, seed=2),
     "cfg3": dict(scene=cfg3_next_week, width=800, height=800, spp=1000, max_depth=50, seed=3),
     "cfg4": dict(scene=cfg4_cornell_box, width=1024, height=1024, spp=4096, max_depth=50, seed=4),
-    "cfg5": dict(scene=test_bezier, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
+    "cfg5": dict(scene=cfg5_patches, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
+    "cfg5_curves": dict(scene=test_bezier, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
 }

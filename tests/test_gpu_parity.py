@@ -12,7 +12,7 @@ SMALL = {"cfg1": (scenes.cfg1_weekend, 200, 100), "cfg2": (scenes.cfg2_random_sp
          "cfg3": (scenes.cfg3_next_week, 80, 80), "cfg4": (scenes.cfg4_cornell_box, 64, 64),
          "bezier": (scenes.test_bezier, 64, 64), "cornell_bezier": (scenes.cornell_bezier, 64, 64),
          "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64),
-         "smoke": (scenes.cornell_smoke, 64, 64)}
+         "smoke": (scenes.cornell_smoke, 64, 64), "patches": (scenes.cfg5_patches, 96, 54)}
 
 
 @pytest.fixture(scope="module", params=list(SMALL))
@@ -46,9 +46,11 @@ def test_prim_bounds_contain_oracle_hits(pair):
     o = S.trace_batch(rays.astype(np.float64))
     aabb = r.prim_bounds().astype(np.float64)
     hit = o["prim"] >= 0
-    if name in ("bezier", "cornell_bezier"):     # Q9: curve hit points are off the curve for |d| != 1
-        hit &= r.flat.prims["type"][np.maximum(o["prim"], 0)] != 5
-    b = aabb[o["prim"][hit]]
+    if name in ("bezier", "cornell_bezier", "patches"):     # Q9: curve hit points are off the curve for |d| != 1
+        hit &= r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]] != 5
+    if name == "patches":                                  # sub-patches: the parent's box is the union of 16 leaf boxes
+        hit &= r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]] != 7
+    b = aabb[r.flat.first_of_logical[o["prim"][hit]]]
     p = o["p"][hit]
     tol = 1e-4 * np.maximum(np.abs(p), 1.0)
     assert np.all(p >= b[:, :3] - tol) and np.all(p <= b[:, 3:] + tol)
@@ -60,7 +62,7 @@ def test_trace_batch_parity(pair, batch):
     if batch == "camera":
         rays = raybatch.camera_grid(r, 64, 64)
     else:
-        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name != "bezier" else 30000, 5)
+        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name not in ("bezier", "patches") else 30000, 5)
     rays64 = rays.astype(np.float64)
     gp = r.trace_batch(rays)
     o64 = S.trace_batch(rays64)
@@ -74,7 +76,7 @@ def test_trace_batch_parity(pair, batch):
     assert c["t_bad"] == 0 and c["n_bad"] == 0
     # uv: rects everywhere; spheres only where |p.y| <= 1 (Q5: asin of the raw point)
     hm = c["hit_mask"]
-    ptype = r.flat.prims["type"][np.maximum(o64["prim"], 0)]
+    ptype = r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o64["prim"], 0)]]
     uv_ok = hm & ((ptype >= 2) | (np.abs(o64["p"][:, 1]) <= 0.9))
     if uv_ok.any():
         assert np.max(np.abs(gp["u"][uv_ok] - o64["uv"][uv_ok, 0])) <= 2e-4
@@ -153,7 +155,7 @@ def test_raygen_parity(orc):
     r.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke", "patches"])
 def test_image_same_stream(name, orc):
     """Image parity under IDENTICAL Philox streams: GPU fp32 vs oracle f64 follow the same paths
     except where rounding flips a decision, so the per-pixel linear difference is tiny for almost

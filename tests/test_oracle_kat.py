@@ -182,3 +182,27 @@ def test_render_cfg1_smoke(orc):
     assert nrays > 40 * 20 * 4 and np.all(np.isfinite(a)) and a.min() >= 0
     top = a[-1].mean(axis=0) / 4                    # sky gradient at the top rows is bluish
     assert top[2] > top[0]
+
+
+def test_patch_flat_matches_plane(orc):
+    """Bicubic patch (north-star extension): a flat control net must intersect like the plane."""
+    from scheme_raytrace_b200.host import bezier as bz
+    cp = [[(-1 + i, -1 + j, -2.0) for j in range(4)] for i in range(4)]
+    S = orc.OracleScene(quantise=False, scene=_scene([bz.make_bezier_patch(cp, LAMB)]))
+    r = S.trace_batch([[0, 0, 0, 0, 0, -1, 0], [0.3, 0.7, 1, 0.1, -0.2, -2, 0], [5, 5, 0, 0, 0, -1, 0], [0, 0, -5, 0, 0, 1, 0]])
+    assert list(r["prim"]) == [0, 0, -1, 0] and np.allclose(r["t"][[0, 1, 3]], (2.0, 1.5, 3.0), atol=1e-9)
+    assert np.allclose(r["uv"][0], (1 / 3, 1 / 3), atol=1e-9) and np.allclose(r["n"][0], (0, 0, 1), atol=1e-9) and np.allclose(r["n"][3], (0, 0, -1), atol=1e-9)
+
+
+def test_patch_revolved_profile_is_round(orc):
+    """A revolved straight profile (cylinder r = 2): hits lie on the cylinder within the cubic
+    circle approximation error (2.7e-4 relative)."""
+    pts = scenes.revolve_profile([(2.0, 0.0), (2.0, 1.0), (2.0, 2.0), (2.0, 3.0)], LAMB)
+    S = orc.OracleScene(quantise=False, scene=_scene(pts))
+    rs = np.random.RandomState(3)
+    ang = rs.uniform(0, 2 * np.pi, 200)
+    rays = np.stack([6 * np.cos(ang), rs.uniform(0.2, 2.8, 200), 6 * np.sin(ang), -np.cos(ang), 0 * ang, -np.sin(ang), 0 * ang], axis=1)
+    r = S.trace_batch(rays)
+    assert np.all(r["prim"] >= 0)
+    rad = np.hypot(r["p"][:, 0], r["p"][:, 2])
+    assert np.max(np.abs(rad - 2.0)) < 2.0 * 3e-4 and np.allclose(r["t"], 6 - rad, atol=1e-9)

@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wave-spp", type=int, default=0, help="path-queue capacity in samples/pixel (0 = library default, ~8M paths)")
     args = ap.parse_args()
     cfg = workload(args.workload)
     if args.spp > 0:
@@ -189,7 +190,7 @@ def main():
     def step_device():
         """value: scene resident in HBM, accumulate into the device buffer, one NCCL reduce."""
         accum.zero_()
-        st = r.render_device(accum.data_ptr(), W, H, s_end - s_begin, max_depth=D, seed=SEED, spp_begin=s_begin)
+        st = r.render_device(accum.data_ptr(), W, H, s_end - s_begin, max_depth=D, seed=SEED, spp_begin=s_begin, wave_spp=args.wave_spp)
         sharding.reduce_accumulators(accum, dist)
         return st
 

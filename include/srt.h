@@ -93,7 +93,7 @@ typedef struct {
   uint32_t seed;               /* Philox key word 1                                      */
   int32_t quirks;              /* SRT_Q* bits                                            */
   float t_min;                 /* main.scm:104: 0.001                                    */
-  int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (~8M paths) */
+  int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (64 Mi paths) */
   int32_t estimator;           /* SRT_EST_*                                              */
   int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately (slower) */
 } SrtRenderParams;

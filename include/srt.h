@@ -143,7 +143,9 @@ int srt_scene_commit(SrtScene*);                  /* H2D + GPU LBVH build       
 /* LBVH inspection (bit-exact check against the host reference build) */
 int srt_bvh_node_count(SrtScene*);
 int srt_bvh_readback(SrtScene*, SrtBvhNode* nodes, int cap);
-int srt_bvh_keys_readback(SrtScene*, uint64_t* keys_sorted, int32_t* order, int cap);
+int srt_bvh_keys_readback(SrtScene*, uint64_t* keys_sorted, int32_t* order, int cap);   /* over the LBVH items */
+/* LBVH item -> primitive id, and the (<= 8) huge primitives kept out of the tree; returns #items */
+int srt_bvh_items_readback(SrtScene*, int32_t* item_prim, int cap, int32_t* global_prims8, int32_t* n_global);
 int srt_prim_bounds_readback(SrtScene*, float* aabbs6, int cap);
 
 /* fixed-ray-batch closest hit through the SAME extend kernel the renderer uses */

@@ -8,6 +8,9 @@
 // intrinsic so that the host reference (compiled with -ffp-contract=off) produces the same bits:
 //   centroid = 0.5*(min+max); g = min(uint(q * 2^21), 2^21-1), q = (c - cmin)/(cmax - cmin)
 //   key = 63-bit Morton (x highest); stable sort; Karras 2012 with index tie-break for equal keys
+//   primitives whose AABB extent is >= half the scene's (at most SRT_MAX_GLOBAL, largest first)
+//   are kept OUT of the tree and tested linearly before traversal (like the reference's own
+//   (list ground bvh-node) scenes, main.scm:215-235)
 //   stored child boxes = union of primitive AABBs as centre c = 0.5*(min+max) and half extent
 //   e = 0.5*(max-min) + S * 2^-21 (S = max |coordinate|; the pad covers fp32 rounding in c, e and in
 //   the traversal's FMA slab test)
@@ -84,10 +87,10 @@ __global__ void k_prim_bounds(DScene sc, float cam_t0, float cam_t1, float* __re
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 __global__ void k_bounds_init(int* b) { if (threadIdx.x < 3) b[threadIdx.x] = f2ord(BIG); else if (threadIdx.x < 6) b[threadIdx.x] = f2ord(-BIG); else if (threadIdx.x == 6) b[6] = f2ord(0.0f); }
-__global__ void k_bounds_reduce(int n, const float* __restrict__ aabb, int* __restrict__ b) {
+__global__ void k_bounds_reduce(int n, const int* __restrict__ item_prim, const float* __restrict__ aabb, int* __restrict__ b) {
   float cmin[3] = {BIG, BIG, BIG}, cmax[3] = {-BIG, -BIG, -BIG}, S = 0.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float* q = aabb + 6 * (size_t)i;
+    const float* q = aabb + 6 * (size_t)item_prim[i];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float c = __fmul_rn(0.5f, __fadd_rn(q[k], q[3 + k]));
@@ -116,10 +119,10 @@ __device__ __forceinline__ unsigned long long expand21(unsigned int v) {
   x = (x | x << 2) & 0x1249249249249249ull;
   return x;
 }
-__global__ void k_morton(int n, const float* __restrict__ aabb, const int* __restrict__ b, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+__global__ void k_morton(int n, const int* __restrict__ item_prim, const float* __restrict__ aabb, const int* __restrict__ b, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* q = aabb + 6 * (size_t)i;
+  const float* q = aabb + 6 * (size_t)item_prim[i];
   unsigned int g[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -206,7 +209,7 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
   if (a != b) return __clzll((long long)(a ^ b));
   return 64 + __clz(i ^ j);
 }
-__global__ void k_karras(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ order,
+__global__ void k_karras(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ order, const int* __restrict__ item_prim,
                          int4* __restrict__ links /* left right parent sibling per node */, int* __restrict__ leaf_parent) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
@@ -222,8 +225,8 @@ __global__ void k_karras(int n, const unsigned long long* __restrict__ keys, con
   do { t = (t + 1) >> 1; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
   int gamma = i + s * d + min(d, 0);
   int a = min(i, j), b = max(i, j);
-  int left = (a == gamma) ? ~order[gamma] : gamma;
-  int right = (b == gamma + 1) ? ~order[gamma + 1] : gamma + 1;
+  int left = (a == gamma) ? ~item_prim[order[gamma]] : gamma;          // leaf reference = ~primitive id
+  int right = (b == gamma + 1) ? ~item_prim[order[gamma + 1]] : gamma + 1;
   links[i].x = left; links[i].y = right;
   if (left >= 0) { links[left].z = i; links[left].w = right; } else leaf_parent[gamma] = i;
   if (right >= 0) { links[right].z = i; links[right].w = left; } else leaf_parent[gamma + 1] = i;
@@ -271,11 +274,14 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
 }
 
 // n <= 1: a single node.
-__global__ void k_single_node(int n, const float* __restrict__ aabb, const int* __restrict__ b, float4* __restrict__ nodes,
+__global__ void k_single_node(int n, const int* __restrict__ item_prim, const float* __restrict__ aabb_all, const int* __restrict__ b, float4* __restrict__ nodes,
                               unsigned long long* keys, int* order) {
   if (threadIdx.x != 0) return;
   float l[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int prim = 0;
   if (n == 1) {
+    prim = item_prim[0];
+    const float* aabb = aabb_all + 6 * (size_t)prim;
     const float pad = __fmul_rn(ord2f(b[6]), 1.0f / 2097152.0f);
     for (int k = 0; k < 3; ++k) { l[k] = __fmul_rn(0.5f, __fadd_rn(aabb[k], aabb[3 + k])); l[3 + k] = __fadd_rn(__fmul_rn(0.5f, __fsub_rn(aabb[3 + k], aabb[k])), pad); }
     order[0] = 0;
@@ -284,29 +290,34 @@ __global__ void k_single_node(int n, const float* __restrict__ aabb, const int* 
   nodes[0] = make_float4(l[0], l[1], l[2], l[3]);
   nodes[1] = make_float4(l[4], l[5], l[0], l[1]);
   nodes[2] = make_float4(l[2], l[3], l[4], l[5]);
-  nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), __int_as_float(-1), __int_as_float(-1));
+  nodes[3] = make_float4(__int_as_float(~prim), __int_as_float(~prim), __int_as_float(-1), __int_as_float(-1));
 }
 
 }  // namespace
 
-// Builds the LBVH for sc (device arrays already uploaded).  All launches on `stream`.
-// Outputs: d_aabb[6n], d_keys[n] (sorted), d_order[n], d_nodes[4*max(n-1,1)]; returns launches.
-int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream) {
-  int n = sc.n_surf, launches = 0;
+// Phase A: primitive AABBs of every scene surface (by primitive id).
+int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream) {
+  if (sc.n_surf > 0) k_prim_bounds<<<(sc.n_surf + 127) / 128, 128, 0, stream>>>(sc, cam_t0, cam_t1, B.d_aabb);
+  return 1;
+}
+
+// Phase B: LBVH over the n_items primitives listed in B.d_item_prim (the "huge" primitives that
+// are tested linearly before traversal are left out).  All launches on `stream`.
+int srt_lbvh_build(int n_items, LbvhBuffers& B, cudaStream_t stream) {
+  int n = n_items, launches = 0;
   k_bounds_init<<<1, 32, 0, stream>>>(B.d_bounds); ++launches;
   if (n > 0) {
-    k_prim_bounds<<<(n + 127) / 128, 128, 0, stream>>>(sc, cam_t0, cam_t1, B.d_aabb); ++launches;
     int rb = min((n + 255) / 256, 1024);
-    k_bounds_reduce<<<rb, 256, 0, stream>>>(n, B.d_aabb, B.d_bounds); ++launches;
+    k_bounds_reduce<<<rb, 256, 0, stream>>>(n, B.d_item_prim, B.d_aabb, B.d_bounds); ++launches;
   }
   if (n <= 1) {
-    k_single_node<<<1, 32, 0, stream>>>(n, B.d_aabb, B.d_bounds, B.d_nodes, B.d_keys[0], B.d_order[0]); ++launches;
+    k_single_node<<<1, 32, 0, stream>>>(n, B.d_item_prim, B.d_aabb, B.d_bounds, B.d_nodes, B.d_keys[0], B.d_order[0]); ++launches;
     B.sorted = 0;
     int one = n;   // depth = number of internal nodes on the path
     cudaMemcpyAsync(B.d_depth, &one, sizeof(int), cudaMemcpyHostToDevice, stream);
     return launches;
   }
-  k_morton<<<(n + 255) / 256, 256, 0, stream>>>(n, B.d_aabb, B.d_bounds, B.d_keys[0], B.d_order[0]); ++launches;
+  k_morton<<<(n + 255) / 256, 256, 0, stream>>>(n, B.d_item_prim, B.d_aabb, B.d_bounds, B.d_keys[0], B.d_order[0]); ++launches;
   int nblk = (n + RS_BLOCK - 1) / RS_BLOCK;
   int cur = 0;
   for (int pass = 0; pass < 8; ++pass) {
@@ -319,7 +330,7 @@ int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B,
   B.sorted = cur;
   cudaMemsetAsync(B.d_visit, 0, sizeof(int) * (size_t)(n - 1), stream);
   cudaMemsetAsync(B.d_depth, 0, sizeof(int), stream);
-  k_karras<<<(n - 1 + 127) / 128, 128, 0, stream>>>(n, B.d_keys[cur], B.d_order[cur], B.d_links, B.d_leaf_parent); ++launches;
+  k_karras<<<(n - 1 + 127) / 128, 128, 0, stream>>>(n, B.d_keys[cur], B.d_order[cur], B.d_item_prim, B.d_links, B.d_leaf_parent); ++launches;
   k_refit<<<(n + 127) / 128, 128, 0, stream>>>(n, B.d_order[cur], B.d_aabb, B.d_links, B.d_leaf_parent, B.d_bounds, B.d_nbox, B.d_visit, B.d_nodes, B.d_depth); ++launches;
   return launches;
 }

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <vector>
 #include <string>
+#include <algorithm>
 #include "srt_host.h"
 
 namespace {
@@ -44,9 +45,10 @@ struct SrtScene {
   // device tables
   DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
   // LBVH
-  LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth;
+  LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth, d_item_prim;
+  std::vector<int> item_prim, global_prims;
   DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
-  int n_nodes = 0, n_surf = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
+  int n_nodes = 0, n_surf = 0, n_items = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
   // wavefront
   WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
   void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
@@ -56,7 +58,8 @@ struct SrtScene {
 
 static void fill_dscene(SrtScene* s) {
   DScene& d = s->ds;
-  d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_xforms = (int)s->xforms.size();
+  d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_items = s->n_items;
+  d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
   d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
@@ -120,7 +123,7 @@ void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
   s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
-  s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_visit.release(); s->d_depth.release();
+  s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
   for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
   s->w_hit.release(); s->w_accum.release(); s->w_ctrl.release(); s->d_accum.release();
@@ -275,18 +278,44 @@ int srt_scene_commit(SrtScene* s) {
     dc.lens_radius = cm.lens_radius; dc.time0 = cm.time0; dc.time1 = cm.time1;
   } else std::memset(&s->dcam, 0, sizeof(s->dcam));
   // ---- LBVH ------------------------------------------------------------------------------------
-  const int nint = ns > 1 ? ns - 1 : 1, nn = n ? n : 1;
+  const int nn = n ? n : 1;
   CK(s->d_aabb.ensure(6 * (size_t)nn)); CK(s->d_bounds.ensure(8)); CK(s->d_keys0.ensure(nn)); CK(s->d_keys1.ensure(nn));
   CK(s->d_order0.ensure(nn)); CK(s->d_order1.ensure(nn)); CK(s->d_hist.ensure(256 * (size_t)((nn + 255) / 256)));
-  CK(s->d_links.ensure(nint)); CK(s->d_leaf_parent.ensure(nn)); CK(s->d_nbox.ensure(6 * (size_t)nint)); CK(s->d_visit.ensure(nint));
-  CK(s->d_depth.ensure(1)); CK(s->d_nodes.ensure(4 * (size_t)nint));
+  CK(s->d_links.ensure(nn)); CK(s->d_leaf_parent.ensure(nn)); CK(s->d_nbox.ensure(6 * (size_t)nn)); CK(s->d_visit.ensure(nn));
+  CK(s->d_depth.ensure(1)); CK(s->d_nodes.ensure(4 * (size_t)nn)); CK(s->d_item_prim.ensure(nn));
   LbvhBuffers& B = s->lb;
   B.d_aabb = s->d_aabb.p; B.d_bounds = s->d_bounds.p; B.d_keys[0] = s->d_keys0.p; B.d_keys[1] = s->d_keys1.p;
   B.d_order[0] = s->d_order0.p; B.d_order[1] = s->d_order1.p; B.d_hist = s->d_hist.p; B.d_links = s->d_links.p;
   B.d_leaf_parent = s->d_leaf_parent.p; B.d_nbox = s->d_nbox.p; B.d_visit = s->d_visit.p; B.d_depth = s->d_depth.p; B.d_nodes = s->d_nodes.p;
-  s->n_nodes = nint;
+  B.d_item_prim = s->d_item_prim.p;
+  s->n_nodes = 1; s->n_items = 0;
   fill_dscene(s);
-  s->commit_launches = srt_lbvh_build(s->ds, s->dcam.time0, s->dcam.time1, B, stream);
+  // phase A: primitive AABBs on the device, read back (n x 24 B) to pick the huge primitives
+  s->commit_launches = srt_lbvh_bounds(s->ds, s->dcam.time0, s->dcam.time1, B, stream);
+  std::vector<float> hb(6 * (size_t)(ns ? ns : 1));
+  if (ns) CK(cudaMemcpyAsync(hb.data(), B.d_aabb, sizeof(float) * 6 * (size_t)ns, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  {
+    // rule (DESIGN.md "LBVH"): extent e_i = max side of AABB i, E = max side of the union; i is
+    // global iff e_i >= 0.5 E; at most SRT_MAX_GLOBAL, largest extent first (ties: lower id)
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    std::vector<float> ext(ns);
+    for (int i = 0; i < ns; ++i) { float e = 0.f; for (int k = 0; k < 3; ++k) { float a0 = hb[6 * i + k], a1 = hb[6 * i + 3 + k]; lo[k] = a0 < lo[k] ? a0 : lo[k]; hi[k] = a1 > hi[k] ? a1 : hi[k]; e = (a1 - a0) > e ? (a1 - a0) : e; } ext[i] = e; }
+    float E = 0.f; for (int k = 0; k < 3; ++k) E = (hi[k] - lo[k]) > E ? (hi[k] - lo[k]) : E;
+    std::vector<int> cand;
+    for (int i = 0; i < ns; ++i) if (ns > 2 && ext[i] >= 0.5f * E) cand.push_back(i);
+    std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return ext[x] > ext[y]; });
+    if ((int)cand.size() > SRT_MAX_GLOBAL) cand.resize(SRT_MAX_GLOBAL);
+    std::sort(cand.begin(), cand.end());
+    s->global_prims = cand; s->item_prim.clear();
+    size_t gi = 0;
+    for (int i = 0; i < ns; ++i) { if (gi < cand.size() && cand[gi] == i) { ++gi; continue; } s->item_prim.push_back(i); }
+  }
+  const int nitems = (int)s->item_prim.size();
+  if (nitems) CK(cudaMemcpyAsync(B.d_item_prim, s->item_prim.data(), sizeof(int) * (size_t)nitems, cudaMemcpyHostToDevice, stream));
+  s->n_items = nitems; s->n_nodes = nitems > 1 ? nitems - 1 : 1;
+  fill_dscene(s);
+  s->commit_launches += srt_lbvh_build(nitems, B, stream);
   CK(cudaGetLastError());
   int depth = 0;
   CK(cudaMemcpyAsync(&depth, B.d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -307,9 +336,17 @@ int srt_bvh_readback(SrtScene* s, SrtBvhNode* nodes, int cap) {
   CK(cudaMemcpy(nodes, s->d_nodes.p, sizeof(SrtBvhNode) * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
   return 0;
 }
+int srt_bvh_items_readback(SrtScene* s, int32_t* item_prim, int cap, int32_t* global_prims8, int32_t* n_global) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (cap < s->n_items || !item_prim || !global_prims8 || !n_global) return fail(SRT_ERR_ARG, "bvh_items_readback: bad argument");
+  for (int i = 0; i < s->n_items; ++i) item_prim[i] = s->item_prim[i];
+  *n_global = (int)s->global_prims.size();
+  for (size_t i = 0; i < s->global_prims.size(); ++i) global_prims8[i] = s->global_prims[i];
+  return s->n_items;
+}
 int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
-  int n = s->n_surf;
+  int n = s->n_items;
   if (cap < n) return fail(SRT_ERR_ARG, "bvh_keys_readback: capacity too small");
   if (n) {
     CK(cudaMemcpy(keys, s->lb.d_keys[s->lb.sorted], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));

@@ -9,11 +9,14 @@
 
 #define SRT_PI 3.14159265358979323846f
 #define SRT_MAX_FLOAT 999999999999.0f  // constant.scm:6
+#define SRT_MAX_GLOBAL 8
 
 // ------------------------------------------------------------------------------------------------
 // Device view of a committed scene ("primitive SoA, material and texture tables, Perlin tables").
 struct DScene {
-  int n_prims, n_surf, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;   // n_surf = scene surfaces (LBVH leaves); the rest are medium boundaries
+  int n_prims, n_surf, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;   // n_surf = scene surfaces; the rest are medium boundaries
+  int n_items;              // surfaces inside the LBVH
+  int n_global; int global_prims[SRT_MAX_GLOBAL];   // huge surfaces tested linearly before traversal
   const int4* prim_hdr;     // x = type | flags << 8, y = material, z = xform, w = 0
   const float4* prim_a;     // sphere: c.xyz r | rect: a0 a1 b0 b1 | bezier: A.xyz width
   const float4* prim_b;     // moving: c1.xyz time0 | rect: k | bezier: B.xyz

@@ -5,7 +5,8 @@
 #include "srt_device.cuh"
 
 struct LbvhBuffers {
-  float* d_aabb = nullptr;                 // 6 per primitive
+  float* d_aabb = nullptr;                 // 6 per primitive (by primitive id)
+  int* d_item_prim = nullptr;              // LBVH item -> primitive id (huge primitives are left out of the tree)
   int* d_bounds = nullptr;                 // 7 ordered-int floats: cmin[3] cmax[3] S
   unsigned long long* d_keys[2] = {nullptr, nullptr};
   int* d_order[2] = {nullptr, nullptr};
@@ -19,7 +20,8 @@ struct LbvhBuffers {
   int sorted = 0;                          // which of d_keys/d_order holds the sorted result
 };
 
-int srt_lbvh_build(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
+int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
+int srt_lbvh_build(int n_items, LbvhBuffers& B, cudaStream_t stream);
 
 // Wavefront queues (SoA, 16-byte vectorised).  Two generations (ping-pong) of the ray/state
 // arrays: shade reads generation g and writes the compacted survivors into generation g^1, regen

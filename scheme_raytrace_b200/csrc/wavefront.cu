@@ -209,7 +209,9 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
       T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
       T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
     }
-    bool more = true;
+    for (int g = 0; g < sc.n_global; ++g)      // huge primitives first, all lanes together (uniform control flow)
+      intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+    bool more = sc.n_items > 0;
     while (more) {
       int pend0 = -1, pend1 = -1;
       more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
@@ -256,6 +258,10 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
       T.ra.seed = seed; T.ra.pixel = (state && more) ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
       T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
     }
+    if (more)
+      for (int g = 0; g < sc.n_global; ++g)
+        intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+    more = more && sc.n_items > 0;
     int park0 = -1, park1 = -1;
     for (;;) {
       const bool parked = park0 >= 0;

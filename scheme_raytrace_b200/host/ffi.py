@@ -24,7 +24,7 @@ SYMBOLS = [
     "srt_device_count", "srt_init", "srt_last_error", "srt_shutdown", "srt_measure_fp32_peak", "srt_scene_create", "srt_scene_destroy",
     "srt_scene_set_prims", "srt_scene_set_xforms", "srt_scene_set_patches", "srt_scene_set_materials", "srt_scene_set_textures",
     "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_set_lights", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
-    "srt_bvh_keys_readback", "srt_prim_bounds_readback", "srt_trace_batch", "srt_render_host", "srt_render_device",
+    "srt_bvh_keys_readback", "srt_bvh_items_readback", "srt_prim_bounds_readback", "srt_trace_batch", "srt_render_host", "srt_render_device",
     "srt_resolve_device", "srt_resolve_host", "srt_save_ppm", "srt_eval_texture", "srt_eval_raygen",
 ]
 
@@ -57,6 +57,7 @@ def load():
     lib.srt_bvh_node_count.argtypes = [vp]
     lib.srt_bvh_readback.argtypes = [vp, vp, i32]
     lib.srt_bvh_keys_readback.argtypes = [vp, vp, vp, i32]
+    lib.srt_bvh_items_readback.argtypes = [vp, vp, i32, vp, vp]
     lib.srt_prim_bounds_readback.argtypes = [vp, vp, i32]
     lib.srt_trace_batch.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp]
     lib.srt_render_host.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]

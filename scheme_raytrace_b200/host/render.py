@@ -64,8 +64,17 @@ class Renderer:
         ffi.check(self.lib.srt_bvh_readback(self.h, _ptr(out), n), "bvh_readback")
         return out
 
-    def bvh_keys(self):
+    def bvh_items(self):
+        """(item -> primitive id of the LBVH leaves, ids of the huge primitives tested before traversal)"""
         n = int(np.sum((self.flat.prims["flags"] & 2) == 0))
+        items, glob, ng = np.zeros(max(n, 1), dtype=np.int32), np.zeros(8, dtype=np.int32), C.c_int32(0)
+        k = self.lib.srt_bvh_items_readback(self.h, _ptr(items), n, _ptr(glob), C.byref(ng))
+        if k < 0:
+            ffi.check(k, "bvh_items_readback")
+        return items[:k], glob[:ng.value]
+
+    def bvh_keys(self):
+        n = len(self.bvh_items()[0])
         keys, order = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.int32)
         ffi.check(self.lib.srt_bvh_keys_readback(self.h, _ptr(keys), _ptr(order), n), "bvh_keys_readback")
         return keys, order

@@ -30,9 +30,19 @@ def test_lbvh_bit_exact(pair, orc):
     byte for byte, over the same (GPU-computed) primitive AABBs."""
     name, scene, r, S, w, h = pair
     aabb = r.prim_bounds()
+    items, glob = r.bvh_items()
+    assert sorted(items.tolist() + glob.tolist()) == list(range(len(aabb)))     # every surface is in the tree or global
+    ext = (aabb[:, 3:] - aabb[:, :3]).max(axis=1)
+    E = (aabb[:, 3:].max(axis=0) - aabb[:, :3].min(axis=0)).max()
+    assert all(ext[gp] >= 0.5 * E for gp in glob) and (len(glob) == 8 or len(aabb) <= 2 or not np.any(ext[items] >= 0.5 * E))
     keys_g, order_g = r.bvh_keys()
     nodes_g = r.bvh_nodes()
-    keys_h, order_h, nodes_h = orc.lbvh_build(aabb)
+    keys_h, order_h, nodes_h = orc.lbvh_build(aabb[items])            # host reference over the same AABBs
+    for side in ("left", "right", "sibling"):                         # its leaf refs are item indices -> primitive ids
+        leaf = nodes_h[side] < 0
+        if side == "sibling":
+            leaf[0] = False                                           # the root's -1 means "none", not leaf ~0
+        nodes_h[side][leaf] = ~items[~nodes_h[side][leaf]]
     assert np.array_equal(keys_g, keys_h)
     assert np.array_equal(order_g, order_h)
     assert nodes_g.tobytes() == nodes_h.tobytes()

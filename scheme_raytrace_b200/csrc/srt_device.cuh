@@ -640,8 +640,15 @@ template <int EST>
 __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float3 d_in, float3 p, float3 n, float u, float v,
                                            const RngAddr& addr, int quirks) {
   Scatter r; r.valid = false; r.emitted = v3(0.f, 0.f, 0.f); r.weight = v3(1.f, 1.f, 1.f); r.dir = v3(0.f, 1.f, 0.f);
-  int4 m = __ldg(&sc.mats[material]);
-  float param = __int_as_float(m.z);
+  const int4 m = __ldg(&sc.mats[material]);
+  const float param = __int_as_float(m.z);
+  // Shared by every material, so done ONCE before the switch with all hit lanes active instead of
+  // once per divergent branch: the first Philox block of this bounce and the texture lookup
+  // ((t:value albedo 0 0 p) for lambertian / metal, (t:value emit u v p) for lights).
+  const float4 xi = rng_block(addr, 0);
+  const bool uv_tex = m.x == SRT_MAT_DIFFUSE_LIGHT || m.x == SRT_MAT_ISOTROPIC;
+  float3 tex = v3(1.f, 1.f, 1.f);
+  if (m.x != SRT_MAT_DIELECTRIC) tex = tex_value(sc, m.y, uv_tex ? u : 0.0f, uv_tex ? v : 0.0f, p, quirks);
   switch (m.x) {
     case SRT_MAT_LAMBERTIAN: {                                   // material.scm:24-39 + onb.scm:8-16
       float len_n = length(n);
@@ -649,7 +656,6 @@ __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float
       float3 a = (fabsf(w.x) > 0.9f) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
       float3 vv = unit(cross(w, a));
       float3 uu = cross(w, vv);
-      float4 xi = rng_block(addr, 0);
       float3 rc = random_cosine_direction(xi.x, xi.y, quirks);
       if (EST == SRT_EST_MIXTURE && sc.n_lights > 0) {
         // mixture(hittable(lights), cosine) pdf.scm:34-41; block 0 = (r1, r2, xi_choice, xi_light), block 1 = (xa, xb)
@@ -666,24 +672,24 @@ __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float
         float spdf = fmaxf(0.0f, dot(n, unit(dir))) / SRT_PI;
         r.dir = dir;
         r.valid = spdf > 0.0f && pdf_val > 0.0f;             // zero-weight paths end here
-        if (r.valid) r.weight = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks) * spdf * (1.0f / pdf_val);
+        if (r.valid) r.weight = tex * spdf * (1.0f / pdf_val);
         break;
       }
       float3 target = uu * rc.x + vv * rc.y + w * rc.z;
       r.dir = unit(target);
       float pdf_cos = dot(w, r.dir);                              // pdf  = (w . dir)/pi
       float spdf_cos = fmaxf(0.0f, dot(n, r.dir));                // spdf = max(0, n . dir)/pi   (material.scm:33-36)
-      float3 atten = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks);   // (t:value albedo 0 0 p)
-      r.weight = atten * spdf_cos * (1.0f / pdf_cos);             // main.scm:113-118
+      r.weight = tex * spdf_cos * (1.0f / pdf_cos);               // main.scm:113-118
       r.valid = true;
       break;
     }
     case SRT_MAT_METAL: {                                        // material.scm:45-57 (specular: weight = albedo)
       float3 refl = reflect(unit(d_in), n);
-      float3 f = random_in_unit_sphere(addr, 0);
+      float3 f = v3(2.0f * xi.x - 1.0f, 2.0f * xi.y - 1.0f, 2.0f * xi.z - 1.0f);   // util.scm:9-15, iteration 0 = block 0
+      if (!(dot(f, f) < 1.0f)) f = random_in_unit_sphere(addr, 1);
       r.dir = refl + f * param;
       r.valid = dot(r.dir, n) > 0.0f;
-      r.weight = tex_value(sc, m.y, 0.0f, 0.0f, p, quirks);
+      r.weight = tex;
       break;
     }
     case SRT_MAT_DIELECTRIC: {                                   // material.scm:76-101 (Q10)
@@ -704,18 +710,19 @@ __device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float
         refr = (vv - outward * dt) * ni_over_nt - outward * sqrtf(disc);
         reflect_prob = schlick(cosine, ref_idx);
       }
-      float4 xi = rng_block(addr, 0);
       r.dir = (xi.x < reflect_prob) ? refl : refr;
       r.valid = true;
       break;
     }
     case SRT_MAT_DIFFUSE_LIGHT: {                                // material.scm:103-111
-      if (dot(n, d_in) < 0.0f) r.emitted = tex_value(sc, m.y, u, v, p, quirks);
+      if (dot(n, d_in) < 0.0f) r.emitted = tex;
       break;
     }
     case SRT_MAT_ISOTROPIC: {                                    // absent upstream; book semantics
-      r.dir = random_in_unit_sphere(addr, 0);
-      r.weight = tex_value(sc, m.y, u, v, p, quirks);
+      float3 f = v3(2.0f * xi.x - 1.0f, 2.0f * xi.y - 1.0f, 2.0f * xi.z - 1.0f);
+      if (!(dot(f, f) < 1.0f)) f = random_in_unit_sphere(addr, 1);
+      r.dir = f;
+      r.weight = tex;
       r.valid = true;
       break;
     }

@@ -331,7 +331,7 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
 // shade: one bounce of `color` (main.scm:100-121) for every live path + compaction of survivors
 // into the other queue generation (warp ballot -> per-warp count -> one atomic per CTA).
 template <int EST>
-__global__ void __launch_bounds__(SHD_THREADS)
+__global__ void __launch_bounds__(SHD_THREADS, 4)
 k_shade(DScene sc, SrtRenderParams p, int g,
         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
         float4* __restrict__ ray_o_next, float4* __restrict__ ray_d_next, float4* __restrict__ state_next,

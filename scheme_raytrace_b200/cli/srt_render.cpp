@@ -1,0 +1,92 @@
+// srt_render — command-line host over the C-ABI (include/srt.h): reads a flat scene file
+// (scheme_raytrace_b200/host/scenefile.py documents the format; scheme/srt-scene.scm writes it from
+// Gauche), commits it, renders and writes the PPM exactly like save-as-ppm (main.scm:439-450).
+//
+//   srt_render scene.srt [--width W] [--height H] [--spp S] [--depth D] [--seed X] [--quirks Q]
+//                        [--estimator E] [--device N] [--out test.ppm]
+//
+// This is the route by which an unmodified Gauche scene script drives the GPU path without a
+// compiled Gauche extension: (use srt-scene) ... (srt:write-scene scene "scene.srt"), then this.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <fstream>
+#include <sstream>
+#include "../../include/srt.h"
+
+static bool expect(std::istream& in, const char* word) { std::string w; in >> w; return (bool)in && w == word; }
+#define CHECK(call) do { int rc_ = (call); if (rc_ != 0) { std::fprintf(stderr, "srt_render: %s failed (%d): %s\n", #call, rc_, srt_last_error()); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::fprintf(stderr, "usage: srt_render scene.srt [--width W --height H --spp S --depth D --seed X --quirks Q --estimator E --device N --out file.ppm]\n"); return 2; }
+  int width = 200, height = 200, spp = 1, depth = 100, quirks = SRT_QUIRKS_REFERENCE, estimator = 0, device = 0;   // main.scm:26,126-127 defaults
+  unsigned seed = 1; std::string out = "test.ppm";
+  for (int i = 2; i + 1 < argc; i += 2) {
+    std::string k = argv[i]; const char* v = argv[i + 1];
+    if (k == "--width") width = std::atoi(v); else if (k == "--height") height = std::atoi(v); else if (k == "--spp") spp = std::atoi(v);
+    else if (k == "--depth") depth = std::atoi(v); else if (k == "--seed") seed = (unsigned)std::strtoul(v, nullptr, 10);
+    else if (k == "--quirks") quirks = std::atoi(v); else if (k == "--estimator") estimator = std::atoi(v);
+    else if (k == "--device") device = std::atoi(v); else if (k == "--out") out = v;
+    else { std::fprintf(stderr, "srt_render: unknown option %s\n", k.c_str()); return 2; }
+  }
+  std::ifstream in(argv[1]);
+  if (!in) { std::fprintf(stderr, "srt_render: cannot open %s\n", argv[1]); return 1; }
+  int version = 0, sky = 0, n = 0;
+  if (!expect(in, "srt-scene") || !(in >> version) || version != 1) { std::fprintf(stderr, "srt_render: not an srt-scene 1 file\n"); return 1; }
+  if (!expect(in, "sky") || !(in >> sky)) return 1;
+  SrtCamera cam; float* cf = (float*)&cam;
+  if (!expect(in, "camera")) return 1;
+  for (int i = 0; i < 24; ++i) in >> cf[i];
+  std::vector<float> ranvec(768); std::vector<int32_t> perm(768);
+  if (!expect(in, "perlin-ranvec")) return 1;
+  for (auto& x : ranvec) in >> x;
+  if (!expect(in, "perlin-perm")) return 1;
+  for (auto& x : perm) in >> x;
+  if (!expect(in, "textures") || !(in >> n)) return 1;
+  std::vector<SrtTexture> tex(n);
+  for (auto& t : tex) { std::memset(&t, 0, sizeof(t)); in >> t.kind >> t.even >> t.odd >> t.scale >> t.rgb[0] >> t.rgb[1] >> t.rgb[2]; }
+  if (!expect(in, "materials") || !(in >> n)) return 1;
+  std::vector<SrtMaterial> mat(n);
+  for (auto& m : mat) { std::memset(&m, 0, sizeof(m)); in >> m.kind >> m.tex >> m.param; }
+  if (!expect(in, "xforms") || !(in >> n)) return 1;
+  std::vector<SrtXform> xf(n);
+  for (auto& x : xf) in >> x.sin_t >> x.cos_t >> x.off[0] >> x.off[1] >> x.off[2];
+  if (!expect(in, "patches") || !(in >> n)) return 1;
+  std::vector<float> patches(48 * (size_t)n); int npatch = n;
+  for (auto& x : patches) in >> x;
+  if (!expect(in, "prims") || !(in >> n)) return 1;
+  std::vector<SrtPrim> prims(n);
+  for (auto& p : prims) { in >> p.type >> p.flags >> p.material >> p.xform; for (int i = 0; i < 16; ++i) in >> p.p[i]; }
+  if (!expect(in, "lights") || !(in >> n)) return 1;
+  std::vector<int32_t> lights(n);
+  for (auto& l : lights) in >> l;
+  if (!in) { std::fprintf(stderr, "srt_render: truncated scene file\n"); return 1; }
+
+  CHECK(srt_init(device));
+  SrtScene* sc = srt_scene_create();
+  if (!sc) { std::fprintf(stderr, "srt_render: %s\n", srt_last_error()); return 1; }
+  CHECK(srt_scene_set_prims(sc, prims.data(), (int)prims.size()));
+  CHECK(srt_scene_set_xforms(sc, xf.data(), (int)xf.size()));
+  CHECK(srt_scene_set_patches(sc, patches.data(), npatch));
+  CHECK(srt_scene_set_materials(sc, mat.data(), (int)mat.size()));
+  CHECK(srt_scene_set_textures(sc, tex.data(), (int)tex.size()));
+  CHECK(srt_scene_set_perlin(sc, ranvec.data(), perm.data(), perm.data() + 256, perm.data() + 512));
+  CHECK(srt_scene_set_camera(sc, &cam));
+  CHECK(srt_scene_set_lights(sc, lights.data(), (int)lights.size()));
+  CHECK(srt_scene_commit(sc));
+  SrtRenderParams p; std::memset(&p, 0, sizeof(p));
+  p.width = width; p.height = height; p.spp_begin = 0; p.spp_end = spp; p.max_depth = depth; p.sky = sky; p.seed = seed;
+  p.quirks = quirks; p.t_min = 0.001f; p.estimator = estimator;
+  std::vector<float> rgb((size_t)width * height * 3, 0.0f);
+  SrtStats st;
+  CHECK(srt_render_host(sc, &p, rgb.data(), &st));          // (trace-all scene 1..spp)
+  std::vector<uint8_t> img(rgb.size());
+  CHECK(srt_resolve_host(rgb.data(), width, height, spp, img.data()));
+  CHECK(srt_save_ppm(out.c_str(), img.data(), width, height));
+  std::fprintf(stderr, "srt_render: %llu rays in %.3f ms (%.1f Mrays/s), %d kernel launches, LBVH %d nodes depth %d -> %s\n",
+               (unsigned long long)st.rays, st.ms_total, st.rays / (st.ms_total * 1e3), st.kernel_launches, st.bvh_nodes, st.bvh_depth, out.c_str());
+  srt_scene_destroy(sc); srt_shutdown();
+  return 0;
+}

@@ -29,8 +29,9 @@ B_PER_RAY_EXTEND = 48     # the extend kernel's part: ray read 32 B + hit record
 # per-ray counts MEASURED by the instrumented build (tools/step_stats.py, profiles/r1_step_stats.txt):
 # node steps per ray (2 box tests each), primitive tests per ray, dominant primitive cost, shade cost.
 FP32_MODEL = {  # workload: (node steps/ray, prim tests/ray, flops per prim test, shade flops/ray)
-    "cfg1": (3.0, 2.5, 35, 110), "cfg2": (12.0, 1.7, 35, 100), "cfg3": (12.0, 1.9, 45, 160),
-    "cfg4": (8.0, 1.3, 42, 100), "cfg5": (14.0, 2.2, 600, 100), "cfg5_curves": (9.0, 2.0, 1500, 100),
+    # (profiles/r1_step_stats.txt; prim tests include the huge primitives tested before traversal)
+    "cfg1": (2.0, 2.4, 35, 110), "cfg2": (9.3, 2.0, 35, 100), "cfg3": (9.8, 2.1, 45, 160),
+    "cfg4": (2.8, 8.3, 24, 100), "cfg5": (11.0, 2.3, 600, 100), "cfg5_curves": (3.0, 1.7, 1500, 100),
 }
 
 

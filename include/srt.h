@@ -95,7 +95,7 @@ typedef struct {
   float t_min;                 /* main.scm:104: 0.001                                    */
   int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (64 Mi paths) */
   int32_t estimator;           /* SRT_EST_*                                              */
-  int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately (slower) */
+  int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately (slower); [1] = 1: no CUDA graph */
 } SrtRenderParams;
 
 typedef struct {

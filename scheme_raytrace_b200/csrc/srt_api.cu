@@ -52,6 +52,7 @@ struct SrtScene {
   // wavefront
   WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
   void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  cudaStream_t work = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // graph capture needs a non-legacy stream
   DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host
   DScene ds; DCamera dcam;
 };
@@ -79,6 +80,8 @@ static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
     CK(cudaMallocHost(&s->h_ctrl, 2 * srt_wave_ctrl_bytes()));
     CK(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
     W.h_ctrl = s->h_ctrl; W.poll_events = s->poll_ev;
+    CK(cudaStreamCreateWithFlags(&s->work, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -129,6 +132,9 @@ void srt_scene_destroy(SrtScene* s) {
   s->w_hit.release(); s->w_accum.release(); s->w_ctrl.release(); s->d_accum.release();
   if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
   for (int i = 0; i < 2; ++i) if (s->poll_ev[i]) cudaEventDestroy(s->poll_ev[i]);
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
+  if (s->work) cudaStreamDestroy(s->work);
   delete s;
 }
 
@@ -401,15 +407,20 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
   if (cap > total) cap = total;
   if (cap > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: queue of %zu paths too large", cap);
   if (int rc = ensure_wave(s, cap, npix)) return rc;
-  cudaStream_t stream = 0;
+  // The loop runs on the scene's own non-blocking stream (CUDA-graph capture is not allowed on the
+  // legacy default stream) but is ordered inside stream 0 by events on both sides, so callers that
+  // bracket the call with events / work on the default stream (torch's current stream) stay correct.
+  cudaStream_t stream = s->work;
+  CK(cudaEventRecord(s->ev_in, 0)); CK(cudaStreamWaitEvent(stream, s->ev_in, 0));
   RenderLaunch L = make_launch(s, p);
   const bool profile = p->reserved[0] == 1;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, stream));
-  WaveBuffers W = s->wb; W.capacity = cap;
+  WaveBuffers W = s->wb; W.capacity = cap; W.use_graph = p->reserved[1] != 1;
   SrtStats st; std::memset(&st, 0, sizeof(st));
   srt_wavefront_render(L, W, d_rgb_sum, stream, &st, profile);
   CK(cudaEventRecord(e1, stream));
+  CK(cudaEventRecord(s->ev_out, stream)); CK(cudaStreamWaitEvent(0, s->ev_out, 0));
   CK(cudaEventSynchronize(e1));
   CK(cudaGetLastError());
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));

@@ -36,6 +36,7 @@ struct WaveBuffers {
   void* ctrl = nullptr;                    // WaveCtrl (device)
   void* h_ctrl = nullptr;                  // 2 x WaveCtrl (pinned host)
   void* poll_events = nullptr;             // 2 x cudaEvent_t
+  bool use_graph = true;                   // replay the iteration batches as a CUDA graph
 };
 
 struct RenderLaunch {
@@ -47,6 +48,7 @@ struct RenderLaunch {
 // returns number of kernel launches; d_rgb_sum accumulates W*H*3 floats
 int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile);
 size_t srt_wave_ctrl_bytes();
+void srt_extend_prepare(const RenderLaunch& L);
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, uint32_t seed, cudaStream_t stream);
 int srt_launch_complete_hits(const DScene& sc, const float4* ray_o, const float4* ray_d, const float4* hit, int n, SrtHit* d_out, cudaStream_t stream);

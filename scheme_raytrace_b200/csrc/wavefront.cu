@@ -537,6 +537,8 @@ static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   return e;
 }
 
+void srt_extend_prepare(const RenderLaunch& L) { (void)extend_variant(L); }
+
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, uint32_t seed, cudaStream_t stream) {
   const ExtendVariant& e = extend_variant(L);
@@ -563,12 +565,11 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   float acc_ext = 0.f, acc_shd = 0.f; int n_ext = 0;
   if (profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
-  const int BATCH = 8;
+  const int BATCH = 8;                          // even, so every batch has identical launch parameters
   WaveCtrl* h = (WaveCtrl*)W.h_ctrl;            // pinned, 2 slots
   cudaEvent_t* ev = (cudaEvent_t*)W.poll_events;
   int g = 0, parity = 1, batch = 0;
-  bool done = false;
-  while (!done) {
+  auto enqueue_batch = [&]() {
     for (int k = 0; k < BATCH; ++k) {
       if (profile) cudaEventRecord(e0, stream);
       launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.state[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, p.seed, stream);
@@ -580,6 +581,23 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
       launches += 2;
       g ^= 1; parity ^= 1;
     }
+  };
+  // The batch of 8 iterations (24 launches) is captured once into a CUDA graph and replayed: the
+  // deep-path drain tail and small frames (cfg1: 320k paths) are launch-bound otherwise.
+  cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
+  if (!profile && W.use_graph) {
+    srt_extend_prepare(L);                      // function attributes / occupancy query outside the capture
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int l0 = launches;
+      enqueue_batch();
+      launches = l0;
+      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) { gexec = nullptr; cudaGetLastError(); }
+    } else cudaGetLastError();
+  }
+  bool done = false;
+  while (!done) {
+    if (gexec) { cudaGraphLaunch(gexec, stream); launches += 3 * BATCH; }
+    else enqueue_batch();
     cudaMemcpyAsync(&h[batch & 1], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
     cudaEventRecord(ev[batch & 1], stream);
     if (batch >= 1) {                             // look at the PREVIOUS batch while this one runs
@@ -589,6 +607,8 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
     }
     ++batch;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
   k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches;
   cudaMemcpyAsync(&h[0], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
   cudaStreamSynchronize(stream);

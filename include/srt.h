@@ -34,6 +34,8 @@ enum {
   SRT_PRIM_YZ_RECT = 4,       /* geometry.scm:414 make-yz-rect        p = y0 y1 z0 z1 k                    */
   SRT_PRIM_BEZIER = 5,        /* bezier.scm:61   make-bezier          p = a.xyz b.xyz c.xyz d.xyz width    */
   SRT_PRIM_CONSTANT_MEDIUM = 6, /* geometry.scm:545 make-constant-medium p = density, first boundary prim, #boundary prims */
+  SRT_PRIM_KLEIN = 8,         /* geometry.scm:644 make-klein (sphere-traced IIS fractal, no bounding box: always
+                               * tested before traversal, at most 8 per scene)   p = centre.xyz */
   SRT_PRIM_PATCH = 7          /* bicubic Bezier (sub-)patch (north-star extension, absent upstream):
                                * p = index into the patch table, u0, v0, size of this sub-patch in its parent's
                                * (u,v) domain; the host pre-splits each patch 2 levels into 16 of these */

@@ -39,7 +39,7 @@ static const double MAX_FLOAT = 999999999999.0;
 static const double PI = 3.141592653589793;  // math.const pi
 
 enum NodeKind { N_SPHERE = 0, N_MOVING_SPHERE = 1, N_XY_RECT = 2, N_XZ_RECT = 3, N_YZ_RECT = 4,
-                N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_PATCH = 7, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
+                N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_PATCH = 7, N_KLEIN = 8, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
 enum MatKind { M_LAMBERTIAN = 0, M_METAL = 1, M_DIELECTRIC = 2, M_DIFFUSE_LIGHT = 3, M_ISOTROPIC = 4 };
 enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3 };
 enum SkyKind { SKY_GRADIENT = 0, SKY_BLACK = 1 };
@@ -497,6 +497,52 @@ template <class T> static bool hit_patch(const Scene& sc, const Node& nd, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// geometry.scm:590-664 — Klein / IIS fractal: a distance field made by inverting the point in six
+// spheres (at most 10 times), sphere-traced for at most 100 steps; normal by central differences.
+static const double KLEIN_POS[6][3] = {{300, 300, 0}, {300, -300, 0}, {-300, 300, 0}, {-300, -300, 0}, {0, 0, 424.26}, {0, 0, -424.26}};   // :590-595
+template <class T> static T klein_dist(V3<T> center, V3<T> pos) {              // dist-func geometry.scm:602-624
+  const T R = T(300), R2 = R * R, KR = T(125);                                 // :596-598
+  pos = sub(pos, center);
+  T dr = 1;
+  for (int iter = 0;;) {
+    if (iter >= 10) return T(0.7) * ((length(pos) - KR) / std::fabs(dr));      // +max-klein-loop+ :600
+    bool inverted = false;
+    for (int k = 0; k < 6; ++k) {
+      V3<T> sp = ld3<T>(KLEIN_POS[k]);
+      if (length(sub(pos, sp)) < R) {
+        V3<T> diff = sub(pos, sp);
+        dr = dr * (R2 / dot(diff, diff));
+        pos = add(scale(scale(diff, R2), T(1) / (length(diff) * length(diff))), sp);
+        ++iter; inverted = true;
+        break;
+      }
+    }
+    if (!inverted) return T(0.7) * ((length(pos) - KR) / std::fabs(dr));
+  }
+}
+template <class T> static V3<T> klein_normal(V3<T> center, V3<T> p) {          // get-normal geometry.scm:626-632
+  const T e = T(0.01);
+  return unit(mk<T>(klein_dist(center, add(p, mk<T>(e, 0, 0))) - klein_dist(center, sub(p, mk<T>(e, 0, 0))),
+                    klein_dist(center, add(p, mk<T>(0, e, 0))) - klein_dist(center, sub(p, mk<T>(0, e, 0))),
+                    klein_dist(center, add(p, mk<T>(0, 0, e))) - klein_dist(center, sub(p, mk<T>(0, 0, e)))));
+}
+template <class T> static bool hit_klein(const Node& nd, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec) {   // make-klein :644-664
+  V3<T> center = ld3<T>(nd.p);
+  V3<T> ray_pos = r.o; T ray_length = 0;
+  for (int iter = 0; iter < 100; ++iter) {                                     // +max-marching-loop+ :635
+    T dist = klein_dist(center, ray_pos);
+    ray_length = ray_length + dist;
+    ray_pos = add(r.o, scale(r.d, ray_length));
+    if (dist < T(0.001) && tmin < ray_length && ray_length < tmax) {
+      rec.t = ray_length; rec.p = point_at(r, ray_length); rec.n = klein_normal(center, ray_pos);
+      rec.mat = nd.material; rec.leaf = nd.leaf_id; rec.u = 0; rec.v = 0;
+      return true;
+    }
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // geometry.scm:14-15 — (hit obj r t-min t-max), dispatch over the object kinds.
 template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r, T tmin, T tmax, HitRec<T>& rec, const RngAddr* rng = nullptr) {
   const Node& nd = sc.nodes[id];
@@ -522,6 +568,7 @@ template <class T> static bool hit_node(const Scene& sc, int id, const Ray<T>& r
     case N_XZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 1, r, tmin, tmax, rec);
     case N_YZ_RECT: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_rect(nd, 0, r, tmin, tmax, rec);
     case N_BEZIER: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_bezier(nd, r, tmin, tmax, rec, (BezStats*)nullptr);
+    case N_KLEIN: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_klein(nd, r, tmin, tmax, rec);
     case N_PATCH: if (sc.exclude_leaf >= 0 && nd.leaf_id == sc.exclude_leaf) return false; return hit_patch(sc, nd, r, tmin, tmax, rec);
     case N_CONSTANT_MEDIUM: {                              // geometry.scm:545-578
       // phase function = lambertian (isotropic is commented out upstream, geometry.scm:546).

@@ -8,7 +8,7 @@ rendering without the CUDA library fails loudly.
 """
 from .host import vec, constant, texture, material, geometry, bezier, camera, perlin, points, pdf  # noqa: F401
 from .host.flatten import flatten_scene, FlatScene  # noqa: F401
-from .host.render import Renderer, trace_all, save_as_ppm, correct_gamma_quantise  # noqa: F401
+from .host.render import Renderer, ProgressiveRenderer, trace_all, save_as_ppm, correct_gamma_quantise  # noqa: F401
 from .host import scenes  # noqa: F401
 
 QUIRKS_REFERENCE = 15

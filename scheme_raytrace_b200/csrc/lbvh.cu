@@ -44,6 +44,8 @@ __device__ void prim_box(const DScene& sc, int i, float cam_t0, float cam_t1, fl
     if (type == SRT_PRIM_XY_RECT) { mn = v3(a.x, a.z, k - 0.0001f); mx = v3(a.y, a.w, k + 0.0001f); }
     else if (type == SRT_PRIM_XZ_RECT) { mn = v3(a.x, k - 0.0001f, a.z); mx = v3(a.y, k + 0.0001f, a.w); }
     else { mn = v3(k - 0.0001f, a.x, a.z); mx = v3(k + 0.0001f, a.y, a.w); }
+  } else if (type == SRT_PRIM_KLEIN) {                             // no bounding box upstream (geometry.scm:662-663): never enters the tree
+    mn = v3(a.x, a.y, a.z); mx = mn;
   } else if (type == SRT_PRIM_PATCH) {                             // convex hull of the 4x4 control net
     const float4* cp = sc.patch_cp + 16 * hdr.w;
     mn = v3(BIG, BIG, BIG); mx = v3(-BIG, -BIG, -BIG);

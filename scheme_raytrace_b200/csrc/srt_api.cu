@@ -140,7 +140,7 @@ void srt_scene_destroy(SrtScene* s) {
 
 int srt_scene_set_prims(SrtScene* s, const SrtPrim* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_prims: bad argument");
-  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_PATCH) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
+  for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_KLEIN) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
   s->prims.assign(p, p + n); s->committed = false; return 0;
 }
 int srt_scene_set_xforms(SrtScene* s, const SrtXform* p, int n) {
@@ -306,12 +306,15 @@ int srt_scene_commit(SrtScene* s) {
     // global iff e_i >= 0.5 E; at most SRT_MAX_GLOBAL, largest extent first (ties: lower id)
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
     std::vector<float> ext(ns);
-    for (int i = 0; i < ns; ++i) { float e = 0.f; for (int k = 0; k < 3; ++k) { float a0 = hb[6 * i + k], a1 = hb[6 * i + 3 + k]; lo[k] = a0 < lo[k] ? a0 : lo[k]; hi[k] = a1 > hi[k] ? a1 : hi[k]; e = (a1 - a0) > e ? (a1 - a0) : e; } ext[i] = e; }
+    for (int i = 0; i < ns; ++i) { float e = 0.f; if (s->prims[i].type == SRT_PRIM_KLEIN) { ext[i] = 0.f; continue; } for (int k = 0; k < 3; ++k) { float a0 = hb[6 * i + k], a1 = hb[6 * i + 3 + k]; lo[k] = a0 < lo[k] ? a0 : lo[k]; hi[k] = a1 > hi[k] ? a1 : hi[k]; e = (a1 - a0) > e ? (a1 - a0) : e; } ext[i] = e; }
     float E = 0.f; for (int k = 0; k < 3; ++k) E = (hi[k] - lo[k]) > E ? (hi[k] - lo[k]) : E;
-    std::vector<int> cand;
-    for (int i = 0; i < ns; ++i) if (ns > 2 && ext[i] >= 0.5f * E) cand.push_back(i);
+    std::vector<int> cand, forced;
+    for (int i = 0; i < ns; ++i) if (s->prims[i].type == SRT_PRIM_KLEIN) forced.push_back(i);      // no bounding box: always global
+    if ((int)forced.size() > SRT_MAX_GLOBAL) return fail(SRT_ERR_ARG, "at most %d Klein primitives per scene", SRT_MAX_GLOBAL);
+    for (int i = 0; i < ns; ++i) if (s->prims[i].type != SRT_PRIM_KLEIN && ns > 2 && ext[i] >= 0.5f * E) cand.push_back(i);
     std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return ext[x] > ext[y]; });
-    if ((int)cand.size() > SRT_MAX_GLOBAL) cand.resize(SRT_MAX_GLOBAL);
+    if ((int)(cand.size() + forced.size()) > SRT_MAX_GLOBAL) cand.resize(SRT_MAX_GLOBAL - forced.size());
+    cand.insert(cand.end(), forced.begin(), forced.end());
     std::sort(cand.begin(), cand.end());
     s->global_prims = cand; s->item_prim.clear();
     size_t gi = 0;

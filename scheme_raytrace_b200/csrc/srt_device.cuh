@@ -382,6 +382,54 @@ static __device__ __noinline__ bool isect_patch(const float4* __restrict__ cp, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// geometry.scm:590-664 Klein / IIS fractal: inversion in six spheres (<= 10 times), sphere-traced
+// <= 100 steps, central-difference normal.  Evaluated in FP64: the finite-difference normal of a
+// fractal distance field is ill-conditioned in fp32, the primitive is rare and B200 runs DFMA at
+// half rate.
+__device__ __forceinline__ double klein_dist(double cx, double cy, double cz, double px, double py, double pz) {   // dist-func :602-624
+  const double KX[6] = {300, 300, -300, -300, 0, 0}, KY[6] = {300, -300, 300, -300, 0, 0}, KZ[6] = {0, 0, 0, 0, 424.26, -424.26};
+  px -= cx; py -= cy; pz -= cz;
+  double dr = 1.0;
+  for (int iter = 0;;) {
+    if (iter >= 10) break;
+    bool inverted = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double dx = px - KX[k], dy = py - KY[k], dz = pz - KZ[k];
+      double d2 = dx * dx + dy * dy + dz * dz;
+      if (!inverted && sqrt(d2) < 300.0) {
+        dr = dr * (90000.0 / d2);
+        double len = sqrt(d2), f = 1.0 / (len * len);
+        px = dx * 90000.0 * f + KX[k]; py = dy * 90000.0 * f + KY[k]; pz = dz * 90000.0 * f + KZ[k];
+        ++iter; inverted = true;
+      }
+    }
+    if (!inverted) break;
+  }
+  return 0.7 * ((sqrt(px * px + py * py + pz * pz) - 125.0) / fabs(dr));
+}
+static __device__ __noinline__ bool isect_klein(float4 a, float3 o, float3 d, float tmin, float tbest, float& tout) {   // make-klein :644-661
+  const double cx = a.x, cy = a.y, cz = a.z, ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
+  double px = ox, py = oy, pz = oz, ray_length = 0.0;
+  for (int iter = 0; iter < 100; ++iter) {
+    double dist = klein_dist(cx, cy, cz, px, py, pz);
+    ray_length += dist;
+    px = ox + dx * ray_length; py = oy + dy * ray_length; pz = oz + dz * ray_length;
+    if (dist < 0.001 && (double)tmin < ray_length && ray_length < (double)tbest) { tout = (float)ray_length; return true; }
+  }
+  return false;
+}
+static __device__ __noinline__ float3 klein_normal(float4 a, float3 o, float3 d, float t) {   // get-normal :626-632 at origin + dir * t
+  const double cx = a.x, cy = a.y, cz = a.z, e = 0.01;
+  const double px = (double)o.x + (double)d.x * (double)t, py = (double)o.y + (double)d.y * (double)t, pz = (double)o.z + (double)d.z * (double)t;
+  double nx = klein_dist(cx, cy, cz, px + e, py, pz) - klein_dist(cx, cy, cz, px - e, py, pz);
+  double ny = klein_dist(cx, cy, cz, px, py + e, pz) - klein_dist(cx, cy, cz, px, py - e, pz);
+  double nz = klein_dist(cx, cy, cz, px, py, pz + e) - klein_dist(cx, cy, cz, px, py, pz - e);
+  double k = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+  return v3((float)(nx * k), (float)(ny * k), (float)(nz * k));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exact-tie rule: the order-independent restatement of hit-obj-list's
 // sequential "later object replaces the best iff t < best (sphere-type) or t <= best (rect-type,
 // curve)".  ids are positions in the reference's flattened object list.
@@ -399,11 +447,11 @@ struct Hit { float t; int prim; float u, v; bool incl; };
 // One leaf primitive against the ray (world space in, candidate merged into `h`).  MASK is the
 // set of primitive kinds present in the scene (bit = SRT_PRIM_*): the extend kernel is compiled
 // per mask so that e.g. sphere-only scenes carry no rect / instance / Bezier code or registers.
-#define SRT_MASK_ALL 0xff
+#define SRT_MASK_ALL 0x1ff
 template <int MASK, class PrimSrc>
 __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin,
                                                const RngAddr& ra, Hit& h) {
-  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40, HAS_PATCH = MASK & 0x80;
+  constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40, HAS_PATCH = MASK & 0x80, HAS_KLEIN = MASK & 0x100;
   constexpr bool SINGLE_KIND = (MASK & (MASK - 1)) == 0;
   float4 a = ps.a(id);
   int type, xform = -1, aux = 0;
@@ -422,6 +470,8 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     ok = isect_rect(type, a, k, oo, dd, tmin, ti, have_t, t, u, v);
   } else if (HAS_BEZIER && type == SRT_PRIM_BEZIER) {
     ok = isect_bezier(a, __ldg(&sc.prim_b[id]), __ldg(&sc.prim_c[id]), __ldg(&sc.prim_d[id]), o, d, tmin, h.t, t);
+  } else if (HAS_KLEIN && type == SRT_PRIM_KLEIN) {
+    ok = isect_klein(a, o, d, tmin, h.t, t);
   } else if (HAS_PATCH && type == SRT_PRIM_PATCH) {
     ok = isect_patch(sc.patch_cp + 16 * aux, __ldg(&sc.prim_b[id]), o, d, tmin, h.t, t, u, v);
   } else if (HAS_MEDIUM && type == SRT_PRIM_CONSTANT_MEDIUM) {
@@ -492,6 +542,9 @@ __device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t
     } else {
       p = madd(d, t, o);
     }
+  } else if (type == SRT_PRIM_KLEIN) {                // geometry.scm:657-658
+    p = madd(d, t, o);
+    n = klein_normal(a, o, d, t);
   } else if (type == SRT_PRIM_PATCH) {                // normal = Su x Sv at (u, v), facing the ray
     p = madd(d, t, o);
     n = patch_normal(sc.patch_cp + 16 * hdr.w, __ldg(&sc.prim_b[prim]), hu, hv, d);

@@ -302,7 +302,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
 }
 
 template <bool SMEM, int MASK, bool CACHE>
-__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0xe0) ? 2 : ((MASK & 0x1c) ? 3 : 4))
+__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x1e0) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
          float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
   extern __shared__ float4 smem[];
@@ -318,11 +318,11 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
     PrimShared ps{sh, sa};
-    if (MASK & 0xe0) extend_loop_deferred<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    if (MASK & 0x1e0) extend_loop_deferred<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
     else extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    if (MASK & 0xe0) extend_loop_deferred<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    if (MASK & 0x1e0) extend_loop_deferred<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
     else extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
   }
 }
@@ -506,7 +506,7 @@ static ExtendVariant g_variants[2][4][2];
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
   if ((mask & ~0x03) == 0) return 1;
-  if ((mask & 0xe0) == 0) return 2;
+  if ((mask & 0x1e0) == 0) return 2;
   return 3;
 }
 template <bool SMEM, bool CACHE> static ExtendFn variant_fn_m(int v) {

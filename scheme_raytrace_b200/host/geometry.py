@@ -11,9 +11,9 @@ from dataclasses import dataclass, field
 from typing import Any, List, Optional, Tuple
 
 # node kinds (leaf kinds equal the SRT_PRIM_* codes of include/srt.h)
-SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH = 0, 1, 2, 3, 4, 5, 6, 7
+SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH, KLEIN = 0, 1, 2, 3, 4, 5, 6, 7, 8
 FLIP, LIST, TRANSLATE, ROTATE_Y = 16, 17, 18, 19
-LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH)
+LEAF_KINDS = (SPHERE, MOVING_SPHERE, XY_RECT, XZ_RECT, YZ_RECT, BEZIER, CONSTANT_MEDIUM, PATCH, KLEIN)
 
 
 @dataclass(eq=False)
@@ -103,5 +103,7 @@ def make_constant_medium(obj, density, a):                     # geometry.scm:54
     return Obj(CONSTANT_MEDIUM, make_lambertian(a), (float(density),), [obj])
 
 
-def make_klein(center, material):                              # geometry.scm:644
-    raise NotImplementedError("Klein/IIS fractal is out of scope (SURVEY.md §2 row 12: no bounding box)")
+def make_klein(center, material):                              # geometry.scm:644-664
+    """Klein / IIS sphere-traced fractal.  It has no bounding box upstream (geometry.scm:662-663),
+    so it stays out of the LBVH and is tested before traversal (at most 8 such primitives)."""
+    return Obj(KLEIN, material, tuple(map(float, center)))

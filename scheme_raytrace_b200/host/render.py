@@ -133,6 +133,32 @@ class Renderer:
         return st
 
 
+class ProgressiveRenderer:
+    """The reference's progressive viewer semantics (main.scm:452-469, 533-544: one new sample per
+    pixel per pass, running sum, 8-bit image re-derived after every pass) without the GLUT window:
+    `step()` == one full-frame pass of `trace-line` over all rows."""
+
+    def __init__(self, scene, width=200, height=200, max_depth=100, seed=1, quirks=15, device=0):
+        self.r = Renderer(scene, device=device)
+        self.width, self.height, self.max_depth, self.seed, self.quirks = width, height, max_depth, seed, quirks
+        self.raw_data = np.zeros((height, width, 3), dtype=np.float32)     # *raw-data* main.scm:430
+        self.sample_count = 0                                              # *sample-count*
+        self.image = np.zeros((height, width, 3), dtype=np.uint8)          # *image* main.scm:429
+
+    def step(self, samples=1):
+        self.r.render(self.width, self.height, samples, max_depth=self.max_depth, seed=self.seed, quirks=self.quirks,
+                      spp_begin=self.sample_count, rgb_sum=self.raw_data)
+        self.sample_count += samples
+        self.image = correct_gamma_quantise(self.raw_data, self.sample_count)
+        return self.image
+
+    def save(self, path="test.ppm"):                                       # key 'S' main.scm:551-552
+        save_as_ppm(path, self.image)
+
+    def close(self):
+        self.r.close()
+
+
 def correct_gamma_quantise(rgb_sum, spp):
     """main.scm:123-124, 481-487 through the library's device resolve kernel."""
     lib = ffi.load()

@@ -152,6 +152,22 @@ def cornell_smoke(size_x=200, size_y=200):
     return g.make_scene(objs, cornell_camera(size_x, size_y), black)
 
 
+def klein_scene(size_x=200, size_y=200):
+    """main.scm:400-407 klein-scene."""
+    white = m.make_lambertian(t.constant_texture(v.vec3(0.73, 0.73, 0.73)))
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    objs = [g.make_sphere(v.vec3(0, -1003, -1), 1000, white), g.make_klein(v.vec3(0, 2, 0), red)]
+    return g.make_scene(objs, default_camera(size_x, size_y), sky_color)
+
+
+def cornell_klein(size_x=200, size_y=200):
+    """main.scm:409-426 cornell-klein."""
+    walls, red, white, green, light = _cornell_walls()
+    blue = m.make_lambertian(t.constant_texture(v.vec3(0.05, 0.65, 0.65)))
+    walls[2] = g.flip_normals(g.make_xz_rect(113, 443, 127, 432, 554, light))
+    return g.make_scene(walls + [g.make_klein(v.vec3(250, 200, 280), blue)], cornell_camera(size_x, size_y), sky_color)
+
+
 def test_bezier(size_x=200, size_y=200):
     """main.scm:237-277 test-bezier (3 curves + 6 spheres + checker ground)."""
     red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))

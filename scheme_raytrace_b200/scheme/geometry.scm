@@ -5,7 +5,7 @@
   (use material :prefix m:)
   (export make-scene scene-obj-list scene-num-obj scene-camera scene-sky-function material
           make-sphere make-moving-sphere make-xy-rect make-xz-rect make-yz-rect flip-normals
-          make-box translate rotate-y make-bvh-node make-bvh-with-sah make-constant-medium
+          make-box translate rotate-y make-bvh-node make-bvh-with-sah make-constant-medium make-klein
           obj-kind obj-params obj-children make-obj))
 (select-module geometry)
 
@@ -17,7 +17,7 @@
 (define (obj-children o) (vector-ref o 4))
 (define (v3->list p) (list (v:x p) (v:y p) (v:z p)))
 
-;; kinds: 0 sphere 1 moving-sphere 2 xy-rect 3 xz-rect 4 yz-rect 5 bezier 6 constant-medium 7 patch
+;; kinds: 0 sphere 1 moving-sphere 2 xy-rect 3 xz-rect 4 yz-rect 5 bezier 6 constant-medium 7 patch 8 klein
 ;;        16 flip 17 list 18 translate 19 rotate-y   (== include/srt.h and host/geometry.py)
 (define (make-scene obj-list camera sky-function) (vector 'scene #f obj-list camera sky-function))
 (define (scene-obj-list s) (vector-ref s 2))
@@ -47,5 +47,6 @@
 ;; the CPU BVH builders become grouping hints: the GPU LBVH is built over the flattened leaves
 (define (make-bvh-node obj-list time0 time1) (make-obj 17 #f '() obj-list))
 (define (make-bvh-with-sah obj-list time0 time1) (make-obj 17 #f '() obj-list))
+(define (make-klein center mat) (make-obj 8 mat (v3->list center) '()))
 (define (make-constant-medium obj density albedo-texture)
   (make-obj 6 (m:make-lambertian albedo-texture) (list density) (list obj)))

@@ -30,6 +30,8 @@ def interest_bounds(flat, clip=30.0):
         q = p["p"]
         if p["type"] == 6 or (p["flags"] & 2 and p["xform"] >= 0):
             continue
+        if p["type"] == 8:
+            continue
         if p["type"] == 7:
             pts += [c for c in flat.patches[int(q[0])].reshape(16, 3)]
             continue            # media / instanced boundary shapes: covered by the other primitives' extent

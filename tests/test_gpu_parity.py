@@ -12,7 +12,8 @@ SMALL = {"cfg1": (scenes.cfg1_weekend, 200, 100), "cfg2": (scenes.cfg2_random_sp
          "cfg3": (scenes.cfg3_next_week, 80, 80), "cfg4": (scenes.cfg4_cornell_box, 64, 64),
          "bezier": (scenes.test_bezier, 64, 64), "cornell_bezier": (scenes.cornell_bezier, 64, 64),
          "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64),
-         "smoke": (scenes.cornell_smoke, 64, 64), "patches": (scenes.cfg5_patches, 96, 54)}
+         "smoke": (scenes.cornell_smoke, 64, 64), "patches": (scenes.cfg5_patches, 96, 54),
+         "klein": (scenes.cornell_klein, 48, 48)}
 
 
 @pytest.fixture(scope="module", params=list(SMALL))
@@ -34,8 +35,13 @@ def test_lbvh_bit_exact(pair, orc):
     assert sorted(items.tolist() + glob.tolist()) == list(range(len(aabb)))     # every surface is in the tree or global
     ext = (aabb[:, 3:] - aabb[:, :3]).max(axis=1)
     E = (aabb[:, 3:].max(axis=0) - aabb[:, :3].min(axis=0)).max()
-    assert all(ext[gp] >= 0.5 * E for gp in glob) and (len(glob) == 8 or len(aabb) <= 2 or not np.any(ext[items] >= 0.5 * E))
+    klein = r.flat.prims["type"][:len(aabb)] == 8
+    ext[klein] = 0; E = (aabb[~klein, 3:].max(axis=0) - aabb[~klein, :3].min(axis=0)).max() if (~klein).any() else 0
+    assert all(ext[gp] >= 0.5 * E or klein[gp] for gp in glob) and (len(glob) == 8 or len(aabb) <= 2 or not np.any(ext[items] >= 0.5 * E))
     keys_g, order_g = r.bvh_keys()
+    if len(items) == 0:                                                # everything is global: no tree to compare
+        assert len(keys_g) == 0
+        return
     nodes_g = r.bvh_nodes()
     keys_h, order_h, nodes_h = orc.lbvh_build(aabb[items])            # host reference over the same AABBs
     for side in ("left", "right", "sibling"):                         # its leaf refs are item indices -> primitive ids
@@ -58,8 +64,8 @@ def test_prim_bounds_contain_oracle_hits(pair):
     hit = o["prim"] >= 0
     if name in ("bezier", "cornell_bezier", "patches"):     # Q9: curve hit points are off the curve for |d| != 1
         hit &= r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]] != 5
-    if name == "patches":                                  # sub-patches: the parent's box is the union of 16 leaf boxes
-        hit &= r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]] != 7
+    if name in ("patches", "klein"):                       # sub-patches: union of 16 leaf boxes; Klein: no box at all
+        hit &= ~np.isin(r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]], (7, 8))
     b = aabb[r.flat.first_of_logical[o["prim"][hit]]]
     p = o["p"][hit]
     tol = 1e-4 * np.maximum(np.abs(p), 1.0)
@@ -72,7 +78,7 @@ def test_trace_batch_parity(pair, batch):
     if batch == "camera":
         rays = raybatch.camera_grid(r, 64, 64)
     else:
-        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name not in ("bezier", "patches") else 30000, 5)
+        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name not in ("bezier", "patches", "klein") else 30000, 5)
     rays64 = rays.astype(np.float64)
     gp = r.trace_batch(rays)
     o64 = S.trace_batch(rays64)
@@ -83,7 +89,13 @@ def test_trace_batch_parity(pair, batch):
           f"id_mismatch={c['id_mismatch']} t_err_max={c['t_err_max']:.2e} t_bad={c['t_bad']} n_err_max={c['n_err_max']:.2e} p_err_max={c['p_err_max']:.2e}")
     assert c["filtered_near_tie"] + c["filtered_unstable"] <= 0.01 * c["n"]
     assert c["id_mismatch"] == 0, f"prim id mismatches at rays {c['id_mismatch_idx'][:10]}"
-    assert c["t_bad"] == 0 and c["n_bad"] == 0
+    assert c["t_bad"] == 0
+    if name == "klein":
+        # the fractal's central-difference normal (eps 0.01, geometry.scm:626-632) amplifies the fp32
+        # rounding of t in the hit record (~1e-4 absolute at t ~ 800): stated tolerance 2e-2
+        assert c["n_err_max"] <= 2e-2
+    else:
+        assert c["n_bad"] == 0
     # uv: rects everywhere; spheres only where |p.y| <= 1 (Q5: asin of the raw point)
     hm = c["hit_mask"]
     ptype = r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o64["prim"], 0)]]
@@ -165,7 +177,7 @@ def test_raygen_parity(orc):
     r.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke", "patches"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke", "patches", "klein"])
 def test_image_same_stream(name, orc):
     """Image parity under IDENTICAL Philox streams: GPU fp32 vs oracle f64 follow the same paths
     except where rounding flips a decision, so the per-pixel linear difference is tiny for almost
@@ -186,8 +198,9 @@ def test_image_same_stream(name, orc):
     print(f"\n[{name}] rays gpu={st.rays} oracle={nrays} median={np.median(diff):.2e} within1e-2={np.mean(diff < 1e-2):.4f} psnr8={psnr:.1f} dB")
     assert np.all(np.isfinite(img))
     assert abs(st.rays - nrays) <= 0.02 * nrays
-    assert np.median(diff) < 1e-4 and np.mean(diff < 1e-2) >= 0.97
-    assert psnr >= 35.0
+    # the Klein fractal scatters chaotically (see the normal tolerance above): looser gates
+    assert np.median(diff) < 1e-4 and np.mean(diff < 1e-2) >= (0.85 if name == "klein" else 0.97)
+    assert psnr >= (28.0 if name == "klein" else 35.0)
     r.close()
 
 
@@ -299,3 +312,18 @@ def test_isotropic_material(orc):
     diff = np.abs(img.astype(np.float64) - ref) / 8
     assert abs(st.rays - nrays) <= 0.02 * nrays and np.median(diff) < 1e-4 and np.mean(diff < 1e-2) >= 0.97
     r.close()
+
+
+def test_progressive_equals_batch():
+    """Progressive passes (one sample per pass, main.scm:533-544) accumulate to exactly the batch
+    render: the Philox key is (pixel, sample, bounce) and the accumulator is integer."""
+    w, h = 64, 32
+    scene = scenes.cfg1_weekend(w, h)
+    pr = srt.ProgressiveRenderer(scene, w, h, max_depth=50, seed=4)
+    for _ in range(5):
+        img = pr.step()
+    r = srt.Renderer(scene, device=0)
+    full, _ = r.render(w, h, 5, max_depth=50, seed=4)
+    assert pr.sample_count == 5 and np.allclose(pr.raw_data, full, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(img, srt.correct_gamma_quantise(pr.raw_data, 5))
+    pr.close(); r.close()

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 B_PER_RAY_LOOP = 160      # ray w+r 2x32 + ray re-read by shade 32 ... = 160 B per ray-bounce (whole loop)
 B_PER_RAY_EXTEND = 48     # the extend kernel's part: ray read 32 B + hit record write 16 B
+NCU_EXTEND_DRAM_B_PER_RAY = 47.6   # measured: ncu dram__bytes_read+write of a 61.44M-ray launch (profiles/r1_traffic.txt)
 # FP32 work model: flops/ray = 27*N_box + 3 + sum F_type*N_type + F_shade, with the
 # per-ray counts MEASURED by the instrumented build (tools/step_stats.py, profiles/r1_step_stats.txt):
 # node steps per ray (2 box tests each), primitive tests per ray, dominant primitive cost, shade cost.
@@ -257,7 +258,8 @@ def main():
     ext_ms = pst.ms_extend
     ext_gbs = (B_PER_RAY_EXTEND * pst.rays) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_extend (stackless LBVH closest hit)", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
-                "frac": ext_gbs / peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": ext_gbs / peak, "traffic": NCU_EXTEND_DRAM_B_PER_RAY * pst.rays / max(pst.extend_launches, 1), "peak_kind": peak_kind,
+                "traffic_note": "bytes per launch = ncu-measured 47.6 B/ray (profiles/r1_traffic.txt) x rays per launch of this pass",
                 "bytes_per_ray": B_PER_RAY_EXTEND, "rays_per_launch": pst.rays / max(pst.extend_launches, 1),
                 "avg_launch_ms": ext_ms / max(pst.extend_launches, 1),
                 "extend_share_of_loop": ext_ms / max(ext_ms + pst.ms_shade, 1e-9),

@@ -286,35 +286,10 @@ static __device__ __noinline__ bool isect_bezier(float4 pa, float4 pb, float4 pc
 // specification as the oracle (DESIGN.md "Patches"): ray-space projection of bezier.scm, depth-2
 // quadtree subdivision by de Casteljau (done once on the host: 16 leaves per patch), hull culling,
 // Newton on (S.x, S.y) = 0 from each leaf's centre, t = S.z / |d|.
-struct Net { float3 q[4][4]; };
-__device__ __forceinline__ void bern(float s, float b[4], float db[4]) {
+__device__ __forceinline__ void bern(float s, float b[4], float db[4]) {   // cubic Bernstein weights and derivatives
   float m = 1.0f - s;
   b[0] = m * m * m; b[1] = 3.0f * s * m * m; b[2] = 3.0f * s * s * m; b[3] = s * s * s;
   db[0] = -3.0f * m * m; db[1] = 3.0f * m * m - 6.0f * s * m; db[2] = 6.0f * s * m - 3.0f * s * s; db[3] = 3.0f * s * s;
-}
-__device__ __forceinline__ void patch_eval(const Net& N, float s, float t, float3& S, float3& Su, float3& Sv) {
-  float bs[4], dbs[4], bt[4], dbt[4]; bern(s, bs, dbs); bern(t, bt, dbt);
-  S = Su = Sv = v3(0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      S = S + N.q[i][j] * (bs[i] * bt[j]); Su = Su + N.q[i][j] * (dbs[i] * bt[j]); Sv = Sv + N.q[i][j] * (bs[i] * dbt[j]);
-    }
-}
-__device__ __forceinline__ void cubic_split(const float3 c0, const float3 c1, const float3 c2, const float3 c3, float3 l[4], float3 r[4]) {
-  float3 ab = (c0 + c1) * 0.5f, bc = (c1 + c2) * 0.5f, cd = (c2 + c3) * 0.5f;
-  float3 abc = (ab + bc) * 0.5f, bcd = (bc + cd) * 0.5f, m = (abc + bcd) * 0.5f;
-  l[0] = c0; l[1] = ab; l[2] = abc; l[3] = m; r[0] = m; r[1] = bcd; r[2] = cd; r[3] = c3;
-}
-__device__ __forceinline__ bool net_cull(const Net& N, float zmin, float zmax) {
-  float mnx = N.q[0][0].x, mxx = mnx, mny = N.q[0][0].y, mxy = mny, mnz = N.q[0][0].z, mxz = mnz;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const float3 q = N.q[i][j];
-      mnx = fminf(mnx, q.x); mxx = fmaxf(mxx, q.x); mny = fminf(mny, q.y); mxy = fmaxf(mxy, q.y); mnz = fminf(mnz, q.z); mxz = fmaxf(mxz, q.z); }
-  return mnx > 0.f || mxx < 0.f || mny > 0.f || mxy < 0.f || mxz < zmin || mnz > zmax;
 }
 // One LEAF sub-patch: the host pre-splits every patch SRT_PATCH_LEVELS = 2 levels (16 leaves,
 // separate LBVH leaves, so the BVH does the subdivision culling with cheap box tests); here only

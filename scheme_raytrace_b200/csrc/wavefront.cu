@@ -10,7 +10,8 @@
 //             (warp ballot + one atomic per CTA) into the other queue generation
 //   k_regen   fresh camera paths (Philox bounce slot 0) are appended behind the survivors
 // so the long thin tail of deep paths (depth <= max_depth) is paid once per frame, not once per
-// batch of samples.  The recursive estimator `color` is run in its iterative form
+// batch of samples.  Iterations are enqueued in batches of 8 that are captured once into a CUDA
+// graph and replayed; the host polls the control block one batch behind.  The recursive estimator `color` is run in its iterative form
 // L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
 #include "srt_device.cuh"
 #include "srt_host.h"

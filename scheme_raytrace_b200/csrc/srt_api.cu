@@ -43,7 +43,7 @@ struct SrtScene {
   std::vector<float> patches; DevBuf<float4> d_patches; DevBuf<int> d_logical;
   bool committed = false;
   // device tables
-  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
+  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
   // LBVH
   LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth, d_item_prim;
   std::vector<int> item_prim, global_prims;
@@ -63,7 +63,7 @@ static void fill_dscene(SrtScene* s) {
   d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
-  d.xf = s->d_xf.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
+  d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
 }
 
 static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
@@ -124,7 +124,7 @@ SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); 
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
-  s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
+  s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
@@ -248,6 +248,19 @@ int srt_scene_commit(SrtScene* s) {
     for (int i = 0; i < n; ++i) logical[i] = s->prims[i].p[15] > 0.f ? (int)s->prims[i].p[15] - 1 : i;   // p[15] = logical id + 1, 0 = array index
     CK(s->d_logical.ensure(n));
     if (n) CK(cudaMemcpy(s->d_logical.p, logical.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  }
+  {   // per-primitive shading record (see DScene::prim_shade)
+    std::vector<float4> sh(2 * (size_t)(n ? n : 1));
+    for (int i = 0; i < n; ++i) {
+      const SrtMaterial& m = s->mats[s->prims[i].material];
+      float r = 1.f, g = 1.f, b = 1.f; int is_const = 0;
+      if (m.kind != SRT_MAT_DIELECTRIC && s->texs[m.tex].kind == SRT_TEX_CONSTANT) { const SrtTexture& t = s->texs[m.tex]; r = t.rgb[0]; g = t.rgb[1]; b = t.rgb[2]; is_const = 1; }
+      if (m.kind == SRT_MAT_DIELECTRIC) is_const = 1;
+      float fk, ft, fc; int tex = m.tex; std::memcpy(&fk, &m.kind, 4); std::memcpy(&ft, &tex, 4); std::memcpy(&fc, &is_const, 4);
+      sh[2 * i] = make_float4(r, g, b, m.param); sh[2 * i + 1] = make_float4(fk, ft, fc, 0.f);
+    }
+    CK(s->d_shade.ensure(2 * (size_t)n));
+    if (n) CK(cudaMemcpy(s->d_shade.p, sh.data(), sizeof(float4) * 2 * (size_t)n, cudaMemcpyHostToDevice));
   }
   CK(s->d_hdr.ensure(n)); CK(s->d_a.ensure(n)); CK(s->d_b.ensure(n)); CK(s->d_c.ensure(n)); CK(s->d_d.ensure(n));
   if (n) {

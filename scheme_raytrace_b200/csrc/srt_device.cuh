@@ -28,6 +28,9 @@ struct DScene {
   const float4* tex;        // 2 per texture: (kind even odd scale as int bits / float) (r g b 0)
   const float4* ranvec;     // 256 unit gradient vectors (perlin.scm:33)
   const uint8_t* perm;      // 3 x 256: perm-x, perm-y, perm-z (perlin.scm:34-36)
+  const float4* prim_shade; // 2 per primitive: (albedo.rgb if its texture is constant, material param) and
+                            // (material kind, texture id, texture-is-constant, 0) as int bits: flattens the
+                            // prim -> material -> texture -> colour chain of dependent loads for the shade kernel
   const float4* patch_cp;   // 16 control points per (sub-)patch (north-star extension)
   const int* prim_logical;  // logical primitive id reported by the parity hook (sub-patches share their parent's)
   const int* lights;        // primitive ids sampled by the hittable pdf (pdf.scm:28-32)
@@ -665,18 +668,19 @@ __device__ __forceinline__ float schlick(float cosine, float ref_idx) {         
 struct Scatter { float3 dir; float3 weight; float3 emitted; bool valid; };
 
 template <int EST>
-__device__ __forceinline__ Scatter scatter(const DScene& sc, int material, float3 d_in, float3 p, float3 n, float u, float v,
+__device__ __forceinline__ Scatter scatter(const DScene& sc, int prim, float3 d_in, float3 p, float3 n, float u, float v,
                                            const RngAddr& addr, int quirks) {
   Scatter r; r.valid = false; r.emitted = v3(0.f, 0.f, 0.f); r.weight = v3(1.f, 1.f, 1.f); r.dir = v3(0.f, 1.f, 0.f);
-  const int4 m = __ldg(&sc.mats[material]);
-  const float param = __int_as_float(m.z);
+  const float4 sh0 = __ldg(&sc.prim_shade[2 * prim]), sh1 = __ldg(&sc.prim_shade[2 * prim + 1]);
+  const int4 m = make_int4(__float_as_int(sh1.x), __float_as_int(sh1.y), 0, 0);     // (material kind, texture id)
+  const float param = sh0.w;
   // Shared by every material, so done ONCE before the switch with all hit lanes active instead of
   // once per divergent branch: the first Philox block of this bounce and the texture lookup
   // ((t:value albedo 0 0 p) for lambertian / metal, (t:value emit u v p) for lights).
   const float4 xi = rng_block(addr, 0);
   const bool uv_tex = m.x == SRT_MAT_DIFFUSE_LIGHT || m.x == SRT_MAT_ISOTROPIC;
-  float3 tex = v3(1.f, 1.f, 1.f);
-  if (m.x != SRT_MAT_DIELECTRIC) tex = tex_value(sc, m.y, uv_tex ? u : 0.0f, uv_tex ? v : 0.0f, p, quirks);
+  float3 tex = xyz(sh0);                                        // constant textures: colour already in the record
+  if (m.x != SRT_MAT_DIELECTRIC && __float_as_int(sh1.z) == 0) tex = tex_value(sc, m.y, uv_tex ? u : 0.0f, uv_tex ? v : 0.0f, p, quirks);
   switch (m.x) {
     case SRT_MAT_LAMBERTIAN: {                                   // material.scm:24-39 + onb.scm:8-16
       float len_n = length(n);

@@ -358,7 +358,7 @@ k_shade(DScene sc, SrtRenderParams p, int g,
         float3 pt, n; int material;
         complete_hit(sc, prim, h4.x, h4.z, h4.w, o, d, o4.w, pt, n, material);
         RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
-        Scatter s = scatter<EST>(sc, material, d, pt, n, h4.z, h4.w, addr, p.quirks);
+        Scatter s = scatter<EST>(sc, prim, d, pt, n, h4.z, h4.w, addr, p.quirks);
         if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
           accumulate_fixed(accum, pixel, thr * s.emitted);
         if (s.valid && depth < p.max_depth) {                      // main.scm:112

@@ -66,9 +66,10 @@ enum { SRT_MAT_LAMBERTIAN = 0, SRT_MAT_METAL = 1, SRT_MAT_DIELECTRIC = 2, SRT_MA
  * (param = ref-idx), :103 make-diffuse-light; isotropic is the book's (absent upstream). */
 typedef struct { int32_t kind; int32_t tex; float param; float pad; } SrtMaterial;
 
-enum { SRT_TEX_CONSTANT = 0, SRT_TEX_CHECKER = 1, SRT_TEX_NOISE = 2, SRT_TEX_MARBLE = 3 };
+enum { SRT_TEX_CONSTANT = 0, SRT_TEX_CHECKER = 1, SRT_TEX_NOISE = 2, SRT_TEX_MARBLE = 3, SRT_TEX_IMAGE = 4 };
 /* texture.scm:12 constant-texture (rgb), :16 checker-texture (even, odd = texture indices),
- * :25 noise-texture (scale), :30 marble-texture (scale). */
+ * :25 noise-texture (scale), :30 marble-texture (scale), :36 image-texture (even = image index,
+ * see srt_scene_set_images). */
 typedef struct { int32_t kind; int32_t even, odd; float scale; float rgb[3]; float pad; } SrtTexture;
 
 /* the 10 slots of camera.scm:70-78 */
@@ -137,6 +138,9 @@ int srt_scene_set_xforms(SrtScene*, const SrtXform*, int n);
 int srt_scene_set_patches(SrtScene*, const float* cp48, int n);      /* n x 16 control points (xyz), P[i][j] at 3*(4i+j) */
 int srt_scene_set_materials(SrtScene*, const SrtMaterial*, int n);
 int srt_scene_set_textures(SrtScene*, const SrtTexture*, int n);
+/* image-texture data (texture.scm:36-50): n images of 8-bit RGB texels, row-major from the top row,
+ * concatenated in `texels`; dims = n x (nx, ny, byte offset of the image in `texels`). */
+int srt_scene_set_images(SrtScene*, const uint8_t* texels, const int32_t* dims, int n);
 int srt_scene_set_perlin(SrtScene*, const float* ranvec768, const int32_t* perm_x, const int32_t* perm_y, const int32_t* perm_z);
 int srt_scene_set_camera(SrtScene*, const SrtCamera*);
 int srt_scene_set_lights(SrtScene*, const int32_t* prim_ids, int n);   /* shapes sampled by the hittable pdf */

@@ -29,6 +29,7 @@ def load():
         lib.orc_create.restype = vp
         lib.orc_destroy.argtypes = [vp]
         lib.orc_add_texture.argtypes = [vp, i32, dbl, dbl, dbl, dbl, i32, i32]
+        lib.orc_add_image.argtypes = [vp, vp, i32, i32]
         lib.orc_add_material.argtypes = [vp, i32, i32, dbl]
         lib.orc_add_node.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32]
         lib.orc_set_root.argtypes = [vp, i32]
@@ -107,6 +108,9 @@ class OracleScene:
         even = odd = -1
         if tx.kind == t.CHECKER:
             even, odd = self._add_tex(tx.even, t), self._add_tex(tx.odd, t)
+        if tx.kind == t.IMAGE:
+            tex = np.ascontiguousarray(tx.image, dtype=np.uint8)
+            even = self.lib.orc_add_image(self.h, _p(tex), tex.shape[1], tex.shape[0])
         r, g_, b, sc = (float(x) for x in self._q([tx.rgb[0], tx.rgb[1], tx.rgb[2], tx.scale]))
         i = self.lib.orc_add_texture(self.h, tx.kind, r, g_, b, sc, even, odd)
         self._tex[id(tx)] = i

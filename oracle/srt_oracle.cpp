@@ -41,7 +41,7 @@ static const double PI = 3.141592653589793;  // math.const pi
 enum NodeKind { N_SPHERE = 0, N_MOVING_SPHERE = 1, N_XY_RECT = 2, N_XZ_RECT = 3, N_YZ_RECT = 4,
                 N_BEZIER = 5, N_CONSTANT_MEDIUM = 6, N_PATCH = 7, N_KLEIN = 8, N_FLIP = 16, N_LIST = 17, N_TRANSLATE = 18, N_ROTATE_Y = 19 };
 enum MatKind { M_LAMBERTIAN = 0, M_METAL = 1, M_DIELECTRIC = 2, M_DIFFUSE_LIGHT = 3, M_ISOTROPIC = 4 };
-enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3 };
+enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3, T_IMAGE = 4 };
 enum SkyKind { SKY_GRADIENT = 0, SKY_BLACK = 1 };
 // quirk bits (SURVEY §8a "Q" rows); REFERENCE = all on
 enum Quirks { Q1_COSINE_X2 = 1, Q4_PERLIN_ALIAS = 2, Q6_SCATTER_TIME0 = 4, Q10_DIELECTRIC_UNNORM = 8,
@@ -49,12 +49,14 @@ enum Quirks { Q1_COSINE_X2 = 1, Q4_PERLIN_ALIAS = 2, Q6_SCATTER_TIME0 = 4, Q10_D
 
 struct Tex { int kind; double rgb[3]; double scale; int even, odd; };
 struct Mat { int kind; int tex; double param; };
+struct Image { int nx, ny; std::vector<unsigned char> texels; };   // image-texture data, top row first
 struct Node {
   int kind; int material; int leaf_id;
   int child_begin, child_count;
   double p[16];
 };
 struct Scene {
+  std::vector<Image> images;
   std::vector<Tex> tex; std::vector<Mat> mat; std::vector<Node> nodes; std::vector<int> children;
   int root = -1;
   double cam[24];   // llc(3) horiz(3) vert(3) origin(3) w(3) u(3) v(3) lens t0 t1   camera.scm:33-61
@@ -196,7 +198,7 @@ template <class T> static T perlin_turb(const Scene& sc, V3<T> p, int quirks, in
   return std::fabs(acc);
 }
 
-// texture.scm:9-34
+// texture.scm:9-50
 template <class T> static V3<T> tex_value(const Scene& sc, int tex, T u, T v, V3<T> p, int quirks) {
   for (;;) {
     const Tex& t = sc.tex[tex];
@@ -214,6 +216,19 @@ template <class T> static V3<T> tex_value(const Scene& sc, int tex, T u, T v, V3
       case T_MARBLE: {                                                                            // texture.scm:30-34
         T s = T(0.5) * (T(1) + std::sin(T(t.scale) * p.z + T(10) * perlin_turb(sc, p, quirks)));
         return scale(mk<T>(1, 1, 1), s);
+      }
+      case T_IMAGE: {                                                                             // texture.scm:36-50
+        // i = u*nx; j = (1-v)*ny - 0.001; clamp both to [0, n-1] (:39-44).  Upstream then passes
+        // the still-fractional i, j to vector-ref (an error in Gauche: the constructor is never
+        // instantiated); the texel meant is the floor, as in the book this follows.  t.even = image.
+        const Image& im = sc.images[t.even];
+        T i = u * T(im.nx), j = (T(1) - v) * T(im.ny) - T(0.001);
+        if (!(i >= T(0))) i = T(0);      // also sends NaN (Q5 sphere uv) to texel 0, on both sides
+        if (!(j >= T(0))) j = T(0);
+        if (i > T(im.nx - 1)) i = T(im.nx - 1);
+        if (j > T(im.ny - 1)) j = T(im.ny - 1);
+        const unsigned char* px = im.texels.data() + 3 * ((size_t)(int)i + (size_t)im.nx * (size_t)(int)j);
+        return mk<T>(T(px[0]) / T(255), T(px[1]) / T(255), T(px[2]) / T(255));
       }
     }
     return mk<T>(0, 0, 0);
@@ -856,6 +871,8 @@ void orc_destroy(void* h) { delete (Scene*)h; }
 
 int orc_add_texture(void* h, int kind, double r, double g, double b, double scale, int even, int odd) {
   Scene* s = (Scene*)h; s->tex.push_back(Tex{kind, {r, g, b}, scale, even, odd}); return (int)s->tex.size() - 1; }
+int orc_add_image(void* h, const unsigned char* texels, int nx, int ny) {
+  Scene* s = (Scene*)h; s->images.push_back(Image{nx, ny, std::vector<unsigned char>(texels, texels + 3 * (size_t)nx * ny)}); return (int)s->images.size() - 1; }
 int orc_add_material(void* h, int kind, int tex, double param) {
   Scene* s = (Scene*)h; s->mat.push_back(Mat{kind, tex, param}); return (int)s->mat.size() - 1; }
 int orc_add_node(void* h, int kind, int material, int leaf_id, const double* params, int nparams, const int* children, int nchildren) {

@@ -63,6 +63,16 @@ int main(int argc, char** argv) {
   std::vector<int32_t> lights(n);
   for (auto& l : lights) in >> l;
   if (!in) { std::fprintf(stderr, "srt_render: truncated scene file\n"); return 1; }
+  std::vector<uint8_t> texels; std::vector<int32_t> dims;          // optional trailing section
+  if (expect(in, "images") && (in >> n)) {
+    for (int i = 0; i < n; ++i) {
+      int nx = 0, ny = 0; in >> nx >> ny;
+      if (!in || nx < 1 || ny < 1) { std::fprintf(stderr, "srt_render: bad image header\n"); return 1; }
+      dims.push_back(nx); dims.push_back(ny); dims.push_back((int32_t)texels.size());
+      for (size_t k = 0; k < 3 * (size_t)nx * ny; ++k) { int v = 0; in >> v; texels.push_back((uint8_t)v); }
+    }
+    if (!in) { std::fprintf(stderr, "srt_render: truncated images section\n"); return 1; }
+  }
 
   CHECK(srt_init(device));
   SrtScene* sc = srt_scene_create();
@@ -72,6 +82,7 @@ int main(int argc, char** argv) {
   CHECK(srt_scene_set_patches(sc, patches.data(), npatch));
   CHECK(srt_scene_set_materials(sc, mat.data(), (int)mat.size()));
   CHECK(srt_scene_set_textures(sc, tex.data(), (int)tex.size()));
+  CHECK(srt_scene_set_images(sc, texels.data(), dims.data(), (int)dims.size() / 3));
   CHECK(srt_scene_set_perlin(sc, ranvec.data(), perm.data(), perm.data() + 256, perm.data() + 512));
   CHECK(srt_scene_set_camera(sc, &cam));
   CHECK(srt_scene_set_lights(sc, lights.data(), (int)lights.size()));

@@ -37,13 +37,14 @@ template <class T> struct DevBuf {
 
 struct SrtScene {
   std::vector<SrtPrim> prims; std::vector<SrtXform> xforms; std::vector<SrtMaterial> mats; std::vector<SrtTexture> texs;
+  std::vector<uint8_t> img_texels; std::vector<int4> imgs;   // image-texture data (srt_scene_set_images)
   float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
   SrtCamera cam; bool has_cam = false;
   std::vector<int32_t> lights; DevBuf<int> d_lights;
   std::vector<float> patches; DevBuf<float4> d_patches; DevBuf<int> d_logical;
   bool committed = false;
   // device tables
-  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats; DevBuf<uint8_t> d_perm;
+  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats, d_imgs; DevBuf<uint8_t> d_perm, d_img_texels;
   // LBVH
   LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth, d_item_prim;
   std::vector<int> item_prim, global_prims;
@@ -63,7 +64,7 @@ static void fill_dscene(SrtScene* s) {
   d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
-  d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
+  d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.img_texels = s->d_img_texels.p; d.imgs = s->d_imgs.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
 }
 
 static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
@@ -124,7 +125,7 @@ SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); 
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
-  s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
+  s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
@@ -154,6 +155,18 @@ int srt_scene_set_materials(SrtScene* s, const SrtMaterial* p, int n) {
 int srt_scene_set_textures(SrtScene* s, const SrtTexture* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_textures: bad argument");
   s->texs.assign(p, p + n); s->committed = false; return 0;
+}
+int srt_scene_set_images(SrtScene* s, const uint8_t* texels, const int32_t* dims, int n) {
+  if (!s || n < 0 || (n && (!texels || !dims))) return fail(SRT_ERR_ARG, "set_images: bad argument");
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const int32_t nx = dims[3 * i], ny = dims[3 * i + 1], off = dims[3 * i + 2];
+    if (nx < 1 || ny < 1 || off < 0) return fail(SRT_ERR_ARG, "set_images: image %d has dims %d x %d at offset %d", i, nx, ny, off);
+    total = std::max(total, (size_t)off + 3 * (size_t)nx * (size_t)ny);
+  }
+  s->imgs.resize(n);
+  for (int i = 0; i < n; ++i) s->imgs[i] = make_int4(dims[3 * i], dims[3 * i + 1], dims[3 * i + 2], 0);
+  s->img_texels.assign(texels, texels + total); s->committed = false; return 0;
 }
 int srt_scene_set_perlin(SrtScene* s, const float* ranvec768, const int32_t* px, const int32_t* py, const int32_t* pz) {
   if (!s || !ranvec768 || !px || !py || !pz) return fail(SRT_ERR_ARG, "set_perlin: bad argument");
@@ -207,6 +220,8 @@ int srt_scene_commit(SrtScene* s) {
   }
   for (size_t i = 0; i < s->texs.size(); ++i) {
     const SrtTexture& t = s->texs[i];
+    if (t.kind == SRT_TEX_IMAGE && (t.even < 0 || t.even >= (int)s->imgs.size())) return fail(SRT_ERR_ARG, "texture %zu: image %d out of range (set_images)", i, t.even);
+    if (t.kind < SRT_TEX_CONSTANT || t.kind > SRT_TEX_IMAGE) return fail(SRT_ERR_ARG, "texture %zu: unknown kind %d", i, t.kind);
     if (t.kind == SRT_TEX_CHECKER && (t.even < 0 || t.odd < 0 || t.even >= (int)s->texs.size() || t.odd >= (int)s->texs.size()))
       return fail(SRT_ERR_ARG, "texture %zu: checker children out of range", i);
   }
@@ -281,6 +296,9 @@ int srt_scene_commit(SrtScene* s) {
   CK(s->d_xf.ensure(2 * nx)); CK(s->d_mats.ensure(nm)); CK(s->d_tex.ensure(2 * nt));
   if (nx) CK(cudaMemcpyAsync(s->d_xf.p, xf.data(), sizeof(float4) * 2 * nx, cudaMemcpyHostToDevice, stream));
   if (nm) CK(cudaMemcpyAsync(s->d_mats.p, mt.data(), sizeof(int4) * nm, cudaMemcpyHostToDevice, stream));
+  CK(s->d_imgs.ensure(s->imgs.size())); CK(s->d_img_texels.ensure(s->img_texels.size()));
+  if (!s->imgs.empty()) CK(cudaMemcpyAsync(s->d_imgs.p, s->imgs.data(), sizeof(int4) * s->imgs.size(), cudaMemcpyHostToDevice, stream));
+  if (!s->img_texels.empty()) CK(cudaMemcpyAsync(s->d_img_texels.p, s->img_texels.data(), s->img_texels.size(), cudaMemcpyHostToDevice, stream));
   if (nt) CK(cudaMemcpyAsync(s->d_tex.p, tx.data(), sizeof(float4) * 2 * nt, cudaMemcpyHostToDevice, stream));
   std::vector<float4> rv(256); std::vector<uint8_t> pm(768);
   for (int i = 0; i < 256; ++i) rv[i] = s->has_perlin ? make_float4(s->ranvec[3 * i], s->ranvec[3 * i + 1], s->ranvec[3 * i + 2], 0) : make_float4(0, 0, 0, 0);

@@ -31,6 +31,8 @@ struct DScene {
   const float4* prim_shade; // 2 per primitive: (albedo.rgb if its texture is constant, material param) and
                             // (material kind, texture id, texture-is-constant, 0) as int bits: flattens the
                             // prim -> material -> texture -> colour chain of dependent loads for the shade kernel
+  const unsigned char* img_texels;   // image-texture texels (8-bit RGB), all images concatenated
+  const int4* imgs;                  // per image: (nx, ny, byte offset, 0)
   const float4* patch_cp;   // 16 control points per (sub-)patch (north-star extension)
   const int* prim_logical;  // logical primitive id reported by the parity hook (sub-patches share their parent's)
   const int* lights;        // primitive ids sampled by the hittable pdf (pdf.scm:28-32)
@@ -581,6 +583,16 @@ __device__ __forceinline__ float3 tex_value(const DScene& sc, int tex, float u, 
       continue;
     }
     if (kind == SRT_TEX_NOISE) { float n = perlin_noise(sc, p * t0.w, quirks); return v3(n, n, n); }   // texture.scm:25
+    if (kind == SRT_TEX_IMAGE) {                                                             // texture.scm:36-50
+      // i = u*nx, j = (1-v)*ny - 0.001, both clamped to [0, n-1]; upstream then indexes its data
+      // vector with the (non-integer) result, which Gauche rejects - the texel is the floor.
+      const int4 im = __ldg(&sc.imgs[__float_as_int(t0.y)]);
+      float fi = u * (float)im.x, fj = (1.0f - v) * (float)im.y - 0.001f;
+      fi = fi >= 0.0f ? fi : 0.0f; fj = fj >= 0.0f ? fj : 0.0f;          // also sends NaN (Q5 uv) to texel 0
+      fi = fi > (float)(im.x - 1) ? (float)(im.x - 1) : fi; fj = fj > (float)(im.y - 1) ? (float)(im.y - 1) : fj;
+      const unsigned char* px = sc.img_texels + (size_t)im.z + 3 * ((size_t)(int)fi + (size_t)im.x * (size_t)(int)fj);
+      return v3((float)__ldg(px) / 255.0f, (float)__ldg(px + 1) / 255.0f, (float)__ldg(px + 2) / 255.0f);
+    }
     float s = 0.5f * (1.0f + sinf(fmaf(t0.w, p.z, 10.0f * perlin_turb(sc, p, quirks))));                // texture.scm:30
     return v3(s, s, s);
   }

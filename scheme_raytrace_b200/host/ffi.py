@@ -23,7 +23,7 @@ class Stats(C.Structure):
 SYMBOLS = [
     "srt_device_count", "srt_init", "srt_last_error", "srt_shutdown", "srt_measure_fp32_peak", "srt_scene_create", "srt_scene_destroy",
     "srt_scene_set_prims", "srt_scene_set_xforms", "srt_scene_set_patches", "srt_scene_set_materials", "srt_scene_set_textures",
-    "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_set_lights", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
+    "srt_scene_set_images", "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_set_lights", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
     "srt_bvh_keys_readback", "srt_bvh_items_readback", "srt_prim_bounds_readback", "srt_trace_batch", "srt_render_host", "srt_render_device",
     "srt_resolve_device", "srt_resolve_host", "srt_save_ppm", "srt_eval_texture", "srt_eval_raygen",
 ]
@@ -50,6 +50,7 @@ def load():
     for name in ("srt_scene_set_prims", "srt_scene_set_xforms", "srt_scene_set_patches", "srt_scene_set_materials", "srt_scene_set_textures"):
         getattr(lib, name).argtypes = [vp, vp, i32]
     lib.srt_scene_set_patches.argtypes = [vp, vp, i32]
+    lib.srt_scene_set_images.argtypes = [vp, vp, vp, i32]
     lib.srt_scene_set_perlin.argtypes = [vp, vp, vp, vp, vp]
     lib.srt_scene_set_camera.argtypes = [vp, vp]
     lib.srt_scene_set_lights.argtypes = [vp, vp, i32]

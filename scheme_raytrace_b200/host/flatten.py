@@ -62,9 +62,11 @@ class FlatScene:
     leaves: list            # leaf Obj per primitive id (host bookkeeping)
     material_objs: list
     texture_objs: list
+    image_texels: np.ndarray = None   # uint8, every image-texture's texels concatenated
+    image_dims: np.ndarray = None     # (n_images, 3) int32: nx, ny, byte offset
 
     def h2d_bytes(self):
-        return int(self.prims.nbytes + self.patches.nbytes + self.xforms.nbytes + self.materials.nbytes + self.textures.nbytes + self.camera.nbytes)
+        return int(self.prims.nbytes + self.patches.nbytes + self.xforms.nbytes + self.materials.nbytes + self.textures.nbytes + self.camera.nbytes + self.image_texels.nbytes)
 
 
 def _compose(chain):
@@ -102,6 +104,7 @@ def flatten_scene(scene):
     boundary = []          # boundary primitives of constant media: appended after the surface primitives
     xform_ids = {}
     mats, mat_ids, texs, tex_ids = [], {}, [], {}
+    images = []            # (nx, ny, byte offset, texels) per image-texture
 
     def tex_id(tx):
         if id(tx) in tex_ids:
@@ -109,6 +112,10 @@ def flatten_scene(scene):
         even = odd = -1
         if tx.kind == t.CHECKER:
             even, odd = tex_id(tx.even), tex_id(tx.odd)
+        if tx.kind == t.IMAGE:
+            even = len(images)
+            off = sum(im[3].size for im in images)
+            images.append((tx.image.shape[1], tx.image.shape[0], off, tx.image.ravel()))
         tex_ids[id(tx)] = len(texs)
         texs.append((tx, even, odd))
         return tex_ids[id(tx)]
@@ -190,4 +197,6 @@ def flatten_scene(scene):
     if scene.camera is not None:
         C.view("<f4")[:] = np.asarray(camera_to_floats(scene.camera), dtype=np.float32)
     PT = np.asarray(patches, dtype=np.float32).reshape(-1, 48)
-    return FlatScene(P, PT, logical, first_of_logical, X, M, T, C, sky_kind(scene.sky_function), leaves, [m for m, _ in mats], [tx for tx, _, _ in texs])
+    return FlatScene(P, PT, logical, first_of_logical, X, M, T, C, sky_kind(scene.sky_function), leaves, [m for m, _ in mats], [tx for tx, _, _ in texs],
+                     np.concatenate([im[3] for im in images]).astype(np.uint8) if images else np.zeros(0, dtype=np.uint8),
+                     np.asarray([im[:3] for im in images], dtype=np.int32).reshape(-1, 3))

@@ -39,6 +39,7 @@ class Renderer:
         ffi.check(lib.srt_scene_set_patches(h, _ptr(f.patches), len(f.patches)), "set_patches")
         ffi.check(lib.srt_scene_set_materials(h, _ptr(f.materials), len(f.materials)), "set_materials")
         ffi.check(lib.srt_scene_set_textures(h, _ptr(f.textures), len(f.textures)), "set_textures")
+        ffi.check(lib.srt_scene_set_images(h, _ptr(f.image_texels), _ptr(f.image_dims), len(f.image_dims)), "set_images")
         rv, px, py, pz = self.perlin
         self._rv32 = np.ascontiguousarray(rv, dtype=np.float32)
         ffi.check(lib.srt_scene_set_perlin(h, _ptr(self._rv32), _ptr(px), _ptr(py), _ptr(pz)), "set_perlin")

@@ -12,6 +12,7 @@ module and by scheme/srt-scene.scm (the Gauche host), read by cli/srt_render.cpp
     patches <n>    then n lines:  48 floats
     prims <n>      then n lines:  type flags material xform p0..p15
     lights <n>     then 1 line :  ids
+    images <n>     then n lines:  nx ny followed by 3*nx*ny texel values 0..255 (optional section)
 """
 import numpy as np
 
@@ -45,3 +46,6 @@ def write_scene_file(path, flat, perlin, lights=()):
             f.write(f"{int(p['type'])} {int(p['flags'])} {int(p['material'])} {int(p['xform'])} {_f(p['p'])}\n")
         f.write(f"lights {len(lights)}\n")
         f.write(" ".join(str(int(i)) for i in lights) + "\n")
+        f.write(f"images {len(flat.image_dims)}\n")
+        for nx, ny, off in flat.image_dims:
+            f.write(f"{int(nx)} {int(ny)} " + " ".join(str(int(x)) for x in flat.image_texels[off:off + 3 * nx * ny]) + "\n")

@@ -258,6 +258,20 @@ def test_scene2(size_x=200, size_y=200):
     return g.make_scene(objs, default_camera(size_x, size_y), black)
 
 
+def image_scene(size_x=200, size_y=200, nx=16, ny=8, seed=11):
+    """image-texture (texture.scm:36-50; never instantiated upstream) on an emissive screen, a
+    lambertian ground (lambertian passes u = v = 0: one texel) and an emissive unit sphere (Q5 uv)."""
+    texels = np.random.RandomState(seed).randint(0, 256, size=nx * ny * 3)
+    img = t.image_texture(texels, nx, ny)
+    objs = [
+        g.make_sphere(v.vec3(0, -1000, -1), 1000, m.make_lambertian(img)),
+        g.make_sphere(v.vec3(0, 2, 0), 2, m.make_lambertian(t.constant_texture(v.vec3(0.7, 0.7, 0.7)))),
+        g.make_xy_rect(-5, 5, 0, 6, -3, m.make_diffuse_light(img)),
+        g.make_sphere(v.vec3(3.2, 0.5, 1.5), 0.5, m.make_diffuse_light(img)),
+    ]
+    return g.make_scene(objs, default_camera(size_x, size_y), black)
+
+
 def line_upped_spheres(nx=10, ny=10, seed=7):
     """main.scm:177-191 + 204-213 test-scene-non-bvh: the reference's own (commented) benchmark."""
     rnd = np.random.RandomState(seed).random_sample

@@ -43,9 +43,9 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cfg1", "smoke", "patches"])
+@pytest.mark.parametrize("name", ["cfg1", "smoke", "patches", "image"])
 def test_cli_matches_python_api(tmp_path, name):
-    fn = {"cfg1": scenes.cfg1_weekend, "smoke": scenes.cornell_smoke, "patches": scenes.cfg5_patches}[name]
+    fn = {"cfg1": scenes.cfg1_weekend, "smoke": scenes.cornell_smoke, "patches": scenes.cfg5_patches, "image": scenes.image_scene}[name]
     w, h, spp = 64, 32, 4
     scene = fn(w, h)
     path, flat = _write(tmp_path, scene)

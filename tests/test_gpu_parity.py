@@ -13,7 +13,7 @@ SMALL = {"cfg1": (scenes.cfg1_weekend, 200, 100), "cfg2": (scenes.cfg2_random_sp
          "bezier": (scenes.test_bezier, 64, 64), "cornell_bezier": (scenes.cornell_bezier, 64, 64),
          "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64),
          "smoke": (scenes.cornell_smoke, 64, 64), "patches": (scenes.cfg5_patches, 96, 54),
-         "klein": (scenes.cornell_klein, 48, 48)}
+         "klein": (scenes.cornell_klein, 48, 48), "image": (scenes.image_scene, 64, 64)}
 
 
 @pytest.fixture(scope="module", params=list(SMALL))
@@ -157,6 +157,29 @@ def test_texture_parity(orc):
             bad = np.abs(a - b).max(axis=1) > 2e-4
             # checker flips on sign(sin*sin*sin): fp32 may disagree only within rounding of a tile edge
             assert bad.mean() <= (0.002 if kind == 1 else 0.0), (kind, quirks, bad.sum(), np.abs(a - b).max())
+    r.close()
+
+
+def test_image_texture_parity(orc):
+    """image-texture lookup (texture.scm:36-50): every texel, clamping beyond [0,1], NaN uv."""
+    scene = scenes.image_scene(32, 32, nx=16, ny=8)
+    r = srt.Renderer(scene, device=0)
+    S = orc.OracleScene(scene, flat=r.flat, perlin=r.perlin)
+    tid = int(np.nonzero(r.flat.textures["kind"] == 4)[0][0])
+    rs = np.random.RandomState(5)
+    # sample points away from texel edges (fp32 u*nx may round across an edge the f64 oracle does not)
+    iu, iv = np.meshgrid(np.arange(16), np.arange(8), indexing="ij")
+    fr = rs.uniform(0.05, 0.9, (2, iu.size))
+    u = (iu.ravel() + fr[0]) / 16.0
+    vv = 1.0 - (iv.ravel() + fr[1] + 0.001) / 8.0
+    uvp = np.zeros((iu.size + 6, 5), dtype=np.float32)
+    uvp[:iu.size, 0], uvp[:iu.size, 1] = u, vv
+    uvp[iu.size:, :2] = [(-0.5, 0.5), (1.5, 0.5), (0.5, -0.5), (0.5, 1.5), (np.nan, 0.5), (0.5, np.nan)]
+    a = r.eval_texture(tid, uvp, 15)
+    b = S.tex_value(tid, uvp.astype(np.float64), 15)
+    assert np.array_equal(a, b.astype(np.float32)), np.abs(a - b).max()
+    img = r.flat.texture_objs[tid].image
+    assert np.array_equal(a[:iu.size], (img[iv.ravel(), iu.ravel()].astype(np.float32) / np.float32(255)))
     r.close()
 
 

@@ -206,3 +206,23 @@ def test_patch_revolved_profile_is_round(orc):
     assert np.all(r["prim"] >= 0)
     rad = np.hypot(r["p"][:, 0], r["p"][:, 2])
     assert np.max(np.abs(rad - 2.0)) < 2.0 * 3e-4 and np.allclose(r["t"], 6 - rad, atol=1e-9)
+
+
+def test_image_texture_lookup(orc):
+    """texture.scm:36-50: i = u*nx, j = (1-v)*ny - 0.001, clamped to [0, n-1], texel = floor; /255.
+    Hand-checked on a 4x2 image (row 0 = top)."""
+    from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, vec as v, scenes
+    data = np.arange(4 * 2 * 3) * 10            # texel (i, j) = 10 * (3*i + 12*j + c)
+    img = t.image_texture(data, 4, 2)
+    scene = g.make_scene([g.make_sphere(v.vec3(0, 0, -1), 0.5, m.make_diffuse_light(img))], scenes.default_camera(), scenes.black)
+    S = orc.OracleScene(scene, quantise=False)
+    uvp = np.array([[0.0, 1.0, 0, 0, 0],        # i=0, j=-0.001 -> 0      : texel (0,0)
+                    [0.3, 0.9, 0, 0, 0],        # i=1.2, j=0.199          : texel (1,0)
+                    [0.99, 0.4, 0, 0, 0],       # i=3.96 -> clamp 3, j=1.199 -> clamp 1: texel (3,1)
+                    [0.0, 0.0, 0, 0, 0],        # lambertian's u=v=0: i=0, j=1.999 -> clamp 1: texel (0,1)
+                    [2.0, -1.0, 0, 0, 0]])      # beyond the edges: texel (3,1)
+    got = S.tex_value(0, uvp, 15)
+    exp = np.array([[0, 10, 20], [30, 40, 50], [210, 220, 230], [120, 130, 140], [210, 220, 230]]) / 255.0
+    assert np.allclose(got, exp, atol=1e-15)
+    with pytest.raises(ValueError):
+        t.image_texture([0] * 5, 2, 1)

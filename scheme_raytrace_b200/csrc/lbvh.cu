@@ -295,7 +295,42 @@ __global__ void k_single_node(int n, const int* __restrict__ item_prim, const fl
   nodes[3] = make_float4(__int_as_float(~prim), __int_as_float(~prim), __int_as_float(-1), __int_as_float(-1));
 }
 
+// Surface-area sums of a built tree: out[0] = sum over internal nodes, out[1] = sum over leaf
+// (child) boxes, out[2] = root.  One CTA, per-thread strided partial sums in double and a fixed
+// shared-memory tree: the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __restrict__ nodes, double* __restrict__ out) {
+  __shared__ double sh[2][256];
+  const int n_nodes = n_items > 1 ? n_items - 1 : 1;
+  double a_int = 0.0, a_leaf = 0.0, a_root = 0.0;
+  for (int i = threadIdx.x; i < n_nodes; i += 256) {
+    const float4 f0 = nodes[4 * i], f1 = nodes[4 * i + 1], f2 = nodes[4 * i + 2], f3 = nodes[4 * i + 3];
+    const double le[3] = {f0.w, f1.x, f1.y}, re[3] = {f2.y, f2.z, f2.w};
+    const double al = 8.0 * (le[0] * le[1] + le[1] * le[2] + le[0] * le[2]), ar = 8.0 * (re[0] * re[1] + re[1] * re[2] + re[0] * re[2]);
+    if (__float_as_int(f3.x) >= 0) a_int += al; else a_leaf += al;
+    if (n_items > 1) { if (__float_as_int(f3.y) >= 0) a_int += ar; else a_leaf += ar; }
+    if (i == 0) {
+      const double lc[3] = {f0.x, f0.y, f0.z}, rc[3] = {f1.z, f1.w, f2.x};
+      double d[3];
+      for (int k = 0; k < 3; ++k) d[k] = fmax(lc[k] + le[k], rc[k] + re[k]) - fmin(lc[k] - le[k], rc[k] - re[k]);
+      a_root = 2.0 * (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
+    }
+  }
+  sh[0][threadIdx.x] = a_int; sh[1][threadIdx.x] = a_leaf;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0][0] + a_root; out[1] = sh[1][0]; out[2] = a_root; }
+}
+
 }  // namespace
+
+// Surface-area sums of the tree just built (see k_tree_area); d_out = 3 doubles on the device.
+int srt_lbvh_tree_area(int n_items, LbvhBuffers& B, double* d_out, cudaStream_t stream) {
+  k_tree_area<<<1, 256, 0, stream>>>(n_items, B.d_nodes, d_out);
+  return 1;
+}
 
 // Phase A: primitive AABBs of every scene surface (by primitive id).
 int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream) {

@@ -44,7 +44,7 @@ struct SrtScene {
   std::vector<float> patches; DevBuf<float4> d_patches; DevBuf<int> d_logical;
   bool committed = false;
   // device tables
-  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats, d_imgs; DevBuf<uint8_t> d_perm, d_img_texels;
+  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats, d_imgs; DevBuf<double> d_tree_area; DevBuf<uint8_t> d_perm, d_img_texels;
   // LBVH
   LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth, d_item_prim;
   std::vector<int> item_prim, global_prims;
@@ -125,7 +125,7 @@ SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); 
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
-  s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
+  s->d_tree_area.release(); s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
@@ -332,30 +332,80 @@ int srt_scene_commit(SrtScene* s) {
   std::vector<float> hb(6 * (size_t)(ns ? ns : 1));
   if (ns) CK(cudaMemcpyAsync(hb.data(), B.d_aabb, sizeof(float) * 6 * (size_t)ns, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
+  // Which surfaces stay OUT of the tree ("global": tested by all lanes before traversal).
+  //  1. Klein primitives (no bounding box upstream) - forced.
+  //  2. huge ones: extent e_i (max side of AABB i) >= 0.5 E, E = max side of the union of all boxes;
+  //     largest first, ties lower id.  These are what the reference's own scenes keep beside the
+  //     BVH, `(list ground bvh-node)` main.scm:215-235.
+  //  3. outliers among the rest (spheres / rects only, e_i >= 1.5 x the median extent of the rest,
+  //     largest first), taken as a PREFIX of length k chosen by the surface-area cost of the
+  //     resulting tree:  cost(k) = (sum internal SA + C_LEAF sum leaf SA) / A_ref + C_GLOBAL k,
+  //     A_ref = root SA at k = 0.  A few big objects among many small ones (the three r = 1 spheres
+  //     of random-scene, main.scm:84-88) inflate every ancestor box on their root path; LBVH
+  //     quality is also not monotone in k (the centroid grid moves), hence measured per k on the
+  //     GPU-built tree rather than guessed.  C_LEAF = 2 node steps (a divergent leaf test),
+  //     C_GLOBAL = 0.25 (a coherent test by all lanes): fitted to cfg2 / cfg3 timings.
+  // At most SRT_MAX_GLOBAL in all; the search only runs when >= 16 items remain.
+  std::vector<int> base, extra;
   {
-    // rule (DESIGN.md "LBVH"): extent e_i = max side of AABB i, E = max side of the union; i is
-    // global iff e_i >= 0.5 E; at most SRT_MAX_GLOBAL, largest extent first (ties: lower id)
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-    std::vector<float> ext(ns);
+    std::vector<float> ext(ns ? ns : 1);
     for (int i = 0; i < ns; ++i) { float e = 0.f; if (s->prims[i].type == SRT_PRIM_KLEIN) { ext[i] = 0.f; continue; } for (int k = 0; k < 3; ++k) { float a0 = hb[6 * i + k], a1 = hb[6 * i + 3 + k]; lo[k] = a0 < lo[k] ? a0 : lo[k]; hi[k] = a1 > hi[k] ? a1 : hi[k]; e = (a1 - a0) > e ? (a1 - a0) : e; } ext[i] = e; }
     float E = 0.f; for (int k = 0; k < 3; ++k) E = (hi[k] - lo[k]) > E ? (hi[k] - lo[k]) : E;
-    std::vector<int> cand, forced;
-    for (int i = 0; i < ns; ++i) if (s->prims[i].type == SRT_PRIM_KLEIN) forced.push_back(i);      // no bounding box: always global
+    std::vector<int> forced;
+    for (int i = 0; i < ns; ++i) if (s->prims[i].type == SRT_PRIM_KLEIN) forced.push_back(i);
     if ((int)forced.size() > SRT_MAX_GLOBAL) return fail(SRT_ERR_ARG, "at most %d Klein primitives per scene", SRT_MAX_GLOBAL);
-    for (int i = 0; i < ns; ++i) if (s->prims[i].type != SRT_PRIM_KLEIN && ns > 2 && ext[i] >= 0.5f * E) cand.push_back(i);
-    std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return ext[x] > ext[y]; });
-    if ((int)(cand.size() + forced.size()) > SRT_MAX_GLOBAL) cand.resize(SRT_MAX_GLOBAL - forced.size());
-    cand.insert(cand.end(), forced.begin(), forced.end());
-    std::sort(cand.begin(), cand.end());
-    s->global_prims = cand; s->item_prim.clear();
-    size_t gi = 0;
-    for (int i = 0; i < ns; ++i) { if (gi < cand.size() && cand[gi] == i) { ++gi; continue; } s->item_prim.push_back(i); }
+    for (int i = 0; i < ns; ++i) if (s->prims[i].type != SRT_PRIM_KLEIN && ns > 2 && ext[i] >= 0.5f * E) base.push_back(i);
+    std::stable_sort(base.begin(), base.end(), [&](int x, int y) { return ext[x] > ext[y]; });
+    if ((int)(base.size() + forced.size()) > SRT_MAX_GLOBAL) base.resize(SRT_MAX_GLOBAL - forced.size());
+    base.insert(base.end(), forced.begin(), forced.end());
+    std::vector<char> taken(ns ? ns : 1, 0);
+    for (int i : base) taken[i] = 1;
+    std::vector<int> rest;
+    for (int i = 0; i < ns; ++i) if (!taken[i]) rest.push_back(i);
+    if (rest.size() >= 16 && (int)base.size() < SRT_MAX_GLOBAL) {
+      std::vector<float> es; for (int i : rest) es.push_back(ext[i]);
+      std::nth_element(es.begin(), es.begin() + es.size() / 2, es.end());
+      const float med = es[es.size() / 2];
+      for (int i : rest) if (s->prims[i].type <= SRT_PRIM_YZ_RECT && ext[i] >= 1.5f * med) extra.push_back(i);
+      std::stable_sort(extra.begin(), extra.end(), [&](int x, int y) { return ext[x] > ext[y]; });
+      if (extra.size() > SRT_MAX_GLOBAL - base.size()) extra.resize(SRT_MAX_GLOBAL - base.size());
+    }
   }
-  const int nitems = (int)s->item_prim.size();
-  if (nitems) CK(cudaMemcpyAsync(B.d_item_prim, s->item_prim.data(), sizeof(int) * (size_t)nitems, cudaMemcpyHostToDevice, stream));
-  s->n_items = nitems; s->n_nodes = nitems > 1 ? nitems - 1 : 1;
+  auto build_with = [&](int k) -> int {          // tree over everything but base + extra[0..k)
+    std::vector<int> g(base); g.insert(g.end(), extra.begin(), extra.begin() + k);
+    std::sort(g.begin(), g.end());
+    s->global_prims = g; s->item_prim.clear();
+    size_t gi = 0;
+    for (int i = 0; i < ns; ++i) { if (gi < g.size() && g[gi] == i) { ++gi; continue; } s->item_prim.push_back(i); }
+    const int nitems = (int)s->item_prim.size();
+    if (nitems && cudaMemcpyAsync(B.d_item_prim, s->item_prim.data(), sizeof(int) * (size_t)nitems, cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
+    s->n_items = nitems; s->n_nodes = nitems > 1 ? nitems - 1 : 1;
+    s->commit_launches += srt_lbvh_build(nitems, B, stream);
+    return nitems;
+  };
+  int chosen = 0;
+  if (!extra.empty()) {
+    const double C_LEAF = 2.0, C_GLOBAL = 0.25;
+    const int nk = (int)extra.size() + 1;
+    CK(s->d_tree_area.ensure(3 * (size_t)nk));
+    for (int k = 0; k < nk; ++k) {
+      const int nitems = build_with(k);
+      if (nitems < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed");
+      s->commit_launches += srt_lbvh_tree_area(nitems, B, s->d_tree_area.p + 3 * k, stream);
+    }
+    std::vector<double> area(3 * (size_t)nk);
+    CK(cudaMemcpyAsync(area.data(), s->d_tree_area.p, sizeof(double) * area.size(), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    double best = 0.0;
+    for (int k = 0; k < nk; ++k) {
+      const double c = (area[3 * k] + C_LEAF * area[3 * k + 1]) / area[2] + C_GLOBAL * k;
+      if (getenv("SRT_DEBUG_COMMIT")) std::fprintf(stderr, "[srt commit] k=%d prim=%d internal %.3f leaf %.3f cost %.3f\n", k, k ? extra[k - 1] : -1, area[3 * k] / area[2], area[3 * k + 1] / area[2], c);
+      if (k == 0 || c < best) { best = c; chosen = k; }
+    }
+  }
+  if (extra.empty() || chosen != (int)extra.size()) { if (build_with(chosen) < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed"); }
   fill_dscene(s);
-  s->commit_launches += srt_lbvh_build(nitems, B, stream);
   CK(cudaGetLastError());
   int depth = 0;
   CK(cudaMemcpyAsync(&depth, B.d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));

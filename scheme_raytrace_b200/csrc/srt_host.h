@@ -22,6 +22,7 @@ struct LbvhBuffers {
 
 int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
 int srt_lbvh_build(int n_items, LbvhBuffers& B, cudaStream_t stream);
+int srt_lbvh_tree_area(int n_items, LbvhBuffers& B, double* d_out3, cudaStream_t stream);
 
 // Wavefront queues (SoA, 16-byte vectorised).  Two generations (ping-pong) of the ray/state
 // arrays: shade reads generation g and writes the compacted survivors into generation g^1, regen

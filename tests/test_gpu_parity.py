@@ -26,6 +26,58 @@ def pair(request, orc):
     r.close()
 
 
+def _tree_areas(nodes, n_items):
+    """Surface-area sums of a host-built tree, as k_tree_area computes them (csrc/lbvh.cu)."""
+    le, re = nodes["le"].astype(np.float64), nodes["re"].astype(np.float64)
+    al = 8 * (le[:, 0] * le[:, 1] + le[:, 1] * le[:, 2] + le[:, 0] * le[:, 2])
+    ar = 8 * (re[:, 0] * re[:, 1] + re[:, 1] * re[:, 2] + re[:, 0] * re[:, 2])
+    if n_items <= 1:
+        ar = ar * 0
+    d = np.maximum(nodes["lc"][0].astype(np.float64) + le[0], nodes["rc"][0].astype(np.float64) + re[0]) - \
+        np.minimum(nodes["lc"][0].astype(np.float64) - le[0], nodes["rc"][0].astype(np.float64) - re[0])
+    root = 2 * (d[0] * d[1] + d[1] * d[2] + d[0] * d[2])
+    a_int = al[nodes["left"] >= 0].sum() + ar[nodes["right"] >= 0].sum() + root
+    a_leaf = al[nodes["left"] < 0].sum() + (ar[nodes["right"] < 0].sum() if n_items > 1 else 0.0)
+    return a_int, a_leaf, root
+
+
+def _global_selection(orc, types, aabb):
+    """The commit rule of csrc/srt_api.cu restated: forced (Klein) + huge (>= 0.5 E) primitives, then
+    the cost-minimal prefix of the outliers (>= 1.5 x median extent) by tree surface area."""
+    n = len(aabb)
+    klein = types == 8
+    ext = (aabb[:, 3:] - aabb[:, :3]).max(axis=1).astype(np.float32)
+    ext[klein] = 0
+    E = np.float32((aabb[~klein, 3:].max(axis=0) - aabb[~klein, :3].min(axis=0)).max()) if (~klein).any() else np.float32(0)
+    forced = np.nonzero(klein)[0].tolist()
+    huge = [i for i in range(n) if not klein[i] and n > 2 and ext[i] >= np.float32(0.5) * E]
+    huge.sort(key=lambda i: -ext[i])                                   # stable: ties keep the lower id first
+    huge = huge[:max(8 - len(forced), 0)]
+    base = huge + forced
+    rest = [i for i in range(n) if i not in set(base)]
+    extra = []
+    if len(rest) >= 16 and len(base) < 8:
+        med = np.sort(ext[rest])[len(rest) // 2]
+        extra = [i for i in rest if types[i] <= 4 and ext[i] >= np.float32(1.5) * med]
+        extra.sort(key=lambda i: -ext[i])
+        extra = extra[:8 - len(base)]
+    if not extra:
+        return base, extra, 0
+    costs = []
+    for k in range(len(extra) + 1):
+        g = set(base + extra[:k])
+        items = np.array([i for i in range(n) if i not in g])
+        _, _, nodes = orc.lbvh_build(aabb[items])
+        a_int, a_leaf, root = _tree_areas(nodes, len(items))
+        if k == 0:
+            ref = root
+        costs.append((a_int + 2.0 * a_leaf) / ref + 0.25 * k)
+    k = int(np.argmin(costs))
+    second = np.partition(costs, 1)[1] if len(costs) > 1 else np.inf
+    assert second - costs[k] > 1e-9 * costs[k], ("ambiguous cost minimum: pick another test scene", costs)
+    return base, extra, k
+
+
 def test_lbvh_bit_exact(pair, orc):
     """GPU Morton keys / sort order / Karras topology / node boxes == sequential host reference,
     byte for byte, over the same (GPU-computed) primitive AABBs."""
@@ -33,11 +85,8 @@ def test_lbvh_bit_exact(pair, orc):
     aabb = r.prim_bounds()
     items, glob = r.bvh_items()
     assert sorted(items.tolist() + glob.tolist()) == list(range(len(aabb)))     # every surface is in the tree or global
-    ext = (aabb[:, 3:] - aabb[:, :3]).max(axis=1)
-    E = (aabb[:, 3:].max(axis=0) - aabb[:, :3].min(axis=0)).max()
-    klein = r.flat.prims["type"][:len(aabb)] == 8
-    ext[klein] = 0; E = (aabb[~klein, 3:].max(axis=0) - aabb[~klein, :3].min(axis=0)).max() if (~klein).any() else 0
-    assert all(ext[gp] >= 0.5 * E or klein[gp] for gp in glob) and (len(glob) == 8 or len(aabb) <= 2 or not np.any(ext[items] >= 0.5 * E))
+    base, extra, k = _global_selection(orc, r.flat.prims["type"][:len(aabb)], aabb)
+    assert sorted(glob.tolist()) == sorted(base + extra[:k]), (glob, base, extra, k)
     keys_g, order_g = r.bvh_keys()
     if len(items) == 0:                                                # everything is global: no tree to compare
         assert len(keys_g) == 0

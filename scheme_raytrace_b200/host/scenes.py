@@ -272,6 +272,20 @@ def image_scene(size_x=200, size_y=200, nx=16, ny=8, seed=11):
     return g.make_scene(objs, default_camera(size_x, size_y), black)
 
 
+def sphere_cloud(n, size_x=64, size_y=64, seed=13):
+    """n small spheres in a 40^3 cube over a ground sphere: sizes the shared-memory staging
+    cannot hold (trees read through L1/L2; >= 65536 nodes also drops the 16-bit far-child cache)."""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-20, 20, (n, 3)); c[:, 1] += 20.5
+    r = rs.uniform(0.15, 0.4, n)       # not smaller: the fp32 normal (p - c)/r loses |c|/r ulps
+    mats = [m.make_lambertian(t.constant_texture(v.vec3(0.2 + 0.1 * k, 0.5, 0.8 - 0.1 * k))) for k in range(6)]
+    mats += [m.make_metal(t.constant_texture(v.vec3(0.8, 0.8, 0.8)), 0.1), m.make_dielectric(1.5)]
+    objs = [g.make_sphere(v.vec3(0, -1000, 0), 1000, m.make_lambertian(_checker()))]
+    objs += [g.make_sphere(v.vec3(*c[i]), float(r[i]), mats[i % len(mats)]) for i in range(n)]
+    camera = cam.make_camera(v.vec3(0, 20, 70), v.vec3(0, 20, 0), v.vec3(0, 1, 0), 40, size_x / size_y, 0.0, 70.0, 0.0, 1.0)
+    return g.make_scene(objs, camera, sky_color)
+
+
 def line_upped_spheres(nx=10, ny=10, seed=7):
     """main.scm:177-191 + 204-213 test-scene-non-bvh: the reference's own (commented) benchmark."""
     rnd = np.random.RandomState(seed).random_sample

@@ -138,15 +138,27 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
 // enters it.  Because that climb is a serial chain of dependent loads executed by few lanes, the
 // 8 most recent far children are additionally cached in two 64-bit registers (16-bit ids,
 // CACHE = true when the tree has < 65536 nodes); the climb only runs when the cache has overflowed.
+// 16-byte read of LBVH word `idx` (4 per node).  Shared-memory trees are addressed through a
+// 32-bit shared-space base computed once per thread: through the generic pointer the compiler
+// re-derives the shared window (S2R SR_CgaCtaId + LEA) in every iteration of the node loop.
+template <bool SMEM>
+__device__ __forceinline__ float4 ld_node(const float4* __restrict__ nodes, uint32_t sbase, int idx) {
+  if (SMEM) {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sbase + 16u * (uint32_t)idx));
+    return r;
+  }
+  return __ldg(&nodes[idx]);
+}
+
 template <bool SMEM, bool CACHE>
-__device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, float tmin, int& pend0, int& pend1) {
+__device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, uint32_t sbase, float tmin, int& pend0, int& pend1) {
   const int node = T.node;
 #ifdef SRT_COUNT_STEPS
   T.nsteps++;
 #endif
-  float4 n0, n1, n2, n3;
-  if (SMEM) { n0 = nodes[4 * node]; n1 = nodes[4 * node + 1]; n2 = nodes[4 * node + 2]; n3 = nodes[4 * node + 3]; }
-  else { n0 = __ldg(&nodes[4 * node]); n1 = __ldg(&nodes[4 * node + 1]); n2 = __ldg(&nodes[4 * node + 2]); n3 = __ldg(&nodes[4 * node + 3]); }
+  const float4 n0 = ld_node<SMEM>(nodes, sbase, 4 * node), n1 = ld_node<SMEM>(nodes, sbase, 4 * node + 1),
+               n2 = ld_node<SMEM>(nodes, sbase, 4 * node + 2), n3 = ld_node<SMEM>(nodes, sbase, 4 * node + 3);
   const float3 inv = T.inv, oi = T.oi, ai = T.ainv;
   // left: c = (n0.x n0.y n0.z) e = (n0.w n1.x n1.y); right: c = (n1.z n1.w n2.x) e = (n2.y n2.z n2.w)
   float lcx = fmaf(n0.x, inv.x, -oi.x), lcy = fmaf(n0.y, inv.y, -oi.y), lcz = fmaf(n0.z, inv.z, -oi.z);
@@ -155,10 +167,14 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   float lt1 = fminf(fminf(fmaf(n0.w, ai.x, lcx), fmaf(n1.x, ai.y, lcy)), fminf(fmaf(n1.y, ai.z, lcz), T.h.t));
   float rt0 = fmaxf(fmaxf(fmaf(-n2.y, ai.x, rcx), fmaf(-n2.z, ai.y, rcy)), fmaxf(fmaf(-n2.w, ai.z, rcz), tmin));
   float rt1 = fminf(fminf(fmaf(n2.y, ai.x, rcx), fmaf(n2.z, ai.y, rcy)), fminf(fmaf(n2.w, ai.z, rcz), T.h.t));
-  bool hl = lt0 <= lt1, hr = rt0 <= rt1;
-  int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
-  if (hl && left < 0) { pend0 = ~left; hl = false; }
-  if (hr && right < 0) { if (pend0 < 0) pend0 = ~right; else pend1 = ~right; hr = false; }
+  const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+  const bool hl0 = lt0 <= lt1, hr0 = rt0 <= rt1;
+  // hit leaf children go to (pend0, pend1) - select form: as branches this was a divergent region
+  // plus byte-packed booleans carried across it
+  const bool ll = hl0 & (left < 0), rl = hr0 & (right < 0);
+  pend0 = ll ? ~left : (rl ? ~right : -1);
+  pend1 = (ll & rl) ? ~right : -1;
+  const bool hl = hl0 & (left >= 0), hr = hr0 & (right >= 0);
   if (hl | hr) {
     bool both = hl & hr;
     bool go_left = both ? (lt0 <= rt0) : hl;                  // near child first
@@ -184,7 +200,7 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   }
   int par = __float_as_int(n3.z), sib = __float_as_int(n3.w);
   for (int k = 0; k < up; ++k) {
-    float4 m = SMEM ? nodes[4 * par + 3] : __ldg(&nodes[4 * par + 3]);
+    const float4 m = ld_node<SMEM>(nodes, sbase, 4 * par + 3);
     par = __float_as_int(m.z); sib = __float_as_int(m.w);
   }
   T.node = sib;
@@ -202,6 +218,8 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
     return;
   }
   Trav T;
+  uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
+  asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     const float4 d4 = ray_d[i];
     trav_init(T, ray_o[i], d4, tmax, i);
@@ -215,7 +233,7 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
     bool more = sc.n_items > 0;
     while (more) {
       int pend0 = -1, pend1 = -1;
-      more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+      more = node_step<SMEM, CACHE>(T, nodes, sbase, tmin, pend0, pend1);
       while (pend0 >= 0) {
 #ifdef SRT_COUNT_STEPS
         T.ntests++;
@@ -249,6 +267,8 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
     return;
   }
   Trav T;
+  uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
+  asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < count; base += gridDim.x * blockDim.x) {   // warp-uniform
     const int i = base + lane;
     bool more = i < count;
@@ -281,7 +301,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
       }
       if (more && !parked) {
         int pend0 = -1, pend1 = -1;
-        more = node_step<SMEM, CACHE>(T, nodes, tmin, pend0, pend1);
+        more = node_step<SMEM, CACHE>(T, nodes, sbase, tmin, pend0, pend1);
         while (pend0 >= 0) {
           const int type = ps.hdr(pend0).x & 0xff;
           if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }

@@ -105,6 +105,7 @@ struct Trav {
   Hit h; int node; unsigned long long trail; int ray;
   RngAddr ra;                                // only read by constant-medium primitives
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
+  uint32_t sp, sp0;                         // TRAV_STACK: shared-space address of the next free / first stack slot
 #ifdef SRT_COUNT_STEPS
   int nsteps, ntests, nmiss;                // instrumented build only (tools/step_stats.py)
 #endif
@@ -120,7 +121,7 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
   T.ainv = v3(fabsf(T.inv.x), fabsf(T.inv.y), fabsf(T.inv.z));
   T.inv_a = 1.0f / dot(T.d, T.d);
   T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
-  T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0;
+  T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0; T.sp = T.sp0;
 #ifdef SRT_COUNT_STEPS
   T.nsteps = 0; T.ntests = 0; T.nmiss = 0;
 #endif
@@ -151,7 +152,17 @@ __device__ __forceinline__ float4 ld_node(const float4* __restrict__ nodes, uint
   return __ldg(&nodes[idx]);
 }
 
-template <bool SMEM, bool CACHE>
+// Backtracking modes (template parameter TRAV):
+//  TRAV_STACK  per-thread stack of 16-bit node ids in shared memory, bvh_depth + 1 entries (a thread
+//              never has more far children pending than internal nodes on its root path): push =
+//              STS.U16, pop = LDS.U16.  Used whenever the tree has < 65536 nodes and the stack fits.
+//  TRAV_CACHE  stackless bit trail + parent/sibling climb, with the 8 most recent far children in
+//              two 64-bit registers.
+//  TRAV_TRAIL  the bit trail alone (>= 65536 nodes).
+enum { TRAV_TRAIL = 0, TRAV_CACHE = 1, TRAV_STACK = 2 };
+__host__ __device__ __forceinline__ int trav_stack_stride(int bvh_depth) { return (bvh_depth + 1) | 1; }   // halfwords per thread, odd: spreads banks
+
+template <bool SMEM, int TRAV>
 __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, uint32_t sbase, float tmin, int& pend0, int& pend1) {
   const int node = T.node;
 #ifdef SRT_COUNT_STEPS
@@ -179,8 +190,15 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
     bool both = hl & hr;
     bool go_left = both ? (lt0 <= rt0) : hl;                  // near child first
     T.node = go_left ? left : right;
+    if (TRAV == TRAV_STACK) {
+      if (both) {
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(T.sp), "h"((unsigned short)(go_left ? right : left)) : "memory");
+        T.sp += 2u;
+      }
+      return true;
+    }
     T.trail = (T.trail << 1) | (both ? 1ull : 0ull);
-    if (CACHE && both) {
+    if (TRAV == TRAV_CACHE && both) {
       unsigned long long far_id = (unsigned long long)(unsigned)(go_left ? right : left);
       T.s1 = (T.s1 << 16) | (T.s0 >> 48);
       T.s0 = (T.s0 << 16) | far_id;
@@ -188,10 +206,18 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
     }
     return true;
   }
+  if (TRAV == TRAV_STACK) {
+    if (T.sp == T.sp0) return false;
+    T.sp -= 2u;
+    unsigned short id;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(id) : "r"(T.sp) : "memory");
+    T.node = (int)id;
+    return true;
+  }
   if (T.trail == 0ull) return false;
   int up = __ffsll((long long)T.trail) - 1;                   // levels up to the pending far child
   T.trail = (T.trail >> up) ^ 1ull;
-  if (CACHE && T.nstk > 0) {
+  if (TRAV == TRAV_CACHE && T.nstk > 0) {
     T.node = (int)(T.s0 & 0xffffull);
     T.s0 = (T.s0 >> 16) | (T.s1 << 48);
     T.s1 >>= 16;
@@ -209,15 +235,16 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
 
 // One ray per lane, 32 consecutive rays per warp (static assignment: dynamic ray fetch and a
 // while-while loop were both measured slower at 32 resident warps/SM, see profiles/README.md).
-template <bool SMEM, int MASK, bool CACHE, class PrimSrc>
+template <bool SMEM, int MASK, int TRAV, class PrimSrc>
 __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
                                             const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                            float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed) {
+                                            float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed, uint32_t stack_base) {
   if (sc.n_surf == 0) {   // empty scene: every ray misses
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
     return;
   }
   Trav T;
+  T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -233,7 +260,7 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
     bool more = sc.n_items > 0;
     while (more) {
       int pend0 = -1, pend1 = -1;
-      more = node_step<SMEM, CACHE>(T, nodes, sbase, tmin, pend0, pend1);
+      more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
       while (pend0 >= 0) {
 #ifdef SRT_COUNT_STEPS
         T.ntests++;
@@ -256,10 +283,10 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
 // candidate queue", one or two entries per lane, in registers).  Cheap primitives (spheres,
 // rects) are still intersected immediately.
 constexpr int EXT_PARK_VOTE = 12;
-template <bool SMEM, int MASK, bool CACHE, class PrimSrc>
+template <bool SMEM, int MASK, int TRAV, class PrimSrc>
 __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
                                                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                                     float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed) {
+                                                     float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed, uint32_t stack_base) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   if (sc.n_surf == 0) {
@@ -267,6 +294,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
     return;
   }
   Trav T;
+  T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < count; base += gridDim.x * blockDim.x) {   // warp-uniform
@@ -301,7 +329,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
       }
       if (more && !parked) {
         int pend0 = -1, pend1 = -1;
-        more = node_step<SMEM, CACHE>(T, nodes, sbase, tmin, pend0, pend1);
+        more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
         while (pend0 >= 0) {
           const int type = ps.hdr(pend0).x & 0xff;
           if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
@@ -322,7 +350,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
   }
 }
 
-template <bool SMEM, int MASK, bool CACHE>
+template <bool SMEM, int MASK, int TRAV>
 __global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x1e0) ? 2 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
          float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
@@ -339,12 +367,14 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
     PrimShared ps{sh, sa};
-    if (MASK & 0x1e0) extend_loop_deferred<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
-    else extend_loop<true, MASK, CACHE>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    const uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np);      // TRAV_STACK: after the staged scene
+    if (MASK & 0x1e0) extend_loop_deferred<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
+    else extend_loop<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
-    if (MASK & 0x1e0) extend_loop_deferred<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
-    else extend_loop<false, MASK, CACHE>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed);
+    const uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(smem);
+    if (MASK & 0x1e0) extend_loop_deferred<false, MASK, TRAV>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
+    else extend_loop<false, MASK, TRAV>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
   }
 }
 
@@ -522,7 +552,7 @@ size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes 
 // Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
 typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
-static ExtendVariant g_variants[2][4][2];
+static ExtendVariant g_variants[2][4][3];
 
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
@@ -530,27 +560,32 @@ static int variant_of(int mask) {
   if ((mask & 0x1e0) == 0) return 2;
   return 3;
 }
-template <bool SMEM, bool CACHE> static ExtendFn variant_fn_m(int v) {
+template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v) {
   switch (v) {
-    case 0: return k_extend<SMEM, 0x01, CACHE>;
-    case 1: return k_extend<SMEM, 0x03, CACHE>;
-    case 2: return k_extend<SMEM, 0x1f, CACHE>;
-    default: return k_extend<SMEM, SRT_MASK_ALL, CACHE>;
+    case 0: return k_extend<SMEM, 0x01, TRAV>;
+    case 1: return k_extend<SMEM, 0x03, TRAV>;
+    case 2: return k_extend<SMEM, 0x1f, TRAV>;
+    default: return k_extend<SMEM, SRT_MASK_ALL, TRAV>;
   }
 }
-static ExtendFn variant_fn(bool smem, int v, bool cache) {
-  if (cache) return smem ? variant_fn_m<true, true>(v) : variant_fn_m<false, true>(v);
-  return smem ? variant_fn_m<true, false>(v) : variant_fn_m<false, false>(v);
+static ExtendFn variant_fn(bool smem, int v, int trav) {
+  if (trav == TRAV_STACK) return smem ? variant_fn_m<true, TRAV_STACK>(v) : variant_fn_m<false, TRAV_STACK>(v);
+  if (trav == TRAV_CACHE) return smem ? variant_fn_m<true, TRAV_CACHE>(v) : variant_fn_m<false, TRAV_CACHE>(v);
+  return smem ? variant_fn_m<true, TRAV_TRAIL>(v) : variant_fn_m<false, TRAV_TRAIL>(v);
 }
 // persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
 static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
-  int cache = L.sc.n_nodes < 65536 ? 1 : 0;          // 16-bit node ids in the far-child register cache
-  ExtendVariant& e = g_variants[which][v][cache];
-  size_t smem = which ? L.extend_smem : 0;
+  // 16-bit node ids: shared-memory stack when it fits beside the staged scene, else the register cache
+  const size_t stack = (size_t)2 * trav_stack_stride(L.sc.bvh_depth) * EXT_THREADS;
+  const bool small_ids = L.sc.n_nodes < 65536;
+  const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling
+  int trav = !small_ids ? TRAV_TRAIL : ((!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE);
+  ExtendVariant& e = g_variants[which][v][trav];
+  size_t smem = (which ? L.extend_smem : 0) + (trav == TRAV_STACK ? stack : 0);
   if (!e.fn || e.smem != smem) {
-    e.fn = variant_fn(which, v, cache); e.smem = smem;
-    if (which) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e.fn = variant_fn(which, v, trav); e.smem = smem;
+    if (smem) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, EXT_THREADS, smem);
     e.bps = bps < 1 ? 1 : bps;

@@ -247,9 +247,15 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
   T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const float4 d4 = ray_d[i];
-    trav_init(T, ray_o[i], d4, tmax, i);
+  // the next ray of this thread is fetched while the current one is traversed
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 o4n = make_float4(0.f, 0.f, 0.f, 0.f), d4n = o4n;
+  if (i < count) { o4n = ray_o[i]; d4n = ray_d[i]; }
+  for (; i < count; i += stride) {
+    const float4 o4 = o4n, d4 = d4n;
+    if (i + stride < count) { o4n = ray_o[i + stride]; d4n = ray_d[i + stride]; }
+    trav_init(T, o4, d4, tmax, i);
     if (MASK & 0x40) {   // Philox address of this ray: (pixel, sample, bounce = depth + 1)
       const int sd = __float_as_int(d4.w);
       T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;

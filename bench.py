@@ -246,7 +246,7 @@ def main():
     e2e_value = rays_e2e / e2e_s / 1e6
     # roofline of the dominant kernel (extend), measured live with CUDA events around every
     # extend launch of one extra profiling pass (events on the launching stream, stream 0)
-    prof_spp = max(1, min(s_end - s_begin, 16))
+    prof_spp = max(1, min(s_end - s_begin, 128))     # enough samples for steady-state iterations (full queue + regeneration)
     accum.zero_()
     p = r.params(W, H, s_begin, s_begin + prof_spp, D, SEED)
     p.reserved[0] = 1
@@ -257,7 +257,7 @@ def main():
     peak, peak_kind = read_peaks()
     ext_ms = pst.ms_extend
     ext_gbs = (B_PER_RAY_EXTEND * pst.rays) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_extend (stackless LBVH closest hit)", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_extend (LBVH closest hit)", "achieved": ext_gbs, "peak": peak, "unit": "GB/s",
                 "frac": ext_gbs / peak, "traffic": NCU_EXTEND_DRAM_B_PER_RAY * pst.rays / max(pst.extend_launches, 1), "peak_kind": peak_kind,
                 "traffic_note": "bytes per launch = ncu-measured 47.6 B/ray (profiles/r1_traffic.txt) x rays per launch of this pass",
                 "bytes_per_ray": B_PER_RAY_EXTEND, "rays_per_launch": pst.rays / max(pst.extend_launches, 1),

@@ -147,8 +147,13 @@ __device__ __forceinline__ bool isect_sphere(float3 c, float r, float3 o, float3
   double disc = b * b - a * cc;
   if (!(disc > 0.0)) return false;
   float bf = (float)b, ccf = (float)cc;
-  float q = -(bf + copysignf(sqrtf((float)disc), bf));
-  float ta = q * inv_a, tb = ccf / q;            // the two roots (-b -/+ sqrt(disc))/a in some order
+  // b, c, disc carry the FP64 accuracy; the fp32 finish uses the 1-instruction approximate sqrt and
+  // divide (<= 2 ulp each: ~2e-7 relative on t, far inside the 1e-4 parity tolerance and the 1e-5
+  // near-tie filter) instead of the ~8-instruction IEEE sequences: this runs for every ray x
+  // every primitive kept outside the tree, and at ~5/32 lanes for leaf tests
+  float sq; asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"((float)disc));
+  float q = -(bf + copysignf(sq, bf));
+  float ta = q * inv_a, tb = __fdividef(ccf, q); // the two roots (-b -/+ sqrt(disc))/a in some order
   float t1 = fminf(ta, tb), t2 = fmaxf(ta, tb);
   if (t1 > tmin) { t = t1; return true; }        // (< t-min temp ...) strict
   if (t2 > tmin) { t = t2; return true; }

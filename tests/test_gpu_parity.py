@@ -309,6 +309,38 @@ def test_sample_range_additivity():
     r.close()
 
 
+def test_full_size_cfg2_properties(orc):
+    """BASELINE.json's headline configuration at its FULL size (1200x800 @ 500 spp, depth 50), checked
+    through size-independent properties: (a) run-to-run determinism (integer accumulation), (b) the
+    two-rank sample-range split sums to the single-GPU frame and its ray counts add exactly, (c) the
+    frame box-filtered 10x10 equals the CPU oracle's render of the same camera at 120x80 (same
+    image-plane footprint per pixel) within the oracle's Monte-Carlo noise."""
+    cfg = scenes.CONFIGS["cfg2"]
+    w, h, spp, depth = cfg["width"], cfg["height"], cfg["spp"], cfg["max_depth"]
+    scene = cfg["scene"](w, h)
+    r = srt.Renderer(scene, device=0)
+    full, st = r.render(w, h, spp, max_depth=depth, seed=cfg["seed"])
+    again, st2 = r.render(w, h, spp, max_depth=depth, seed=cfg["seed"])
+    assert st.rays == st2.rays and np.array_equal(full, again)                                  # (a)
+    lo, st_lo = r.render(w, h, spp // 2, max_depth=depth, seed=cfg["seed"], spp_begin=0)
+    hi, st_hi = r.render(w, h, spp - spp // 2, max_depth=depth, seed=cfg["seed"], spp_begin=spp // 2)
+    assert st_lo.rays + st_hi.rays == st.rays                                                   # (b)
+    assert np.allclose(lo + hi, full, rtol=2e-6, atol=1e-4)
+    assert np.all(np.isfinite(full)) and full.min() >= 0.0
+    assert 3.5 < st.rays / (w * h * spp) < 5.0                  # mean path length of the Weekend scene
+    small = cfg["scene"](w // 10, h // 10)
+    S = orc.OracleScene(small)
+    ospp = 96
+    ref, _ = S.render(w // 10, h // 10, ospp, max_depth=depth, seed=77)
+    ref /= ospp
+    box = (full.astype(np.float64) / spp).reshape(h // 10, 10, w // 10, 10, 3).mean(axis=(1, 3))  # (c)
+    rel = abs(box.mean() - ref.mean()) / ref.mean()
+    rmse = np.sqrt(np.mean((box - ref) ** 2))
+    print(f"\n[cfg2 full size] rays {st.rays} ({st.rays / (st.ms_total * 1e3):.0f} Mrays/s)  mean {box.mean():.4f} vs oracle {ref.mean():.4f} (rel {rel:.2e})  rmse {rmse:.4f}")
+    assert rel < 0.01 and rmse < 0.06
+    r.close()
+
+
 def test_resolve_and_ppm(orc, tmp_path):
     rs = np.random.RandomState(0)
     rgb = (rs.random_sample((20, 30, 3)) * 40).astype(np.float32)

@@ -414,7 +414,7 @@ int srt_scene_commit(SrtScene* s) {
   CK(cudaEventElapsedTime(&s->ms_commit, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   s->bvh_depth = depth; s->ds.bvh_depth = depth;
-  if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level stackless trail", depth);
+  if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level traversal bound", depth);
   s->committed = true;
   return 0;
 }

@@ -3,8 +3,9 @@
 // Replaces trace-all -> get-ray -> color -> g:hit / m:scatter / m:emitted (main.scm:100-121,
 // 471-491; camera.scm:80-92; geometry.scm:14-15; material.scm:15-22).  STREAMING wavefront: one
 // queue of up to `capacity` paths is kept full; every iteration runs
-//   k_extend  closest hit: stackless LBVH traversal (bit-trail, near child first), the whole
-//             node array + primitive headers staged in shared memory
+//   k_extend  closest hit: LBVH traversal (near child first, per-thread stack of 16-bit node ids in
+//             shared memory; stackless bit-trail fallback for huge trees), the whole node array +
+//             primitive headers staged in shared memory
 //   k_shade   hit-record completion, material scatter / emitted, sky on miss; terminated paths add
 //             their radiance into a 64-bit fixed-point accumulator; survivors are compacted
 //             (warp ballot + one atomic per CTA) into the other queue generation
@@ -84,10 +85,11 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// extend: stackless closest-hit traversal.  Node = 64 B: left box, right box, (left, right,
-// parent, sibling).  Trail bit k (from the LSB) = "the far child at the k-th level above is
-// still pending".  Backtracking follows parent links up to the lowest set bit and enters the
-// sibling.  No per-thread stack, no local memory.
+// extend: closest-hit traversal.  Node = 64 B: left box, right box, (left, right, parent,
+// sibling).  Pending far children: see the TRAV_* modes at node_step (shared-memory stack by
+// default; the stackless fallback keeps a bit trail - bit k from the LSB = "the far child at the
+// k-th level above is still pending" - and follows parent links up to the lowest set bit, then
+// enters the sibling).  No local memory in either mode.
 struct PrimShared {
   const int4* h; const float4* pa;
   __device__ __forceinline__ int4 hdr(int i) const { return h[i]; }

@@ -94,7 +94,7 @@ def workload(name):
     return cfg
 
 
-def cpu_oracle_rate(cfg, name, budget_s=15.0, nthreads=0):
+def cpu_oracle_rate(cfg, name, budget_s=12.0, nthreads=0):
     """Times the oracle (CPU restatement, linear hit-obj-list like the reference) on a bounded
     sample of the same workload: the same scene at 1/8 x 1/8 resolution, spp scaled to ~budget_s."""
     from oracle import oracle as O
@@ -104,7 +104,7 @@ def cpu_oracle_rate(cfg, name, budget_s=15.0, nthreads=0):
     S = O.OracleScene(scene)
     cores = nthreads if nthreads > 0 else (os.cpu_count() or 1)
     t0 = time.perf_counter(); _, nr = S.render(w, h, 1, max_depth=cfg["max_depth"], seed=cfg["seed"], nthreads=cores); dt1 = time.perf_counter() - t0
-    spp = int(max(1, min(64, budget_s / max(dt1, 1e-3))))
+    spp = int(max(1, min(1024, budget_s / max(dt1, 1e-3))))      # ~budget_s seconds of CPU work on all host threads
     t0 = time.perf_counter(); _, nrays = S.render(w, h, spp, max_depth=cfg["max_depth"], seed=cfg["seed"], nthreads=cores); dt = time.perf_counter() - t0
     mrays = nrays / dt / 1e6
     return dict(value=mrays, unit="Mrays/s", cores=cores, kind="port",
@@ -127,7 +127,7 @@ def run_reference(args, cfg):
     cores = os.cpu_count() or 1
     t0 = time.perf_counter(); S.render(w, h, 1, max_depth=cfg["max_depth"], seed=cfg["seed"], nthreads=cores); dt1 = time.perf_counter() - t0
     total = max(args.steps + args.warmup, 1)
-    spp = int(max(1, min(32, (90.0 / total) / max(dt1, 1e-3))))
+    spp = int(max(1, min(256, (90.0 / total) / max(dt1, 1e-3))))     # a few seconds of CPU work per step
     for _ in range(args.warmup):
         S.render(w, h, spp, max_depth=cfg["max_depth"], seed=cfg["seed"], nthreads=cores)
     t0 = time.perf_counter(); nrays = 0

@@ -247,7 +247,12 @@ int srt_scene_commit(SrtScene* s) {
   std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
   for (int i = 0; i < n; ++i) {
     const SrtPrim& p = s->prims[i]; const float* q = p.p;
-    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, p.type == SRT_PRIM_PATCH ? (int)q[0] : 0);
+    // aux: patch index for patches; the bits of the plane constant k for rects (saves the extend
+    // kernel a global load per rect test: the header is staged in shared memory)
+    int aux = 0;
+    if (p.type == SRT_PRIM_PATCH) aux = (int)q[0];
+    else if (p.type >= SRT_PRIM_XY_RECT && p.type <= SRT_PRIM_YZ_RECT) std::memcpy(&aux, &q[4], 4);
+    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, aux);
     a[i] = b[i] = c[i] = d[i] = make_float4(0, 0, 0, 0);
     switch (p.type) {
       case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;

@@ -178,8 +178,8 @@ __device__ __forceinline__ bool isect_rect(int type, float4 a, float k, float3 o
   float pb = fmaf(tt, cmp3(d, ib), cmp3(o, ib));
   if (pa < a.x || pa > a.y || pb < a.z || pb > a.w) return false;
   t = tt;
-  u = (pa - a.x) / (a.y - a.x);
-  v = (pb - a.z) / (a.w - a.z);
+  u = __fdividef(pa - a.x, a.y - a.x);                   // uv feeds texture lookups only: 2-ulp divide
+  v = __fdividef(pb - a.z, a.w - a.z);
   return true;
 }
 // t = (k - o'[axis]) / d'[axis] for an instanced rect, with the rotate-y / translate of origin and
@@ -449,7 +449,7 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     float4 b = __ldg(&sc.prim_b[id]), c = __ldg(&sc.prim_c[id]);
     ok = isect_sphere(moving_center(a, b, c, time), a.w, o, d, inv_a, tmin, t);
   } else if (HAS_RECT && type <= SRT_PRIM_YZ_RECT) {
-    float k = __ldg(&sc.prim_b[id]).x;
+    float k = __int_as_float(aux);                       // plane constant, carried in the header (srt_api.cu)
     float3 oo = o, dd = d; float ti = 0.f; bool have_t = false;
     if (xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); ti = rect_t_f64(x, type, k, o, d); have_t = true; }
     ok = isect_rect(type, a, k, oo, dd, tmin, ti, have_t, t, u, v);

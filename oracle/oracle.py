@@ -235,6 +235,27 @@ def bezier_hit(cps, width, ray7, t_min=0.001, t_max=999999999999.0):
     return dict(hit=bool(hit), t=t.value, p=p, n=n, max_depth=md.value, converge_calls=calls.value)
 
 
+def reflect(v, n):                             # material.scm:41-43
+    a, b, o = _d(v), _d(n), np.zeros(3)
+    load().orc_reflect(_p(a), _p(b), _p(o))
+    return o
+
+
+def refract(v, n, ni_over_nt, quirks=15):      # material.scm:59-67 -> (ok, refracted)
+    a, b, o = _d(v), _d(n), np.zeros(3)
+    lib = load()
+    lib.orc_refract.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]
+    ok = lib.orc_refract(_p(a), _p(b), float(ni_over_nt), int(quirks), _p(o))
+    return bool(ok), o
+
+
+def schlick(cosine, ref_idx):                  # material.scm:69-74
+    lib = load()
+    lib.orc_schlick.argtypes = [C.c_double, C.c_double]
+    lib.orc_schlick.restype = C.c_double
+    return lib.orc_schlick(float(cosine), float(ref_idx))
+
+
 def aabb_hit(bmin, bmax, ray7, t_min, t_max):
     a, b, r = _d(bmin), _d(bmax), _d(ray7)
     return bool(load().orc_aabb_hit(_p(a), _p(b), _p(r), t_min, t_max))

@@ -982,6 +982,14 @@ void orc_get_ray(void* h, double s_, double t_, double xi_time, uint32_t seed, u
   Scene* s = (Scene*)h; RngAddr a{seed, pixel, sample, 0u};
   Ray<double> r = get_ray<double>(*s, s_, t_, xi_time, a);
   ray7[0] = r.o.x; ray7[1] = r.o.y; ray7[2] = r.o.z; ray7[3] = r.d.x; ray7[4] = r.d.y; ray7[5] = r.d.z; ray7[6] = r.time; }
+// material.scm:41-43, 59-67, 69-74 helper functions, for hand-derived known-answer tests
+void orc_reflect(const double* v3, const double* n3, double* out3) { V3<double> r = reflect<double>(ld3<double>(v3), ld3<double>(n3)); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+int orc_refract(const double* v3, const double* n3, double ni_over_nt, int quirks, double* out3) {
+  V3<double> r = mk<double>(0, 0, 0);
+  bool ok = refract<double>(ld3<double>(v3), ld3<double>(n3), ni_over_nt, r, quirks);
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; return ok ? 1 : 0;
+}
+double orc_schlick(double cosine, double ref_idx) { return schlick<double>(cosine, ref_idx); }
 void orc_sky(void* h, const double* d3, double* rgb) {
   Scene* s = (Scene*)h; Ray<double> r{mk<double>(0, 0, 0), ld3<double>(d3), 0.0}; V3<double> c = sky_value<double>(*s, r); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; }
 void orc_onb_cosine(const double* n3, double r1, double r2, int quirks, double* target3) {

@@ -226,3 +226,48 @@ def test_image_texture_lookup(orc):
     assert np.allclose(got, exp, atol=1e-15)
     with pytest.raises(ValueError):
         t.image_texture([0] * 5, 2, 1)
+
+
+def test_material_helpers_hand_derived(orc):
+    """material.scm:41-43 reflect, :59-67 refract (with and without Q10), :69-74 schlick - values
+    worked out by hand from the source lines."""
+    assert np.allclose(orc.reflect([1, -1, 0], [0, 1, 0]), [1, 1, 0], atol=1e-15)          # v - 2 (v.n) n
+    assert np.allclose(orc.reflect([0, -3, 0], [0, 1, 0]), [0, 3, 0], atol=1e-15)          # length is kept (Q10: d unnormalised)
+    # head-on, v = (0,-2,0) unnormalised, n = (0,1,0), ni/nt = 1/1.5: uv = (0,-1,0), dt = -1, disc = 1
+    #   upstream (Q10): r (v - n dt) - n sqrt(disc) = (0,-2+1,0)/1.5 - (0,1,0) = (0,-5/3,0)
+    #   book:           r (uv - n dt) - n           = (0,0,0)/1.5    - (0,1,0) = (0,-1,0)
+    ok, r = orc.refract([0, -2, 0], [0, 1, 0], 1 / 1.5, quirks=15)
+    assert ok and np.allclose(r, [0, -5.0 / 3.0, 0], atol=1e-15)
+    ok, r = orc.refract([0, -2, 0], [0, 1, 0], 1 / 1.5, quirks=0)
+    assert ok and np.allclose(r, [0, -1, 0], atol=1e-15)
+    # 45 degrees into glass: uv = (1,-1,0)/sqrt2, dt = -1/sqrt2, disc = 1 - (1/2.25)(1/2) = 7/9;
+    #   book: r (uv - n dt) - n sqrt(disc) = (1/sqrt2/1.5, 0, 0) - (0, sqrt7/3, 0): Snell sin(t) = sin(45)/1.5
+    ok, r = orc.refract([1, -1, 0], [0, 1, 0], 1 / 1.5, quirks=0)
+    assert ok and np.allclose(r, [1 / np.sqrt(2) / 1.5, -np.sqrt(7) / 3, 0], atol=1e-15) and abs(np.linalg.norm(r) - 1) < 1e-15
+    # grazing from inside glass (ni/nt = 1.5): disc = 1 - 2.25 (1 - dt^2) < 0 -> total internal reflection
+    ok, _ = orc.refract([1, -0.1, 0], [0, 1, 0], 1.5)
+    assert not ok
+    # ni/nt = 1, dt = 0 exactly (v perpendicular to n): disc = 1 - 1*(1 - 0) = 0 is NOT refracted (`(> discriminant 0)`)
+    ok, _ = orc.refract([1, 0, 0], [0, 1, 0], 1.0)
+    assert not ok
+    assert abs(orc.schlick(1.0, 1.5) - 0.04) < 1e-15            # r0 = ((1-1.5)/(1+1.5))^2
+    assert abs(orc.schlick(0.0, 1.5) - 1.0) < 1e-15
+    assert abs(orc.schlick(0.5, 1.5) - (0.04 + 0.96 / 32)) < 1e-15
+
+
+def test_sampling_helpers_hand_derived(orc):
+    """util.scm:37-44 random-cosine-direction through onb.scm:8-36 (Q1: x, y scaled by 2) and the
+    sky gradient main.scm:91-95, by hand."""
+    lib = orc.load()
+    out = np.zeros(3)
+    n = np.array([0.0, 0.0, 1.0])                     # w = n, a = (1,0,0), v = unit(w x a) = (0,1,0), u = w x v = (-1,0,0)
+    for quirks, k in ((15, 2.0), (0, 1.0)):
+        lib.orc_onb_cosine(orc._p(n), 0.25, 0.36, quirks, orc._p(out))      # phi = pi/2: x = 0, y = k*0.6, z = sqrt(1-0.36) = 0.8
+        assert np.allclose(out, [-0.0 * k, 0.6 * k, 0.8], atol=1e-15), (quirks, out)
+        lib.orc_onb_cosine(orc._p(n), 0.0, 0.25, quirks, orc._p(out))       # phi = 0: x = k*0.5 -> along u = (-1,0,0)
+        assert np.allclose(out, [-0.5 * k, 0.0, np.sqrt(0.75)], atol=1e-15), (quirks, out)
+    from scheme_raytrace_b200.host import geometry as g, scenes
+    S = orc.OracleScene(g.make_scene([], scenes.default_camera(), scenes.sky_color), quantise=False)
+    assert np.allclose(S.sky([0, 1, 0]), [0.5, 0.7, 1.0], atol=1e-15)       # t = 1
+    assert np.allclose(S.sky([0, -2, 0]), [1.0, 1.0, 1.0], atol=1e-15)      # t = 0 (direction is normalised first)
+    assert np.allclose(S.sky([3, 0, 0]), [0.75, 0.85, 1.0], atol=1e-15)     # t = 0.5

@@ -411,6 +411,28 @@ def test_large_scene_global_memory_tree(orc, n):
     r.close()
 
 
+def test_constant_medium_free_flight_law_gpu(orc):
+    """The analytic free-flight law of tests/test_oracle_kat.py on the CUDA path, and ray-by-ray
+    agreement with the oracle (same Philox address: pixel = ray index)."""
+    from tests.test_oracle_kat import _medium_scene
+    R, rho, n = 2.0, 0.3, 200000
+    scene = _medium_scene(R, rho)
+    r = srt.Renderer(scene, device=0)
+    rays = np.tile(np.array([0, 0, -10, 0, 0, 2.0, 0.0], dtype=np.float32), (n, 1))
+    gp = r.trace_batch(rays)
+    hit = gp["prim"] >= 0
+    L, q = 2 * R, np.exp(-rho * 2 * R)
+    assert abs(hit.mean() - (1 - q)) < 4 * np.sqrt(q * (1 - q) / n)
+    dist = (gp["t"][hit] - 4.0) * 2.0
+    assert abs(dist.mean() - (1 / rho - L * q / (1 - q))) < 0.01
+    o = orc.OracleScene(scene, flat=r.flat).trace_batch(rays.astype(np.float64))
+    same = (o["prim"] >= 0) == hit
+    assert same.mean() > 0.9999                                     # xi within fp32 rounding of the exit decides a handful
+    both = hit & (o["prim"] >= 0)
+    assert np.max(np.abs(gp["t"][both] - o["t"][both]) / o["t"][both]) < 1e-4
+    r.close()
+
+
 def test_mixture_pdf_estimator(orc):
     """Rest-of-Life estimator mixture(hittable(light), cosine) (pdf.scm:18-41; the hittable part is
     absent upstream -> parity unpinned): GPU == oracle under identical streams, and with the

@@ -271,3 +271,26 @@ def test_sampling_helpers_hand_derived(orc):
     assert np.allclose(S.sky([0, 1, 0]), [0.5, 0.7, 1.0], atol=1e-15)       # t = 1
     assert np.allclose(S.sky([0, -2, 0]), [1.0, 1.0, 1.0], atol=1e-15)      # t = 0 (direction is normalised first)
     assert np.allclose(S.sky([3, 0, 0]), [0.75, 0.85, 1.0], atol=1e-15)     # t = 0.5
+
+
+def _medium_scene(R, rho):
+    from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, vec as v, scenes
+    white = m.make_lambertian(t.constant_texture(v.vec3(1, 1, 1)))
+    med = g.make_constant_medium(g.make_sphere(v.vec3(0, 0, 0), R, white), rho, t.constant_texture(v.vec3(1, 1, 1)))
+    return g.make_scene([med], scenes.default_camera(), scenes.black)
+
+
+def test_constant_medium_free_flight_law(orc):
+    """geometry.scm:545-578: hit distance inside the boundary = -log(xi)/density, accepted if it ends
+    before the exit.  Along a diameter of length L (|d| = 2): P(hit) = 1 - exp(-rho L) and
+    E[distance | hit] = 1/rho - L exp(-rho L)/(1 - exp(-rho L)), from the exponential law."""
+    R, rho, n = 2.0, 0.3, 200000
+    S = orc.OracleScene(_medium_scene(R, rho), quantise=False)
+    rays = np.tile(np.array([0, 0, -10, 0, 0, 2.0, 0.0]), (n, 1))
+    o = S.trace_batch(rays)
+    hit = o["prim"] >= 0
+    L, q = 2 * R, np.exp(-rho * 2 * R)
+    assert abs(hit.mean() - (1 - q)) < 4 * np.sqrt(q * (1 - q) / n)
+    dist = (o["t"][hit] - 4.0) * 2.0                      # enters at z = -2: t = 4; |d| = 2
+    assert dist.min() > 0 and dist.max() < L
+    assert abs(dist.mean() - (1 / rho - L * q / (1 - q))) < 0.01

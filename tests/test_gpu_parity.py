@@ -411,6 +411,18 @@ def test_large_scene_global_memory_tree(orc, n):
     r.close()
 
 
+@pytest.mark.parametrize("quirks", [15, 0])
+def test_furnace_analytic_radiance_gpu(quirks):
+    """The analytic furnace of tests/test_oracle_kat.py rendered by the CUDA path: every pixel on the
+    sphere is weight_X * Le and every pixel off it is Le, to fp32 rounding."""
+    from tests.test_oracle_kat import _furnace_cases, check_furnace
+    for name, scene, expected in _furnace_cases():
+        r = srt.Renderer(scene, device=0)
+        img, st = r.render(32, 32, 4, max_depth=50, seed=9, quirks=quirks)
+        check_furnace(img / 4, expected, 2e-6)
+        r.close()
+
+
 def test_constant_medium_free_flight_law_gpu(orc):
     """The analytic free-flight law of tests/test_oracle_kat.py on the CUDA path, and ray-by-ray
     agreement with the oracle (same Philox address: pixel = ray index)."""

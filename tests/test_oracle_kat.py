@@ -294,3 +294,39 @@ def test_constant_medium_free_flight_law(orc):
     dist = (o["t"][hit] - 4.0) * 2.0                      # enters at z = -2: t = 4; |d| = 2
     assert dist.min() > 0 and dist.max() < L
     assert abs(dist.mean() - (1 / rho - L * q / (1 - q))) < 0.01
+
+
+FURNACE_LE = 0.75
+
+
+def _furnace_cases():
+    """A unit sphere of material X at the centre of an emitting enclosure (sphere of radius -100:
+    the negative radius turns the normal inward, geometry.scm:146-175, so n.d < 0 and the
+    diffuse-light emits, material.scm:103-111).  A convex sphere is never re-hit, so every path is
+    camera -> [sphere ->] emitter and `color` (main.scm:100-121) gives exactly Le off the sphere and
+    weight_X * Le on it: albedo for lambertian (atten * spdf / pdf = albedo for a unit normal, with or
+    without Q1) and for fuzz-0 metal, 1 for the dielectric."""
+    from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, vec as v, scenes, camera as cam
+    light = m.make_diffuse_light(t.constant_texture(v.vec3(FURNACE_LE, FURNACE_LE, FURNACE_LE)))
+    c = cam.make_camera(v.vec3(0, 0, 5), v.vec3(0, 0, 0), v.vec3(0, 1, 0), 40, 1.0, 0.0, 5.0, 0.0, 1.0)
+    cases = (("lambertian", m.make_lambertian(t.constant_texture(v.vec3(0.5, 0.25, 0.8))), (0.5, 0.25, 0.8)),
+             ("metal", m.make_metal(t.constant_texture(v.vec3(0.9, 0.6, 0.3)), 0.0), (0.9, 0.6, 0.3)),
+             ("dielectric", m.make_dielectric(1.5), (1.0, 1.0, 1.0)))
+    for name, mat, w in cases:
+        objs = [g.make_sphere(v.vec3(0, 0, 0), -100.0, light), g.make_sphere(v.vec3(0, 0, 0), 1.0, mat)]
+        yield name, g.make_scene(objs, c, scenes.black), np.asarray(w) * FURNACE_LE
+
+
+def check_furnace(img, expected, tol):
+    on = img[12:20, 12:20].reshape(-1, 3)            # pixels whose footprint lies on the sphere
+    off = np.concatenate([img[:4].reshape(-1, 3), img[-4:].reshape(-1, 3)])
+    assert np.abs(on - expected).max() < tol, np.abs(on - expected).max()
+    assert np.abs(off - FURNACE_LE).max() < tol
+
+
+@pytest.mark.parametrize("quirks", [15, 0])
+def test_furnace_analytic_radiance(orc, quirks):
+    for name, scene, expected in _furnace_cases():
+        S = orc.OracleScene(scene, quantise=False)
+        img, _ = S.render(32, 32, 4, max_depth=50, seed=9, quirks=quirks)
+        check_furnace(img / 4, expected, 1e-12)

@@ -364,7 +364,7 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
          float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
   extern __shared__ float4 smem[];
   const int count = count_ptr ? *count_ptr : count_fixed;
-  if (count == 0) return;
+  if ((int)(blockIdx.x * blockDim.x) >= count) return;      // no ray for this CTA (drain tail): skip the staging too
   if (SMEM) {
     // stage the whole LBVH + primitive headers ("shared-memory staging of BVH top levels":
     // for the <= few-thousand-primitive scenes of the reference the top levels are all levels)

@@ -109,7 +109,7 @@ struct Trav {
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
   uint32_t sp, sp0;                         // TRAV_STACK: shared-space address of the next free / first stack slot
 #ifdef SRT_COUNT_STEPS
-  int nsteps, ntests, nmiss;                // instrumented build only (tools/step_stats.py)
+  int nsteps, ntests, nmiss, maxsp;         // instrumented build only (tools/step_stats.py); maxsp = deepest stack use
 #endif
 };
 __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float tmax, int ray) {
@@ -125,7 +125,7 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
   T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
   T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0; T.sp = T.sp0;
 #ifdef SRT_COUNT_STEPS
-  T.nsteps = 0; T.ntests = 0; T.nmiss = 0;
+  T.nsteps = 0; T.ntests = 0; T.nmiss = 0; T.maxsp = 0;
 #endif
 }
 
@@ -196,6 +196,9 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
       if (both) {
         asm volatile("st.shared.u16 [%0], %1;" :: "r"(T.sp), "h"((unsigned short)(go_left ? right : left)) : "memory");
         T.sp += 2u;
+#ifdef SRT_COUNT_STEPS
+        T.maxsp = max(T.maxsp, (int)((T.sp - T.sp0) >> 1));
+#endif
       }
       return true;
     }
@@ -277,7 +280,7 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
       }
     }
 #ifdef SRT_COUNT_STEPS
-    T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
+    T.h.u = (float)T.nsteps; T.h.v = (float)(T.ntests + 1000 * T.maxsp);   // decoded by tools/step_stats.py
 #endif
     hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
   }
@@ -352,7 +355,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
       }
     }
 #ifdef SRT_COUNT_STEPS
-    T.h.u = (float)T.nsteps; T.h.v = (float)T.ntests;
+    T.h.u = (float)T.nsteps; T.h.v = (float)(T.ntests + 1000 * T.maxsp);   // decoded by tools/step_stats.py
 #endif
     if (i < count) hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
   }

@@ -20,8 +20,11 @@ p = r.params(w, h, 0, 1)
 pix = np.arange(w * h, dtype=np.int32)
 rays = r.eval_raygen(p, pix, np.zeros_like(pix))
 rs = np.random.RandomState(0)
+worst_sp = 0
 for bounce in range(4):
     hit = r.trace_batch(rays)
+    maxsp = (hit['v'] // 1000).astype(int); hit['v'] = hit['v'] % 1000     # instrumented build packs the deepest stack use
+    worst_sp = max(worst_sp, int(maxsp.max()))
     print(f"{name} bounce {bounce}: rays {len(rays)}  hit {np.mean(hit['prim'] >= 0):.3f}  node steps/ray mean {hit['u'].mean():.1f} p50 {np.median(hit['u']):.0f} p95 {np.percentile(hit['u'], 95):.0f} max {hit['u'].max():.0f}"
           f"  prim tests/ray mean {hit['v'].mean():.2f} max {hit['v'].max():.0f}")
     m = hit["prim"] >= 0
@@ -29,4 +32,6 @@ for bounce in range(4):
     n = hit["n"][m]; n /= np.linalg.norm(n, axis=1, keepdims=True)
     d = n + rs.normal(size=n.shape) * 0.7
     rays = np.concatenate([hit["p"][m], d, np.zeros((m.sum(), 1))], axis=1).astype(np.float32)
-print("bvh depth", r.render(8, 8, 1)[1].bvh_depth, "nodes", len(r.bvh_nodes()))
+depth = r.render(8, 8, 1)[1].bvh_depth
+print("bvh depth", depth, "nodes", len(r.bvh_nodes()), "| deepest traversal-stack use", worst_sp, "of", depth + 1, "allocated entries")
+assert worst_sp <= depth + 1

@@ -32,7 +32,7 @@ NCU_EXTEND_DRAM_B_PER_RAY = 47.6   # measured: ncu dram__bytes_read+write of a 6
 FP32_MODEL = {  # workload: (node steps/ray, prim tests/ray, flops per prim test, shade flops/ray)
     # (profiles/r1_step_stats.txt; prim tests include the primitives tested before traversal)
     "cfg1": (2.0, 2.4, 35, 110), "cfg2": (7.8, 4.6, 35, 100), "cfg3": (8.9, 3.8, 45, 160),
-    "cfg4": (2.8, 8.3, 24, 100), "cfg5": (11.0, 2.3, 600, 100), "cfg5_curves": (3.0, 1.7, 1500, 100),
+    "cfg4": (2.8, 8.3, 24, 100), "cfg5": (11.0, 2.3, 600, 100), "cfg5_teapot": (11.0, 2.3, 600, 100), "cfg5_curves": (3.0, 1.7, 1500, 100),
 }
 
 

@@ -200,8 +200,8 @@ def cornell_bezier(size_x=200, size_y=200):
 _K = 0.5522847498307936      # cubic Bezier circle constant
 
 # Profile curves (radius, height) of the rotationally symmetric parts of the Utah teapot (rim,
-# upper body, lower body, lid knob, lid, bottom).  Handle and spout are NOT included: their
-# control nets cannot be reproduced from memory and there is no network (SURVEY §7 "hard parts").
+# upper body, lower body, lid knob, lid, bottom), on exact quarter circles (_K).  The full Newell
+# data set, handle and spout included, is `utah_teapot` below.
 TEAPOT_PROFILES = [
     [(1.4, 2.25), (1.3375, 2.38125), (1.4375, 2.38125), (1.5, 2.25)],
     [(1.5, 2.25), (1.75, 1.725), (2.0, 1.2), (2.0, 0.75)],
@@ -225,6 +225,91 @@ def revolve_profile(profile, material, center=(0.0, 0.0, 0.0), scale=1.0):
 
 def teapot_patches(material, center=(0.0, 0.0, 0.0), scale=1.0):
     return [pt for prof in TEAPOT_PROFILES for pt in revolve_profile(prof, material, center, scale)]
+
+
+# The Utah teapot (Newell 1975) in its compact public-domain form: 127 control points (teapot
+# frame: z up, spout towards +x, the data cover the y <= 0 side) and 10 bicubic patches.  The six
+# rotationally symmetric patches (rim, body x2, lid x2, bottom) are replicated into the four
+# quadrants by mirroring x and y, handle and spout (two patches each) into the two halves by
+# mirroring y: 6 x 4 + 4 x 2 = 32 patches.
+TEAPOT_CP = [
+    (0.2, 0, 2.7), (0.2, -0.112, 2.7), (0.112, -0.2, 2.7), (0, -0.2, 2.7),
+    (1.3375, 0, 2.53125), (1.3375, -0.749, 2.53125), (0.749, -1.3375, 2.53125), (0, -1.3375, 2.53125),
+    (1.4375, 0, 2.53125), (1.4375, -0.805, 2.53125), (0.805, -1.4375, 2.53125), (0, -1.4375, 2.53125),
+    (1.5, 0, 2.4), (1.5, -0.84, 2.4), (0.84, -1.5, 2.4), (0, -1.5, 2.4),
+    (1.75, 0, 1.875), (1.75, -0.98, 1.875), (0.98, -1.75, 1.875), (0, -1.75, 1.875),
+    (2, 0, 1.35), (2, -1.12, 1.35), (1.12, -2, 1.35), (0, -2, 1.35),
+    (2, 0, 0.9), (2, -1.12, 0.9), (1.12, -2, 0.9), (0, -2, 0.9),
+    (-2, 0, 0.9),
+    (2, 0, 0.45), (2, -1.12, 0.45), (1.12, -2, 0.45), (0, -2, 0.45),
+    (1.5, 0, 0.225), (1.5, -0.84, 0.225), (0.84, -1.5, 0.225), (0, -1.5, 0.225),
+    (1.5, 0, 0.15), (1.5, -0.84, 0.15), (0.84, -1.5, 0.15), (0, -1.5, 0.15),
+    (-1.6, 0, 2.025), (-1.6, -0.3, 2.025), (-1.5, -0.3, 2.25), (-1.5, 0, 2.25),
+    (-2.3, 0, 2.025), (-2.3, -0.3, 2.025), (-2.5, -0.3, 2.25), (-2.5, 0, 2.25),
+    (-2.7, 0, 2.025), (-2.7, -0.3, 2.025), (-3, -0.3, 2.25), (-3, 0, 2.25),
+    (-2.7, 0, 1.8), (-2.7, -0.3, 1.8), (-3, -0.3, 1.8), (-3, 0, 1.8),
+    (-2.7, 0, 1.575), (-2.7, -0.3, 1.575), (-3, -0.3, 1.35), (-3, 0, 1.35),
+    (-2.5, 0, 1.125), (-2.5, -0.3, 1.125), (-2.65, -0.3, 0.9375), (-2.65, 0, 0.9375),
+    (-2, -0.3, 0.9), (-1.9, -0.3, 0.6), (-1.9, 0, 0.6),
+    (1.7, 0, 1.425), (1.7, -0.66, 1.425), (1.7, -0.66, 0.6), (1.7, 0, 0.6),
+    (2.6, 0, 1.425), (2.6, -0.66, 1.425), (3.1, -0.66, 0.825), (3.1, 0, 0.825),
+    (2.3, 0, 2.1), (2.3, -0.25, 2.1), (2.4, -0.25, 2.025), (2.4, 0, 2.025),
+    (2.7, 0, 2.4), (2.7, -0.25, 2.4), (3.3, -0.25, 2.4), (3.3, 0, 2.4),
+    (2.8, 0, 2.475), (2.8, -0.25, 2.475), (3.525, -0.25, 2.49375), (3.525, 0, 2.49375),
+    (2.9, 0, 2.475), (2.9, -0.15, 2.475), (3.45, -0.15, 2.5125), (3.45, 0, 2.5125),
+    (2.8, 0, 2.4), (2.8, -0.15, 2.4), (3.2, -0.15, 2.4), (3.2, 0, 2.4),
+    (0, 0, 3.15), (0.8, 0, 3.15), (0.8, -0.45, 3.15), (0.45, -0.8, 3.15), (0, -0.8, 3.15),
+    (0, 0, 2.85),
+    (1.4, 0, 2.4), (1.4, -0.784, 2.4), (0.784, -1.4, 2.4), (0, -1.4, 2.4),
+    (0.4, 0, 2.55), (0.4, -0.224, 2.55), (0.224, -0.4, 2.55), (0, -0.4, 2.55),
+    (1.3, 0, 2.55), (1.3, -0.728, 2.55), (0.728, -1.3, 2.55), (0, -1.3, 2.55),
+    (1.3, 0, 2.4), (1.3, -0.728, 2.4), (0.728, -1.3, 2.4), (0, -1.3, 2.4),
+    (0, 0, 0), (1.425, -0.798, 0), (1.5, 0, 0.075), (1.425, 0, 0), (0.798, -1.425, 0),
+    (0, -1.5, 0.075), (0, -1.425, 0), (1.5, -0.84, 0.075), (0.84, -1.5, 0.075),
+]
+TEAPOT_PATCHES = [   # (part, mirrored copies, 16 control-point indices, row = u, column = v)
+    ("rim", 4, (102, 103, 104, 105, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)),
+    ("body", 4, (12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27)),
+    ("body", 4, (24, 25, 26, 27, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40)),
+    ("lid", 4, (96, 96, 96, 96, 97, 98, 99, 100, 101, 101, 101, 101, 0, 1, 2, 3)),
+    ("lid", 4, (0, 1, 2, 3, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 116, 117)),
+    ("bottom", 4, (118, 118, 118, 118, 124, 122, 119, 121, 123, 126, 125, 120, 40, 39, 38, 37)),
+    ("handle", 2, (41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56)),
+    ("handle", 2, (53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 28, 65, 66, 67)),
+    ("spout", 2, (68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83)),
+    ("spout", 2, (80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92, 93, 94, 95)),
+]
+
+
+def utah_teapot(material, center=(0.0, 0.0, 0.0), scale=1.0, parts=None):
+    """All 32 bicubic patches of the Utah teapot as `make-bezier-patch` objects.  Teapot frame
+    (x, y, z-up) -> world (x, z, -y), base of the pot at `center`.  `parts` restricts the result to
+    some of rim / body / lid / bottom / handle / spout."""
+    out = []
+    for part, copies, idx in TEAPOT_PATCHES:
+        if parts is not None and part not in parts:
+            continue
+        for sx, sy in ((1, 1), (1, -1), (-1, 1), (-1, -1))[:copies]:
+            cp = [[(center[0] + scale * sx * TEAPOT_CP[idx[4 * i + j]][0], center[1] + scale * TEAPOT_CP[idx[4 * i + j]][2],
+                    center[2] - scale * sy * TEAPOT_CP[idx[4 * i + j]][1]) for j in range(4)] for i in range(4)]
+            out.append(b.make_bezier_patch(cp, material))
+    return out
+
+
+def teapot_scene(size_x=3840, size_y=2160):
+    """configs[4] with the complete teapot: one full 32-patch Utah teapot (lambertian) flanked by a
+    fuzzy-metal and a red lambertian copy at 2/3 scale on a checker ground, under the gradient sky.
+    Patches are a north-star extension (absent upstream): parity vs the oracle's identical
+    definition only."""
+    white = m.make_lambertian(t.constant_texture(v.vec3(0.73, 0.73, 0.73)))
+    red = m.make_lambertian(t.constant_texture(v.vec3(0.65, 0.05, 0.05)))
+    gold = m.make_metal(t.constant_texture(v.vec3(0.8, 0.6, 0.2)), 0.1)
+    objs = [g.make_sphere(v.vec3(0, -1000, 0), 1000, m.make_lambertian(_checker()))]
+    objs += utah_teapot(white, (0.0, 0.0, 0.0), 1.0)
+    objs += utah_teapot(gold, (-4.6, 0.0, -1.0), 0.66)
+    objs += utah_teapot(red, (4.4, 0.0, 0.0), 0.66)
+    c = cam.make_camera(v.vec3(0, 5, 11), v.vec3(0, 1.3, 0), v.vec3(0, 1, 0), 35, size_x / size_y, 0, 1, 0, 1)
+    return g.make_scene(objs, c, sky_color)
 
 
 def cfg5_patches(size_x=3840, size_y=2160):
@@ -309,5 +394,6 @@ CONFIGS = {
     "cfg3": dict(scene=cfg3_next_week, width=800, height=800, spp=1000, max_depth=50, seed=3),
     "cfg4": dict(scene=cfg4_cornell_box, width=1024, height=1024, spp=4096, max_depth=50, seed=4),
     "cfg5": dict(scene=cfg5_patches, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
+    "cfg5_teapot": dict(scene=teapot_scene, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
     "cfg5_curves": dict(scene=test_bezier, width=3840, height=2160, spp=1024, max_depth=50, seed=5),
 }

@@ -13,7 +13,8 @@ SMALL = {"cfg1": (scenes.cfg1_weekend, 200, 100), "cfg2": (scenes.cfg2_random_sp
          "bezier": (scenes.test_bezier, 64, 64), "cornell_bezier": (scenes.cornell_bezier, 64, 64),
          "scene2": (scenes.test_scene2, 64, 64), "bvh100": (scenes.test_scene_bvh, 64, 64),
          "smoke": (scenes.cornell_smoke, 64, 64), "patches": (scenes.cfg5_patches, 96, 54),
-         "klein": (scenes.cornell_klein, 48, 48), "image": (scenes.image_scene, 64, 64)}
+         "klein": (scenes.cornell_klein, 48, 48), "image": (scenes.image_scene, 64, 64),
+         "teapot": (scenes.teapot_scene, 96, 54)}
 
 
 @pytest.fixture(scope="module", params=list(SMALL))
@@ -111,9 +112,9 @@ def test_prim_bounds_contain_oracle_hits(pair):
     o = S.trace_batch(rays.astype(np.float64))
     aabb = r.prim_bounds().astype(np.float64)
     hit = o["prim"] >= 0
-    if name in ("bezier", "cornell_bezier", "patches"):     # Q9: curve hit points are off the curve for |d| != 1
+    if name in ("bezier", "cornell_bezier", "patches", "teapot"):     # Q9: curve hit points are off the curve for |d| != 1
         hit &= r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]] != 5
-    if name in ("patches", "klein"):                       # sub-patches: union of 16 leaf boxes; Klein: no box at all
+    if name in ("patches", "teapot", "klein"):             # sub-patches: union of 16 leaf boxes; Klein: no box at all
         hit &= ~np.isin(r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o["prim"], 0)]], (7, 8))
     b = aabb[r.flat.first_of_logical[o["prim"][hit]]]
     p = o["p"][hit]
@@ -127,7 +128,7 @@ def test_trace_batch_parity(pair, batch):
     if batch == "camera":
         rays = raybatch.camera_grid(r, 64, 64)
     else:
-        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name not in ("bezier", "patches", "klein") else 30000, 5)
+        rays = raybatch.random_rays(raybatch.interest_bounds(r.flat), 100000 if name not in ("bezier", "patches", "teapot", "klein") else 30000, 5)
     rays64 = rays.astype(np.float64)
     gp = r.trace_batch(rays)
     o64 = S.trace_batch(rays64)
@@ -249,7 +250,7 @@ def test_raygen_parity(orc):
     r.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke", "patches", "klein"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "bezier", "smoke", "patches", "klein", "teapot"])
 def test_image_same_stream(name, orc):
     """Image parity under IDENTICAL Philox streams: GPU fp32 vs oracle f64 follow the same paths
     except where rounding flips a decision, so the per-pixel linear difference is tiny for almost

@@ -330,3 +330,40 @@ def test_furnace_analytic_radiance(orc, quirks):
         S = orc.OracleScene(scene, quantise=False)
         img, _ = S.render(32, 32, 4, max_depth=50, seed=9, quirks=quirks)
         check_furnace(img / 4, expected, 1e-12)
+
+
+def test_utah_teapot_data_and_seams(orc):
+    """The complete 32-patch Utah teapot (`scenes.utah_teapot`): 127 control points / 10 patches of
+    the compact Newell data set; mirrored copies join on the symmetry planes; the known extent of
+    the pot (spout tip x = 3.525 / handle x = -3 / knob z = 3.15, in teapot units); rays aimed at
+    the handle and the spout hit handle and spout patches on the oracle."""
+    from scheme_raytrace_b200.host import geometry as g
+    assert len(scenes.TEAPOT_CP) == 127 and len(scenes.TEAPOT_PATCHES) == 10
+    assert all(len(idx) == 16 and max(idx) < 127 for _, _, idx in scenes.TEAPOT_PATCHES)
+    used = sorted({i for _, _, idx in scenes.TEAPOT_PATCHES for i in idx})
+    assert used == list(range(127))                                  # every control point belongs to a patch
+    cp = np.asarray(scenes.TEAPOT_CP)
+    for part, copies, idx in scenes.TEAPOT_PATCHES:
+        net = cp[list(idx)].reshape(4, 4, 3)
+        e0, e1 = net[:, 0], net[:, 3]                                # the v = 0 and v = 1 edges lie in mirror planes
+        if copies == 4:                                              # quadrant patch: one edge in y = 0, the other in x = 0
+            assert (np.all(e0[:, 1] == 0) and np.all(e1[:, 0] == 0)) or (np.all(e0[:, 0] == 0) and np.all(e1[:, 1] == 0)), part
+        else:                                                        # handle / spout halves: both edges in y = 0
+            assert np.all(e0[:, 1] == 0) and np.all(e1[:, 1] == 0), part
+    pot = scenes.utah_teapot(LAMB)
+    assert len(pot) == 32 and all(o.kind == g.PATCH for o in pot)
+    allcp = np.asarray([o.params for o in pot]).reshape(-1, 3)      # world frame: (x, z_teapot, -y_teapot)
+    assert np.allclose(allcp.min(axis=0), (-3.0, 0.0, -2.0)) and np.allclose(allcp.max(axis=0), (3.525, 3.15, 2.0))
+    parts = [part for part, copies, _ in scenes.TEAPOT_PATCHES for _ in range(copies)]
+    S = orc.OracleScene(quantise=False, scene=_scene(pot))
+    rays = [[-2.9, 1.8, 5, 0, 0, -1, 0],         # through the handle loop's outer arc
+            [2.5, 1.6, 5, 0, 0, -1, 0],          # through the spout
+            [0.0, 1.2, 5, 0, 0, -1, 0],          # body, front
+            [0.0, 5.0, 0.1, 0, -1, 0, 0],        # straight down onto the lid knob (degenerate pole row)
+            [0.3, -5.0, 0.2, 0, 1, 0, 0],        # straight up onto the bottom
+            [-2.2, 1.6, 5, 0, 0, -1, 0]]         # through the hole of the handle: miss
+    r = S.trace_batch(rays)
+    assert [parts[i] if i >= 0 else None for i in r["prim"]] == ["handle", "spout", "body", "lid", "bottom", None]
+    assert np.all(np.isfinite(r["n"])) and np.allclose(np.linalg.norm(r["n"][:5], axis=1), 1.0)
+    assert abs(r["p"][2][2] - 2.0) < 0.04 and r["n"][2][2] > 0.95    # body radius just under 2 near the equator
+    assert 0 <= r["p"][4][1] < 0.01 and np.allclose(r["n"][4], (0, -1, 0), atol=0.05)   # nearly flat bottom at height 0

@@ -150,9 +150,13 @@ def test_trace_batch_parity(pair, batch):
     hm = c["hit_mask"]
     ptype = r.flat.prims["type"][r.flat.first_of_logical[np.maximum(o64["prim"], 0)]]
     uv_ok = hm & ((ptype >= 2) | (np.abs(o64["p"][:, 1]) <= 0.9))
-    if uv_ok.any():
-        assert np.max(np.abs(gp["u"][uv_ok] - o64["uv"][uv_ok, 0])) <= 2e-4
-        assert np.max(np.abs(gp["v"][uv_ok] - o64["uv"][uv_ok, 1])) <= 2e-4
+    # bicubic patches (extension): (u, v) is the Newton root of a 2x2 system that is ill-conditioned towards
+    # silhouettes and the degenerate pole rows of the teapot's lid / bottom: stated tolerance 1e-3 there
+    for sel, tol in ((uv_ok & (ptype != 7), 2e-4), (uv_ok & (ptype == 7), 1e-3)):
+        if sel.any():
+            print(f"[{name}/{batch}] uv_err_max={max(np.max(np.abs(gp['u'][sel] - o64['uv'][sel, 0])), np.max(np.abs(gp['v'][sel] - o64['uv'][sel, 1]))):.2e} (tol {tol:g}, {int(sel.sum())} rays)")
+            assert np.max(np.abs(gp["u"][sel] - o64["uv"][sel, 0])) <= tol
+            assert np.max(np.abs(gp["v"][sel] - o64["uv"][sel, 1])) <= tol
 
 
 def test_structured_ties_cornell(orc):

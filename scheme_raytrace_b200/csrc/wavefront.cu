@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int EXT_THREADS = 256;
+constexpr int EXT_THREADS = 256, EXT_THREADS_HEAVY = 512;
 constexpr int SHD_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------
@@ -289,82 +289,109 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
 // Variant for scenes with EXPENSIVE primitives (Bezier curve / patch, constant medium: thousands of
 // instructions per test).  Interleaving such a test with traversal serialises it lane by lane
 // (each lane reaches its leaf in a different iteration).  Here a lane that reaches an expensive
-// leaf PARKS; a warp vote runs the test block only when >= EXT_PARK_VOTE lanes are parked or no
-// lane can make progress otherwise, so the block executes with many active lanes ("deferred
-// candidate queue", one or two entries per lane, in registers).  Cheap primitives (spheres,
-// rects) are still intersected immediately.
-constexpr int EXT_PARK_VOTE = 12;
+// leaf PARKS; a warp vote runs the test block only when >= `vote` lanes are parked or no lane can
+// make progress otherwise, so the block executes with many active lanes ("deferred candidate
+// queue", one or two entries per lane, in registers).  Cheap primitives (spheres, rects) are still
+// intersected immediately.
+//
+// Lanes are REFILLED: a lane whose ray is finished writes its hit record and becomes idle; as soon
+// as >= `refill` lanes are idle they take the next rays of the warp's current 32-ray chunk (idle
+// lanes in lane order take consecutive rays, so the fetch stays a contiguous segment).  Without the
+// refill every 32-ray batch ended with a drain in which the few lanes that still had a parked test
+// ran it almost alone (ncu source page, cfg5_teapot: 8 of 32 lanes at the entry of the patch test,
+// 5.4 in its Newton loop, 9.3 in the node loop).  For the cheap sphere / rect variants the same
+// refill was measured slower (bookkeeping > idle lanes recovered, profiles/README.md); here one test
+// is worth hundreds of node steps.
+constexpr int EXT_PARK_VOTE = 16, EXT_REFILL_MIN = 16;   // measured sweep: profiles/README.md (tools/sweep_deferred.sh)
 template <bool SMEM, int MASK, int TRAV, class PrimSrc>
 __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
                                                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
-                                                     float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed, uint32_t stack_base) {
+                                                     float4* __restrict__ hit, int count, float tmin, float tmax, uint32_t seed, uint32_t stack_base, int tune) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   if (sc.n_surf == 0) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) hit[i] = make_float4(tmax, __int_as_float(-1), 0.f, 0.f);
     return;
   }
+  const int vote = tune & 0xff, refill = (tune >> 8) & 0xff;
   Trav T;
   T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
-  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < count; base += gridDim.x * blockDim.x) {   // warp-uniform
-    const int i = base + lane;
-    bool more = i < count;
-    const float4 d4 = more ? ray_d[i] : make_float4(1.f, 1.f, 1.f, 0.f);
-    trav_init(T, more ? ray_o[i] : make_float4(0.f, 0.f, 0.f, 0.f), d4, tmax, i);
-    {
-      const int sd = __float_as_int(d4.w);
-      T.ra.seed = seed; T.ra.pixel = (state && more) ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
-      T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
+  const int stride = gridDim.x * blockDim.x;
+  int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;   // warp-uniform: the warp's current 32-ray chunk
+  int cur = 0;                                                // rays of that chunk already handed out (warp-uniform)
+  int ray = -1;                                               // this lane's ray, -1 = idle
+  bool more = false;
+  int park0 = -1, park1 = -1;
+  for (;;) {
+    if (ray >= 0 && !more && park0 < 0) {                     // finished: retire
+#ifdef SRT_COUNT_STEPS
+      T.h.u = (float)T.nsteps; T.h.v = (float)(T.ntests + 1000 * T.maxsp);   // decoded by tools/step_stats.py
+#endif
+      hit[ray] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
+      ray = -1;
     }
-    if (more)
-      for (int g = 0; g < sc.n_global; ++g)
-        intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
-    more = more && sc.n_items > 0;
-    int park0 = -1, park1 = -1;
-    for (;;) {
-      const bool parked = park0 >= 0;
-      const unsigned pm = __ballot_sync(full, parked);
-      const unsigned rm = __ballot_sync(full, more && !parked);
-      if ((pm | rm) == 0u) break;
-      if (__popc(pm) >= EXT_PARK_VOTE || rm == 0u) {
-        if (parked) {
+    const unsigned idle = __ballot_sync(full, ray < 0);
+    if (base < count && __popc(idle) >= refill) {             // hand the next rays of the chunk to the idle lanes
+      const int take = min(__popc(idle), 32 - cur);
+      const int i = base + cur + __popc(idle & ((1u << lane) - 1u));
+      if (ray < 0 && i < base + cur + take && i < count) {
+        const float4 d4 = ray_d[i];
+        trav_init(T, ray_o[i], d4, tmax, i);
+        const int sd = __float_as_int(d4.w);
+        T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
+        T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
+        for (int g = 0; g < sc.n_global; ++g)
+          intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+        ray = i; more = sc.n_items > 0;
+      }
+      cur += take;
+      if (cur == 32) { cur = 0; base += stride; }
+    }
+    const bool parked = park0 >= 0;
+    const unsigned pm = __ballot_sync(full, parked);
+    const unsigned rm = __ballot_sync(full, ray >= 0 && more && !parked);
+    if ((pm | rm) == 0u) {                                    // nothing to step or test: lanes are idle or about to retire
+      if (base >= count && __ballot_sync(full, ray >= 0) == 0u) break;
+      continue;
+    }
+    if (__popc(pm) >= vote || rm == 0u) {
+      if (parked) {
+#ifdef SRT_COUNT_STEPS
+        T.ntests++;
+#endif
+        intersect_prim<MASK>(sc, ps, park0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+        park0 = park1; park1 = -1;
+      }
+      continue;
+    }
+    if (ray >= 0 && more && !parked) {
+      int pend0 = -1, pend1 = -1;
+      more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
+      while (pend0 >= 0) {
+        const int type = ps.hdr(pend0).x & 0xff;
+        if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
+        else {
 #ifdef SRT_COUNT_STEPS
           T.ntests++;
 #endif
-          intersect_prim<MASK>(sc, ps, park0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
-          park0 = park1; park1 = -1;
+          intersect_prim<MASK & 0x1f>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
         }
-        continue;
-      }
-      if (more && !parked) {
-        int pend0 = -1, pend1 = -1;
-        more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
-        while (pend0 >= 0) {
-          const int type = ps.hdr(pend0).x & 0xff;
-          if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
-          else {
-#ifdef SRT_COUNT_STEPS
-            T.ntests++;
-#endif
-            intersect_prim<MASK & 0x1f>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
-          }
-          pend0 = pend1; pend1 = -1;
-        }
+        pend0 = pend1; pend1 = -1;
       }
     }
-#ifdef SRT_COUNT_STEPS
-    T.h.u = (float)T.nsteps; T.h.v = (float)(T.ntests + 1000 * T.maxsp);   // decoded by tools/step_stats.py
-#endif
-    if (i < count) hit[i] = make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v);
   }
 }
 
+// CTA size: 256 threads, 4 (spheres) or 3 (+ rects / instances) CTAs per SM.  The variant with the
+// expensive primitives needs 128 registers, i.e. at most 512 threads per SM; it runs as ONE 512-thread
+// CTA per SM so that those 16 warps share one staged copy of the scene (as 2 x 256 the teapot scene's
+// 147 KB tree allowed a single 256-thread CTA: 8 warps/SM, issue slots 39 % busy).
 template <bool SMEM, int MASK, int TRAV>
-__global__ void __launch_bounds__(EXT_THREADS, (MASK & 0x1e0) ? 2 : ((MASK & 0x1c) ? 3 : 4))
+__global__ void __launch_bounds__((MASK & 0x1e0) ? EXT_THREADS_HEAVY : EXT_THREADS, (MASK & 0x1e0) ? 1 : ((MASK & 0x1c) ? 3 : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
-         float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed) {
+         float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed, int tune) {
   extern __shared__ float4 smem[];
   const int count = count_ptr ? *count_ptr : count_fixed;
   if ((int)(blockIdx.x * blockDim.x) >= count) return;      // no ray for this CTA (drain tail): skip the staging too
@@ -379,12 +406,12 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     __syncthreads();
     PrimShared ps{sh, sa};
     const uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np);      // TRAV_STACK: after the staged scene
-    if (MASK & 0x1e0) extend_loop_deferred<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
+    if (MASK & 0x1e0) extend_loop_deferred<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base, tune);
     else extend_loop<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
   } else {
     PrimGlobal ps{sc.prim_hdr, sc.prim_a};
     const uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(smem);
-    if (MASK & 0x1e0) extend_loop_deferred<false, MASK, TRAV>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
+    if (MASK & 0x1e0) extend_loop_deferred<false, MASK, TRAV>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base, tune);
     else extend_loop<false, MASK, TRAV>(sc, sc.nodes, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
   }
 }
@@ -561,8 +588,8 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
 // Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
-typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t);
-struct ExtendVariant { ExtendFn fn; int bps; size_t smem; };
+typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t, int);
+struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
 static ExtendVariant g_variants[2][4][3];
 
 static int variant_of(int mask) {
@@ -588,17 +615,18 @@ static ExtendFn variant_fn(bool smem, int v, int trav) {
 static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
   // 16-bit node ids: shared-memory stack when it fits beside the staged scene, else the register cache
-  const size_t stack = (size_t)2 * trav_stack_stride(L.sc.bvh_depth) * EXT_THREADS;
+  const int threads = v == 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
+  const size_t stack = (size_t)2 * trav_stack_stride(L.sc.bvh_depth) * threads;
   const bool small_ids = L.sc.n_nodes < 65536;
   const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling
   int trav = !small_ids ? TRAV_TRAIL : ((!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE);
   ExtendVariant& e = g_variants[which][v][trav];
   size_t smem = (which ? L.extend_smem : 0) + (trav == TRAV_STACK ? stack : 0);
   if (!e.fn || e.smem != smem) {
-    e.fn = variant_fn(which, v, trav); e.smem = smem;
+    e.fn = variant_fn(which, v, trav); e.smem = smem; e.threads = threads;
     if (smem) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bps = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, EXT_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, threads, smem);
     e.bps = bps < 1 ? 1 : bps;
   }
   return e;
@@ -609,7 +637,14 @@ void srt_extend_prepare(const RenderLaunch& L) { (void)extend_variant(L); }
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, uint32_t seed, cudaStream_t stream) {
   const ExtendVariant& e = extend_variant(L);
-  e.fn<<<L.sm_count * e.bps, EXT_THREADS, e.smem, stream>>>(L.sc, ray_o, ray_d, state, hit, d_count, count, tmin, tmax, seed);
+  // deferred-test tuning (heavy variant only): park vote | refill threshold << 8; env overrides are for A/B runs
+  static const int tune = [] {
+    const char* a = getenv("SRT_PARK_VOTE"); const char* b = getenv("SRT_REFILL_MIN");
+    int vote = a ? atoi(a) : EXT_PARK_VOTE, refill = b ? atoi(b) : EXT_REFILL_MIN;
+    vote = vote < 1 ? 1 : (vote > 32 ? 32 : vote); refill = refill < 1 ? 1 : (refill > 32 ? 32 : refill);
+    return vote | (refill << 8);
+  }();
+  e.fn<<<L.sm_count * e.bps, e.threads, e.smem, stream>>>(L.sc, ray_o, ray_d, state, hit, d_count, count, tmin, tmax, seed, tune);
   return 1;
 }
 

@@ -113,3 +113,28 @@ def test_flatten_constant_medium():
     assert np.all((f.prims["flags"][:8] & 2) == 0) and np.all((f.prims["flags"][8:] & 2) == 2)     # boundaries form a suffix
     assert tuple(f.prims[6]["p"][:3]) == (np.float32(0.01), 8.0, 6.0) and tuple(f.prims[7]["p"][1:3]) == (14.0, 6.0)
     assert f.materials[f.prims[6]["material"]]["kind"] == 0        # phase function = lambertian (geometry.scm:546)
+
+
+def test_points_csv_to_bezier_chain(tmp_path, orc):
+    """points.scm:10-50: CSV -> points (x magnitude) -> tightness-0.5 control points -> curve objects.
+    Expected control points worked out by hand: [p1, p1 + (p2 - p0)/6, p2 - (p3 - p1)/6, p2]."""
+    from scheme_raytrace_b200.host import points as pts, bezier as bz
+    f = tmp_path / "pts.csv"
+    f.write_text("0,0,0\n1,0,0\n2,1,0\n3,1,0\n4,0,0\n")
+    P = pts.load_points(str(f), 2)
+    assert [tuple(p) for p in P] == [(0, 0, 0), (2, 0, 0), (4, 2, 0), (6, 2, 0), (8, 0, 0)]
+    segs = pts.points_to_bezier(P)                           # last = n - 2 = 3: i = 1, 2
+    assert len(segs) == 2
+    exp = [[(2, 0, 0), (2 + 4 / 6, 2 / 6, 0), (4 - 4 / 6, 2 - 2 / 6, 0), (4, 2, 0)],
+           [(4, 2, 0), (4 + 4 / 6, 2 + 2 / 6, 0), (6 - 4 / 6, 2 + 2 / 6, 0), (6, 2, 0)]]
+    assert np.allclose(np.asarray(segs, float), np.asarray(exp, float), atol=1e-15)
+    assert np.allclose(np.subtract(segs[0][3], segs[0][2]), np.subtract(segs[1][1], segs[1][0]))   # C1 at the joint
+    mat = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
+    objs = pts.bezier_to_objs(segs, 0.2, mat)
+    assert len(objs) == 2 and all(o.kind == g.BEZIER for o in objs)
+    flat = srt.flatten_scene(g.make_scene(objs, scenes.default_camera(), scenes.sky_color))
+    assert list(flat.prims["type"]) == [5, 5] and np.allclose(flat.prims["p"][1][:3], (4, 2, 0))
+    # the oracle sees the chain: a ray aimed at the joint hits one of the two segments
+    S = orc.OracleScene(g.make_scene(objs, scenes.default_camera(), scenes.sky_color), quantise=False)
+    r = S.trace_batch([[4.03, 2.0, 5, 0, 0, -1, 0], [3.0, 5.0, 5, 0, 0, -1, 0]])
+    assert r["prim"][0] in (0, 1) and r["prim"][1] == -1

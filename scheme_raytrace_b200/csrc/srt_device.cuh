@@ -306,7 +306,10 @@ __device__ __forceinline__ void bern(float s, float b[4], float db[4]) {   // cu
 // hull cull + Newton from the leaf's centre, with the projected net held in registers (no local
 // memory: the smem-staged BVH leaves almost no L1).  dom = (u0, v0, size) of the leaf in the
 // parent patch's domain; u/v out are GLOBAL.
-static __device__ __noinline__ bool isect_patch(const float4* __restrict__ cp, float4 dom, float3 o, float3 dir, float tmin, float tbest,
+#ifndef SRT_PATCH_INLINE
+#define SRT_PATCH_INLINE __noinline__
+#endif
+static __device__ SRT_PATCH_INLINE bool isect_patch(const float4* __restrict__ cp, float4 dom, float3 o, float3 dir, float tmin, float tbest,
                                                 float& tout, float& uout, float& vout) {
   // ray-space projection (bezier.scm:13-55)
   float3 ud = unit(dir);
@@ -350,7 +353,12 @@ static __device__ __noinline__ bool isect_patch(const float4* __restrict__ cp, f
     }
     float det = Sux * Svy - Svx * Suy;
     if (!(fabsf(det) > 1e-30f)) break;
+#ifdef SRT_EXP_FAST_NEWTON
+    const float idet = __frcp_rn(det);
+    float ds = (-Sx * Svy + Sy * Svx) * idet, dt = (-Sux * Sy + Suy * Sx) * idet;
+#else
     float ds = (-Sx * Svy + Sy * Svx) / det, dt = (-Sux * Sy + Suy * Sx) / det;
+#endif
     s += ds; t += dt;
     if (!(fabsf(s) < 4.0f) || !(fabsf(t) < 4.0f)) break;
     if (fmaxf(fabsf(ds), fabsf(dt)) < 1e-5f) { conv = true; break; }
@@ -432,7 +440,9 @@ struct Hit { float t; int prim; float u, v; bool incl; };
 // One leaf primitive against the ray (world space in, candidate merged into `h`).  MASK is the
 // set of primitive kinds present in the scene (bit = SRT_PRIM_*): the extend kernel is compiled
 // per mask so that e.g. sphere-only scenes carry no rect / instance / Bezier code or registers.
+#ifndef SRT_MASK_ALL
 #define SRT_MASK_ALL 0x1ff
+#endif
 template <int MASK, class PrimSrc>
 __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin,
                                                const RngAddr& ra, Hit& h) {

@@ -19,7 +19,10 @@
 
 namespace {
 
-constexpr int EXT_THREADS = 256, EXT_THREADS_HEAVY = 512;
+#ifndef SRT_HEAVY_THREADS
+#define SRT_HEAVY_THREADS 512
+#endif
+constexpr int EXT_THREADS = 256, EXT_THREADS_HEAVY = SRT_HEAVY_THREADS;
 constexpr int SHD_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------

@@ -590,22 +590,27 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
 // =================================================================================================
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
-// Kernel variants by primitive mix: spheres only | spheres + moving spheres | no Bezier | all.
+// Kernel variants by primitive mix.
 typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t, int);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
-static ExtendVariant g_variants[2][4][3];
+static ExtendVariant g_variants[2][5][3];
 
+// spheres | + moving spheres | + rects / instances | + bicubic patches | everything (curves, media, Klein).
+// The patch variant exists because the curve's subdivision stack (1.3 KB of local memory per thread) and
+// the Klein / medium code cost the patch scenes 14 % when merely compiled in (cfg5_teapot 2.61 -> 2.96 Grays/s).
 static int variant_of(int mask) {
   if ((mask & ~0x01) == 0) return 0;
   if ((mask & ~0x03) == 0) return 1;
   if ((mask & 0x1e0) == 0) return 2;
-  return 3;
+  if ((mask & 0x160) == 0) return 3;
+  return 4;
 }
 template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v) {
   switch (v) {
     case 0: return k_extend<SMEM, 0x01, TRAV>;
     case 1: return k_extend<SMEM, 0x03, TRAV>;
     case 2: return k_extend<SMEM, 0x1f, TRAV>;
+    case 3: return k_extend<SMEM, 0x9f, TRAV>;
     default: return k_extend<SMEM, SRT_MASK_ALL, TRAV>;
   }
 }
@@ -618,7 +623,7 @@ static ExtendFn variant_fn(bool smem, int v, int trav) {
 static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
   // 16-bit node ids: shared-memory stack when it fits beside the staged scene, else the register cache
-  const int threads = v == 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
+  const int threads = v >= 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
   const size_t stack = (size_t)2 * trav_stack_stride(L.sc.bvh_depth) * threads;
   const bool small_ids = L.sc.n_nodes < 65536;
   const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling

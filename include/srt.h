@@ -82,7 +82,10 @@ enum { SRT_SKY_GRADIENT = 0 /* main.scm:91 sky-color */, SRT_SKY_BLACK = 1 /* ma
 #define SRT_Q4_PERLIN_ALIAS 2       /* perlin.scm:76      */
 #define SRT_Q6_SCATTER_TIME0 4      /* ray.scm:8-9        */
 #define SRT_Q10_DIELECTRIC_UNNORM 8 /* material.scm:59-67 */
-#define SRT_QUIRKS_REFERENCE 15
+#define SRT_Q15_LOCAL_TRIPLE_EVAL 16 /* onb.scm:27-36: the `local` macro mentions its operand three times, so
+                                        (local uvw (random-cosine-direction)) (material.scm:27, pdf.scm:26) draws three
+                                        directions and takes x, y, z from the 1st, 2nd, 3rd */
+#define SRT_QUIRKS_REFERENCE 31
 
 /* radiance estimator: the reference's `color` (main.scm:100-121, cosine sampling only), or the
  * Rest-of-Life mixture(hittable(lights), cosine) pdf (pdf.scm:18-41; hittable part unpinned) */

@@ -187,7 +187,7 @@ class OracleScene:
         if rc != 0:
             raise ValueError(f"orc_set_lights failed ({rc})")
 
-    def render(self, width, height, spp, max_depth=50, seed=1, quirks=15, spp_begin=0, nthreads=0, precision=64, rgb_sum=None, estimator=0):
+    def render(self, width, height, spp, max_depth=50, seed=1, quirks=31, spp_begin=0, nthreads=0, precision=64, rgb_sum=None, estimator=0):
         if rgb_sum is None:
             rgb_sum = np.zeros((height, width, 3), dtype=np.float64)
         if nthreads <= 0:
@@ -197,13 +197,13 @@ class OracleScene:
                             _p(rgb_sum), C.byref(nrays), estimator)
         return rgb_sum, int(nrays.value)
 
-    def tex_value(self, tex, uvp, quirks=15):
+    def tex_value(self, tex, uvp, quirks=31):
         uvp = _d(uvp).reshape(-1, 5)
         out = np.zeros((len(uvp), 3))
         self.lib.orc_tex_value(self.h, tex, len(uvp), _p(uvp), quirks, _p(out))
         return out
 
-    def noise(self, p, quirks=15, turb=False):
+    def noise(self, p, quirks=31, turb=False):
         p = _d(p).reshape(-1, 3)
         out = np.zeros(len(p))
         self.lib.orc_noise(self.h, len(p), _p(p), quirks, int(turb), _p(out))
@@ -241,7 +241,7 @@ def reflect(v, n):                             # material.scm:41-43
     return o
 
 
-def refract(v, n, ni_over_nt, quirks=15):      # material.scm:59-67 -> (ok, refracted)
+def refract(v, n, ni_over_nt, quirks=31):      # material.scm:59-67 -> (ok, refracted)
     a, b, o = _d(v), _d(n), np.zeros(3)
     lib = load()
     lib.orc_refract.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p]

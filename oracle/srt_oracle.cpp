@@ -4,11 +4,18 @@
 // may include, link or call this file.  It is used by tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs as the CHECKER and the CPU baseline.
 //
-// PARITY STATUS: "parity unpinned" by reference tests — the reference ships no tests, no golden
-// vectors and no Scheme runtime exists in the build container.  This file follows
-// the reference .scm sources line by line (each function cites file:line under /root/reference);
-// it is pinned only by the hand-verifiable known-answer vectors KAT1-10 of SURVEY.md §8c
-// (tests/test_oracle_kat.py).
+// PARITY STATUS: pinned against outputs of the reference's own code.  The reference ships no tests or
+// golden vectors and no Gauche runtime exists in the build container, so its .scm files are executed,
+// unmodified, by the minimal interpreter oracle/minischeme.py; tests/golden/make_reference_golden.py
+// freezes g:hit records of every constructor and of main.scm's scenes, camera rays, Perlin tables /
+// noise / textures, the material helper functions and whole trace-all frames (random-real scripted with
+// this file's Philox draws) into tests/golden/ref_*.json, and tests/test_reference_golden.py requires
+// this file (f64, un-quantised scene) to reproduce them to 1e-12 (observed: bit-identical hit records;
+// radiance sums to 1e-9; 8-bit image exact).  Caveat: the interpreter is not Gauche itself.  Parts the
+// reference does not contain (metal / dielectric under `color`, isotropic, the hittable pdf, patches)
+// remain "parity unpinned" and say so where they are defined.  Each function cites the file:line under
+// /root/reference it follows; hand-derived known-answer vectors (KAT1-10 of SURVEY.md §8c and more) are
+// in tests/test_oracle_kat.py.
 //
 // The whole engine is templated on the arithmetic type: <double> is the truth the GPU path is
 // compared against (the reference computes in IEEE f64); <float> exists to flag rays on which the
@@ -45,7 +52,7 @@ enum TexKind { T_CONSTANT = 0, T_CHECKER = 1, T_NOISE = 2, T_MARBLE = 3, T_IMAGE
 enum SkyKind { SKY_GRADIENT = 0, SKY_BLACK = 1 };
 // quirk bits (SURVEY §8a "Q" rows); REFERENCE = all on
 enum Quirks { Q1_COSINE_X2 = 1, Q4_PERLIN_ALIAS = 2, Q6_SCATTER_TIME0 = 4, Q10_DIELECTRIC_UNNORM = 8,
-              Q_REFERENCE = 15 };
+              Q15_LOCAL_TRIPLE_EVAL = 16, Q_REFERENCE = 31 };
 
 struct Tex { int kind; double rgb[3]; double scale; int even, odd; };
 struct Mat { int kind; int tex; double param; };
@@ -140,6 +147,24 @@ template <class T> static V3<T> random_cosine_direction(T r1, T r2, int quirks) 
   T x = std::cos(phi) * k * std::sqrt(r2);
   T y = std::sin(phi) * k * std::sqrt(r2);
   return mk<T>(x, y, z);
+}
+
+// onb.scm:27-36 — Q15.  `local` is a syntax-rules macro and its two-operand form mentions the operand
+// `a` three times, so (local uvw (random-cosine-direction)) at material.scm:27 and pdf.scm:26 EVALUATES
+// (random-cosine-direction) three times (6 random-real draws): x comes from the first direction, y from
+// the second and z from the third.  (Found by executing the reference, tests/golden/ref_materials.json.)
+// Draw slots: first evaluation = block 0 (x, y) as without the quirk; second = block 2 (x, y); third =
+// block 2 (z, w), of which only r2 = w is used (its r1 only feeds the discarded x, y).
+template <class T> static V3<T> cosine_direction_triple(const T* r6, int quirks) {     // r6: the six draws in call order
+  V3<T> a = random_cosine_direction<T>(r6[0], r6[1], quirks), b = random_cosine_direction<T>(r6[2], r6[3], quirks),
+        c = random_cosine_direction<T>(r6[4], r6[5], quirks);
+  return mk<T>(a.x, b.y, c.z);
+}
+template <class T> static V3<T> cosine_direction_for_local(const RngAddr& addr, const T* block0, int quirks) {
+  if (!(quirks & Q15_LOCAL_TRIPLE_EVAL)) return random_cosine_direction<T>(block0[0], block0[1], quirks);
+  T w4[4]; rng_block<T>(addr, 2, w4);
+  T r6[6] = {block0[0], block0[1], w4[0], w4[1], w4[2], w4[3]};
+  return cosine_direction_triple<T>(r6, quirks);
 }
 
 template <class T> static V3<T> random_to_sphere(T radius, T distance_sq, T r1, T r2) {             // util.scm:46-54
@@ -733,7 +758,7 @@ template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int dept
           int li = std::min((int)(u4[3] * T(sc.lights.size())), (int)sc.lights.size() - 1);
           dir = light_random<T>(sc, sc.lights[li], rec.p, v4[0], v4[1]);
         } else {
-          dir = onb_local(uvw, random_cosine_direction<T>(u4[0], u4[1], cx.quirks));   // (generate p1): cosine pdf
+          dir = onb_local(uvw, cosine_direction_for_local<T>(addr, u4, cx.quirks));   // (generate p1): cosine pdf
         }
         Ray<T> scattered{rec.p, dir, time0};
         T pdf_val = T(0.5) * lights_pdf_value<T>(sc, rec.p, dir) + T(0.5) * cosine_pdf_value<T>(uvw.w, dir);
@@ -744,7 +769,7 @@ template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int dept
           return scale(mul(scale(atten, spdf), color(sc, scattered, depth + 1, addr, cx, nrays)), T(1) / pdf_val);
         return mk<T>(0, 0, 0);
       }
-      V3<T> target = onb_local(uvw, random_cosine_direction<T>(u4[0], u4[1], cx.quirks));
+      V3<T> target = onb_local(uvw, cosine_direction_for_local<T>(addr, u4, cx.quirks));
       Ray<T> scattered{rec.p, unit(target), time0};
       V3<T> atten = tex_value<T>(sc, m.tex, T(0), T(0), rec.p, cx.quirks);
       T pdf = dot(uvw.w, scattered.d) / T(PI);
@@ -994,6 +1019,14 @@ void orc_sky(void* h, const double* d3, double* rgb) {
   Scene* s = (Scene*)h; Ray<double> r{mk<double>(0, 0, 0), ld3<double>(d3), 0.0}; V3<double> c = sky_value<double>(*s, r); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; }
 void orc_onb_cosine(const double* n3, double r1, double r2, int quirks, double* target3) {
   Onb<double> o = make_onb_from_w(ld3<double>(n3)); V3<double> t = onb_local(o, random_cosine_direction<double>(r1, r2, quirks));
+  target3[0] = t.x; target3[1] = t.y; target3[2] = t.z; }
+void orc_onb_local(const double* n3, const double* a3, double* out3) {                     // onb.scm:8-16, 27-36
+  Onb<double> o = make_onb_from_w(ld3<double>(n3)); V3<double> t = onb_local(o, ld3<double>(a3));
+  out3[0] = t.x; out3[1] = t.y; out3[2] = t.z; }
+// (local uvw (random-cosine-direction)) as the reference evaluates it (Q15): r6 = its six random-real draws in call order
+void orc_onb_local_cosine(const double* n3, const double* r6, int quirks, double* target3) {
+  Onb<double> o = make_onb_from_w(ld3<double>(n3));
+  V3<double> t = onb_local(o, (quirks & Q15_LOCAL_TRIPLE_EVAL) ? cosine_direction_triple<double>(r6, quirks) : random_cosine_direction<double>(r6[0], r6[1], quirks));
   target3[0] = t.x; target3[1] = t.y; target3[2] = t.z; }
 
 // Render: accumulates samples [spp_begin, spp_end) into rgb_sum (w*h*3 doubles, y=0 bottom row).

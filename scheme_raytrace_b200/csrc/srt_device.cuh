@@ -712,6 +712,16 @@ __device__ __forceinline__ Scatter scatter(const DScene& sc, int prim, float3 d_
       float3 vv = unit(cross(w, a));
       float3 uu = cross(w, vv);
       float3 rc = random_cosine_direction(xi.x, xi.y, quirks);
+      if (quirks & SRT_Q15_LOCAL_TRIPLE_EVAL) {
+        // Q15, onb.scm:27-36: `local` expands its operand three times, so the reference draws three cosine
+        // directions and keeps x of the first (above), y of the second and z of the third.  Draw slots:
+        // block 2 = (r1', r2', -, r2'') — the third evaluation's r1 only feeds its discarded x, y.
+        const float4 xk = rng_block(addr, 2);
+        float s2, c2;
+        sincospif(2.0f * xk.x, &s2, &c2);
+        rc.y = s2 * (((quirks & SRT_Q1_COSINE_X2) ? 2.0f : 1.0f) * sqrtf(xk.y));
+        rc.z = sqrtf(1.0f - xk.w);
+      }
       if (EST == SRT_EST_MIXTURE && sc.n_lights > 0) {
         // mixture(hittable(lights), cosine) pdf.scm:34-41; block 0 = (r1, r2, xi_choice, xi_light), block 1 = (xa, xb)
         float4 xj = rng_block(addr, 1);

@@ -1,0 +1,399 @@
+"""Golden vectors produced by RUNNING THE REFERENCE'S OWN SOURCES (build container only).
+
+    python tests/golden/make_reference_golden.py            # rewrites tests/golden/ref_*.json
+
+The reference is Gauche Scheme and no Scheme runtime exists in the build image, so its .scm files
+are executed, unmodified and from where they lie (/root/reference), by the minimal interpreter
+oracle/minischeme.py (its header lists where Gauche behaviour had to be restated: numeric tower,
+f64vector / array primitives, libm).  Everything written here is an OUTPUT OF REFERENCE CODE:
+
+  ref_prims.json      closest hits of the reference's constructors (sphere, moving sphere, rects, flip, box,
+                      translate / rotate-y instances, Bezier curve) called through `g:hit` on seeded rays
+  ref_scenes.json     `g:hit` on the scenes main.scm itself defines (cornell-box, test-scene2, test-scene,
+                      cornell-bezier), on rays made by the reference's own `cam:get-ray` and on seeded rays
+  ref_textures.json   the Perlin tables perlin.scm builds at module load (from the scripted random-real) and
+                      `noise`, `turb`, checker / noise / marble texture values
+  ref_materials.json  `reflect`, `refract`, `schlick`, `(local uvw (random-cosine-direction))` (six draws: Q15), sky-color,
+                      lambertian scatter / scattering-pdf, diffuse-light emitted
+  ref_color.json      main.scm's `trace-all` (color, running sum, gamma, 8-bit) on cornell-box and test-scene2
+                      with `random-real` scripted to return the oracle's Philox draws in the reference's call
+                      order, so the oracle (and the CUDA path) must reproduce the radiance of every pixel
+
+`random-real` is scripted by this file (srfi-27's MT19937 stream is not a parity target).  Rays and
+primitive parameters are fp32-representable so that the CUDA path can be fed the very same inputs.
+The .json files travel to the GPU box; this script and /root/reference do not need to.
+"""
+import json
+import os
+import sys
+import threading
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+REFERENCE = os.environ.get("SRT_REFERENCE", "/root/reference")
+
+from oracle.minischeme import Interp, Sym, F64, Values, read_all   # noqa: E402
+from tests import raybatch                                          # noqa: E402
+from tests.refspec import build_host, host_scene                    # noqa: E402
+
+MAXF = 999999999999
+
+
+def v3(*a):
+    return F64(float(x) for x in a)
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+class Ref:
+    """The reference, loaded."""
+
+    def __init__(self, random_real):
+        self.it = Interp(REFERENCE, random_real)
+        for mod in ["vec", "util", "ray", "onb", "perlin", "texture", "material", "geometry", "bezier", "camera", "pdf", "points", "constant"]:
+            self.it.require(mod)
+        self.lam = self.call("material", "make-lambertian", self.call("texture", "constant-texture", v3(0.5, 0.5, 0.5)))
+
+    def call(self, module, name, *args):
+        return self.it.call(module, name, *args)
+
+    def build(self, spec):
+        k, c = spec[0], self.call
+        if k == "sphere":
+            return c("geometry", "make-sphere", v3(*spec[1]), spec[2], self.lam)
+        if k == "moving-sphere":
+            return c("geometry", "make-moving-sphere", v3(*spec[1]), v3(*spec[2]), spec[3], spec[4], spec[5], self.lam)
+        if k in ("xy-rect", "xz-rect", "yz-rect"):
+            return c("geometry", "make-" + k, *spec[1:6], self.lam)
+        if k == "flip":
+            return c("geometry", "flip-normals", self.build(spec[1]))
+        if k == "box":
+            return c("geometry", "make-box", v3(*spec[1]), v3(*spec[2]), self.lam)
+        if k == "translate":
+            return c("geometry", "translate", self.build(spec[1]), v3(*spec[2]))
+        if k == "rotate-y":
+            return c("geometry", "rotate-y", self.build(spec[1]), spec[2])
+        if k == "bezier":
+            return c("bezier", "make-bezier", v3(*spec[1]), v3(*spec[2]), v3(*spec[3]), v3(*spec[4]), spec[5], self.lam)
+        raise ValueError(k)
+
+    def hit(self, obj, ray7, t_min=0.001, t_max=MAXF):
+        ray = self.call("ray", "make-ray-with-time", v3(*ray7[0:3]), v3(*ray7[3:6]), float(ray7[6]))
+        r = self.call("geometry", "hit", obj, ray, t_min, t_max)
+        if r[0] is False:
+            return None
+        rec = r[1]
+        return dict(t=float(rec[0]), p=list(rec[1]), n=list(rec[2]), u=float(rec[4]), v=float(rec[5]))
+
+    def load_main(self, names):
+        """Take the named top-level definitions (and the module header) out of main.scm."""
+        forms = read_all(open(os.path.join(REFERENCE, "main.scm")).read())
+        main = None
+        for form in forms:
+            if not isinstance(form, list) or not form:
+                continue
+            if form[0] == "define-module":
+                self.it.eval(form, self.it.user)
+                main = self.it.modules["main"]
+            elif form[0] in ("define", "define-inline") and main is not None:
+                name = form[1][0] if isinstance(form[1], list) else form[1]
+                if name in names:
+                    self.it.eval(form, main)
+        return main
+
+
+def hits_table(ref, obj, rays):
+    hit, t, p, n, uv = [], [], [], [], []
+    for r in rays:
+        h = ref.hit(obj, r)
+        hit.append(h is not None)
+        t.append(h["t"] if h else 0.0)
+        p.append(h["p"] if h else [0.0, 0.0, 0.0])
+        n.append(h["n"] if h else [0.0, 0.0, 0.0])
+        uv.append([h["u"], h["v"]] if h else [0.0, 0.0])
+    return dict(rays=[list(map(float, r)) for r in rays], hit=hit, t=t, p=p, n=n, uv=uv)
+
+
+def stability_mask(scene, rays):
+    """Rays on which the CUDA path (fp32) may legitimately differ (used only by the GPU test), decided with
+    the oracle: near-ties and fp32-flipped decisions exactly like tests/raybatch.compare, plus rays that are
+    ill-conditioned for the 1e-4 bar in fp32 - the reference algorithm itself, evaluated in fp32 (f32 oracle),
+    is already off by more than half the bar in t or normal (a small sphere far away: the rounding of t is
+    divided by the radius in the normal)."""
+    from oracle import oracle as O
+    S = O.OracleScene(scene)
+    r64 = np.asarray(rays, np.float64)
+    o, o32 = S.trace_batch(r64), S.trace_batch(r64, precision=32)
+    t2 = S.second_best_t(r64, o["prim"])
+    near = (o["prim"] >= 0) & (np.abs(t2 - o["t"]) < 1e-5 * np.abs(o["t"])) & (t2 != o["t"])
+    both = (o["prim"] >= 0) & (o32["prim"] == o["prim"])
+    t_err = np.abs(o32["t"] - o["t"]) / np.maximum(np.abs(o["t"]), 1e-30)
+    n_err = np.linalg.norm(o32["n"] - o["n"], axis=1) / np.maximum(np.linalg.norm(o["n"], axis=1), 1e-30)
+    ill = both & ((t_err > 5e-5) | (n_err > 5e-5))
+    return [bool(x) for x in (near | (o32["prim"] != o["prim"]) | ill)]
+
+
+PRIM_CASES = [
+    ("sphere", ["sphere", [0.5, -0.25, -1.0], 0.75]),
+    ("sphere-negative-radius", ["sphere", [-1.0, 0.0, -1.0], -0.45]),
+    ("sphere-huge", ["sphere", [0.0, -1000.0, 0.0], 1000.0]),
+    ("moving-sphere", ["moving-sphere", [0.0, 0.25, 0.0], [0.0, 0.75, 0.5], 0.0, 1.0, 0.5]),
+    ("xy-rect", ["xy-rect", 3.0, 5.0, 1.0, 3.0, -2.0]),
+    ("xz-rect", ["xz-rect", 213.0, 343.0, 227.0, 332.0, 554.0]),
+    ("yz-rect-flipped", ["flip", ["yz-rect", 0.0, 555.0, 0.0, 555.0, 555.0]]),
+    ("box", ["box", [0.0, 0.0, 0.0], [165.0, 330.0, 165.0]]),
+    ("box-rotated-translated", ["translate", ["rotate-y", ["box", [0.0, 0.0, 0.0], [165.0, 165.0, 165.0]], -18.0], [130.0, 0.0, 65.0]]),
+    ("box-rotated-translated-2", ["translate", ["rotate-y", ["box", [0.0, 0.0, 0.0], [165.0, 330.0, 165.0]], 15.0], [265.0, 0.0, 295.0]]),
+    ("bezier", ["bezier", [-1.0, 0.0, -1.0], [-0.8125, 1.0, 1.0], [0.8125, -1.0, 1.0], [1.0, 0.0, -1.0], 0.125]),
+]
+
+
+INSTANCE_BOUNDS = {(130.0, 0.0, 65.0): ([78.0, -1.0, 64.0], [339.0, 166.0, 274.0]),
+                   (265.0, 0.0, 295.0): ([264.0, -1.0, 251.0], [468.0, 331.0, 456.0])}
+
+
+def curve_point(spec, s):
+    a, b, c, d = (np.asarray(q, float) for q in spec[1:5])
+    return a * (1 - s) ** 3 + 3 * b * (1 - s) ** 2 * s + 3 * c * (1 - s) * s ** 2 + d * s ** 3
+
+
+def rays_for(spec, n, seed):
+    """Half the batch: seeded rays through the object's extent (tests/raybatch.random_rays); the other half
+    keeps those origins but aims at a point of the object's box (a Bezier curve: a point of the centre line
+    displaced by up to 1.5 half-widths), so that thin objects are hit and grazed, not only missed."""
+    from scheme_raytrace_b200.host import geometry as g, scenes
+    from scheme_raytrace_b200.host.flatten import flatten_scene
+    flat = flatten_scene(g.make_scene([build_host(spec)], scenes.default_camera(), scenes.sky_color))
+    lo, hi = raybatch.interest_bounds(flat, clip=4.0)
+    if spec[0] == "translate":                       # instances: the extent of the transformed box, by hand (+-1 like interest_bounds)
+        lo, hi = (np.asarray(q, float) for q in INSTANCE_BOUNDS[tuple(spec[2])])
+    rays = raybatch.random_rays((lo, hi), n, seed).astype(np.float64)
+    rs = np.random.RandomState(seed + 5000)
+    for r in rays[n // 2:]:
+        if spec[0] == "bezier":
+            aim = curve_point(spec, rs.uniform(0.02, 0.98)) + rs.normal(size=3) * spec[5] * 0.5
+        else:
+            aim = (lo + 1.0) + rs.random_sample(3) * ((hi - 1.0) - (lo + 1.0))
+        d = aim - r[0:3]
+        r[3:6] = d / np.linalg.norm(d) * rs.uniform(0.5, 2.0)
+    return f32(rays)
+
+
+def make_prims(ref):
+    from scheme_raytrace_b200.host import geometry as g, scenes
+    cases = []
+    for i, (name, spec) in enumerate(PRIM_CASES):
+        n = 64 if spec[0] == "bezier" else 200
+        rays = rays_for(spec, n, 100 + i)
+        obj = ref.build(spec)
+        tab = hits_table(ref, obj, rays)
+        tab["unstable"] = stability_mask(g.make_scene([build_host(spec)], scenes.default_camera(), scenes.sky_color), rays)
+        cases.append(dict(name=name, spec=spec, **tab))
+        print(f"prims/{name}: {sum(tab['hit'])}/{n} hits, {sum(tab['unstable'])} flagged")
+    return dict(source="reference constructors of geometry.scm / bezier.scm through g:hit (oracle/minischeme.py)", t_min=0.001, t_max=MAXF, cases=cases)
+
+
+MAIN_NAMES = {"+max-depth+", "+black+", "+white+", "sky-color", "black", "color", "correct-gamma", "*size-x*", "*size-y*",
+              "*cornell-camera*", "*camera*", "test-scene", "test-scene2", "cornell-box", "cornell-bezier", "trace-all",
+              "*image*", "*raw-data*"}
+
+
+def make_scenes(ref, main):
+    out = []
+    for i, name in enumerate(["cornell-box", "test-scene2", "test-scene", "cornell-bezier"]):
+        scene = main.lookup(Sym(name))
+        cam = ref.call("geometry", "scene-camera", scene)
+        # (i) camera rays from the reference's own get-ray on a 12 x 12 grid of (s, t); random-real is scripted
+        cam_rays = []
+        for a in range(12):
+            for b in range(12):
+                ray = ref.call("camera", "get-ray", cam, (a + 0.5) / 12, (b + 0.5) / 12)
+                cam_rays.append(list(ray[0]) + list(ray[1]) + [float(ray[2])])
+        cam_rays = f32(cam_rays)                       # rounded to fp32 AFTER the reference made them; stored as the inputs of g:hit
+        # (ii) seeded rays through the scene's extent
+        from scheme_raytrace_b200.host.flatten import flatten_scene
+        hs = host_scene(name)
+        nr = 60 if name == "cornell-bezier" else 200
+        rnd = raybatch.random_rays(raybatch.interest_bounds(flatten_scene(hs)), nr, 200 + i).astype(np.float64)
+        rays = np.concatenate([cam_rays, rnd])
+        tab = hits_table(ref, scene, rays)
+        tab["unstable"] = stability_mask(hs, rays)
+        tab["n_camera_rays"] = len(cam_rays)
+        out.append(dict(name=name, **tab))
+        print(f"scenes/{name}: {sum(tab['hit'])}/{len(rays)} hits, {sum(tab['unstable'])} flagged")
+    return dict(source="scenes defined by main.scm, closest hit by (g:hit scene ray 0.001 +max-float+); the first n_camera_rays rays were made by cam:get-ray",
+                scenes=out)
+
+
+def make_textures(ref):
+    it = ref.it
+    per = it.modules["perlin"]
+    ranvec = [list(x) for x in per.lookup(Sym("+ranvec+"))]
+    perms = [list(per.lookup(Sym(n))) for n in ("+perm-x+", "+perm-y+", "+perm-z+")]
+    rs = np.random.RandomState(7)
+    pts = f32(np.concatenate([rs.uniform(-6, 6, (150, 3)), rs.uniform(-300, 300, (50, 3))]))
+    noise = [float(ref.call("perlin", "noise", v3(*p))) for p in pts]
+    turb = [float(ref.call("perlin", "turb", v3(*p))) for p in pts]
+    tex = {"checker": ref.call("texture", "checker-texture", ref.call("texture", "constant-texture", v3(0.2, 0.3, 0.1)), ref.call("texture", "constant-texture", v3(0.9, 0.9, 0.9))),
+           "noise4": ref.call("texture", "noise-texture", 4), "marble1": ref.call("texture", "marble-texture", 1), "marble0.25": ref.call("texture", "marble-texture", 0.25)}
+    vals = {k: [list(ref.call("texture", "value", tx, 0, 0, v3(*p))) for p in pts] for k, tx in tex.items()}
+    print(f"textures: {len(pts)} points, noise range [{min(noise):.3f}, {max(noise):.3f}]")
+    return dict(source="perlin.scm tables as built at module load from the scripted random-real; noise / turb / t:value outputs",
+                ranvec=ranvec, perm_x=perms[0], perm_y=perms[1], perm_z=perms[2], points=[list(p) for p in pts], noise=noise, turb=turb, textures=vals)
+
+
+def make_materials(ref, main, rng):
+    rs = np.random.RandomState(11)
+    out = dict(source="material.scm / util.scm / onb.scm / main.scm procedures called directly")
+    vs, ns = f32(rs.normal(size=(40, 3)) * rs.uniform(0.5, 3, (40, 1))), rs.normal(size=(40, 3))
+    ns = f32(ns / np.linalg.norm(ns, axis=1, keepdims=True))
+    out["reflect"] = [dict(v=list(a), n=list(b), out=list(ref.call("material", "reflect", v3(*a), v3(*b)))) for a, b in zip(vs, ns)]
+    refr = []
+    for a, b, ratio in zip(vs, ns, [1 / 1.5, 1.5] * 20):
+        r = ref.call("material", "refract", v3(*a), v3(*b), ratio)
+        refr.append(dict(v=list(a), n=list(b), ni_over_nt=ratio, ok=r[0] is not False, out=list(r[1]) if r[0] is not False else None))
+    out["refract"] = refr
+    out["schlick"] = [dict(cosine=float(c), ref_idx=1.5, out=float(ref.call("material", "schlick", float(c), 1.5))) for c in f32(rs.uniform(0, 1, 20))]
+    cos = []
+    for b in ns[:30]:
+        r6 = [float(x) for x in f32(rs.uniform(0.001, 0.999, 6))]
+        rng.script = list(r6)
+        uvw = ref.call("onb", "make-onb-from-w", v3(*b))
+        d = ref.it.eval([Sym("local"), Sym("uvw"), [Sym("random-cosine-direction")]], _env_with(ref.it.modules["material"], uvw=uvw))
+        assert not rng.script, "(local uvw (random-cosine-direction)) is expected to consume six draws (Q15)"
+        cos.append(dict(w=list(b), draws=r6, out=list(d)))
+    out["onb_cosine"] = cos
+    # the same macro with a VARIABLE operand (the single-evaluation case): onb.scm:31-36 itself
+    loc = []
+    for b, a in zip(ns[:10], vs[10:20]):
+        uvw = ref.call("onb", "make-onb-from-w", v3(*b))
+        d = ref.it.eval([Sym("local"), Sym("uvw"), Sym("a")], _env_with(ref.it.modules["material"], uvw=uvw, a=v3(*a)))
+        loc.append(dict(w=list(b), a=list(a), out=list(d)))
+    out["onb_local"] = loc
+    sky = main.lookup(Sym("sky-color"))
+    out["sky"] = [dict(d=list(a), out=list(ref.it.apply(sky, [ref.call("ray", "make-ray", v3(0, 0, 0), v3(*a))]))) for a in vs[:20]]
+    # lambertian scatter + scattering-pdf and diffuse-light emitted on a hit record
+    lam, scat = ref.lam, []
+    for a, b in zip(vs[:20], ns[:20]):
+        r6 = [float(x) for x in f32(rs.uniform(0.001, 0.999, 6))]
+        rng.script = list(r6)
+        rec = ref.call("ray", "make-hit-record", 1.0, v3(1, 2, 3), v3(*b), lam, 0, 0)
+        ray = ref.call("ray", "make-ray", v3(0, 0, 0), v3(*a))
+        valid, scattered, atten, pdf = ref.call("material", "scatter", lam, ray, rec)
+        spdf = ref.call("material", "scattering-pdf", lam, ray, rec, scattered)
+        assert not rng.script
+        scat.append(dict(n=list(b), draws=r6, dir=list(scattered[1]), time=float(scattered[2]), atten=list(atten), pdf=float(pdf), spdf=float(spdf)))
+    out["lambertian"] = scat
+    light = ref.call("material", "make-diffuse-light", ref.call("texture", "constant-texture", v3(4, 4, 4)))
+    em = []
+    for a, b in zip(vs[:20], ns[:20]):
+        rec = ref.call("ray", "make-hit-record", 1.0, v3(1, 2, 3), v3(*b), light, 0.25, 0.75)
+        e = ref.call("material", "emitted", light, ref.call("ray", "make-ray", v3(0, 0, 0), v3(*a)), rec, 0.25, 0.75, v3(1, 2, 3))
+        em.append(dict(d=list(a), n=list(b), out=list(e)))
+    out["diffuse_light_emitted"] = em
+    print("materials: done")
+    return out
+
+
+def _env_with(module, **vars):
+    from oracle.minischeme import Env
+    return Env(module, {Sym(k): val for k, val in vars.items()})
+
+
+class ScriptedRng:
+    """random-real for the reference.  Default: the constant 0.5 (lens disk -> zero offset, shutter time
+    0.5).  `script`: a list consumed first.  `path`: (seed, pixel-of-call, sample) -> the oracle's Philox
+    draws in the order main.scm / camera.scm / material.scm consume them along one path."""
+
+    def __init__(self):
+        self.script, self.path, self.k = [], None, 0
+
+    def __call__(self):
+        if self.script:
+            return self.script.pop(0)
+        if self.path is None:
+            return 0.5
+        from oracle import oracle as O
+        seed, pixel, sample = self.path
+        k = self.k
+        self.k += 1
+        if k < 2:
+            return float(O.rng_block(seed, pixel, sample, 0, 0)[k])        # u, v jitter (main.scm:476-477)
+        if k < 4:
+            return 0.5                                                     # lens disk (camera.scm:81): radius 0 in these scenes
+        if k == 4:
+            return float(O.rng_block(seed, pixel, sample, 0, 0)[2])        # shutter time (camera.scm:84)
+        # lambertian at depth j (material.scm:27): (local uvw (random-cosine-direction)) evaluates its operand THREE
+        # times (onb.scm:27-36, Q15) = 6 draws per scatter: block 0 (x, y), then block 2 (x, y), (z, w) of bounce j + 1
+        j, c = divmod(k - 5, 6)
+        return float(O.rng_block(seed, pixel, sample, j + 1, 0)[c]) if c < 2 else float(O.rng_block(seed, pixel, sample, j + 1, 2)[c - 2])
+
+
+def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
+    it = ref.it
+    forms = {}
+    for form in read_all(open(os.path.join(REFERENCE, "main.scm")).read()):
+        if isinstance(form, list) and form and form[0] == "define" and not isinstance(form[1], list) and form[1] in ("*image*", "*raw-data*"):
+            forms[form[1]] = form
+    main.vars[Sym("*size-x*")] = size           # parameters of the run, like +max-depth+; the cameras keep aspect 1
+    main.vars[Sym("*size-y*")] = size
+    main.vars[Sym("+max-depth+")] = max_depth
+    color = main.lookup(Sym("color"))
+    state = dict(pixel=0)
+
+    def color_hook(ray, scene):                  # instrumentation only: tells the scripted RNG where a path ends
+        r = it.apply(color, [ray, scene])
+        state["pixel"] += 1
+        rng.path, rng.k = (seed, state["pixel"], rng.path[2]), 0
+        return r
+    main.vars[Sym("color")] = color_hook
+    out = []
+    for name in ["cornell-box", "test-scene2"]:
+        scene = main.lookup(Sym(name))
+        it.eval(forms["*image*"], main)
+        it.eval(forms["*raw-data*"], main)
+        for s in range(spp):
+            state["pixel"] = 0
+            rng.path, rng.k = (seed, 0, s), 0
+            it.call("main", "trace-all", scene, s + 1)
+        raw = [list(x) for x in main.lookup(Sym("*raw-data*"))]
+        img = list(main.lookup(Sym("*image*")))
+        out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img))
+        print(f"color/{name}: mean radiance {np.mean(raw) / spp:.4f}")
+    rng.path = None
+    main.vars[Sym("color")] = color
+    return dict(source="main.scm trace-all (color, running sum, correct-gamma, 8-bit) with random-real returning the oracle's Philox draws "
+                       "(key (pixel, seed), counter (sample, bounce, block, 0)) in the reference's call order; y = 0 is the bottom row",
+                runs=out)
+
+
+def main():
+    rng = ScriptedRng()
+    rs = np.random.RandomState(3)
+    rng.script = [float(x) for x in rs.random_sample(256 + 3 * 256 + 3 * 255)]     # consumed by perlin.scm at module load
+    ref = Ref(rng)
+    assert not rng.script, "perlin.scm consumed a different number of random-real calls than expected"
+    main_mod = ref.load_main(MAIN_NAMES)
+
+    def dump(name, obj):
+        with open(os.path.join(HERE, name), "w") as f:
+            json.dump(obj, f)
+        print("wrote", name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KB")
+    dump("ref_prims.json", make_prims(ref))
+    dump("ref_scenes.json", make_scenes(ref, main_mod))
+    dump("ref_textures.json", make_textures(ref))
+    dump("ref_materials.json", make_materials(ref, main_mod, rng))
+    dump("ref_color.json", make_color(ref, main_mod, rng))
+
+
+if __name__ == "__main__":
+    sys.setrecursionlimit(200000)
+    threading.stack_size(512 * 1024 * 1024)
+    t = threading.Thread(target=main)
+    t.start()
+    t.join()

@@ -1,0 +1,35 @@
+"""Object specs shared by the reference-golden generator (tests/golden/make_reference_golden.py, which
+builds them with the REFERENCE's constructors through oracle/minischeme.py) and by the tests (which
+build the same objects with the host mirror of the constructor API).  A spec is a nested list:
+["sphere", c, r] ["moving-sphere", c0, c1, t0, t1, r] ["xy-rect"|"xz-rect"|"yz-rect", a0, a1, b0, b1, k]
+["flip", obj] ["box", p0, p1] ["translate", obj, offset] ["rotate-y", obj, degrees] ["bezier", a, b, c, d, width]."""
+from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, bezier as bz, vec as v
+
+
+def build_host(spec, mat=None):
+    mat = mat or m.make_lambertian(t.constant_texture(v.vec3(0.5, 0.5, 0.5)))
+    k = spec[0]
+    if k == "sphere":
+        return g.make_sphere(v.vec3(*spec[1]), spec[2], mat)
+    if k == "moving-sphere":
+        return g.make_moving_sphere(v.vec3(*spec[1]), v.vec3(*spec[2]), spec[3], spec[4], spec[5], mat)
+    if k in ("xy-rect", "xz-rect", "yz-rect"):
+        return {"xy-rect": g.make_xy_rect, "xz-rect": g.make_xz_rect, "yz-rect": g.make_yz_rect}[k](*spec[1:6], mat)
+    if k == "flip":
+        return g.flip_normals(build_host(spec[1], mat))
+    if k == "box":
+        return g.make_box(v.vec3(*spec[1]), v.vec3(*spec[2]), mat)
+    if k == "translate":
+        return g.translate(build_host(spec[1], mat), v.vec3(*spec[2]))
+    if k == "rotate-y":
+        return g.rotate_y(build_host(spec[1], mat), spec[2])
+    if k == "bezier":
+        return bz.make_bezier(v.vec3(*spec[1]), v.vec3(*spec[2]), v.vec3(*spec[3]), v.vec3(*spec[4]), spec[5], mat)
+    raise ValueError(k)
+
+
+def host_scene(name, size_x=200, size_y=200):
+    """The host mirror of a scene that the generator takes from the reference's main.scm."""
+    from scheme_raytrace_b200.host import scenes
+    return {"cornell-box": scenes.cfg4_cornell_box, "test-scene2": scenes.test_scene2, "cornell-bezier": scenes.cornell_bezier,
+            "test-scene": lambda sx, sy: g.make_scene(scenes.test_scene_objects(), scenes.default_camera(sx, sy), scenes.black)}[name](size_x, size_y)

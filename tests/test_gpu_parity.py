@@ -416,7 +416,7 @@ def test_large_scene_global_memory_tree(orc, n):
     r.close()
 
 
-@pytest.mark.parametrize("quirks", [15, 0])
+@pytest.mark.parametrize("quirks", [31, 15, 0])
 def test_furnace_analytic_radiance_gpu(quirks):
     """The analytic furnace of tests/test_oracle_kat.py rendered by the CUDA path: every pixel on the
     sphere is weight_X * Le and every pixel off it is Le, to fp32 rounding."""

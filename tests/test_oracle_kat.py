@@ -266,6 +266,14 @@ def test_sampling_helpers_hand_derived(orc):
         assert np.allclose(out, [-0.0 * k, 0.6 * k, 0.8], atol=1e-15), (quirks, out)
         lib.orc_onb_cosine(orc._p(n), 0.0, 0.25, quirks, orc._p(out))       # phi = 0: x = k*0.5 -> along u = (-1,0,0)
         assert np.allclose(out, [-0.5 * k, 0.0, np.sqrt(0.75)], atol=1e-15), (quirks, out)
+    # Q15 (onb.scm:27-36): (local uvw (random-cosine-direction)) evaluates its operand three times; draws in call order
+    # (r1, r2), (r1', r2'), (r1'', r2''): x = cos(0)*2*sqrt(.25) = 1 of the 1st, y = sin(pi/2)*2*sqrt(.36) = 1.2 of the 2nd,
+    # z = sqrt(1-.64) = .6 of the 3rd -> u*1 + v*1.2 + w*.6
+    r6 = np.array([0.0, 0.25, 0.25, 0.36, 0.7, 0.64])
+    lib.orc_onb_local_cosine(orc._p(n), orc._p(r6), 31, orc._p(out))
+    assert np.allclose(out, [-1.0, 1.2, 0.6], atol=1e-15), out
+    lib.orc_onb_local_cosine(orc._p(n), orc._p(r6), 15, orc._p(out))         # without the quirk: the first evaluation alone
+    assert np.allclose(out, [-1.0, 0.0, np.sqrt(0.75)], atol=1e-15), out
     from scheme_raytrace_b200.host import geometry as g, scenes
     S = orc.OracleScene(g.make_scene([], scenes.default_camera(), scenes.sky_color), quantise=False)
     assert np.allclose(S.sky([0, 1, 0]), [0.5, 0.7, 1.0], atol=1e-15)       # t = 1
@@ -324,7 +332,7 @@ def check_furnace(img, expected, tol):
     assert np.abs(off - FURNACE_LE).max() < tol
 
 
-@pytest.mark.parametrize("quirks", [15, 0])
+@pytest.mark.parametrize("quirks", [31, 15, 0])
 def test_furnace_analytic_radiance(orc, quirks):
     for name, scene, expected in _furnace_cases():
         S = orc.OracleScene(scene, quantise=False)

@@ -1,0 +1,218 @@
+"""CPU (-m "not gpu"): the oracle against OUTPUTS OF THE REFERENCE ITSELF.
+
+`tests/golden/ref_*.json` were produced by executing /root/reference/*.scm, unmodified, with
+oracle/minischeme.py (tests/golden/make_reference_golden.py, build container only).  They are what
+pins the oracle: it is evaluated here WITHOUT the fp32 rounding of the scene tables
+(`quantise=False`), i.e. as the f64 restatement of the Scheme code on the same f64 inputs, and must
+reproduce the reference's numbers to the last few ulps:
+
+    hit / miss of every ray                        exact
+    t, p, normal, u, v of g:hit                    |err| <= 1e-12 * max(1, |ref|)
+    Perlin noise / turb / texture values           <= 1e-12
+    reflect / refract / schlick / cosine+onb / sky <= 1e-12
+    trace-all radiance sums, 10 x 10 x 2 spp       <= 1e-9 relative (a sum of products over <= 12 bounces);
+    8-bit image                                    exact
+
+A final test re-runs a slice of the generator when /root/reference is present (this container),
+so the committed files cannot drift from the interpreter + reference pair that made them.
+"""
+import json
+import os
+import numpy as np
+import pytest
+from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, scenes
+from tests.refspec import build_host, host_scene
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-12
+
+
+def load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+def _check_hits(O, scene, case, t_min=0.001, t_max=999999999999.0):
+    S = O.OracleScene(scene, quantise=False)
+    rays = np.asarray(case["rays"], np.float64)
+    assert np.array_equal(rays.astype(np.float32).astype(np.float64), rays), "golden rays must be fp32-representable"
+    o = S.trace_batch(rays, t_min, t_max)
+    hit = np.asarray(case["hit"], bool)
+    assert np.array_equal(o["prim"] >= 0, hit), np.nonzero((o["prim"] >= 0) != hit)[0][:10]
+    worst = 0.0
+    for key, mine in (("t", o["t"]), ("p", o["p"]), ("n", o["n"]), ("uv", o["uv"])):
+        ref = np.asarray(case[key], np.float64)
+        a, b = mine[hit], ref[hit]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key          # Q5: sphere u, v are NaN where asin leaves its domain
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+        if err.size:
+            worst = max(worst, float(np.nanmax(err)))
+    assert worst <= TOL, worst
+    return int(hit.sum()), worst
+
+
+def test_reference_primitives(orc):
+    P = load("ref_prims.json")
+    kinds = set()
+    for case in P["cases"]:
+        scene = g.make_scene([build_host(case["spec"])], scenes.default_camera(), scenes.sky_color)
+        nhit, worst = _check_hits(orc, scene, case, P["t_min"], P["t_max"])
+        assert nhit >= 20, (case["name"], nhit)        # every constructor is actually exercised by hits
+        kinds.add(case["spec"][0])
+    assert kinds == {"sphere", "moving-sphere", "xy-rect", "xz-rect", "flip", "box", "translate", "bezier"}
+
+
+def test_reference_scenes(orc):
+    for case in load("ref_scenes.json")["scenes"]:
+        nhit, _ = _check_hits(orc, host_scene(case["name"]), case)
+        assert nhit > 150, case["name"]
+
+
+def test_reference_camera_rays(orc):
+    """The first n_camera_rays rays of every scene came out of the reference's cam:get-ray on a 12 x 12 (s, t)
+    grid (lens radius 0, shutter draw 0.5); the oracle's get_ray must produce the same rays."""
+    for case in load("ref_scenes.json")["scenes"]:
+        S = orc.OracleScene(host_scene(case["name"]), quantise=False)
+        k = 0
+        for a in range(12):
+            for b in range(12):
+                mine = S.get_ray((a + 0.5) / 12, (b + 0.5) / 12, 0.5, 1, 0, 0)
+                ref = np.asarray(case["rays"][k])
+                k += 1
+                # the stored rays were rounded to fp32 after the reference made them
+                assert np.allclose(mine.astype(np.float32), ref.astype(np.float32), rtol=2e-7, atol=1e-30), (case["name"], a, b)
+        assert k == case["n_camera_rays"]
+
+
+def _ref_perlin(T):
+    return (np.asarray(T["ranvec"], np.float64), np.asarray(T["perm_x"], np.int32), np.asarray(T["perm_y"], np.int32), np.asarray(T["perm_z"], np.int32))
+
+
+def test_reference_perlin_and_textures(orc):
+    T = load("ref_textures.json")
+    rv, px, py, pz = _ref_perlin(T)
+    assert rv.shape == (256, 3) and sorted(px) == list(range(256)) and sorted(py) == list(range(256)) and sorted(pz) == list(range(256))
+    assert np.allclose(np.linalg.norm(rv, axis=1), 1.0, atol=1e-12)                    # perlin.scm:16-23 unit gradients
+    lam = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
+    tex = {"checker": t.checker_texture(t.constant_texture((0.2, 0.3, 0.1)), t.constant_texture((0.9, 0.9, 0.9))),
+           "noise4": t.noise_texture(4), "marble1": t.marble_texture(1), "marble0.25": t.marble_texture(0.25)}
+    objs = [g.make_sphere((i, 0, 0), 0.25, m.make_lambertian(tx)) for i, tx in enumerate(tex.values())]
+    scene = g.make_scene(objs + [g.make_sphere((9, 9, 9), 0.25, lam)], scenes.default_camera(), scenes.sky_color)
+    S = orc.OracleScene(scene, perlin=(rv, px, py, pz), quantise=False)
+    pts = np.asarray(T["points"], np.float64)
+    assert np.abs(S.noise(pts) - np.asarray(T["noise"])).max() <= TOL
+    assert np.abs(S.noise(pts, turb=True) - np.asarray(T["turb"])).max() <= TOL
+    uvp = np.concatenate([np.zeros((len(pts), 2)), pts], axis=1)
+    for name, tx in tex.items():
+        tid = S._tex[id(tx)]
+        mine = S.tex_value(tid, uvp)
+        assert np.abs(mine - np.asarray(T["textures"][name])).max() <= TOL, name
+
+
+def test_host_perlin_tables_are_the_references():
+    """perlin.scm:10-30 builds its tables at module load from random-real; the generator scripted random-real
+    with numpy's RandomState(3) stream, which is also what the host mirror `perlin_generate(3)` (the tables the
+    product uploads by default) draws from: same draws => the reference's tables, bit for bit."""
+    from scheme_raytrace_b200.host.perlin import perlin_generate
+    T = load("ref_textures.json")
+    rv, px, py, pz = perlin_generate(3)
+    assert np.array_equal(rv, np.asarray(T["ranvec"], np.float64))
+    assert np.array_equal(px, T["perm_x"]) and np.array_equal(py, T["perm_y"]) and np.array_equal(pz, T["perm_z"])
+
+
+def test_reference_material_functions(orc):
+    M = load("ref_materials.json")
+    for k in M["reflect"]:
+        assert np.abs(orc.reflect(k["v"], k["n"]) - k["out"]).max() <= TOL
+    n_ok = 0
+    for k in M["refract"]:
+        ok, out = orc.refract(k["v"], k["n"], k["ni_over_nt"])
+        assert ok == k["ok"]
+        if ok:
+            n_ok += 1
+            assert np.abs(out - k["out"]).max() <= TOL * max(1.0, np.abs(k["out"]).max())
+    assert 5 < n_ok < len(M["refract"])                # both branches (refracted / total internal reflection) present
+    for k in M["schlick"]:
+        assert abs(orc.schlick(k["cosine"], k["ref_idx"]) - k["out"]) <= TOL
+    lib = orc.load()
+    for k in M["onb_local"]:                           # onb.scm:27-36 with a variable operand: u*a.x + v*a.y + w*a.z
+        w, a, out = np.asarray(k["w"], np.float64), np.asarray(k["a"], np.float64), np.zeros(3)
+        lib.orc_onb_local(w.ctypes.data, a.ctypes.data, out.ctypes.data)
+        assert np.abs(out - k["out"]).max() <= TOL
+    for k in M["onb_cosine"]:
+        # Q15: (local uvw (random-cosine-direction)) consumed SIX draws in the reference: the macro evaluates its
+        # operand three times.  The oracle with the quirk reproduces the result; without it, it does not.
+        w, r6, out = np.asarray(k["w"], np.float64), np.asarray(k["draws"], np.float64), np.zeros(3)
+        lib.orc_onb_local_cosine(w.ctypes.data, r6.ctypes.data, 31, out.ctypes.data)
+        assert np.abs(out - k["out"]).max() <= TOL
+        lib.orc_onb_local_cosine(w.ctypes.data, r6.ctypes.data, 15, out.ctypes.data)
+        assert np.abs(out - k["out"]).max() > 1e-3
+    lam = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
+    S = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, lam)], scenes.default_camera(), scenes.sky_color), quantise=False)
+    for k in M["sky"]:                                 # main.scm:91-95 sky-color
+        assert np.abs(S.sky(k["d"]) - k["out"]).max() <= TOL
+    for k in M["lambertian"]:
+        # material.scm:24-39: scattered direction = unit(local uvw (random-cosine-direction)), time 0 (Q6),
+        # pdf = dot(w, dir) / pi, scattering-pdf = max(0, cos) / pi, attenuation = albedo
+        nrm, r6, out = np.asarray(k["n"], np.float64), np.asarray(k["draws"], np.float64), np.zeros(3)
+        lib.orc_onb_local_cosine(nrm.ctypes.data, r6.ctypes.data, 31, out.ctypes.data)
+        d = out / np.linalg.norm(out)
+        assert np.abs(d - k["dir"]).max() <= TOL and k["time"] == 0.0
+        assert abs(np.dot(nrm / np.linalg.norm(nrm), d) / np.pi - k["pdf"]) <= TOL
+        assert abs(max(0.0, np.dot(nrm, d)) / np.pi - k["spdf"]) <= TOL
+        assert k["atten"] == [0.5, 0.5, 0.5]
+    seen = set()
+    for k in M["diffuse_light_emitted"]:               # material.scm:103-111: emits only towards the side the normal points to
+        facing = float(np.dot(k["n"], k["d"])) < 0.0
+        seen.add(facing)
+        assert k["out"] == ([4.0, 4.0, 4.0] if facing else [0.0, 0.0, 0.0])
+    assert seen == {True, False}
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_reference_trace_all(orc, idx):
+    """main.scm's trace-all, run by the reference on 10 x 10 x 2 spp with random-real returning the
+    oracle's Philox draws: the oracle's render must reproduce every pixel's radiance sum and 8-bit value."""
+    run = load("ref_color.json")["runs"][idx]
+    w, h, spp = run["width"], run["height"], run["spp"]
+    scene = host_scene(run["scene"], w, h)
+    S = orc.OracleScene(scene, quantise=False)
+    img, nrays = S.render(w, h, spp, max_depth=run["max_depth"], seed=run["seed"], nthreads=1)
+    raw = np.asarray(run["raw_data"], np.float64).reshape(h, w, 3)
+    assert raw.max() > 0 and nrays > w * h * spp
+    err = np.abs(img - raw) / np.maximum(np.abs(raw), 1.0)
+    assert err.max() <= 1e-9, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    img8 = orc.resolve(img, spp)                                    # y = 0 bottom row, like *image* (main.scm:484-488)
+    ref8 = np.asarray(run["image"], np.int64).reshape(h, w, -1)[..., :3]
+    assert np.array_equal(img8.astype(np.int64), ref8)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("SRT_REFERENCE", "/root/reference")), reason="the reference sources only exist in the build container")
+def test_committed_files_match_a_fresh_run_of_the_reference():
+    """Re-executes the reference (minischeme) for the cheap tables and compares with the committed JSON."""
+    import sys
+    import threading
+    from tests.golden import make_reference_golden as mk
+    out = {}
+
+    def work():
+        sys.setrecursionlimit(200000)
+        rng = mk.ScriptedRng()
+        rng.script = [float(x) for x in np.random.RandomState(3).random_sample(256 + 3 * 256 + 3 * 255)]
+        ref = mk.Ref(rng)
+        main_mod = ref.load_main(mk.MAIN_NAMES)
+        out["textures"] = mk.make_textures(ref)
+        out["materials"] = mk.make_materials(ref, main_mod, rng)
+        name, spec = mk.PRIM_CASES[0]
+        rays = mk.rays_for(spec, 200, 100)
+        out["sphere"] = mk.hits_table(ref, ref.build(spec), rays)
+    threading.stack_size(256 * 1024 * 1024)
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    threading.stack_size(0)
+    assert json.loads(json.dumps(out["textures"])) == load("ref_textures.json")
+    assert json.loads(json.dumps(out["materials"])) == load("ref_materials.json")
+    gold = load("ref_prims.json")["cases"][0]
+    for k in ("rays", "hit", "t", "p", "n", "uv"):
+        assert json.loads(json.dumps(out["sphere"][k])) == gold[k], k

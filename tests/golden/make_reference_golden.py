@@ -135,7 +135,15 @@ def stability_mask(scene, rays):
     t_err = np.abs(o32["t"] - o["t"]) / np.maximum(np.abs(o["t"]), 1e-30)
     n_err = np.linalg.norm(o32["n"] - o["n"], axis=1) / np.maximum(np.linalg.norm(o["n"], axis=1), 1e-30)
     ill = both & ((t_err > 5e-5) | (n_err > 5e-5))
-    return [bool(x) for x in (near | (o32["prim"] != o["prim"]) | ill)]
+    # edge rays: the f64 answer itself flips when one direction component moves by 2 fp32 ulps (a ray that runs
+    # exactly into the floor / wall edge of the Cornell room hits at x = 0.0 in f64; any rounding puts it outside)
+    edge = np.zeros(len(r64), bool)
+    for axis in range(3):
+        for sgn in (-1.0, 1.0):
+            q = r64.copy()
+            q[:, 3 + axis] *= 1.0 + sgn * 2.4e-7
+            edge |= S.trace_batch(q)["prim"] != o["prim"]
+    return [bool(x) for x in (near | (o32["prim"] != o["prim"]) | ill | edge)]
 
 
 PRIM_CASES = [
@@ -208,11 +216,14 @@ def make_scenes(ref, main):
     for i, name in enumerate(["cornell-box", "test-scene2", "test-scene", "cornell-bezier"]):
         scene = main.lookup(Sym(name))
         cam = ref.call("geometry", "scene-camera", scene)
-        # (i) camera rays from the reference's own get-ray on a 12 x 12 grid of (s, t); random-real is scripted
-        cam_rays = []
+        # (i) camera rays from the reference's own get-ray on a 12 x 12 grid of (s, t); random-real is scripted (0.5)
+        # (the grid is offset off-centre: on a symmetric grid the diagonal rays of the Cornell camera run EXACTLY into
+        # the edges of the room - hit at x = 0.0 in f64, a coin flip under any rounding)
+        cam_rays, cam_st = [], []
         for a in range(12):
             for b in range(12):
-                ray = ref.call("camera", "get-ray", cam, (a + 0.5) / 12, (b + 0.5) / 12)
+                cam_st.append(((a + 0.37) / 12, (b + 0.61) / 12))
+                ray = ref.call("camera", "get-ray", cam, *cam_st[-1])
                 cam_rays.append(list(ray[0]) + list(ray[1]) + [float(ray[2])])
         cam_rays = f32(cam_rays)                       # rounded to fp32 AFTER the reference made them; stored as the inputs of g:hit
         # (ii) seeded rays through the scene's extent
@@ -224,6 +235,7 @@ def make_scenes(ref, main):
         tab = hits_table(ref, scene, rays)
         tab["unstable"] = stability_mask(hs, rays)
         tab["n_camera_rays"] = len(cam_rays)
+        tab["camera_st"] = [list(x) for x in cam_st]
         out.append(dict(name=name, **tab))
         print(f"scenes/{name}: {sum(tab['hit'])}/{len(rays)} hits, {sum(tab['unstable'])} flagged")
     return dict(source="scenes defined by main.scm, closest hit by (g:hit scene ray 0.001 +max-float+); the first n_camera_rays rays were made by cam:get-ray",

@@ -22,6 +22,8 @@ Fidelity notes (where Gauche's behaviour had to be restated rather than executed
     sum_k a[i][k] * b[k][j] from exact 0 in index order (lib/gauche/array.scm);
   * `sort` is a stable merge sort on the caller's predicate (the reference's comparators return
     -1 / 1, both true - SURVEY Q12 - so its BVH builders are not used for golden vectors);
+  * a multiple-value result used as a procedure ARGUMENT keeps its first value (Gauche's behaviour; R7RS leaves it
+    undefined) - `get-normal` of the Klein primitive relies on it;
   * `random-real` is whatever callable the host installs: random STREAMS are not a parity target.
 """
 import math
@@ -606,6 +608,9 @@ class Interp:
             else:
                 f = self.eval(head, env)
             args = [self.eval(a, env) for a in x[1:]]
+            for i, a in enumerate(args):                     # Gauche: multiple values reaching a one-value continuation keep the first
+                if type(a) is Values:                        # (geometry.scm:628-633 subtracts two (dist-func ...) results, each (values d n))
+                    args[i] = a[0] if a else None
             if isinstance(f, Closure):
                 env = self.bind(f, args)
                 for b in f.body[:-1]:

@@ -682,6 +682,28 @@ template <class T> static T schlick(T cosine, T ref_idx) {                      
   return r0 + (T(1) - r0) * std::pow(T(1) - cosine, T(5));
 }
 
+// material.scm:45-53 — metal: reflect the unit direction, add fuzz * random-in-unit-sphere (rejection iteration j draws
+// block j of the bounce), valid iff the result leaves the surface.
+template <class T> static bool metal_scatter(V3<T> d, V3<T> n, T fuzz, const RngAddr& addr, V3<T>& out) {
+  V3<T> reflected = reflect(unit(d), n);
+  V3<T> fuzzv = random_in_unit_sphere<T>(addr, 0);
+  out = add(reflected, scale(fuzzv, fuzz));
+  return dot(out, n) > T(0);
+}
+// material.scm:76-98 — dielectric: xi < reflect-prob picks the reflected direction (Q10: raw d throughout).
+template <class T> static V3<T> dielectric_scatter(V3<T> d, V3<T> n, T ref_idx, T xi, int quirks) {
+  V3<T> din = (quirks & Q10_DIELECTRIC_UNNORM) ? d : unit(d);
+  V3<T> reflected = reflect(din, n);
+  T dd = dot(din, n);
+  V3<T> outward = (dd > T(0)) ? scale(n, T(-1)) : n;
+  T ni_over_nt = (dd > T(0)) ? ref_idx : T(1) / ref_idx;
+  T cosine = (dd > T(0)) ? (dd * ref_idx) / length(din) : (-dd) / length(din);
+  V3<T> refracted;
+  bool ok = refract(din, outward, ni_over_nt, refracted, quirks);
+  T reflect_prob = ok ? schlick(cosine, ref_idx) : T(1);
+  return (xi < reflect_prob) ? reflected : refracted;
+}
+
 // main.scm:91-98
 template <class T> static V3<T> sky_value(const Scene& sc, const Ray<T>& r) {
   if (sc.sky == SKY_BLACK) return mk<T>(0, 0, 0);
@@ -785,27 +807,16 @@ template <class T> static V3<T> color(const Scene& sc, const Ray<T>& r, int dept
       // HEAD's `color` cannot run metal/dielectric (3 values into a 4-value receive, SURVEY §8a
       // M2/M3); intended Weekend semantics: specular, weight = attenuation, emitted = 0.
       // IMAGE-LEVEL PARITY UNPINNED; the scatter arithmetic below is pinned by source.
-      V3<T> reflected = reflect(unit(r.d), rec.n);
-      V3<T> fuzzv = random_in_unit_sphere<T>(addr, 0);
-      Ray<T> scattered{rec.p, add(reflected, scale(fuzzv, T(m.param))), time0};
-      bool valid = dot(scattered.d, rec.n) > T(0);
+      V3<T> sdir;
+      bool valid = metal_scatter<T>(r.d, rec.n, T(m.param), addr, sdir);
+      Ray<T> scattered{rec.p, sdir, time0};
       V3<T> atten = tex_value<T>(sc, m.tex, T(0), T(0), rec.p, cx.quirks);
       if (depth < cx.max_depth && valid) return mul(atten, color(sc, scattered, depth + 1, addr, cx, nrays));
       return mk<T>(0, 0, 0);
     }
     case M_DIELECTRIC: {                                            // material.scm:76-101
-      T ref_idx = T(m.param);
-      V3<T> din = (cx.quirks & Q10_DIELECTRIC_UNNORM) ? r.d : unit(r.d);
-      V3<T> reflected = reflect(din, rec.n);
-      T dd = dot(din, rec.n);
-      V3<T> outward = (dd > T(0)) ? scale(rec.n, T(-1)) : rec.n;
-      T ni_over_nt = (dd > T(0)) ? ref_idx : T(1) / ref_idx;
-      T cosine = (dd > T(0)) ? (dd * ref_idx) / length(din) : (-dd) / length(din);
-      V3<T> refracted;
-      bool ok = refract(din, outward, ni_over_nt, refracted, cx.quirks);
-      T reflect_prob = ok ? schlick(cosine, ref_idx) : T(1);
       T u4[4]; rng_block<T>(addr, 0, u4);
-      Ray<T> scattered{rec.p, (u4[0] < reflect_prob) ? reflected : refracted, time0};
+      Ray<T> scattered{rec.p, dielectric_scatter<T>(r.d, rec.n, T(m.param), u4[0], cx.quirks), time0};
       if (depth < cx.max_depth) return color(sc, scattered, depth + 1, addr, cx, nrays);   // attenuation (1,1,1)
       return mk<T>(0, 0, 0);
     }
@@ -1028,6 +1039,23 @@ void orc_onb_local_cosine(const double* n3, const double* r6, int quirks, double
   Onb<double> o = make_onb_from_w(ld3<double>(n3));
   V3<double> t = onb_local(o, (quirks & Q15_LOCAL_TRIPLE_EVAL) ? cosine_direction_triple<double>(r6, quirks) : random_cosine_direction<double>(r6[0], r6[1], quirks));
   target3[0] = t.x; target3[1] = t.y; target3[2] = t.z; }
+
+// test hooks for the reference-executed goldens (tests/golden/ref_scatter.json)
+int orc_metal_scatter(const double* d3, const double* n3, double fuzz, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, double* out3) {
+  RngAddr a{seed, pixel, sample, bounce}; V3<double> o;
+  bool valid = metal_scatter<double>(ld3<double>(d3), ld3<double>(n3), fuzz, a, o);
+  out3[0] = o.x; out3[1] = o.y; out3[2] = o.z; return valid ? 1 : 0; }
+void orc_dielectric_scatter(const double* d3, const double* n3, double ref_idx, double xi, int quirks, double* out3) {
+  V3<double> o = dielectric_scatter<double>(ld3<double>(d3), ld3<double>(n3), ref_idx, xi, quirks);
+  out3[0] = o.x; out3[1] = o.y; out3[2] = o.z; }
+void orc_random_in_unit_sphere(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t first_block, double* out3) {
+  RngAddr a{seed, pixel, sample, bounce}; V3<double> o = random_in_unit_sphere<double>(a, first_block); out3[0] = o.x; out3[1] = o.y; out3[2] = o.z; }
+void orc_random_in_unit_disk(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t first_block, double* out3) {
+  RngAddr a{seed, pixel, sample, bounce}; V3<double> o = random_in_unit_disk<double>(a, first_block); out3[0] = o.x; out3[1] = o.y; out3[2] = o.z; }
+void orc_random_to_sphere(double radius, double distance_sq, double r1, double r2, double* out3) {
+  V3<double> o = random_to_sphere<double>(radius, distance_sq, r1, r2); out3[0] = o.x; out3[1] = o.y; out3[2] = o.z; }
+double orc_cosine_pdf_value(const double* w3, const double* dir3) {                        // pdf.scm:18-23 (w normalised by make-onb-from-w)
+  Onb<double> o = make_onb_from_w(ld3<double>(w3)); return cosine_pdf_value<double>(o.w, ld3<double>(dir3)); }
 
 // Render: accumulates samples [spp_begin, spp_end) into rgb_sum (w*h*3 doubles, y=0 bottom row).
 int orc_render(void* h, int w, int hh, int spp_begin, int spp_end, int max_depth, uint32_t seed, int quirks,

@@ -2,7 +2,8 @@
 builds them with the REFERENCE's constructors through oracle/minischeme.py) and by the tests (which
 build the same objects with the host mirror of the constructor API).  A spec is a nested list:
 ["sphere", c, r] ["moving-sphere", c0, c1, t0, t1, r] ["xy-rect"|"xz-rect"|"yz-rect", a0, a1, b0, b1, k]
-["flip", obj] ["box", p0, p1] ["translate", obj, offset] ["rotate-y", obj, degrees] ["bezier", a, b, c, d, width]."""
+["flip", obj] ["box", p0, p1] ["translate", obj, offset] ["rotate-y", obj, degrees] ["bezier", a, b, c, d, width]
+["medium", boundary-obj, density] (phase texture = constant (1,1,1)) ["klein", center]."""
 from scheme_raytrace_b200.host import geometry as g, material as m, texture as t, bezier as bz, vec as v
 
 
@@ -25,11 +26,20 @@ def build_host(spec, mat=None):
         return g.rotate_y(build_host(spec[1], mat), spec[2])
     if k == "bezier":
         return bz.make_bezier(v.vec3(*spec[1]), v.vec3(*spec[2]), v.vec3(*spec[3]), v.vec3(*spec[4]), spec[5], mat)
+    if k == "medium":
+        return g.make_constant_medium(build_host(spec[1], mat), spec[2], t.constant_texture(v.vec3(1, 1, 1)))
+    if k == "klein":
+        return g.make_klein(v.vec3(*spec[1]), mat)
     raise ValueError(k)
 
 
 def host_scene(name, size_x=200, size_y=200):
     """The host mirror of a scene that the generator takes from the reference's main.scm."""
     from scheme_raytrace_b200.host import scenes
+    non_bvh = lambda sx, sy: g.make_scene([g.make_sphere(v.vec3(0, -100.5, -1), 100, m.make_lambertian(scenes._checker()))] + scenes.line_upped_spheres(10, 10),
+                                          scenes.default_camera(sx, sy), scenes.sky_color)
     return {"cornell-box": scenes.cfg4_cornell_box, "test-scene2": scenes.test_scene2, "cornell-bezier": scenes.cornell_bezier,
+            "cornell-smoke": scenes.cornell_smoke, "klein-scene": scenes.klein_scene, "cornell-klein": scenes.cornell_klein,
+            "test-bezier": scenes.test_bezier, "test-scene-bvh": scenes.test_scene_bvh, "test-scene-bvh-sah": scenes.test_scene_bvh,
+            "test-scene-non-bvh": non_bvh,
             "test-scene": lambda sx, sy: g.make_scene(scenes.test_scene_objects(), scenes.default_camera(sx, sy), scenes.black)}[name](size_x, size_y)

@@ -48,7 +48,9 @@ def _check(scene, case, label, t_min=0.001, t_max=999999999999.0):
     uv_err = np.maximum(np.abs(gp["u"][uv_ok] - uvr[uv_ok, 0]), np.abs(gp["v"][uv_ok] - uvr[uv_ok, 1]))
     print(f"\n[reference {label}] rays={len(rays)} hits={int(sel.sum())} t_err_max={t_err.max():.2e} n_err_max={n_err.max():.2e} "
           f"p_err_max={p_err.max():.2e} uv_err_max={(uv_err.max() if uv_err.size else 0.0):.2e} ({int(uv_ok.sum())} uv rays)")
-    assert t_err.max() <= 1e-4 and n_err.max() <= 1e-4 and p_err.max() <= 1e-4
+    klein = ptype_of[sel] == 8     # central-difference normal of the fractal (eps 0.01): stated tolerance 2e-2, as in tests/test_gpu_parity.py
+    assert t_err.max() <= 1e-4 and p_err.max() <= 1e-4
+    assert (n_err[~klein].max() if (~klein).any() else 0.0) <= 1e-4 and (n_err[klein].max() if klein.any() else 0.0) <= 2e-2
     if uv_err.size:
         assert uv_err.max() <= 2e-4
 

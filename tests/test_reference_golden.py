@@ -68,6 +68,31 @@ def test_reference_scenes(orc):
         assert nhit > 150, case["name"]
 
 
+def test_reference_medium_and_klein(orc):
+    """make-constant-medium (geometry.scm:545-578; sphere and instanced-box boundaries; the
+    free-flight draw is scripted per (ray, leaf), see the generator's tag_medium) and the sphere-traced Klein
+    primitive (geometry.scm:596-664)."""
+    P = load("ref_prims2.json")
+    for case in P["cases"]:
+        scene = g.make_scene([build_host(case["spec"])], scenes.default_camera(), scenes.sky_color)
+        nhit, _ = _check_hits(orc, scene, case, P["t_min"], P["t_max"])
+        assert nhit >= 40, (case["name"], nhit)
+
+
+def test_reference_scenes_with_media_klein_curves_and_the_references_bvh(orc):
+    """More scenes of main.scm: cornell-smoke, cornell-klein, klein-scene, test-bezier (curves inside make-bvh-node)
+    and test-scene-non-bvh / -bvh / -bvh-sah.  The last three hold the same 100 spheres as a plain list, under the
+    reference's own make-bvh-node and under make-bvh-with-sah: the reference's BVH traversals return what its list
+    returns, and the oracle (which treats make-bvh-* as grouping) reproduces all three - the equivalence the LBVH
+    replacement rests on."""
+    names = set()
+    for case in load("ref_scenes2.json")["scenes"]:
+        nhit, _ = _check_hits(orc, host_scene(case["name"]), case)
+        assert nhit > 80, case["name"]
+        names.add(case["name"])
+    assert {"cornell-smoke", "cornell-klein", "klein-scene", "test-bezier", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"} <= names
+
+
 def test_reference_camera_rays(orc):
     """The first n_camera_rays rays of every scene came out of the reference's cam:get-ray on a 12 x 12 (s, t)
     grid `camera_st` (lens radius 0, shutter draw 0.5); the oracle's get_ray must produce the same rays."""
@@ -164,6 +189,72 @@ def test_reference_material_functions(orc):
         seen.add(facing)
         assert k["out"] == ([4.0, 4.0, 4.0] if facing else [0.0, 0.0, 0.0])
     assert seen == {True, False}
+
+
+def test_reference_scatter_samplers_camera_aabb(orc):
+    """ref_scatter.json: metal / dielectric scatter closures called directly, the rejection samplers, random-to-sphere,
+    the cosine / mixture pdf values, get-ray with a lens and a shutter interval, the AABB slab test."""
+    import ctypes as C
+    R = load("ref_scatter.json")
+    lib = orc.load()
+    u32, dbl, vp = C.c_uint32, C.c_double, C.c_void_p
+    lib.orc_metal_scatter.argtypes = [vp, vp, dbl, u32, u32, u32, u32, vp]
+    lib.orc_dielectric_scatter.argtypes = [vp, vp, dbl, dbl, C.c_int32, vp]
+    lib.orc_random_in_unit_sphere.argtypes = [u32, u32, u32, u32, u32, vp]
+    lib.orc_random_in_unit_disk.argtypes = [u32, u32, u32, u32, u32, vp]
+    lib.orc_random_to_sphere.argtypes = [dbl, dbl, dbl, dbl, vp]
+    lib.orc_cosine_pdf_value.argtypes = [vp, vp]
+    lib.orc_cosine_pdf_value.restype = dbl
+    out = np.zeros(3)
+    seen = set()
+    for k in R["metal"]:                               # material.scm:45-53
+        d, n = np.asarray(k["d"], np.float64), np.asarray(k["n"], np.float64)
+        valid = lib.orc_metal_scatter(d.ctypes.data, n.ctypes.data, k["fuzz"], *k["addr"], out.ctypes.data)
+        assert bool(valid) == k["valid"] and np.abs(out - k["dir"]).max() <= TOL, k
+        assert k["time"] == 0.0 and k["atten"] == [0.8, 0.6, 0.2]          # Q6: make-ray drops the ray's time (0.75 here)
+        seen.add(k["valid"])
+    assert seen == {True, False}
+    differs = 0
+    for k in R["dielectric"]:                          # material.scm:76-98 (Q10: raw d in reflect / refract)
+        d, n = np.asarray(k["d"], np.float64), np.asarray(k["n"], np.float64)
+        lib.orc_dielectric_scatter(d.ctypes.data, n.ctypes.data, k["ref_idx"], k["xi"], 31, out.ctypes.data)
+        assert k["valid"] and np.abs(out - k["dir"]).max() <= TOL * max(1.0, np.abs(k["dir"]).max()), k
+        assert k["time"] == 0.0 and k["atten"] == [1.0, 1.0, 1.0]
+        lib.orc_dielectric_scatter(d.ctypes.data, n.ctypes.data, k["ref_idx"], k["xi"], 31 & ~8, out.ctypes.data)
+        differs += np.abs(out - k["dir"]).max() > 1e-3
+    assert differs > len(R["dielectric"]) // 2         # the reference really is in Q10 mode (un-normalised d)
+    for k in R["random_in_unit_sphere"]:               # util.scm:9-15
+        lib.orc_random_in_unit_sphere(*k["addr"], k["first_block"], out.ctypes.data)
+        assert np.abs(out - k["out"]).max() <= TOL and np.dot(out, out) < 1
+    for k in R["random_in_unit_disk"]:                 # util.scm:17-23
+        lib.orc_random_in_unit_disk(*k["addr"], k["first_block"], out.ctypes.data)
+        assert np.abs(out - k["out"]).max() <= TOL and out[2] == 0.0
+    for k in R["random_to_sphere"]:                    # util.scm:46-54
+        lib.orc_random_to_sphere(k["radius"], k["distance_sq"], k["r1"], k["r2"], out.ctypes.data)
+        assert np.abs(out - k["out"]).max() <= TOL
+    for k in R["cosine_pdf"]:                          # pdf.scm:18-23, 34-37
+        w, w2, dv = (np.asarray(k[x], np.float64) for x in ("w", "w2", "direction"))
+        a = lib.orc_cosine_pdf_value(w.ctypes.data, dv.ctypes.data)
+        b = lib.orc_cosine_pdf_value(w2.ctypes.data, dv.ctypes.data)
+        assert abs(a - k["value"]) <= TOL and abs(0.5 * a + 0.5 * b - k["mixture_value"]) <= TOL
+    for cam in R["camera"]:                            # camera.scm:63-92
+        a = cam["args"]
+        slots = orc.make_camera(a[0], a[1], a[2], *a[3:])
+        ref_slots = np.concatenate([np.atleast_1d(np.asarray(x, np.float64)) for x in cam["slots"]])
+        assert np.abs(slots - ref_slots).max() <= TOL * max(1.0, np.abs(ref_slots).max())
+        from scheme_raytrace_b200.host import camera as hc
+        c = hc.make_camera(a[0], a[1], a[2], *a[3:])
+        S = orc.OracleScene(g.make_scene([g.make_sphere((0, 0, 0), 1, m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5))))], c, scenes.sky_color), quantise=False)
+        for k in cam["rays"]:
+            mine = S.get_ray(k["s"], k["t"], k["xi_time"], *k["addr"])
+            assert np.abs(mine - k["ray"]).max() <= TOL * max(1.0, np.abs(k["ray"]).max()), k
+        assert len({r["ray"][6] for r in cam["rays"]}) > 10            # the shutter draw varies
+    hits = 0
+    for k in R["aabb"]:                                # geometry.scm:73-105 (Q11)
+        got = orc.aabb_hit(k["bmin"], k["bmax"], k["o"] + k["d"] + [0.0], k["t_min"], k["t_max"])
+        assert got == k["hit"], k
+        hits += got
+    assert 10 < hits < len(R["aabb"]) - 10
 
 
 @pytest.mark.parametrize("idx", [0, 1])

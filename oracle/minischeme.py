@@ -117,6 +117,14 @@ class SchemeError(Exception):
     pass
 
 
+class _Eof:
+    def __repr__(self):
+        return "#<eof>"
+
+
+EOF = _Eof()
+
+
 DOT = Sym(".")
 
 
@@ -719,6 +727,45 @@ class Interp:
         d("format", lambda *a: " ".join(map(str, a))); d("error", self._error); d("errorf", self._error); d("undefined", lambda: None)
         d("string-append", lambda *a: "".join(a)); d("number->string", str); d("string->number", lambda s: parse_atom(s)); d("symbol->string", str)
         d("x->string", str); d("string-split", lambda s, sep: to_list(s.split(sep)))
+        # what the repo's own Gauche host (scheme_raytrace_b200/scheme/*.scm) needs on top of the reference's vocabulary
+        d("set-car!", lambda p, x: setattr(p, "car", x)); d("set-cdr!", lambda p, x: setattr(p, "cdr", x))
+        d("caar", lambda p: p.car.car); d("cdar", lambda p: p.car.cdr); d("cdddr", lambda p: p.cdr.cdr.cdr); d("cadddr", lambda p: p.cdr.cdr.cdr.car)
+        d("fold-right", lambda f, init, l: __import__("functools").reduce(lambda acc, x: self.apply(f, [x, acc]), reversed(list(l)), init))
+        d("append-map", lambda f, *ls: to_list([y for a in zip(*[list(l) for l in ls]) for y in self.apply(f, list(a))]))
+        d("make-list", lambda n, fill=None: to_list([fill] * n)); d("string-join", lambda l, sep=" ": sep.join(list(l)))
+        d("exact?", lambda x: isinstance(x, (int, Fraction)) and not isinstance(x, bool)); d("inexact?", lambda x: isinstance(x, float))
+        d("integer?", lambda x: (isinstance(x, int) and not isinstance(x, bool)) or (isinstance(x, float) and x == math.floor(x)))
+        d("with-output-to-file", self._with_output_to_file)
+        d("with-input-from-file", self._with_input_from_file); d("read-line", self._read_line); d("eof-object?", lambda x: x is EOF)
+        d("port-for-each", self._port_for_each)          # points.scm:12-18 reads its CSV with these
+        d("run-process", lambda *a, **k: self._error("run-process: no subprocesses in this interpreter"))
+
+    def _with_input_from_file(self, path, thunk):
+        with open(path) as f:
+            saved, self.inp = getattr(self, "inp", None), iter(f.read().splitlines())
+        try:
+            return self.apply(thunk, [])
+        finally:
+            self.inp = saved
+
+    def _read_line(self, *_):
+        return next(self.inp, EOF)
+
+    def _port_for_each(self, fn, reader):
+        while True:
+            x = self.apply(reader, [])
+            if x is EOF:
+                return None
+            self.apply(fn, [x])
+
+    def _with_output_to_file(self, path, thunk):
+        saved, self.out = self.out, []
+        try:
+            self.apply(thunk, [])
+            with open(path, "w") as f:
+                f.write("".join(self.out))
+        finally:
+            self.out = saved
 
     def _error(self, *a):
         raise SchemeError(" ".join(map(str, a)))

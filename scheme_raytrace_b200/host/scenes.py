@@ -333,12 +333,11 @@ def cfg5_patches(size_x=3840, size_y=2160):
 def test_scene2(size_x=200, size_y=200):
     """main.scm:316-328 test-scene2 (marble + lights, black sky)."""
     per_tex = t.marble_texture(1)
-    light = m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))
     objs = [
         g.make_sphere(v.vec3(0, -1000, -1), 1000, m.make_lambertian(per_tex)),
         g.make_sphere(v.vec3(0, 2, 0), 2, m.make_lambertian(per_tex)),
-        g.make_sphere(v.vec3(0, 7, 0), 2, light),
-        g.make_xy_rect(3, 5, 1, 3, -2, light),
+        g.make_sphere(v.vec3(0, 7, 0), 2, m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))),
+        g.make_xy_rect(3, 5, 1, 3, -2, m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))),
     ]
     return g.make_scene(objs, default_camera(size_x, size_y), black)
 

@@ -304,3 +304,57 @@ def test_committed_files_match_a_fresh_run_of_the_reference():
     gold = load("ref_prims.json")["cases"][0]
     for k in ("rays", "hit", "t", "p", "n", "uv"):
         assert json.loads(json.dumps(out["sphere"][k])) == gold[k], k
+
+
+# --------------------------------------------------------------------------------------------------
+# converged images rendered by the reference itself (tests/golden/make_reference_render.py)
+def render_stats(gold, key, mine_mean, mine_spp):
+    """Compares a converged render (`mine_mean`, linear radiance per sample) with the reference's own CPU render of
+    the same scene (independent random numbers).  The reference render carries its per-pixel sum and sum of squares,
+    so the difference is judged against ITS Monte-Carlo standard error: z = diff / se per channel value.  `bias_z` is the
+    image-wide sum of the differences over its standard error, per colour channel (the three channels of a pixel share
+    their paths, so they are not independent observations), the largest of the three."""
+    w, h, n = (int(x) for x in gold[key + "_meta"])
+    s1, s2 = gold[key + "_sum"], gold[key + "_sumsq"]
+    mean = s1 / n
+    var = np.maximum(s2 / n - mean ** 2, 0.0) * n / (n - 1)
+    se = np.sqrt(var / n * (1.0 + n / mine_spp))                 # both renders are noisy; ours has mine_spp samples
+    ok = se > 1e-12                                              # (a pixel that only ever saw the black part of a scene)
+    diff = mine_mean - mean
+    z = diff[ok] / se[ok]
+    a, b = np.minimum(mine_mean, 1.0), np.minimum(mean, 1.0)
+    rmse = float(np.sqrt(np.mean((a - b) ** 2)))
+    a8, b8 = np.floor(255.99 * np.sqrt(a)), np.floor(255.99 * np.sqrt(b))       # main.scm:123-124, 481-487
+    psnr8 = float(10 * np.log10(255.0 ** 2 / max(np.mean((a8 - b8) ** 2), 1e-12)))
+    return dict(median_abs_z=float(np.median(np.abs(z))), frac_within_3=float(np.mean(np.abs(z) < 3)), frac_within_4=float(np.mean(np.abs(z) < 4)),
+                bias_z=max((float((diff[..., c] * ok[..., c]).sum() / np.sqrt(((se[..., c] * ok[..., c]) ** 2).sum())) for c in range(3)), key=abs),
+                rel_mean=float(mine_mean.mean() / mean.mean()),
+                rmse=rmse, expected_rmse=float(np.sqrt(np.mean(np.minimum(se, 1.0) ** 2))), psnr8=psnr8, n=n, width=w, height=h)
+
+
+RENDER_SCENES = {"cornell_box": "cornell-box", "test_bezier": "test-bezier"}
+
+
+@pytest.mark.parametrize("key", list(RENDER_SCENES))
+def test_converged_image_against_the_references_own_render(orc, key):
+    """North star, second criterion: the converged image must match the reference's CPU render.  The oracle renders the
+    same scene at 4096 spp with its own Philox stream; tolerance, stated: per channel value the difference is within the
+    reference render's Monte-Carlo standard error - median |z| in [0.45, 0.95] (0.674 for pure noise), >= 97.5 % of the
+    values within 3 se and >= 99.5 % within 4 se (radiance samples are heavy-tailed at ~100-500 spp), no global bias beyond 4 se of the summed image (per channel), mean radiance within 2 %, RMSE of the clamped
+    linear image <= 1.3 x the noise-predicted RMSE.  Without Q15 (quirks = 15: one cosine direction per scatter instead
+    of the three the `local` macro evaluates) the Cornell box FAILS the same test - the quirk is visible in the image."""
+    gold = np.load(os.path.join(GOLD, "ref_render.npz"))
+    w, h, n = (int(x) for x in gold[key + "_meta"])
+    S = orc.OracleScene(host_scene(RENDER_SCENES[key], w, h), quantise=False)
+    spp = 4096
+    img, _ = S.render(w, h, spp, max_depth=100, seed=77)
+    st = render_stats(gold, key, img / spp, spp)
+    print(f"\n[reference render {key}] {st}")
+    assert 0.45 <= st["median_abs_z"] <= 0.95 and st["frac_within_3"] >= 0.975 and st["frac_within_4"] >= 0.995
+    assert abs(st["bias_z"]) <= 4.0 and abs(st["rel_mean"] - 1.0) <= 0.02
+    assert st["rmse"] <= 1.3 * st["expected_rmse"]
+    if key == "cornell_box":
+        img15, _ = S.render(w, h, spp, max_depth=100, seed=77, quirks=15)
+        st15 = render_stats(gold, key, img15 / spp, spp)
+        print(f"[reference render {key}, quirks=15] {st15}")
+        assert abs(st15["bias_z"]) > 4.0 or st15["frac_within_3"] < 0.975 or st15["median_abs_z"] > 0.95

@@ -117,6 +117,32 @@ class SchemeError(Exception):
     pass
 
 
+def scheme_format(*a):
+    """(format [#f] "control string" arg ...) -> string, with the directives the reference uses: ~D ~A ~S ~% ~~
+    (main.scm:442,449 builds the PPM header and rows with ~D)."""
+    if a and a[0] is False:
+        a = a[1:]
+    if not a or not isinstance(a[0], str) or isinstance(a[0], Sym):
+        return " ".join(map(str, a))
+    fmt, args, out, i, k = a[0], list(a[1:]), [], 0, 0
+    while i < len(fmt):
+        c = fmt[i]
+        if c == "~" and i + 1 < len(fmt):
+            dct = fmt[i + 1].upper()
+            i += 2
+            if dct in "DAS":
+                out.append(str(args[k])); k += 1
+            elif dct == "%":
+                out.append("\n")
+            elif dct == "~":
+                out.append("~")
+            else:
+                raise SchemeError(f"format: unsupported directive ~{dct}")
+        else:
+            out.append(c); i += 1
+    return "".join(out)
+
+
 class _Eof:
     def __repr__(self):
         return "#<eof>"
@@ -724,7 +750,7 @@ class Interp:
         d("values", lambda *a: a[0] if len(a) == 1 else Values(a))
         d("call-with-values", lambda prod, cons: self.apply(cons, list(v) if isinstance(v := self.apply(prod, []), Values) else [v]))
         d("display", lambda x, *_: self.out.append(str(x))); d("print", lambda *a: self.out.append(" ".join(map(str, a)) + "\n")); d("newline", lambda *_: self.out.append("\n"))
-        d("format", lambda *a: " ".join(map(str, a))); d("error", self._error); d("errorf", self._error); d("undefined", lambda: None)
+        d("format", scheme_format); d("error", self._error); d("errorf", self._error); d("undefined", lambda: None)
         d("string-append", lambda *a: "".join(a)); d("number->string", str); d("string->number", lambda s: parse_atom(s)); d("symbol->string", str)
         d("x->string", str); d("string-split", lambda s, sep: to_list(s.split(sep)))
         # what the repo's own Gauche host (scheme_raytrace_b200/scheme/*.scm) needs on top of the reference's vocabulary

@@ -15,7 +15,7 @@ f64vector / array primitives, libm).  Everything written here is an OUTPUT OF RE
                       `noise`, `turb`, checker / noise / marble texture values
   ref_materials.json  `reflect`, `refract`, `schlick`, `(local uvw (random-cosine-direction))` (six draws: Q15), sky-color,
                       lambertian scatter / scattering-pdf, diffuse-light emitted
-  ref_color.json      main.scm's `trace-all` (color, running sum, gamma, 8-bit) on cornell-box and test-scene2
+  ref_color.json      main.scm's `trace-all` (color, running sum, gamma, 8-bit) and `save-as-ppm` on cornell-box and test-scene2
                       with `random-real` scripted to return the oracle's Philox draws in the reference's call
                       order, so the oracle (and the CUDA path) must reproduce the radiance of every pixel
 
@@ -245,7 +245,7 @@ def make_prims(ref, case_list=None, seed0=100):
     return dict(source="reference constructors of geometry.scm / bezier.scm through g:hit (oracle/minischeme.py)", t_min=0.001, t_max=MAXF, cases=cases)
 
 
-MAIN_NAMES = {"line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
+MAIN_NAMES = {"save-as-ppm", "line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
               "test-bezier", "cornell-smoke", "klein-scene", "cornell-klein", "+max-depth+", "+black+", "+white+", "sky-color", "black", "color", "correct-gamma", "*size-x*", "*size-y*",
               "*cornell-camera*", "*camera*", "test-scene", "test-scene2", "cornell-box", "cornell-bezier", "trace-all",
               "*image*", "*raw-data*"}
@@ -543,7 +543,16 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
             it.call("main", "trace-all", scene, s + 1)
         raw = [list(x) for x in main.lookup(Sym("*raw-data*"))]
         img = list(main.lookup(Sym("*image*")))
-        out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img))
+        import tempfile
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:           # (save-as-ppm nx ny) writes "test.ppm" into the current directory (main.scm:440)
+            os.chdir(tmp)
+            try:
+                it.call("main", "save-as-ppm", size, size)
+                ppm = open("test.ppm").read()
+            finally:
+                os.chdir(cwd)
+        out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img, ppm=ppm))
         print(f"color/{name}: mean radiance {np.mean(raw) / spp:.4f}")
     rng.path = None
     main.vars[Sym("color")] = color

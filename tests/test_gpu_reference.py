@@ -93,7 +93,7 @@ def test_reference_textures():
 
 
 @pytest.mark.parametrize("idx", [0, 1])
-def test_reference_trace_all(idx):
+def test_reference_trace_all(idx, tmp_path):
     """main.scm's own trace-all (color, running sum, gamma, 8-bit) was run by the reference with random-real
     returning this repo's Philox draws in the reference's call order; the CUDA path renders the same
     frame (same seed => same draws) and must land on the reference's radiance."""
@@ -112,3 +112,7 @@ def test_reference_trace_all(idx):
           f"within1e-2={np.mean(diff < 1e-2):.4f} 8-bit: equal={np.mean(lsb == 0):.4f} within1={np.mean(lsb <= 1):.4f}")
     assert np.median(diff) < 1e-4 and np.mean(diff < 1e-2) >= 0.97
     assert np.mean(lsb <= 1) >= 0.97
+    # main.scm:439-450 save-as-ppm: the library's writer on the REFERENCE's 8-bit image must give the reference's file, byte for byte
+    path = str(tmp_path / "test.ppm")
+    srt.save_as_ppm(path, b8.astype(np.uint8))
+    assert open(path).read() == run["ppm"]

@@ -258,7 +258,7 @@ def test_reference_scatter_samplers_camera_aabb(orc):
 
 
 @pytest.mark.parametrize("idx", [0, 1])
-def test_reference_trace_all(orc, idx):
+def test_reference_trace_all(orc, idx, tmp_path):
     """main.scm's trace-all, run by the reference on 10 x 10 x 2 spp with random-real returning the
     oracle's Philox draws: the oracle's render must reproduce every pixel's radiance sum and 8-bit value."""
     run = load("ref_color.json")["runs"][idx]
@@ -273,6 +273,12 @@ def test_reference_trace_all(orc, idx):
     img8 = orc.resolve(img, spp)                                    # y = 0 bottom row, like *image* (main.scm:484-488)
     ref8 = np.asarray(run["image"], np.int64).reshape(h, w, -1)[..., :3]
     assert np.array_equal(img8.astype(np.int64), ref8)
+    path = str(tmp_path / "test.ppm")                               # main.scm:439-450 save-as-ppm: the file the reference wrote, byte for byte
+    assert orc.save_ppm(path, img8) == 0
+    assert open(path).read() == run["ppm"] and run["ppm"].startswith(f"P3\n {w} {h}\n255\n")
+    import scheme_raytrace_b200 as srt                              # the product's writer (a host function of libsrt.so: no GPU involved)
+    srt.save_as_ppm(str(tmp_path / "lib.ppm"), ref8.astype(np.uint8))
+    assert open(str(tmp_path / "lib.ppm")).read() == run["ppm"]
 
 
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("SRT_REFERENCE", "/root/reference")), reason="the reference sources only exist in the build container")

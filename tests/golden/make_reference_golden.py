@@ -487,6 +487,7 @@ class ScriptedRng:
     def __init__(self):
         self.script, self.path, self.k = [], None, 0
         self.medium_leaf, self.ray_index, self.gen = None, 0, None
+        self.lens, self.pathgen = False, None
 
     def __call__(self):
         if self.script:
@@ -498,20 +499,57 @@ class ScriptedRng:
             return float(O.rng_block(0, self.ray_index, 0, 1, 16 + self.medium_leaf)[0])
         if self.path is None:
             return 0.5
-        from oracle import oracle as O
-        seed, pixel, sample = self.path
-        k = self.k
+        if self.k == 0:
+            self.pathgen = self.path_stream(*self.path)
         self.k += 1
-        if k < 2:
-            return float(O.rng_block(seed, pixel, sample, 0, 0)[k])        # u, v jitter (main.scm:476-477)
-        if k < 4:
-            return 0.5                                                     # lens disk (camera.scm:81): radius 0 in these scenes
-        if k == 4:
-            return float(O.rng_block(seed, pixel, sample, 0, 0)[2])        # shutter time (camera.scm:84)
-        # lambertian at depth j (material.scm:27): (local uvw (random-cosine-direction)) evaluates its operand THREE
-        # times (onb.scm:27-36, Q15) = 6 draws per scatter: block 0 (x, y), then block 2 (x, y), (z, w) of bounce j + 1
-        j, c = divmod(k - 5, 6)
-        return float(O.rng_block(seed, pixel, sample, j + 1, 0)[c]) if c < 2 else float(O.rng_block(seed, pixel, sample, j + 1, 2)[c - 2])
+        return float(next(self.pathgen))
+
+    def path_stream(self, seed, pixel, sample):
+        """The draws of one path in the reference's call order, each taken from the Philox slot the oracle / the CUDA
+        path assign to it (key (pixel, seed), counter (sample, bounce, block, 0))."""
+        from oracle import oracle as O
+        b0 = O.rng_block(seed, pixel, sample, 0, 0)
+        yield b0[0]                                                # u, v jitter (main.scm:476-477)
+        yield b0[1]
+        if not self.lens:
+            yield 0.5                                              # lens disk (camera.scm:81): radius 0, the first candidate (0, 0) is accepted
+            yield 0.5                                              # and multiplied by zero - the oracle draws nothing
+        else:
+            j, done = 1, False                                     # random-in-unit-disk (util.scm:17-23): two candidates per block from block 1 on
+            while not done:
+                u = O.rng_block(seed, pixel, sample, 0, j)
+                for h in (0, 2):
+                    yield u[h]
+                    yield u[h + 1]
+                    if (2 * u[h] - 1) ** 2 + (2 * u[h + 1] - 1) ** 2 < 1:
+                        done = True
+                        break
+                j += 1
+        yield b0[2]                                                # shutter time (camera.scm:84)
+        depth = 0
+        while True:
+            # lambertian at this depth (material.scm:27): (local uvw (random-cosine-direction)) evaluates its operand THREE
+            # times (onb.scm:27-36, Q15) = 6 draws per scatter: block 0 (x, y), then block 2 (x, y), (z, w) of bounce depth + 1
+            a, b = O.rng_block(seed, pixel, sample, depth + 1, 0), O.rng_block(seed, pixel, sample, depth + 1, 2)
+            for x in (a[0], a[1], b[0], b[1], b[2], b[3]):
+                yield x
+            depth += 1
+
+
+NEXTWEEK_SCENE = """
+(define ref-nextweek-scene
+  (g:make-scene
+   (list (g:make-sphere (v:vec3 0 -1000 0) 1000
+                        (m:make-lambertian (t:checker-texture (t:constant-texture (v:vec3 0.2 0.3 0.1))
+                                                              (t:constant-texture (v:vec3 0.9 0.9 0.9)))))
+         (g:make-moving-sphere (v:vec3 0 1 0) (v:vec3 0 1.75 0) 0 1 0.75
+                               (m:make-lambertian (t:constant-texture (v:vec3 0.7 0.3 0.1))))
+         (g:make-sphere (v:vec3 -2.5 1 0) 1 (m:make-lambertian (t:noise-texture 4)))
+         (g:make-sphere (v:vec3 2.5 1 0) 1 (m:make-lambertian (t:marble-texture 1)))
+         (g:flip-normals (g:make-xz-rect -1 1 -1 1 3.5 (m:make-diffuse-light (t:constant-texture (v:vec3 4 4 4))))))
+   (cam:make-camera (v:vec3 13 2 3) (v:vec3 0 0 0) (v:vec3 0 1 0) 20 1 0.5 10 0 1)
+   sky-color))
+"""
 
 
 def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
@@ -533,8 +571,14 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
         return r
     main.vars[Sym("color")] = color_hook
     out = []
-    for name in ["cornell-box", "test-scene2"]:
+    # a third scene, not in main.scm but built with the reference's constructors and rendered by the reference's trace-all:
+    # the Next-Week features in one path loop - moving sphere (shutter 0..1, Q6), thin-lens camera, checker / noise / marble
+    # textures, a flipped light, sky-color
+    for form in read_all(NEXTWEEK_SCENE):
+        it.eval(form, main)
+    for name in ["cornell-box", "test-scene2", "ref-nextweek-scene"]:
         scene = main.lookup(Sym(name))
+        rng.lens = name == "ref-nextweek-scene"
         it.eval(forms["*image*"], main)
         it.eval(forms["*raw-data*"], main)
         for s in range(spp):
@@ -552,9 +596,16 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
                 ppm = open("test.ppm").read()
             finally:
                 os.chdir(cwd)
+        # L4 (main.scm:481-487): a negative radiance sum (the noise texture goes negative, texture.scm:25-28) makes correct-gamma
+        # take the sqrt of a negative number - a complex in Gauche, which `min` then rejects with an error.  The interpreter does
+        # not model that: such pixels are stored as -1 (undefined upstream) and the PPM text is dropped for the run.
+        undefined = [any(c < 0 for c in px) for px in raw]
+        if any(undefined):
+            img = [-1 if undefined[i // 3] else q for i, q in enumerate(img)]
+            ppm = None
         out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img, ppm=ppm))
         print(f"color/{name}: mean radiance {np.mean(raw) / spp:.4f}")
-    rng.path = None
+    rng.path, rng.lens = None, False
     main.vars[Sym("color")] = color
     return dict(source="main.scm trace-all (color, running sum, correct-gamma, 8-bit) with random-real returning the oracle's Philox draws "
                        "(key (pixel, seed), counter (sample, bounce, block, 0)) in the reference's call order; y = 0 is the bottom row",

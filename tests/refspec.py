@@ -33,6 +33,18 @@ def build_host(spec, mat=None):
     raise ValueError(k)
 
 
+def ref_nextweek_scene(size_x=200, size_y=200):
+    """Mirror of NEXTWEEK_SCENE in tests/golden/make_reference_golden.py."""
+    from scheme_raytrace_b200.host import scenes, camera as cam
+    objs = [g.make_sphere(v.vec3(0, -1000, 0), 1000, m.make_lambertian(t.checker_texture(t.constant_texture(v.vec3(0.2, 0.3, 0.1)), t.constant_texture(v.vec3(0.9, 0.9, 0.9))))),
+            g.make_moving_sphere(v.vec3(0, 1, 0), v.vec3(0, 1.75, 0), 0, 1, 0.75, m.make_lambertian(t.constant_texture(v.vec3(0.7, 0.3, 0.1)))),
+            g.make_sphere(v.vec3(-2.5, 1, 0), 1, m.make_lambertian(t.noise_texture(4))),
+            g.make_sphere(v.vec3(2.5, 1, 0), 1, m.make_lambertian(t.marble_texture(1))),
+            g.flip_normals(g.make_xz_rect(-1, 1, -1, 1, 3.5, m.make_diffuse_light(t.constant_texture(v.vec3(4, 4, 4)))))]
+    c = cam.make_camera(v.vec3(13, 2, 3), v.vec3(0, 0, 0), v.vec3(0, 1, 0), 20, 1, 0.5, 10, 0, 1)
+    return g.make_scene(objs, c, scenes.sky_color)
+
+
 def host_scene(name, size_x=200, size_y=200):
     """The host mirror of a scene that the generator takes from the reference's main.scm."""
     from scheme_raytrace_b200.host import scenes
@@ -41,5 +53,5 @@ def host_scene(name, size_x=200, size_y=200):
     return {"cornell-box": scenes.cfg4_cornell_box, "test-scene2": scenes.test_scene2, "cornell-bezier": scenes.cornell_bezier,
             "cornell-smoke": scenes.cornell_smoke, "klein-scene": scenes.klein_scene, "cornell-klein": scenes.cornell_klein,
             "test-bezier": scenes.test_bezier, "test-scene-bvh": scenes.test_scene_bvh, "test-scene-bvh-sah": scenes.test_scene_bvh,
-            "test-scene-non-bvh": non_bvh,
+            "test-scene-non-bvh": non_bvh, "ref-nextweek-scene": ref_nextweek_scene,
             "test-scene": lambda sx, sy: g.make_scene(scenes.test_scene_objects(), scenes.default_camera(sx, sy), scenes.black)}[name](size_x, size_y)

@@ -92,7 +92,7 @@ def test_reference_textures():
     r.close()
 
 
-@pytest.mark.parametrize("idx", [0, 1])
+@pytest.mark.parametrize("idx", [0, 1, 2])
 def test_reference_trace_all(idx, tmp_path):
     """main.scm's own trace-all (color, running sum, gamma, 8-bit) was run by the reference with random-real
     returning this repo's Philox draws in the reference's call order; the CUDA path renders the same
@@ -107,12 +107,13 @@ def test_reference_trace_all(idx, tmp_path):
     diff = np.abs(img.astype(np.float64) - raw) / spp
     a8 = srt.correct_gamma_quantise(img, spp).astype(np.int64)
     b8 = np.asarray(run["image"], np.int64).reshape(h, w, -1)[..., :3]
-    lsb = np.abs(a8 - b8)
+    lsb = np.abs(a8 - b8)[b8 >= 0]                  # -1: undefined upstream (negative radiance sum under sqrt)
     print(f"\n[reference trace-all {run['scene']}] rays={st.rays} median={np.median(diff):.2e} max={diff.max():.2e} "
           f"within1e-2={np.mean(diff < 1e-2):.4f} 8-bit: equal={np.mean(lsb == 0):.4f} within1={np.mean(lsb <= 1):.4f}")
     assert np.median(diff) < 1e-4 and np.mean(diff < 1e-2) >= 0.97
     assert np.mean(lsb <= 1) >= 0.97
     # main.scm:439-450 save-as-ppm: the library's writer on the REFERENCE's 8-bit image must give the reference's file, byte for byte
-    path = str(tmp_path / "test.ppm")
-    srt.save_as_ppm(path, b8.astype(np.uint8))
-    assert open(path).read() == run["ppm"]
+    if run["ppm"] is not None:
+        path = str(tmp_path / "test.ppm")
+        srt.save_as_ppm(path, b8.astype(np.uint8))
+        assert open(path).read() == run["ppm"]

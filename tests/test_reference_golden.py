@@ -257,7 +257,7 @@ def test_reference_scatter_samplers_camera_aabb(orc):
     assert 10 < hits < len(R["aabb"]) - 10
 
 
-@pytest.mark.parametrize("idx", [0, 1])
+@pytest.mark.parametrize("idx", [0, 1, 2])
 def test_reference_trace_all(orc, idx, tmp_path):
     """main.scm's trace-all, run by the reference on 10 x 10 x 2 spp with random-real returning the
     oracle's Philox draws: the oracle's render must reproduce every pixel's radiance sum and 8-bit value."""
@@ -272,7 +272,12 @@ def test_reference_trace_all(orc, idx, tmp_path):
     assert err.max() <= 1e-9, (err.max(), np.unravel_index(err.argmax(), err.shape))
     img8 = orc.resolve(img, spp)                                    # y = 0 bottom row, like *image* (main.scm:484-488)
     ref8 = np.asarray(run["image"], np.int64).reshape(h, w, -1)[..., :3]
-    assert np.array_equal(img8.astype(np.int64), ref8)
+    defined = ref8 >= 0                                             # -1: negative radiance sum, a Gauche error upstream; clamped to 0 here
+    assert np.array_equal(img8.astype(np.int64)[defined], ref8[defined]) and defined.mean() > 0.9
+    assert np.all(img8[~defined] == 0) and np.all(raw[~defined.all(axis=2)].min(axis=1) < 0)
+    if run["ppm"] is None:
+        assert idx == 2
+        return
     path = str(tmp_path / "test.ppm")                               # main.scm:439-450 save-as-ppm: the file the reference wrote, byte for byte
     assert orc.save_ppm(path, img8) == 0
     assert open(path).read() == run["ppm"] and run["ppm"].startswith(f"P3\n {w} {h}\n255\n")

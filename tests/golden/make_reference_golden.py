@@ -245,7 +245,7 @@ def make_prims(ref, case_list=None, seed0=100):
     return dict(source="reference constructors of geometry.scm / bezier.scm through g:hit (oracle/minischeme.py)", t_min=0.001, t_max=MAXF, cases=cases)
 
 
-MAIN_NAMES = {"save-as-ppm", "line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
+MAIN_NAMES = {"save-as-ppm", "trace-line", "line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
               "test-bezier", "cornell-smoke", "klein-scene", "cornell-klein", "+max-depth+", "+black+", "+white+", "sky-color", "black", "color", "correct-gamma", "*size-x*", "*size-y*",
               "*cornell-camera*", "*camera*", "test-scene", "test-scene2", "cornell-box", "cornell-bezier", "trace-all",
               "*image*", "*raw-data*"}
@@ -587,6 +587,16 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
             it.call("main", "trace-all", scene, s + 1)
         raw = [list(x) for x in main.lookup(Sym("*raw-data*"))]
         img = list(main.lookup(Sym("*image*")))
+        # the progressive viewer's route (main.scm:452-469, 533-544): animate calls trace-line row by row, one new sample per
+        # pass.  Same draws => it must leave the same *raw-data* / *image* behind as trace-all did.
+        it.eval(forms["*image*"], main)
+        it.eval(forms["*raw-data*"], main)
+        for s in range(spp):
+            state["pixel"] = 0
+            rng.path, rng.k = (seed, 0, s), 0
+            for y in range(size):
+                it.call("main", "trace-line", scene, y, s + 1)
+        assert [list(x) for x in main.lookup(Sym("*raw-data*"))] == raw and list(main.lookup(Sym("*image*"))) == img, "trace-line != trace-all"
         import tempfile
         cwd = os.getcwd()
         with tempfile.TemporaryDirectory() as tmp:           # (save-as-ppm nx ny) writes "test.ppm" into the current directory (main.scm:440)
@@ -603,7 +613,8 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
         if any(undefined):
             img = [-1 if undefined[i // 3] else q for i, q in enumerate(img)]
             ppm = None
-        out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img, ppm=ppm))
+        out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img, ppm=ppm,
+                        trace_line_equals_trace_all=True))
         print(f"color/{name}: mean radiance {np.mean(raw) / spp:.4f}")
     rng.path, rng.lens = None, False
     main.vars[Sym("color")] = color

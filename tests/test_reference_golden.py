@@ -263,6 +263,7 @@ def test_reference_trace_all(orc, idx, tmp_path):
     oracle's Philox draws: the oracle's render must reproduce every pixel's radiance sum and 8-bit value."""
     run = load("ref_color.json")["runs"][idx]
     w, h, spp = run["width"], run["height"], run["spp"]
+    assert run["trace_line_equals_trace_all"]                        # the generator also ran the viewer's row-by-row trace-line (main.scm:452-469): same frame
     scene = host_scene(run["scene"], w, h)
     S = orc.OracleScene(scene, quantise=False)
     img, nrays = S.render(w, h, spp, max_depth=run["max_depth"], seed=run["seed"], nthreads=1)

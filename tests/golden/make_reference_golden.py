@@ -116,8 +116,11 @@ def tag_medium(ref, medium, leaf_id):
     """Instrumentation only: tells the scripted random-real WHICH constant medium is drawing its free-flight
     sample (geometry.scm:562), so that it can return the draw the oracle / the C-ABI's trace_batch assign to that
     leaf - Philox key (ray index, seed 0), counter (sample 0, bounce 1, block 16 + leaf id, 0), component 0 -
-    independent of visit order.  The medium's own hit closure runs unchanged."""
+    independent of visit order; inside a path (make_color) the key is (pixel, seed) and the counter (sample, depth + 1,
+    16 + leaf id, 0) of the path being traced.  The medium's own hit closure runs unchanged."""
     inner, it, rng = medium[0], ref.it, ref.rng
+    if getattr(inner, "srt_tagged", False):
+        return
 
     def hit_fn(ray, t_min, t_max):
         rng.medium_leaf = leaf_id
@@ -125,6 +128,7 @@ def tag_medium(ref, medium, leaf_id):
             return it.apply(inner, [ray, t_min, t_max])
         finally:
             rng.medium_leaf = None
+    hit_fn.srt_tagged = True
     medium[0] = hit_fn
 
 
@@ -487,7 +491,7 @@ class ScriptedRng:
     def __init__(self):
         self.script, self.path, self.k = [], None, 0
         self.medium_leaf, self.ray_index, self.gen = None, 0, None
-        self.lens, self.pathgen = False, None
+        self.lens, self.pathgen, self.cur_depth = False, None, -1
 
     def __call__(self):
         if self.script:
@@ -496,11 +500,14 @@ class ScriptedRng:
             return next(self.gen)
         if self.medium_leaf is not None:           # see tag_medium
             from oracle import oracle as O
+            if self.path is not None:              # inside a path: the hit at depth d draws from bounce d + 1; cur_depth = depth of the last scatter drawn
+                seed, pixel, sample = self.path
+                return float(O.rng_block(seed, pixel, sample, self.cur_depth + 2, 16 + self.medium_leaf)[0])
             return float(O.rng_block(0, self.ray_index, 0, 1, 16 + self.medium_leaf)[0])
         if self.path is None:
             return 0.5
         if self.k == 0:
-            self.pathgen = self.path_stream(*self.path)
+            self.pathgen, self.cur_depth = self.path_stream(*self.path), -1
         self.k += 1
         return float(next(self.pathgen))
 
@@ -531,6 +538,7 @@ class ScriptedRng:
             # lambertian at this depth (material.scm:27): (local uvw (random-cosine-direction)) evaluates its operand THREE
             # times (onb.scm:27-36, Q15) = 6 draws per scatter: block 0 (x, y), then block 2 (x, y), (z, w) of bounce depth + 1
             a, b = O.rng_block(seed, pixel, sample, depth + 1, 0), O.rng_block(seed, pixel, sample, depth + 1, 2)
+            self.cur_depth = depth
             for x in (a[0], a[1], b[0], b[1], b[2], b[3]):
                 yield x
             depth += 1
@@ -576,8 +584,12 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
     # textures, a flipped light, sky-color
     for form in read_all(NEXTWEEK_SCENE):
         it.eval(form, main)
-    for name in ["cornell-box", "test-scene2", "ref-nextweek-scene"]:
+    for name in ["cornell-box", "test-scene2", "ref-nextweek-scene", "cornell-smoke"]:
         scene = main.lookup(Sym(name))
+        if name == "cornell-smoke":                # constant media inside the path loop: the free-flight draw comes from block 16 + leaf of the hit's bounce
+            objs = list(ref.call("geometry", "scene-obj-list", scene))
+            tag_medium(ref, objs[6], 6)
+            tag_medium(ref, objs[7], 7)
         rng.lens = name == "ref-nextweek-scene"
         it.eval(forms["*image*"], main)
         it.eval(forms["*raw-data*"], main)

@@ -92,7 +92,7 @@ def test_reference_textures():
     r.close()
 
 
-@pytest.mark.parametrize("idx", [0, 1, 2])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
 def test_reference_trace_all(idx, tmp_path):
     """main.scm's own trace-all (color, running sum, gamma, 8-bit) was run by the reference with random-real
     returning this repo's Philox draws in the reference's call order; the CUDA path renders the same

@@ -93,7 +93,7 @@ class Ref:
         if r[0] is False:
             return None
         rec = r[1]
-        return dict(t=float(rec[0]), p=list(rec[1]), n=list(rec[2]), u=float(rec[4]), v=float(rec[5]))
+        return dict(t=float(rec[0]), p=list(rec[1]), n=list(rec[2]), u=float(rec[4]), v=float(rec[5]), material=rec[3])
 
     def load_main(self, names):
         """Take the named top-level definitions (and the module header) out of main.scm."""
@@ -132,17 +132,26 @@ def tag_medium(ref, medium, leaf_id):
     medium[0] = hit_fn
 
 
-def hits_table(ref, obj, rays):
-    hit, t, p, n, uv = [], [], [], [], []
+def hits_table(ref, obj, rays, leaf_materials=None):
+    """`leaf_materials`: the material objects of the scene's leaves in depth-first list order, when every leaf has its OWN
+    material object - the hit record's material (ray.scm:27) then identifies WHICH object the reference hit, and the table
+    gets a `prim` column (the north star's "primitive ids must match the reference's intersection routines")."""
+    hit, t, p, n, uv, prim = [], [], [], [], [], []
     for i, r in enumerate(rays):
         ref.rng.ray_index = i
         h = ref.hit(obj, r)
+        if leaf_materials is not None:
+            prim.append(-1 if h is None else [k for k, mat in enumerate(leaf_materials) if mat is h["material"]][0])
         hit.append(h is not None)
         t.append(h["t"] if h else 0.0)
         p.append(h["p"] if h else [0.0, 0.0, 0.0])
         n.append(h["n"] if h else [0.0, 0.0, 0.0])
         uv.append([h["u"], h["v"]] if h else [0.0, 0.0])
-    return dict(rays=[list(map(float, r)) for r in rays], hit=hit, t=t, p=p, n=n, uv=uv)
+    out = dict(rays=[list(map(float, r)) for r in rays], hit=hit, t=t, p=p, n=n, uv=uv)
+    if leaf_materials is not None:
+        assert len({id(mat) for mat in leaf_materials}) == len(leaf_materials)
+        out["prim"] = prim
+    return out
 
 
 def stability_mask(scene, rays):
@@ -283,10 +292,22 @@ def make_scenes(ref, main, names=None, seed0=200):
         hs = host_scene(name)
         nr = 60 if name in ("cornell-bezier", "test-bezier", "cornell-klein", "klein-scene") else 200
         rnd = raybatch.random_rays(raybatch.interest_bounds(flatten_scene(hs)), nr, seed0 + i).astype(np.float64)
+        if name.startswith("test-scene-"):           # the 10 x 10 sphere grid: 150 more rays aimed at (or just past) individual spheres, so that many ids occur
+            rs = np.random.RandomState(seed0 + 50 + i)
+            o3 = np.stack([rs.uniform(-2, 11, 150), rs.uniform(0.2, 5, 150), rs.uniform(-2, 11, 150)], axis=1)
+            aim = np.stack([rs.randint(0, 10, 150), np.zeros(150), rs.randint(0, 10, 150)], axis=1) + rs.normal(size=(150, 3)) * 0.3
+            d3 = aim - o3
+            d3 *= (rs.uniform(0.5, 2.0, 150) / np.linalg.norm(d3, axis=1))[:, None]
+            rnd = np.concatenate([rnd, f32(np.concatenate([o3, d3, rs.random_sample((150, 1))], axis=1))])
         rays = np.concatenate([cam_rays[::3] if "klein" in name else cam_rays, rnd])
         cam_rays = cam_rays[::3] if "klein" in name else cam_rays
         cam_st = cam_st[::3] if "klein" in name else cam_st
-        tab = hits_table(ref, scene, rays)
+        leaf_materials = None
+        if name in ("test-scene", "test-scene2", "test-scene-non-bvh"):             # every object of the list has its own material object
+            leaf_materials = [o[2] for o in ref.call("geometry", "scene-obj-list", scene)]
+        elif name in ("test-scene-bvh", "test-scene-bvh-sah"):                      # ground + the BVH over *spheres-list* (depth-first list order)
+            leaf_materials = [list(ref.call("geometry", "scene-obj-list", scene))[0][2]] + [o[2] for o in main.lookup(Sym("*spheres-list*"))]
+        tab = hits_table(ref, scene, rays, leaf_materials)
         tab["unstable"] = stability_mask(hs, rays)
         tab["n_camera_rays"] = len(cam_rays)
         tab["camera_st"] = [list(x) for x in cam_st]

@@ -2,8 +2,9 @@
 (tests/golden/ref_*.json: /root/reference/*.scm executed by oracle/minischeme.py in the build
 container, see tests/golden/make_reference_golden.py).  No oracle call at run time.
 
-Bars (the reference returns hit records without primitive ids, so identity is hit / miss + t + normal):
-    hit / miss            exact on every ray the fixture does not flag as near-tie / fp32-unstable
+Bars (the reference's hit records carry no primitive id; where every object of a scene has its own material object the
+material in the record identifies the object and the id must be EQUAL, elsewhere identity is hit / miss + t + normal):
+    primitive id, hit / miss   exact on every ray the fixture does not flag as near-tie / fp32-unstable
     t, normal             <= 1e-4 relative           u, v   <= 2e-4 absolute (rects; spheres for |p.y| <= 0.9, Q5)
     texture values        <= 2e-4 absolute for |p| <= 6 (checker: points within rounding of a tile edge skipped)
     trace-all radiance    same Philox draws as the reference run: median |diff| < 1e-4 per sample, >= 97 % of the
@@ -37,8 +38,11 @@ def _check(scene, case, label, t_min=0.001, t_max=999999999999.0):
     r.close()
     keep = ~np.asarray(case["unstable"], bool)
     hit = np.asarray(case["hit"], bool)
-    assert keep.mean() >= 0.99
+    assert keep.mean() >= 0.98         # (the sphere-grid scenes carry rays aimed at sphere rims on purpose: up to 1.4 % of them graze)
     assert np.array_equal((gp["prim"] >= 0)[keep], hit[keep]), np.nonzero(keep & ((gp["prim"] >= 0) != hit))[0][:10]
+    if "prim" in case:        # which object the reference hit (material identity in its hit record): primitive ids must be EQUAL
+        want = np.asarray(case["prim"])
+        assert np.array_equal(gp["prim"][keep], want[keep]), np.nonzero(keep & (gp["prim"] != want))[0][:10]
     sel = keep & hit
     tr, nr, pr, uvr = (np.asarray(case[k], np.float64) for k in ("t", "n", "p", "uv"))
     t_err = np.abs(gp["t"][sel] - tr[sel]) / np.abs(tr[sel])

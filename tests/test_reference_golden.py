@@ -39,6 +39,8 @@ def _check_hits(O, scene, case, t_min=0.001, t_max=999999999999.0):
     o = S.trace_batch(rays, t_min, t_max)
     hit = np.asarray(case["hit"], bool)
     assert np.array_equal(o["prim"] >= 0, hit), np.nonzero((o["prim"] >= 0) != hit)[0][:10]
+    if "prim" in case:        # the object the reference hit, identified by the material object in its hit record: ids must be EQUAL
+        assert np.array_equal(o["prim"], np.asarray(case["prim"])), np.nonzero(o["prim"] != np.asarray(case["prim"]))[0][:10]
     worst = 0.0
     for key, mine in (("t", o["t"]), ("p", o["p"]), ("n", o["n"]), ("uv", o["uv"])):
         ref = np.asarray(case[key], np.float64)
@@ -63,9 +65,12 @@ def test_reference_primitives(orc):
 
 
 def test_reference_scenes(orc):
+    with_ids = 0
     for case in load("ref_scenes.json")["scenes"]:
         nhit, _ = _check_hits(orc, host_scene(case["name"]), case)
         assert nhit > 150, case["name"]
+        with_ids += "prim" in case
+    assert with_ids == 2          # test-scene, test-scene2 (+ the three 101-sphere scenes of ref_scenes2.json): primitive ids against the reference
 
 
 def test_reference_medium_and_klein(orc):
@@ -91,6 +96,8 @@ def test_reference_scenes_with_media_klein_curves_and_the_references_bvh(orc):
         assert nhit > 80, case["name"]
         names.add(case["name"])
     assert {"cornell-smoke", "cornell-klein", "klein-scene", "test-bezier", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"} <= names
+    ids = {c["name"]: c["prim"] for c in load("ref_scenes2.json")["scenes"] if "prim" in c}
+    assert set(ids) == {"test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"} and all(len(set(v)) >= 60 for v in ids.values())
 
 
 def test_reference_camera_rays(orc):

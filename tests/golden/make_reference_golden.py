@@ -258,20 +258,56 @@ def make_prims(ref, case_list=None, seed0=100):
     return dict(source="reference constructors of geometry.scm / bezier.scm through g:hit (oracle/minischeme.py)", t_min=0.001, t_max=MAXF, cases=cases)
 
 
-MAIN_NAMES = {"save-as-ppm", "trace-line", "line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
+MAIN_NAMES = {"random-scene", "save-as-ppm", "trace-line", "line-upped-spheres", "*spheres-list*", "*bvh-sah-node*", "*bvh-node*", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah",
               "test-bezier", "cornell-smoke", "klein-scene", "cornell-klein", "+max-depth+", "+black+", "+white+", "sky-color", "black", "color", "correct-gamma", "*size-x*", "*size-y*",
               "*cornell-camera*", "*camera*", "test-scene", "test-scene2", "cornell-box", "cornell-bezier", "trace-all",
               "*image*", "*raw-data*"}
 
 
 SCENES1 = ["cornell-box", "test-scene2", "test-scene", "cornell-bezier"]
-SCENES2 = ["cornell-smoke", "cornell-klein", "klein-scene", "test-bezier", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"]
+SCENES2 = ["cornell-smoke", "cornell-klein", "klein-scene", "test-bezier", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah", "random-scene"]
+RANDOM_SCENE_SEED = 41
+
+
+def reference_random_scene(ref, main):
+    """main.scm:31-89 (random-scene), the generator behind cfg2 / cfg3.  At HEAD its last form calls (g:make-scene obj-list)
+    with one argument although make-scene takes three (geometry.scm:52): executed as is, it raises - checked here.  For the
+    golden the call is repeated with g:make-scene replaced, inside module main only, by a procedure that hands back the
+    object list; random-real replays numpy's RandomState(RANDOM_SCENE_SEED) stream, which is what the host mirror
+    `scenes.random_scene(seed, -5, 10, moving=True, checker_ground=True)` draws from."""
+    from oracle.minischeme import SchemeError
+    rs = np.random.RandomState(RANDOM_SCENE_SEED)
+    ref.rng.gen = iter(lambda: float(rs.random_sample()), None)
+    try:
+        ref.it.call("main", "random-scene")
+        raise AssertionError("random-scene was expected to fail on make-scene's arity")
+    except SchemeError as e:
+        assert "wrong number of arguments" in str(e), e
+    rs = np.random.RandomState(RANDOM_SCENE_SEED)
+    ref.rng.gen = iter(lambda: float(rs.random_sample()), None)
+    main.vars[Sym("g:make-scene")] = lambda *a: a[0]
+    try:
+        obj_list = ref.it.call("main", "random-scene")
+    finally:
+        del main.vars[Sym("g:make-scene")]
+        ref.rng.gen = None
+    return ref.call("geometry", "make-scene", obj_list, main.lookup(Sym("*camera*")), main.lookup(Sym("sky-color")))
+
+
+def material_row(ref, mat):
+    """(kind, rgb of the texture at the origin or None, parameter) read out of a reference material vector:
+    lambertian #(scatter spdf emitted albedo), metal #(scatter emitted albedo fuzz), dielectric #(scatter emitted ref-idx)."""
+    if len(mat) == 3:
+        return ["dielectric", None, float(mat[2])]
+    if isinstance(mat[3], list):
+        return ["lambertian", [float(x) for x in ref.call("texture", "value", mat[3], 0, 0, v3(0.05, 0.05, 0.05))], 0.0]
+    return ["metal", [float(x) for x in ref.call("texture", "value", mat[2], 0, 0, v3(0.05, 0.05, 0.05))], float(mat[3])]
 
 
 def make_scenes(ref, main, names=None, seed0=200):
     out = []
     for i, name in enumerate(names or SCENES1):
-        scene = main.lookup(Sym(name))
+        scene = reference_random_scene(ref, main) if name == "random-scene" else main.lookup(Sym(name))
         if name == "cornell-smoke":                # list positions 6, 7 = leaves 6, 7 (the boundary boxes are not scene primitives)
             objs = list(ref.call("geometry", "scene-obj-list", scene))
             tag_medium(ref, objs[6], 6)
@@ -303,7 +339,7 @@ def make_scenes(ref, main, names=None, seed0=200):
         cam_rays = cam_rays[::3] if "klein" in name else cam_rays
         cam_st = cam_st[::3] if "klein" in name else cam_st
         leaf_materials = None
-        if name in ("test-scene", "test-scene2", "test-scene-non-bvh"):             # every object of the list has its own material object
+        if name in ("test-scene", "test-scene2", "test-scene-non-bvh", "random-scene"):   # every object of the list has its own material object
             leaf_materials = [o[2] for o in ref.call("geometry", "scene-obj-list", scene)]
         elif name in ("test-scene-bvh", "test-scene-bvh-sah"):                      # ground + the BVH over *spheres-list* (depth-first list order)
             leaf_materials = [list(ref.call("geometry", "scene-obj-list", scene))[0][2]] + [o[2] for o in main.lookup(Sym("*spheres-list*"))]
@@ -311,6 +347,8 @@ def make_scenes(ref, main, names=None, seed0=200):
         tab["unstable"] = stability_mask(hs, rays)
         tab["n_camera_rays"] = len(cam_rays)
         tab["camera_st"] = [list(x) for x in cam_st]
+        if name == "random-scene":                 # the material table the reference built: kind, albedo, fuzz / ref-idx per object
+            tab["materials"] = [material_row(ref, mat) for mat in leaf_materials]
         out.append(dict(name=name, **tab))
         print(f"scenes/{name}: {sum(tab['hit'])}/{len(rays)} hits, {sum(tab['unstable'])} flagged")
     return dict(source="scenes defined by main.scm, closest hit by (g:hit scene ray 0.001 +max-float+); the first n_camera_rays rays were made by cam:get-ray",

@@ -54,4 +54,6 @@ def host_scene(name, size_x=200, size_y=200):
             "cornell-smoke": scenes.cornell_smoke, "klein-scene": scenes.klein_scene, "cornell-klein": scenes.cornell_klein,
             "test-bezier": scenes.test_bezier, "test-scene-bvh": scenes.test_scene_bvh, "test-scene-bvh-sah": scenes.test_scene_bvh,
             "test-scene-non-bvh": non_bvh, "ref-nextweek-scene": ref_nextweek_scene,
+            # main.scm:31-89 in its reference form (grid [-5, 10), moving lambertians, checker ground); 41 = RANDOM_SCENE_SEED of the generator
+            "random-scene": lambda sx, sy: g.make_scene(scenes.random_scene(41, -5, 10, moving=True, checker_ground=True), scenes.default_camera(sx, sy), scenes.sky_color),
             "test-scene": lambda sx, sy: g.make_scene(scenes.test_scene_objects(), scenes.default_camera(sx, sy), scenes.black)}[name](size_x, size_y)

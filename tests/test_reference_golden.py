@@ -97,7 +97,32 @@ def test_reference_scenes_with_media_klein_curves_and_the_references_bvh(orc):
         names.add(case["name"])
     assert {"cornell-smoke", "cornell-klein", "klein-scene", "test-bezier", "test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"} <= names
     ids = {c["name"]: c["prim"] for c in load("ref_scenes2.json")["scenes"] if "prim" in c}
-    assert set(ids) == {"test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah"} and all(len(set(v)) >= 60 for v in ids.values())
+    assert set(ids) == {"test-scene-non-bvh", "test-scene-bvh", "test-scene-bvh-sah", "random-scene"}
+    assert all(len(set(v)) >= 60 for k, v in ids.items() if k != "random-scene")
+
+
+def test_reference_random_scene_generator():
+    """main.scm:31-89 random-scene, the generator behind cfg2 / cfg3, EXECUTED (its broken last form - make-scene with
+    one argument - was confirmed to raise and then bypassed, see the generator): the host mirror
+    `scenes.random_scene(seed, -5, 10, moving=True, checker_ground=True)` fed the same random stream builds the same
+    objects in the same order - geometry and ids through the hit records above, and here the material table:
+    kind, albedo (the reference's texture evaluated), fuzz / refractive index of all 226 objects."""
+    from scheme_raytrace_b200.host.flatten import flatten_scene
+    case = [c for c in load("ref_scenes2.json")["scenes"] if c["name"] == "random-scene"][0]
+    flat = flatten_scene(host_scene("random-scene"))
+    assert len(case["materials"]) == len(flat.prims) == 226
+    kinds = {"lambertian": 0, "metal": 1, "dielectric": 2}
+    seen = set()
+    for i, (kind, rgb, param) in enumerate(case["materials"]):
+        mrow = flat.materials[flat.prims[i]["material"]]
+        assert int(mrow["kind"]) == kinds[kind], i
+        seen.add(kind)
+        assert np.float32(mrow["param"]) == np.float32(param), i
+        if rgb is not None and i != len(case["materials"]) - 1:              # (the last object is the checker ground)
+            trow = flat.textures[mrow["tex"]]
+            assert int(trow["kind"]) == 0 and np.array_equal(trow["rgb"], np.asarray(rgb, np.float32)), i
+    assert seen == set(kinds)
+    assert sum(int(p["type"]) == 1 for p in flat.prims) > 100               # moving spheres (the lambertians)
 
 
 def test_reference_camera_rays(orc):

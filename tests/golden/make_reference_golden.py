@@ -421,6 +421,29 @@ def make_materials(ref, main, rng):
         e = ref.call("material", "emitted", light, ref.call("ray", "make-ray", v3(0, 0, 0), v3(*a)), rec, 0.25, 0.75, v3(1, 2, 3))
         em.append(dict(d=list(a), n=list(b), out=list(e)))
     out["diffuse_light_emitted"] = em
+    # What HEAD cannot run (SURVEY "five facts" 3), established by running it.  Each entry is the error the call raised.
+    from oracle.minischeme import SchemeError, to_list
+    errs = {}
+
+    def failing(label, thunk):
+        try:
+            thunk()
+            errs[label] = None
+        except SchemeError as e:
+            errs[label] = str(e)
+    color = main.lookup(Sym("color"))
+    for label, mat in (("color_on_metal", ref.call("material", "make-metal", ref.call("texture", "constant-texture", v3(0.8, 0.6, 0.2)), 0.3)),
+                       ("color_on_dielectric", ref.call("material", "make-dielectric", 1.5))):
+        scene = ref.call("geometry", "make-scene", to_list([ref.call("geometry", "make-sphere", v3(0, 0, -1), 0.5, mat)]),
+                         main.lookup(Sym("*camera*")), sky)
+        rng.script = [0.25] * 8
+        failing(label, lambda: ref.it.apply(color, [ref.call("ray", "make-ray", v3(0, 0, 0), v3(0, 0, -1)), scene]))
+        rng.script = []
+    sph = ref.call("geometry", "make-sphere", v3(0, 0, -1), 0.5, lam)
+    hp = ref.call("pdf", "make-hitable-pdf", sph, v3(0, 0, 0))
+    failing("hitable_pdf_value", lambda: ref.call("pdf", "pdf-value", hp, v3(0, 0, -1)))
+    failing("hitable_pdf_generate", lambda: ref.call("pdf", "generate", hp))
+    out["head_errors"] = errs
     print("materials: done")
     return out
 

@@ -221,6 +221,12 @@ def test_reference_material_functions(orc):
         seen.add(facing)
         assert k["out"] == ([4.0, 4.0, 4.0] if facing else [0.0, 0.0, 0.0])
     assert seen == {True, False}
+    # what HEAD cannot run, as the reference itself reported it when executed (SURVEY "five facts" 3): `color` receives the
+    # three values of the metal / dielectric scatter into four variables; make-hitable-pdf calls procedures that do not exist.
+    # These are the parts the oracle defines from the book series and labels "parity unpinned".
+    e = M["head_errors"]
+    assert "3 values where 4" in e["color_on_metal"] and "3 values where 4" in e["color_on_dielectric"]
+    assert "g:pdf-value" in e["hitable_pdf_value"] and "g:random" in e["hitable_pdf_generate"]
 
 
 def test_reference_scatter_samplers_camera_aabb(orc):

@@ -8,10 +8,13 @@ implements just enough of R7RS + the Gauche extensions the reference uses (modul
 :prefix`, `define-inline`, `receive` / `let-values`, `dotimes`, `inc!`, `push!`, generalised
 `set!`, `let-optionals*`, hygienic non-ellipsis `syntax-rules`, `f64vector-*`, `gauche.array`
 `array-mul`, srfi-27 `random-real` supplied by the caller) to load `/root/reference/*.scm`
-UNMODIFIED and call their procedures.  `tests/golden/make_reference_golden.py` uses it, in the build
-container only, to freeze reference outputs into `tests/golden/ref_*.json`; the oracle and the
-CUDA path are then checked against those files.  Nothing is copied from the reference: the sources
-are read from where they lie at generation time.
+UNMODIFIED and call their procedures.  `tests/golden/make_reference_golden.py` and
+`make_reference_render.py` use it, in the build container only, to freeze reference outputs into
+`tests/golden/ref_*`; the oracle and the CUDA path are then checked against those files.  Nothing is
+copied from the reference: the sources are read from where they lie at generation time.  It also
+executes the repo's own Gauche host modules (`scheme_raytrace_b200/scheme/*.scm`, which add `format`
+directives, file ports, a few srfi-1 procedures to the vocabulary) in `tests/test_scheme_host.py`;
+its own semantics are pinned by `tests/test_minischeme.py`.
 
 Fidelity notes (where Gauche's behaviour had to be restated rather than executed):
   * numbers: exact integers / rationals (fractions.Fraction) / IEEE doubles with the usual

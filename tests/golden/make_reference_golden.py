@@ -448,6 +448,73 @@ def make_materials(ref, main, rng):
     return out
 
 
+TIE_OBJECTS = [["box", [0, 0, 0], [1, 1, 1]], ["sphere", [0, 0, -1], 0.5], ["xy-rect", -1, 1, -1, 1, -0.5], ["sphere", [3, 0, 0], 1],
+               ["xy-rect", 2, 4, -1, 1, 0], ["box", [1, 0, 0], [2, 1, 1]]]
+TIE_RAYS = [
+    [2, 0.5, 2, -1, 0, -1, 0],        # box edge shared by two faces
+    [2, 2, 2, -1, -1, -1, 0],         # box corner (three faces)
+    [0.5, 0.5, 5, 0, 0, -1, 0],       # straight through the box
+    [0, 0, 0, 0, 0, -1, 0],           # sphere front == rect plane (strict vs inclusive tie)
+    [0, 0, 5, 0, 0, -1, 0],
+    [3, 0, 5, 0, 0, -1, 0],           # sphere then coplanar rect through its centre
+    [1, 0.5, 5, 0, 0, -1, 0],         # shared face plane x = 1 of the two boxes, ray in the plane
+    [1.5, 0.5, 5, 0, 0, -1, 0],
+    [-5, 0.5, 0.5, 1, 0, 0, 0],       # through both boxes, coincident faces at x = 1
+    [5, 0.5, 0.5, -1, 0, 0, 0],
+    [0.5, 5, 0.5, 0, -1, 0, 0],
+    [0.5, 0.5, 0.5, 0, 0, 1, 0],      # from inside the box
+    [3, 0, 0, 0, 1, 0, 0],            # from the sphere centre, in the rect plane (parallel: t = NaN)
+    [0, 0.5, 0.5, 1, 0, 0, 0],        # origin ON a face (t = 0 < t-min), exits through the opposite one
+    [0.5, 0.5, -1, 0, 0, 1, 0],       # sphere centre towards the box: exits the sphere at t = 0.5, rect at -0.5 in between
+    [2, 1, 0.5, -1, 0, 0, 0],         # along a box edge line (y = 1 is the inclusive rect bound)
+]
+
+
+# tie rule proper: sphere (strict <) against rect (inclusive range test) at exactly equal t, identical twins of
+# each kind, in both list orders; no ray lies in a rect's plane here
+TIE_OBJECTS_B = [["sphere", [0, 0, -1], 0.5], ["xy-rect", -1, 1, -1, 1, -0.5], ["sphere", [0, 0, -1], 0.5], ["xy-rect", -1, 1, -1, 1, -0.5],
+                 ["sphere", [0, 0, 2], 0.5], ["xy-rect", -2, 2, -2, 2, 2.5]]
+TIE_RAYS_B = [[0, 0, 5, 0, 0, -1, 0], [0, 0, 5, 0, 0, -2, 0.5], [0.125, 0.25, 5, 0, 0, -1, 0], [0, 0, -5, 0, 0, 1, 0], [0, 0, 1, 0, 0, -1, 0],
+              [0, 0, 0.5, 0, 0, 1, 0], [0.75, 0.75, 5, 0, 0, -1, 0], [0, 0, -1, 0, 0, 1, 0], [0, 0, -1, 0, 0, -1, 0], [1, 1, 5, 0, 0, -1, 0], [1, -1, 5, 0, 0, -1, 0]]
+
+
+def make_ties(ref):
+    a = make_ties_scene(ref, TIE_OBJECTS, TIE_RAYS)
+    b = make_ties_scene(ref, TIE_OBJECTS_B, TIE_RAYS_B)
+    c = make_ties_scene(ref, TIE_OBJECTS_B[::-1], TIE_RAYS_B)
+    return dict(source=a.pop("source"), t_min=0.001, scenes=[a, b, c])
+
+
+def make_ties_scene(ref, TIE_OBJECTS, TIE_RAYS):
+    """ref_ties.json: the structured adversarial rays of tests/test_gpu_parity.test_structured_ties_cornell through the
+    REFERENCE's hit-obj-list (geometry.scm:33-50): exact ties between objects (strict `<` of spheres vs inclusive range
+    test of rects, list order), rays inside a rect's plane (NaN), origins on a surface, t-max just before / beyond a hit.
+    Every object has its own material, so the record tells which object won."""
+    mats = [ref.call("material", "make-lambertian", ref.call("texture", "constant-texture", v3(0.1 * (i + 1), 0.5, 0.5))) for i in range(len(TIE_OBJECTS))]
+    objs = []
+    for spec, mat in zip(TIE_OBJECTS, mats):
+        saved, ref.lam = ref.lam, mat
+        objs.append(ref.build(spec))
+        ref.lam = saved
+    from oracle.minischeme import to_list
+    scene = ref.call("geometry", "make-scene", to_list(objs), None, None)
+    runs = []
+    for tmax in (MAXF, 4.0, 3.999, 4.001, 1.0, 0.5):
+        rows = []
+        for r in TIE_RAYS:
+            ray = ref.call("ray", "make-ray-with-time", v3(*r[0:3]), v3(*r[3:6]), float(r[6]))
+            res = ref.call("geometry", "hit", scene, ray, 0.001, tmax)
+            if res[0] is False:
+                rows.append(dict(obj=-1))
+            else:
+                rec = res[1]
+                rows.append(dict(obj=[k for k, mm in enumerate(mats) if mm is rec[3]][0], t=float(rec[0]), n=list(rec[2]), p=list(rec[1])))
+        runs.append(dict(t_max=tmax, hits=rows))
+    print(f"ties: {len(TIE_RAYS)} rays x {len(runs)} t-max values, hits at t-max = inf: {sum(h['obj'] >= 0 for h in runs[0]['hits'])}")
+    return dict(source="geometry.scm:33-50 hit-obj-list over boxes / spheres / rects, each object with its own material", objects=TIE_OBJECTS,
+                rays=TIE_RAYS, runs=runs)
+
+
 def make_scatter(ref, rng):
     """ref_scatter.json: the scatter closures of metal / dielectric called directly (under `color` they cannot run at
     HEAD: 3 values into a 4-value receive), the rejection samplers, random-to-sphere, the cosine pdf,
@@ -736,6 +803,7 @@ def main():
     dump("ref_textures.json", make_textures(ref))
     dump("ref_materials.json", make_materials(ref, main_mod, rng))
     dump("ref_scatter.json", make_scatter(ref, rng))
+    dump("ref_ties.json", make_ties(ref))
     dump("ref_color.json", make_color(ref, main_mod, rng))
 
 

@@ -101,6 +101,47 @@ def test_reference_scenes_with_media_klein_curves_and_the_references_bvh(orc):
     assert all(len(set(v)) >= 60 for k, v in ids.items() if k != "random-scene")
 
 
+def test_reference_tie_rule_and_edge_rays(orc):
+    """ref_ties.json: exact ties, edges, corners, coincident faces, origins on a surface and t-max on either side of a hit,
+    through the reference's hit-obj-list.  The winner (which object, by material identity), t and normal must be the
+    oracle's.  One documented divergence: a ray lying IN a rect's plane gives t = 0/0 = NaN upstream, every
+    comparison is false, the NaN hit is accepted and poisons closest-so-far; the oracle and the CUDA path reject NaN t.
+    Those rays (origin coordinate on a rect's plane constant with a zero direction component) are only counted - one of
+    them shows the poisoning: at t-max 0.5 the reference returns a hit at t = 1.0."""
+    F = load("ref_ties.json")
+    compared = poisoned = ties_seen = 0
+    for T in F["scenes"]:
+        objs = [build_host(spec) for spec in T["objects"]]
+        leaf_to_obj = []
+        for k, spec in enumerate(T["objects"]):
+            leaf_to_obj += [k] * (6 if spec[0] == "box" else 1)
+        S = orc.OracleScene(g.make_scene(objs, scenes.default_camera(), scenes.sky_color), quantise=False)
+        rays = np.asarray(T["rays"], np.float64)
+        planes = []                                   # (axis, k) of every rect of the scene
+        for spec in T["objects"]:
+            if spec[0] == "box":
+                planes += [(a, spec[1][a]) for a in range(3)] + [(a, spec[2][a]) for a in range(3)]
+            elif spec[0].endswith("-rect"):
+                planes.append(({"xy-rect": 2, "xz-rect": 1, "yz-rect": 0}[spec[0]], spec[5]))
+        in_plane = [any(r[3 + a] == 0 and r[a] == k for a, k in planes) for r in T["rays"]]
+        assert all(np.isnan(h["t"]) <= in_plane[i] for i, h in enumerate(T["runs"][0]["hits"]) if h["obj"] >= 0)    # every NaN record comes from such a ray
+        for run in T["runs"]:
+            o = S.trace_batch(rays, F["t_min"], run["t_max"])
+            for i, h in enumerate(run["hits"]):
+                if in_plane[i]:                       # NaN may have passed through closest-so-far even if the final record is finite
+                    poisoned += 1
+                    continue
+                mine = leaf_to_obj[o["prim"][i]] if o["prim"][i] >= 0 else -1
+                assert mine == h["obj"], (T["objects"], run["t_max"], i, mine, h)
+                if mine >= 0:
+                    assert o["t"][i] == h["t"] and np.array_equal(o["n"][i], np.asarray(h["n"], np.float64)), (run["t_max"], i)
+                    # an exact tie: another object of the scene is hit at the very same t (the winner is then decided by the rule alone)
+                    t2 = S.trace_batch(rays[i:i + 1], F["t_min"], run["t_max"], exclude_leaf=int(o["prim"][i]))
+                    ties_seen += bool(t2["prim"][0] >= 0 and t2["t"][0] == o["t"][i])
+                compared += 1
+    assert compared >= 150 and 0 < poisoned < compared and ties_seen >= 30, (compared, poisoned, ties_seen)
+
+
 def test_reference_random_scene_generator():
     """main.scm:31-89 random-scene, the generator behind cfg2 / cfg3, EXECUTED (its broken last form - make-scene with
     one argument - was confirmed to raise and then bypassed, see the generator): the host mirror

@@ -478,11 +478,26 @@ TIE_RAYS_B = [[0, 0, 5, 0, 0, -1, 0], [0, 0, 5, 0, 0, -2, 0.5], [0.125, 0.25, 5,
               [0, 0, 0.5, 0, 0, 1, 0], [0.75, 0.75, 5, 0, 0, -1, 0], [0, 0, -1, 0, 0, 1, 0], [0, 0, -1, 0, 0, -1, 0], [1, 1, 5, 0, 0, -1, 0], [1, -1, 5, 0, 0, -1, 0]]
 
 
+def make_bezier_kats(ref):
+    """KAT7-10 of SURVEY.md 8(c) were derived by the survey from a transliteration, "not from Gauche".  Here the reference's
+    own bezier.scm answers the same rays (curve of main.scm:259-263, origin (0, 5, 5))."""
+    from tests.test_golden import KAT, bezier_kat_ray
+    bz = KAT["bezier"]
+    obj = ref.build(["bezier"] + bz["cp"] + [bz["width"]])
+    out = []
+    for k in bz["cases"]:
+        ray = bezier_kat_ray(k)
+        h = ref.hit(obj, ray, KAT["t_min"], KAT["t_max"])
+        out.append(dict(kat=k["kat"], ray=[float(x) for x in ray], hit=h is not None, t=h and h["t"], p=h and h["p"], n=h and h["n"]))
+    print("bezier KATs:", [(o["kat"], o["hit"], o["t"]) for o in out])
+    return out
+
+
 def make_ties(ref):
     a = make_ties_scene(ref, TIE_OBJECTS, TIE_RAYS)
     b = make_ties_scene(ref, TIE_OBJECTS_B, TIE_RAYS_B)
     c = make_ties_scene(ref, TIE_OBJECTS_B[::-1], TIE_RAYS_B)
-    return dict(source=a.pop("source"), t_min=0.001, scenes=[a, b, c])
+    return dict(source=a.pop("source"), t_min=0.001, scenes=[a, b, c], bezier_kats=make_bezier_kats(ref))
 
 
 def make_ties_scene(ref, TIE_OBJECTS, TIE_RAYS):

@@ -27,6 +27,9 @@ Fidelity notes (where Gauche's behaviour had to be restated rather than executed
     -1 / 1, both true - SURVEY Q12 - so its BVH builders are not used for golden vectors);
   * a multiple-value result used as a procedure ARGUMENT keeps its first value (Gauche's behaviour; R7RS leaves it
     undefined) - `get-normal` of the Klein primitive relies on it;
+  * procedure arguments are evaluated left to right (R7RS and Gauche leave the order unspecified).  It only decides WHICH
+    draw feeds which component where one call has several `(random-real)` operands (util.scm:10,18; the three evaluations
+    of Q15): the draws are i.i.d., so distributions, and therefore every parity statement, are unaffected;
   * `random-real` is whatever callable the host installs: random STREAMS are not a parity target.
 """
 import math

@@ -748,7 +748,8 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
     # textures, a flipped light, sky-color
     for form in read_all(NEXTWEEK_SCENE):
         it.eval(form, main)
-    for name in ["cornell-box", "test-scene2", "ref-nextweek-scene", "cornell-smoke"]:
+    # (test-bezier last: curve hits carry the un-normalised normal -d (Q9), which scales the lambertian weight by its length)
+    for name in ["cornell-box", "test-scene2", "ref-nextweek-scene", "cornell-smoke", "test-bezier"]:
         scene = main.lookup(Sym(name))
         if name == "cornell-smoke":                # constant media inside the path loop: the free-flight draw comes from block 16 + leaf of the hit's bounce
             objs = list(ref.call("geometry", "scene-obj-list", scene))

@@ -354,7 +354,7 @@ def test_reference_scatter_samplers_camera_aabb(orc):
     assert 10 < hits < len(R["aabb"]) - 10
 
 
-@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4])
 def test_reference_trace_all(orc, idx, tmp_path):
     """main.scm's trace-all, run by the reference on 10 x 10 x 2 spp with random-real returning the
     oracle's Philox draws: the oracle's render must reproduce every pixel's radiance sum and 8-bit value."""

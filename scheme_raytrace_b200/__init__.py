@@ -11,4 +11,4 @@ from .host.flatten import flatten_scene, FlatScene  # noqa: F401
 from .host.render import Renderer, ProgressiveRenderer, trace_all, save_as_ppm, correct_gamma_quantise  # noqa: F401
 from .host import scenes  # noqa: F401
 
-QUIRKS_REFERENCE = 31
+from .host.ffi import QUIRKS_REFERENCE  # noqa: F401,E402

@@ -6,6 +6,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libsrt.so")
 
 
+# quirk bits of include/srt.h (SURVEY 8a Q rows + Q15); QUIRKS_REFERENCE reproduces upstream HEAD
+Q1_COSINE_X2, Q4_PERLIN_ALIAS, Q6_SCATTER_TIME0, Q10_DIELECTRIC_UNNORM, Q15_LOCAL_TRIPLE_EVAL = 1, 2, 4, 8, 16
+QUIRKS_REFERENCE = 31
+
+
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_begin", C.c_int32), ("spp_end", C.c_int32),
                 ("max_depth", C.c_int32), ("sky", C.c_int32), ("seed", C.c_uint32), ("quirks", C.c_int32),

@@ -94,7 +94,7 @@ class Renderer:
         ffi.check(self.lib.srt_trace_batch(self.h, _ptr(rays), len(rays), t_min, t_max, _ptr(out)), "trace_batch")
         return out
 
-    def eval_texture(self, tex, uvp, quirks=31):
+    def eval_texture(self, tex, uvp, quirks=ffi.QUIRKS_REFERENCE):
         uvp = np.ascontiguousarray(uvp, dtype=np.float32).reshape(-1, 5)
         out = np.zeros((len(uvp), 3), dtype=np.float32)
         ffi.check(self.lib.srt_eval_texture(self.h, tex, _ptr(uvp), len(uvp), quirks, _ptr(out)), "eval_texture")
@@ -108,7 +108,7 @@ class Renderer:
         return out
 
     # -- rendering --------------------------------------------------------------------------
-    def params(self, width, height, spp_begin, spp_end, max_depth=50, seed=1, quirks=31, t_min=0.001, wave_spp=0, sky=None, estimator=0):
+    def params(self, width, height, spp_begin, spp_end, max_depth=50, seed=1, quirks=ffi.QUIRKS_REFERENCE, t_min=0.001, wave_spp=0, sky=None, estimator=0):
         p = ffi.RenderParams()
         p.width, p.height, p.spp_begin, p.spp_end = width, height, spp_begin, spp_end
         p.max_depth, p.seed, p.quirks, p.t_min, p.wave_spp = max_depth, seed, quirks, t_min, wave_spp
@@ -116,7 +116,7 @@ class Renderer:
         p.estimator = estimator
         return p
 
-    def render(self, width, height, spp, max_depth=50, seed=1, quirks=31, spp_begin=0, rgb_sum=None, wave_spp=0, estimator=0):
+    def render(self, width, height, spp, max_depth=50, seed=1, quirks=ffi.QUIRKS_REFERENCE, spp_begin=0, rgb_sum=None, wave_spp=0, estimator=0):
         """Adds samples [spp_begin, spp_begin+spp) into rgb_sum (H,W,3) float32 (row 0 = bottom).
         Host buffers in and out (D2H inside the call)."""
         if rgb_sum is None:
@@ -126,7 +126,7 @@ class Renderer:
         ffi.check(self.lib.srt_render_host(self.h, C.byref(p), _ptr(rgb_sum), C.byref(st)), "render_host")
         return rgb_sum, st
 
-    def render_device(self, d_ptr, width, height, spp, max_depth=50, seed=1, quirks=31, spp_begin=0, wave_spp=0, estimator=0):
+    def render_device(self, d_ptr, width, height, spp, max_depth=50, seed=1, quirks=ffi.QUIRKS_REFERENCE, spp_begin=0, wave_spp=0, estimator=0):
         """Same, accumulating into a DEVICE buffer (e.g. a torch tensor's data_ptr())."""
         p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, wave_spp=wave_spp, estimator=estimator)
         st = ffi.Stats()
@@ -139,7 +139,7 @@ class ProgressiveRenderer:
     pixel per pass, running sum, 8-bit image re-derived after every pass) without the GLUT window:
     `step()` == one full-frame pass of `trace-line` over all rows."""
 
-    def __init__(self, scene, width=200, height=200, max_depth=100, seed=1, quirks=31, device=0):
+    def __init__(self, scene, width=200, height=200, max_depth=100, seed=1, quirks=ffi.QUIRKS_REFERENCE, device=0):
         self.r = Renderer(scene, device=device)
         self.width, self.height, self.max_depth, self.seed, self.quirks = width, height, max_depth, seed, quirks
         self.raw_data = np.zeros((height, width, 3), dtype=np.float32)     # *raw-data* main.scm:430
@@ -178,7 +178,7 @@ def save_as_ppm(path, image):
     ffi.check(lib.srt_save_ppm(str(path).encode(), _ptr(image), w, h), "save_ppm")
 
 
-def trace_all(scene, sample_count, width=200, height=200, max_depth=100, seed=1, quirks=31, device=0):
+def trace_all(scene, sample_count, width=200, height=200, max_depth=100, seed=1, quirks=ffi.QUIRKS_REFERENCE, device=0):
     """(trace-all scene k) for k = 1..sample_count in one call (main.scm:471-491): returns the
     running sum *raw-data* and the 8-bit *image*."""
     r = Renderer(scene, device=device)

@@ -138,3 +138,13 @@ def test_points_csv_to_bezier_chain(tmp_path, orc):
     S = orc.OracleScene(g.make_scene(objs, scenes.default_camera(), scenes.sky_color), quantise=False)
     r = S.trace_batch([[4.03, 2.0, 5, 0, 0, -1, 0], [3.0, 5.0, 5, 0, 0, -1, 0]])
     assert r["prim"][0] in (0, 1) and r["prim"][1] == -1
+
+
+def test_quirk_bits_match_header():
+    """host/ffi.py's quirk bits are the #defines of include/srt.h; the reference mask carries Q15 (found by executing the reference)."""
+    import re
+    from scheme_raytrace_b200.host import ffi
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "srt.h")).read()
+    hdr = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SRT_(Q\w+)\s+(\d+)", text)}
+    mine = {k: v for k, v in vars(ffi).items() if re.fullmatch(r"Q\d+_\w+|QUIRKS_REFERENCE", k)}
+    assert hdr == mine and mine["QUIRKS_REFERENCE"] == sum(v for k, v in mine.items() if k != "QUIRKS_REFERENCE") == 31

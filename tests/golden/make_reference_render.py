@@ -26,7 +26,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # scenes of main.scm that HEAD's `color` can run (lambertian / diffuse-light only) and that are lit
-SCENES = {"cornell-box": dict(width=20, height=20, spp=256), "test-bezier": dict(width=24, height=24, spp=96)}
+SCENES = {"cornell-box": dict(width=20, height=20, spp=256), "test-bezier": dict(width=24, height=24, spp=96),
+          "cornell-smoke": dict(width=16, height=16, spp=256), "test-scene2": dict(width=16, height=16, spp=256)}
 WORKERS = int(os.environ.get("SRT_WORKERS", "8"))
 # a second batch with other seeds can be ADDED to an existing file (sums and sums of squares accumulate):
 #   SRT_RENDER_BATCH=1 python tests/golden/make_reference_render.py
@@ -87,10 +88,11 @@ def main():
         res[key + "_meta"] = np.array([cfg["width"], cfg["height"], cfg["spp"]])
         print(f"{name}: {cfg['width']}x{cfg['height']} @ {cfg['spp']} spp, mean radiance {s1.mean() / cfg['spp']:.4f}, {time.time() - t0:.0f} s", flush=True)
     path = os.path.join(HERE, "ref_render.npz")
-    if BATCH > 0:
+    if os.path.exists(path) and (BATCH > 0 or ONLY):             # accumulate into / keep the other scenes of an existing file
         old = np.load(path)
-        for k in res:
-            res[k] = res[k] + old[k] if not k.endswith("_meta") else np.array([old[k][0], old[k][1], old[k][2] + res[k][2]])
+        for k in list(res):
+            if BATCH > 0 and k in old.files:
+                res[k] = res[k] + old[k] if not k.endswith("_meta") else np.array([old[k][0], old[k][1], old[k][2] + res[k][2]])
         for k in old.files:
             res.setdefault(k, old[k])
     np.savez_compressed(path, **res)

@@ -13,7 +13,10 @@
   (if (null? rest) first (fold-vec op (op first (car rest)) (cdr rest))))
 (define (sum . vs) (fold-vec f64vector-add (car vs) (cdr vs)))
 (define (diff . vs) (fold-vec f64vector-sub (car vs) (cdr vs)))
-(define (prod . vs) (fold-vec f64vector-mul (car vs) (cdr vs)))
+;; the reference folds prod from the RIGHT (vec.scm:35-39 reduce-right): v1 * (v2 * v3) - kept, it differs from the left fold by an ulp
+(define (prod . vs)
+  (let ((r (reverse vs)))
+    (fold-vec (lambda (acc v) (f64vector-mul v acc)) (car r) (cdr r))))
 (define (quot . vs) (fold-vec f64vector-div (car vs) (cdr vs)))
 (define (scale v k) (f64vector-mul v k))
 (define (dot a b) (f64vector-dot a b))

@@ -231,3 +231,36 @@ def test_reference_points_module_loads_unchanged_on_the_scheme_host(tmp_path):
     assert len(got) == len(want) == 4
     for (kind, params), w in zip(got, want):
         assert kind == g.BEZIER == w.kind and np.allclose(params, w.params, rtol=1e-15, atol=1e-15)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference sources only exist in the build container")
+def test_vec_modules_agree_with_the_references():
+    """vec.scm of the reference, vec.scm of the repo's Scheme host and host/vec.py on the same operands: sum / diff / prod
+    (variadic), scale, quot, dot, length, sq-len, unit, cross - equal to the last bit."""
+    rs = np.random.RandomState(8)
+    vs = [tuple(float(x) for x in rs.normal(size=3) * 3) for _ in range(12)]
+    ops = [("sum", 3), ("diff", 3), ("prod", 3), ("sum", 2), ("diff", 2), ("quot", 2), ("dot", 2), ("cross", 2), ("length", 1), ("sq-len", 1), ("unit", 1)]
+
+    def run(load_path):
+        def work():
+            it = interpreter(load_path)
+            it.require("vec")
+            out = []
+            for name, n in ops:
+                for k in range(0, 12 - n + 1, n):
+                    r = it.call("vec", name, *[it.call("vec", "vec3", *vs[k + j]) for j in range(n)])
+                    out.append([float(x) for x in r] if isinstance(r, list) else float(r))
+            out.append([float(x) for x in it.call("vec", "scale", it.call("vec", "vec3", *vs[0]), 2.5)])
+            return out
+        return in_big_stack(work)
+    ref, mine = run([REFERENCE]), run([HOST])
+    assert ref == mine
+    py = []
+    fn = {"sum": v.sum, "diff": v.diff, "prod": v.prod, "dot": v.dot, "cross": v.cross, "length": v.length, "sq-len": v.sq_len, "unit": v.unit,
+          "quot": lambda a, b: (a[0] / b[0], a[1] / b[1], a[2] / b[2])}
+    for name, n in ops:
+        for k in range(0, 12 - n + 1, n):
+            r = fn[name](*[vs[k + j] for j in range(n)])
+            py.append(list(r) if isinstance(r, tuple) else float(r))
+    py.append(list(v.scale(vs[0], 2.5)))
+    assert py == ref

@@ -101,7 +101,10 @@ typedef struct {
   float t_min;                 /* main.scm:104: 0.001                                    */
   int32_t wave_spp;            /* path-queue capacity in samples/pixel; 0 = auto (64 Mi paths) */
   int32_t estimator;           /* SRT_EST_*                                              */
-  int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately (slower); [1] = 1: no CUDA graph */
+  int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately and count rays per bounce (slower);
+                                * [1] = 1: no CUDA graph; [2] = 1: rgb_sum of srt_render_host / _multi is write-only
+                                * (the frame starts from zero: skips the upload of the running sum);
+                                * [3] = 1: drain through the wavefront instead of the one-launch tail kernel (A/B, tests) */
 } SrtRenderParams;
 
 typedef struct {
@@ -112,10 +115,11 @@ typedef struct {
   int32_t kernel_launches;     /* kernels launched by this call                          */
   int32_t waves;               /* extend/shade/regen iterations of the streaming wavefront */
   int32_t bvh_nodes, bvh_depth;
-  uint64_t rays_per_bounce[8]; /* reserved (not tracked by the streaming wavefront)      */
+  uint64_t rays_per_bounce[8]; /* closest-hit queries by bounce 0..6 and >= 7; only when params.reserved[0]==1 */
   float ms_extend, ms_shade;   /* per-kernel device time, only when params.reserved[0]==1 */
   int32_t extend_launches;     /* extend launches timed for ms_extend                    */
-  int32_t pad;
+  int32_t tail_runs;           /* times the one-launch drain kernel finished the queue   */
+  uint64_t nonfinite;          /* NaN / Inf radiance contributions dropped (0 inside the reference's domain) */
 } SrtStats;
 
 /* 64-byte node of the LBVH as the traversal kernel reads it: the two child boxes as centre and
@@ -129,7 +133,16 @@ typedef struct { int32_t prim; int32_t material; float t, u, v; float p[3], n[3]
 typedef struct SrtScene SrtScene;
 
 int srt_device_count(void);
-int srt_init(int device);                         /* selects the device; fails without sm_100  */
+int srt_init(int device);                         /* selects the device new scenes are created on; fails without sm_100.
+                                                   * Every scene remembers its device; several scenes on several GPUs may coexist. */
+/* One process, n GPUs (the caller this path replaces, (trace-all scene k) main.scm:471-491, is one
+ * process): devices 0..n-1 (0 = all visible), peer access from the first device, one NCCL communicator
+ * per device (ncclCommInitAll; libnccl is dlopen'ed - absent NCCL, or SRT_MULTI_REDUCE=p2p, selects the
+ * library's own peer-read reduce kernel).  Scenes created afterwards (until the next plain srt_init) live
+ * on the first device; srt_scene_commit() commits one replica of them per GPU and srt_render_multi() uses them all. */
+int srt_init_multi(int n_gpus);
+int srt_multi_device_count(void);
+int srt_multi_reduce_mode(int32_t* nccl_version); /* 0 = ncclReduce, 1 = peer-read kernel */
 const char* srt_last_error(void);
 void srt_shutdown(void);
 int srt_measure_fp32_peak(float* tflops);         /* FFMA microbenchmark: the FP32 roofline denominator */
@@ -165,6 +178,20 @@ int srt_trace_batch(SrtScene*, const SrtRay* rays, int n, float t_min, float t_m
  * a device pointer on the scene's device (multi-GPU reduce is done by the caller on it). */
 int srt_render_host(SrtScene*, const SrtRenderParams*, float* rgb_sum, SrtStats* stats);
 int srt_render_device(SrtScene*, const SrtRenderParams*, float* d_rgb_sum, SrtStats* stats);
+
+/* The same over the n GPUs of srt_init_multi from this one process: the sample range is split into n
+ * contiguous ranges, the per-GPU 64-bit fixed-point accumulators are combined on the first GPU with ONE
+ * reduce over NVLink (exact integer sum: the frame is bit-identical to the single-GPU frame), then
+ * rgb_sum += frame and image = gamma + 8-bit of rgb_sum / spp_end.  rgb_sum (W*H*3 floats) and image
+ * (W*H*3 bytes) are HOST buffers, either may be NULL.  params.reserved[2] == 1: rgb_sum is write-only. */
+int srt_render_multi(SrtScene*, const SrtRenderParams*, float* rgb_sum, uint8_t* image, SrtStats* stats);
+
+/* Progressive passes (main.scm:452-469 trace-line, :493-503 display): the running sum *raw-data* stays
+ * RESIDENT on the device between calls.  One call adds samples [spp_begin, spp_end) and returns only the
+ * 8-bit frame (host, W*H*3) of the spp_end samples so far; spp_begin == 0 starts a new accumulation,
+ * otherwise spp_begin must equal the previous call's spp_end.  _read copies the running sum out. */
+int srt_progressive_step(SrtScene*, const SrtRenderParams*, uint8_t* image, SrtStats* stats);
+int srt_progressive_read(SrtScene*, float* rgb_sum, int32_t* spp);
 
 /* main.scm:123-124,481-487 correct-gamma + quantise; :439-450 save-as-ppm */
 int srt_resolve_device(const float* d_rgb_sum, int width, int height, int spp, uint8_t* d_image);

@@ -7,18 +7,46 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <thread>
+#include <mutex>
+#include <dlfcn.h>
 #include "srt_host.h"
 
 namespace {
 
 thread_local std::string g_err;
-int g_device = -1, g_sm_count = 0;
+// g_device = the device srt_init selected: new scenes are created on it.  Every scene remembers its
+// own device and every entry point makes that device current, so several scenes on several GPUs can
+// live in one process (srt_render_multi drives one replica per GPU from one thread each).
+int g_device = -1;
+bool g_create_multi = false;   // the last init call was srt_init_multi: scenes created now are replicated on every GPU
+struct DeviceInfo { bool ready = false; int sm_count = 0; };
+DeviceInfo g_dev[SRT_MAX_DEVICES];
+std::mutex g_dev_mu;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
   g_err = buf; return code;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SRT_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+int ensure_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(SRT_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)"); }
+  if (device < 0 || device >= n || device >= SRT_MAX_DEVICES) return fail(SRT_ERR_ARG, "device %d out of range (%d visible)", device, n);
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (!g_dev[device].ready) {
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SRT_ERR_NO_DEVICE, "device %d is sm_%d%d; libsrt is built for sm_100a only", device, prop.major, prop.minor);
+    g_dev[device].sm_count = prop.multiProcessorCount; g_dev[device].ready = true;
+  }
+  return 0;
+}
+struct EventPair {     // timing events that do not leak on the early-return error paths
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
 
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -32,6 +60,50 @@ template <class T> struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
+
+
+// ---- multi-GPU state (srt_init_multi) -------------------------------------------------------------
+// One process drives n GPUs (the caller the path replaces, (trace-all scene k) main.scm:471-491, is
+// one process).  NCCL is loaded with dlopen so that libsrt.so has no link-time dependency on it and
+// single-GPU hosts never need it; types / enums below mirror nccl.h (ncclUint64 = 5, ncclSum = 0).
+typedef struct ncclComm* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, NcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+  int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr;
+};
+struct Multi {
+  int n = 0; int devs[SRT_MAX_DEVICES];
+  bool peer[SRT_MAX_DEVICES];            // root (devs[0]) can read device r's memory directly
+  NcclApi nccl; NcclComm comms[SRT_MAX_DEVICES]; bool have_nccl = false; int nccl_version = 0;
+  int reduce_mode = 0;                   // 0 = NCCL reduce of the integer accumulators, 1 = fused peer-read kernel on the root
+};
+Multi g_multi;
+std::mutex g_multi_mu;
+
+bool nccl_load(NcclApi& a) {
+  if (a.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) { a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (a.lib) break; }
+  if (!a.lib) return false;
+  a.CommInitAll = (int (*)(NcclComm*, int, const int*))dlsym(a.lib, "ncclCommInitAll");
+  a.CommDestroy = (int (*)(NcclComm))dlsym(a.lib, "ncclCommDestroy");
+  a.Reduce = (int (*)(const void*, void*, size_t, int, int, int, NcclComm, cudaStream_t))dlsym(a.lib, "ncclReduce");
+  a.GetErrorString = (const char* (*)(int))dlsym(a.lib, "ncclGetErrorString");
+  a.GetVersion = (int (*)(int*))dlsym(a.lib, "ncclGetVersion");
+  a.GroupStart = (int (*)())dlsym(a.lib, "ncclGroupStart"); a.GroupEnd = (int (*)())dlsym(a.lib, "ncclGroupEnd");
+  if (!a.CommInitAll || !a.CommDestroy || !a.Reduce || !a.GroupStart || !a.GroupEnd) { dlclose(a.lib); a = NcclApi(); return false; }
+  return true;
+}
+void multi_shutdown() {
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  if (g_multi.have_nccl) for (int r = 0; r < g_multi.n; ++r) if (g_multi.comms[r]) g_multi.nccl.CommDestroy(g_multi.comms[r]);
+  g_multi.have_nccl = false; g_multi.n = 0;
+}
 
 }  // namespace
 
@@ -54,12 +126,23 @@ struct SrtScene {
   WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
   void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   cudaStream_t work = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // graph capture needs a non-legacy stream
-  DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host
+  DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host / srt_render_multi
+  DevBuf<uint8_t> d_image;   // 8-bit frame of srt_render_multi / srt_progressive_step
+  DevBuf<float> d_prog; int prog_w = 0, prog_h = 0, prog_spp = 0;   // device-resident running sum of the progressive path (*raw-data*, main.scm:430)
+  DevBuf<unsigned long long> d_stage;   // multi-GPU: peers' accumulators staged on the root when peer access is unavailable
+  GraphCache gcache;         // executable graph of one iteration batch (wavefront.cu)
+  int device = 0;            // the CUDA device this scene lives on
+  bool multi = false;        // created under srt_init_multi: commit keeps one replica per GPU, srt_render_multi uses them
+  unsigned long long version = 0;       // bumped by every set_*; replicas re-commit when it differs
+  std::vector<SrtScene*> replicas;      // srt_render_multi: one copy of the scene per extra GPU (owned)
+  unsigned long long replica_version = ~0ull;
+  cudaEvent_t ev_done = nullptr;        // multi-GPU: "this replica's accumulator is complete"
   DScene ds; DCamera dcam;
 };
 
 static void fill_dscene(SrtScene* s) {
   DScene& d = s->ds;
+  std::memset(&d, 0, sizeof(d));             // padding too: the bytes are part of the graph-cache key
   d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_items = s->n_items;
   d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
@@ -73,8 +156,9 @@ static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
     for (int g = 0; g < 2; ++g) { CK(s->w_ro[g].ensure(paths)); CK(s->w_rd[g].ensure(paths)); CK(s->w_st[g].ensure(paths)); }
     CK(s->w_hit.ensure(paths));
     for (int g = 0; g < 2; ++g) { W.ray_o[g] = s->w_ro[g].p; W.ray_d[g] = s->w_rd[g].p; W.state[g] = s->w_st[g].p; }
-    W.hit = s->w_hit.p; W.capacity = paths;
+      W.hit = s->w_hit.p; W.capacity = paths;
   }
+  W.graph = &s->gcache;
   if (npix) { CK(s->w_accum.ensure(3 * npix)); W.accum64 = s->w_accum.p; }
   if (!W.ctrl) { CK(s->w_ctrl.ensure(srt_wave_ctrl_bytes())); W.ctrl = s->w_ctrl.p; }
   if (!s->h_ctrl) {
@@ -88,12 +172,18 @@ static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
 }
 
 static RenderLaunch make_launch(SrtScene* s, const SrtRenderParams* p) {
-  RenderLaunch L; L.sc = s->ds; L.cam = s->dcam; if (p) L.p = *p; else std::memset(&L.p, 0, sizeof(L.p));
-  L.sm_count = g_sm_count; L.extend_smem = srt_extend_smem_bytes(s->ds);
+  RenderLaunch L; std::memset(&L, 0, sizeof(L));
+  L.sc = s->ds; L.cam = s->dcam; if (p) L.p = *p;
+  L.device = s->device; L.sm_count = g_dev[s->device].sm_count; L.extend_smem = srt_extend_smem_bytes(s->ds);
   L.bvh_in_smem = L.extend_smem <= (size_t)200 * 1024;
-  L.prim_mask = 0; for (const SrtPrim& q : s->prims) L.prim_mask |= 1 << q.type;
+  L.prim_mask = 0;
+  for (const SrtPrim& q : s->prims) {
+    L.prim_mask |= 1 << q.type;
+    if (q.xform >= 0 && q.type <= SRT_PRIM_MOVING_SPHERE) L.prim_mask |= SRT_MASK_XF_SPHERE;
+  }
   return L;
 }
+#define USE_DEVICE(s) CK(cudaSetDevice((s)->device))
 
 extern "C" {
 
@@ -102,29 +192,43 @@ const char* srt_last_error(void) { return g_err.c_str(); }
 int srt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 int srt_init(int device) {
-  int n = srt_device_count();
-  if (n <= 0) return fail(SRT_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
-  if (device < 0 || device >= n) return fail(SRT_ERR_ARG, "device %d out of range (%d visible)", device, n);
-  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(SRT_ERR_NO_DEVICE, "device %d is sm_%d%d; libsrt is built for sm_100a only", device, prop.major, prop.minor);
+  if (int rc = ensure_device(device)) return rc;
   CK(cudaSetDevice(device));
-  g_device = device; g_sm_count = prop.multiProcessorCount;
+  g_device = device; g_create_multi = false;
   return 0;
 }
-void srt_shutdown(void) { g_device = -1; }
+void srt_shutdown(void) { multi_shutdown(); g_device = -1; }
 
 int srt_measure_fp32_peak(float* tflops) {
   if (!tflops) return fail(SRT_ERR_ARG, "measure_fp32_peak: null argument");
   if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded");
-  *tflops = srt_measure_fma_tflops(g_sm_count, 0);
+  CK(cudaSetDevice(g_device));
+  *tflops = srt_measure_fma_tflops(g_dev[g_device].sm_count, 0);
   CK(cudaGetLastError());
   return 0;
 }
 
-SrtScene* srt_scene_create(void) { SrtScene* s = new (std::nothrow) SrtScene(); if (!s) g_err = "out of host memory"; return s; }
+static SrtScene* scene_create_on(int device) {
+  SrtScene* s = new (std::nothrow) SrtScene();
+  if (!s) { g_err = "out of host memory"; return nullptr; }
+  s->device = device;
+  return s;
+}
+SrtScene* srt_scene_create(void) {
+  if (g_device < 0) { g_err = "srt_init() has not succeeded (no CPU fallback)"; return nullptr; }
+  SrtScene* s = scene_create_on(g_device);
+  if (s) s->multi = g_create_multi && g_multi.n > 1;
+  return s;
+}
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
+  for (SrtScene* r : s->replicas) srt_scene_destroy(r);
+  s->replicas.clear();
+  cudaSetDevice(s->device);
+  srt_graph_cache_release(s->gcache);
+  s->d_image.release(); s->d_prog.release(); s->d_stage.release();
+  if (s->ev_done) cudaEventDestroy(s->ev_done);
   s->d_tree_area.release(); s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
@@ -142,19 +246,19 @@ void srt_scene_destroy(SrtScene* s) {
 int srt_scene_set_prims(SrtScene* s, const SrtPrim* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_prims: bad argument");
   for (int i = 0; i < n; ++i) if (p[i].type < SRT_PRIM_SPHERE || p[i].type > SRT_PRIM_KLEIN) return fail(SRT_ERR_ARG, "prim %d: unknown type %d", i, p[i].type);
-  s->prims.assign(p, p + n); s->committed = false; return 0;
+  s->prims.assign(p, p + n); s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_xforms(SrtScene* s, const SrtXform* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_xforms: bad argument");
-  s->xforms.assign(p, p + n); s->committed = false; return 0;
+  s->xforms.assign(p, p + n); s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_materials(SrtScene* s, const SrtMaterial* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_materials: bad argument");
-  s->mats.assign(p, p + n); s->committed = false; return 0;
+  s->mats.assign(p, p + n); s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_textures(SrtScene* s, const SrtTexture* p, int n) {
   if (!s || n < 0 || (n && !p)) return fail(SRT_ERR_ARG, "set_textures: bad argument");
-  s->texs.assign(p, p + n); s->committed = false; return 0;
+  s->texs.assign(p, p + n); s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_images(SrtScene* s, const uint8_t* texels, const int32_t* dims, int n) {
   if (!s || n < 0 || (n && (!texels || !dims))) return fail(SRT_ERR_ARG, "set_images: bad argument");
@@ -166,32 +270,33 @@ int srt_scene_set_images(SrtScene* s, const uint8_t* texels, const int32_t* dims
   }
   s->imgs.resize(n);
   for (int i = 0; i < n; ++i) s->imgs[i] = make_int4(dims[3 * i], dims[3 * i + 1], dims[3 * i + 2], 0);
-  s->img_texels.assign(texels, texels + total); s->committed = false; return 0;
+  s->img_texels.assign(texels, texels + total); s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_perlin(SrtScene* s, const float* ranvec768, const int32_t* px, const int32_t* py, const int32_t* pz) {
   if (!s || !ranvec768 || !px || !py || !pz) return fail(SRT_ERR_ARG, "set_perlin: bad argument");
   std::memcpy(s->ranvec, ranvec768, sizeof(s->ranvec));
   std::memcpy(s->perm[0], px, 1024); std::memcpy(s->perm[1], py, 1024); std::memcpy(s->perm[2], pz, 1024);
-  s->has_perlin = true; s->committed = false; return 0;
+  s->has_perlin = true; s->committed = false; ++s->version; return 0;
 }
 int srt_scene_set_camera(SrtScene* s, const SrtCamera* c) {
   if (!s || !c) return fail(SRT_ERR_ARG, "set_camera: bad argument");
-  s->cam = *c; s->has_cam = true; s->committed = false; return 0;
+  s->cam = *c; s->has_cam = true; s->committed = false; ++s->version; return 0;
 }
 
 int srt_scene_set_patches(SrtScene* s, const float* cp48, int n) {
   if (!s || n < 0 || (n && !cp48)) return fail(SRT_ERR_ARG, "set_patches: bad argument");
-  s->patches.assign(cp48, cp48 + 48 * (size_t)n); s->committed = false; return 0;
+  s->patches.assign(cp48, cp48 + 48 * (size_t)n); s->committed = false; ++s->version; return 0;
 }
 
 int srt_scene_set_lights(SrtScene* s, const int32_t* prim_ids, int n) {
   if (!s || n < 0 || (n && !prim_ids)) return fail(SRT_ERR_ARG, "set_lights: bad argument");
-  s->lights.assign(prim_ids, prim_ids + n); s->committed = false; return 0;
+  s->lights.assign(prim_ids, prim_ids + n); s->committed = false; ++s->version; return 0;
 }
 
-int srt_scene_commit(SrtScene* s) {
+static int commit_impl(SrtScene* s) {
   if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
-  if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded");
+  if (int rc = ensure_device(s->device)) return rc;
+  USE_DEVICE(s);
   const int n = (int)s->prims.size();
   // validate indices (the kernels trust the tables)
   for (int i = 0; i < n; ++i) {
@@ -199,6 +304,9 @@ int srt_scene_commit(SrtScene* s) {
     if (p.material < 0 || p.material >= (int)s->mats.size()) return fail(SRT_ERR_ARG, "prim %d: material %d out of range", i, p.material);
     if (p.xform >= (int)s->xforms.size()) return fail(SRT_ERR_ARG, "prim %d: xform %d out of range", i, p.xform);
     if (p.type == SRT_PRIM_PATCH && ((int)p.p[0] < 0 || (size_t)p.p[0] >= s->patches.size() / 48 || p.xform >= 0)) return fail(SRT_ERR_ARG, "prim %d: bad patch index / instanced patch", i);
+    // instance transforms (geometry.scm:465-543) are applied to rects (box faces) and spheres; a curve,
+    // Klein set or medium under translate / rotate-y would be intersected untransformed: refuse it
+    if (p.xform >= 0 && p.type > SRT_PRIM_YZ_RECT) return fail(SRT_ERR_ARG, "prim %d: type %d cannot be instanced (translate / rotate-y apply to spheres, rects and boxes)", i, p.type);
   }
   // surfaces first, medium boundaries (SRT_PRIM_FLAG_BOUNDARY) as a suffix
   int ns = 0; while (ns < n && !(s->prims[ns].flags & SRT_PRIM_FLAG_BOUNDARY)) ++ns;
@@ -229,10 +337,12 @@ int srt_scene_commit(SrtScene* s) {
     int id = s->lights[i];
     if (id < 0 || id >= n) return fail(SRT_ERR_ARG, "light %zu: primitive %d out of range", i, id);
     const SrtPrim& p = s->prims[id];
-    if (p.xform >= 0 || p.type == SRT_PRIM_MOVING_SPHERE || p.type == SRT_PRIM_BEZIER) return fail(SRT_ERR_ARG, "light %zu: only un-instanced spheres and rects can be sampled", i);
+    const bool shape_ok = p.type == SRT_PRIM_SPHERE || (p.type >= SRT_PRIM_XY_RECT && p.type <= SRT_PRIM_YZ_RECT);
+    if (!shape_ok || p.xform >= 0 || (p.flags & SRT_PRIM_FLAG_BOUNDARY)) return fail(SRT_ERR_ARG, "light %zu: only un-instanced spheres and rects can be sampled (pdf.scm:28-32)", i);
   }
   cudaStream_t stream = 0;
-  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  EventPair tm; CK(tm.create());
+  cudaEvent_t e0 = tm.a, e1 = tm.b;
   CK(cudaEventRecord(e0, stream));
   {
     size_t np16 = s->patches.size() / 3;
@@ -417,16 +527,173 @@ int srt_scene_commit(SrtScene* s) {
   CK(cudaEventRecord(e1, stream));
   CK(cudaEventSynchronize(e1));
   CK(cudaEventElapsedTime(&s->ms_commit, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   s->bvh_depth = depth; s->ds.bvh_depth = depth;
   if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level traversal bound", depth);
   s->committed = true;
   return 0;
 }
 
+static int check_params(const SrtRenderParams* p);
+static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats);
+
+// host tables of `src` -> `dst` (a replica of the scene on another GPU)
+static void copy_tables(SrtScene* dst, const SrtScene* src) {
+  dst->prims = src->prims; dst->xforms = src->xforms; dst->mats = src->mats; dst->texs = src->texs;
+  dst->img_texels = src->img_texels; dst->imgs = src->imgs; dst->lights = src->lights; dst->patches = src->patches;
+  std::memcpy(dst->ranvec, src->ranvec, sizeof(src->ranvec)); std::memcpy(dst->perm, src->perm, sizeof(src->perm));
+  dst->has_perlin = src->has_perlin; dst->cam = src->cam; dst->has_cam = src->has_cam;
+  dst->committed = false;
+}
+
+// H2D + GPU LBVH build.  After srt_init_multi(n) a scene on the first device is committed on every
+// GPU: the replicas are built concurrently (one host thread per device) while the caller's thread
+// builds the primary.
+int srt_scene_commit(SrtScene* s) {
+  if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
+  const int n = g_multi.n;
+  if (!s->multi || n <= 1 || s->device != g_multi.devs[0]) return commit_impl(s);
+  while ((int)s->replicas.size() < n - 1) {
+    SrtScene* r = scene_create_on(g_multi.devs[s->replicas.size() + 1]);
+    if (!r) return fail(SRT_ERR_CUDA, "commit: cannot create the replica for device %d", g_multi.devs[s->replicas.size() + 1]);
+    s->replicas.push_back(r);
+  }
+  std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
+  std::vector<std::thread> th;
+  for (int r = 1; r < n; ++r) {
+    copy_tables(s->replicas[r - 1], s);
+    th.emplace_back([&, r] { rc[r] = commit_impl(s->replicas[r - 1]); if (rc[r]) msg[r] = g_err; });
+  }
+  rc[0] = commit_impl(s);
+  for (std::thread& t : th) t.join();
+  if (rc[0]) return rc[0];
+  for (int r = 1; r < n; ++r) if (rc[r]) return fail(rc[r], "commit on device %d: %s", g_multi.devs[r], msg[r].c_str());
+  s->replica_version = s->version;
+  return 0;
+}
+
+// ---- multi-GPU behind the boundary -----------------------------------------------
+int srt_init_multi(int n_gpus) {
+  const int avail = srt_device_count();
+  if (avail <= 0) return fail(SRT_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  const int n = n_gpus <= 0 ? avail : n_gpus;
+  if (n > avail || n > SRT_MAX_DEVICES) return fail(SRT_ERR_ARG, "init_multi: %d GPUs requested, %d visible (max %d)", n, avail, SRT_MAX_DEVICES);
+  if (g_multi.n == n) { CK(cudaSetDevice(g_multi.devs[0])); g_device = g_multi.devs[0]; g_create_multi = true; return 0; }
+  multi_shutdown();
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  Multi& M = g_multi;
+  for (int r = 0; r < n; ++r) { M.devs[r] = r; M.peer[r] = false; M.comms[r] = nullptr; if (int rc = ensure_device(r)) return rc; }
+  CK(cudaSetDevice(M.devs[0]));
+  for (int r = 1; r < n; ++r) {               // the root reads the peers' accumulators over NVLink
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, M.devs[0], M.devs[r]) == cudaSuccess && can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(M.devs[r], 0);
+      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) M.peer[r] = true;
+    }
+    cudaGetLastError();
+  }
+  const char* mode = getenv("SRT_MULTI_REDUCE");
+  M.reduce_mode = (mode && std::strcmp(mode, "p2p") == 0) ? 1 : 0;
+  M.have_nccl = false;
+  if (n > 1 && M.reduce_mode == 0 && nccl_load(M.nccl)) {
+    int e = M.nccl.CommInitAll(M.comms, n, M.devs);
+    if (e == 0) { M.have_nccl = true; if (M.nccl.GetVersion) M.nccl.GetVersion(&M.nccl_version); }
+    else { for (int r = 0; r < n; ++r) M.comms[r] = nullptr; cudaGetLastError(); }
+  }
+  if (!M.have_nccl) M.reduce_mode = 1;        // NCCL absent: the root's fused peer-read kernel does the reduce
+  CK(cudaSetDevice(M.devs[0]));
+  g_device = M.devs[0]; M.n = n; g_create_multi = true;
+  return 0;
+}
+int srt_multi_device_count(void) { return g_multi.n; }
+/* 0 = one NCCL reduce of the accumulators, 1 = the root's fused peer-read kernel; NCCL version as an int (e.g. 22703) */
+int srt_multi_reduce_mode(int32_t* nccl_version) { if (nccl_version) *nccl_version = g_multi.have_nccl ? g_multi.nccl_version : 0; return g_multi.reduce_mode; }
+
+// (trace-all scene k) over n GPUs from ONE process: the frame's samples [spp_begin, spp_end) are
+// split into n contiguous sample ranges, one per GPU (one host thread each drives that GPU's
+// wavefront loop); the per-GPU 64-bit fixed-point accumulators are combined on the first GPU - one
+// ncclReduce(uint64, sum) over NVLink, or the root's own peer-read kernel - which is exact, so the
+// frame is BIT-IDENTICAL to the single-GPU frame; then rgb_sum += frame, gamma + 8-bit (main.scm:481-487).
+// rgb_sum / image are HOST buffers (either may be NULL); reserved[2] == 1: rgb_sum is write-only.
+int srt_render_multi(SrtScene* s, const SrtRenderParams* p, float* rgb_sum, uint8_t* image, SrtStats* stats) {
+  Multi& M = g_multi;
+  if (M.n < 1) return fail(SRT_ERR_ARG, "render_multi: srt_init_multi() has not succeeded");
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (!p) return fail(SRT_ERR_ARG, "render_multi: null argument");
+  if (int rc = check_params(p)) return rc;
+  if (p->spp_end <= 0) return fail(SRT_ERR_ARG, "render_multi: spp_end must be positive");
+  if (s->multi && s->device != M.devs[0]) return fail(SRT_ERR_ARG, "render_multi: the scene lives on device %d, not on the first device of srt_init_multi (create it after that call)", s->device);
+  const int n = s->multi ? M.n : 1;                 // a scene created under plain srt_init renders on its own GPU only
+  if (n > 1 && ((int)s->replicas.size() != n - 1 || s->replica_version != s->version)) return fail(SRT_ERR_NOT_COMMITTED, "render_multi: commit the scene after srt_init_multi()");
+  USE_DEVICE(s);
+  const size_t npix = (size_t)p->width * p->height, n3 = 3 * npix;
+  const int spp = p->spp_end - p->spp_begin;
+  CK(s->d_accum.ensure(n3));
+  if (!rgb_sum || p->reserved[2] == 1) CK(cudaMemsetAsync(s->d_accum.p, 0, sizeof(float) * n3, 0));
+  else CK(cudaMemcpyAsync(s->d_accum.p, rgb_sum, sizeof(float) * n3, cudaMemcpyHostToDevice, 0));
+  std::vector<SrtStats> st(n); std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
+  auto work = [&](int r) {
+    SrtScene* sc = r == 0 ? s : s->replicas[r - 1];
+    SrtRenderParams q = *p;
+    q.spp_begin = p->spp_begin + (int)((long long)r * spp / n); q.spp_end = p->spp_begin + (int)((long long)(r + 1) * spp / n);
+    rc[r] = render_impl(sc, &q, nullptr, &st[r]);
+    if (rc[r]) msg[r] = g_err;
+  };
+  std::vector<std::thread> th;
+  for (int r = 1; r < n; ++r) th.emplace_back(work, r);
+  work(0);
+  for (std::thread& t : th) t.join();
+  for (int r = 0; r < n; ++r) if (rc[r]) return fail(rc[r], "render on device %d: %s", M.devs[r], msg[r].c_str());
+  // every rank's accumulator is complete (render_impl returns synchronised).  Combine on the root.
+  USE_DEVICE(s);
+  int launches = 0;
+  if (image) CK(s->d_image.ensure(n3));
+  if (n > 1 && M.reduce_mode == 0) {
+    if (M.nccl.GroupStart() != 0) return fail(SRT_ERR_CUDA, "render_multi: ncclGroupStart failed");
+    int e = 0;
+    for (int r = 0; r < n && e == 0; ++r) {
+      SrtScene* sc = r == 0 ? s : s->replicas[r - 1];
+      e = M.nccl.Reduce(sc->wb.accum64, sc->wb.accum64, n3, 5 /* ncclUint64 */, 0 /* ncclSum */, 0, M.comms[r], sc->work);
+    }
+    const int e2 = M.nccl.GroupEnd();
+    if (e || e2) return fail(SRT_ERR_CUDA, "render_multi: ncclReduce failed: %s", M.nccl.GetErrorString ? M.nccl.GetErrorString(e ? e : e2) : "?");
+    USE_DEVICE(s);
+    CK(cudaStreamSynchronize(s->work));
+    launches += n;
+    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->wb.accum64, nullptr, 0, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
+  } else {
+    const unsigned long long* peers[SRT_MAX_DEVICES]; int np = 0;
+    for (int r = 1; r < n; ++r) {
+      SrtScene* sc = s->replicas[r - 1];
+      if (M.peer[r]) peers[np++] = sc->wb.accum64;
+      else {                                   // no peer access: stage the accumulator on the root first
+        CK(s->d_stage.ensure((size_t)(n - 1) * n3));
+        CK(cudaMemcpyPeerAsync(s->d_stage.p + (size_t)(r - 1) * n3, s->device, sc->wb.accum64, sc->device, sizeof(unsigned long long) * n3, 0));
+        peers[np++] = s->d_stage.p + (size_t)(r - 1) * n3;
+      }
+    }
+    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->wb.accum64, peers, np, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
+  }
+  CK(cudaGetLastError());
+  if (rgb_sum) CK(cudaMemcpyAsync(rgb_sum, s->d_accum.p, sizeof(float) * n3, cudaMemcpyDeviceToHost, 0));
+  if (image) CK(cudaMemcpyAsync(image, s->d_image.p, n3, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    for (int r = 0; r < n; ++r) {
+      stats->rays += st[r].rays; stats->paths += st[r].paths; stats->kernel_launches += st[r].kernel_launches; stats->nonfinite += st[r].nonfinite;
+      stats->tail_runs += st[r].tail_runs;
+      stats->ms_total = std::max(stats->ms_total, st[r].ms_total); stats->waves = std::max(stats->waves, st[r].waves);
+      for (int k = 0; k < 8; ++k) stats->rays_per_bounce[k] += st[r].rays_per_bounce[k];
+    }
+    stats->kernel_launches += launches; stats->ms_commit = s->ms_commit; stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth;
+  }
+  return 0;
+}
+
 int srt_bvh_node_count(SrtScene* s) { return (s && s->committed) ? s->n_nodes : 0; }
 int srt_bvh_readback(SrtScene* s, SrtBvhNode* nodes, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   if (cap < s->n_nodes || !nodes) return fail(SRT_ERR_ARG, "bvh_readback: capacity %d < %d nodes", cap, s->n_nodes);
   CK(cudaMemcpy(nodes, s->d_nodes.p, sizeof(SrtBvhNode) * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
   return 0;
@@ -441,6 +708,7 @@ int srt_bvh_items_readback(SrtScene* s, int32_t* item_prim, int cap, int32_t* gl
 }
 int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   int n = s->n_items;
   if (cap < n) return fail(SRT_ERR_ARG, "bvh_keys_readback: capacity too small");
   if (n) {
@@ -451,6 +719,7 @@ int srt_bvh_keys_readback(SrtScene* s, uint64_t* keys, int32_t* order, int cap) 
 }
 int srt_prim_bounds_readback(SrtScene* s, float* aabbs6, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   int n = s->n_surf;
   if (cap < n) return fail(SRT_ERR_ARG, "prim_bounds_readback: capacity too small");
   if (n) CK(cudaMemcpy(aabbs6, s->d_aabb.p, sizeof(float) * 6 * (size_t)n, cudaMemcpyDeviceToHost));
@@ -459,6 +728,7 @@ int srt_prim_bounds_readback(SrtScene* s, float* aabbs6, int cap) {
 
 int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t_max, SrtHit* out) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   if (n < 0 || (n && (!rays || !out))) return fail(SRT_ERR_ARG, "trace_batch: bad argument");
   if (n == 0) return 0;
   if (int rc = ensure_wave(s, (size_t)n, 0)) return rc;
@@ -477,25 +747,40 @@ int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t
   return 0;
 }
 
+static int check_params(const SrtRenderParams* p) {
+  if (p->width <= 0 || p->height <= 0 || p->spp_begin < 0 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4096)
+    return fail(SRT_ERR_ARG, "render: bad parameters (%dx%d, spp [%d,%d), depth %d)", p->width, p->height, p->spp_begin, p->spp_end, p->max_depth);
+  if (p->max_depth > 4095 || p->spp_end > (1 << 20)) return fail(SRT_ERR_ARG, "render: max_depth <= 4095 and spp_end <= 2^20 (packed path state)");
+  if (p->estimator != SRT_EST_REFERENCE && p->estimator != SRT_EST_MIXTURE) return fail(SRT_ERR_ARG, "render: unknown estimator %d", p->estimator);
+  if (p->sky != SRT_SKY_GRADIENT && p->sky != SRT_SKY_BLACK) return fail(SRT_ERR_ARG, "render: unknown sky %d", p->sky);
+  if ((size_t)p->width * (size_t)p->height > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: frame of %d x %d pixels too large", p->width, p->height);
+  return 0;
+}
+
+// Renders samples [spp_begin, spp_end) on the scene's device.  d_rgb_sum != nullptr: the frame is
+// added to that float buffer; nullptr: it is left in the scene's 64-bit accumulator (multi-GPU).
 static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
-  if (!p || !d_rgb_sum) return fail(SRT_ERR_ARG, "render: null argument");
-  if (p->width <= 0 || p->height <= 0 || p->spp_end < p->spp_begin || p->max_depth < 0 || p->max_depth > 4096)
-    return fail(SRT_ERR_ARG, "render: bad parameters (%dx%d, spp [%d,%d), depth %d)", p->width, p->height, p->spp_begin, p->spp_end, p->max_depth);
+  if (!p) return fail(SRT_ERR_ARG, "render: null argument");
+  if (int rc = check_params(p)) return rc;
   if (!s->has_cam) return fail(SRT_ERR_ARG, "render: no camera set");
+  USE_DEVICE(s);
   const size_t npix = (size_t)p->width * p->height;
   const int spp = p->spp_end - p->spp_begin;
   if (stats) std::memset(stats, 0, sizeof(*stats));
-  if (spp == 0) return 0;
-  if (p->max_depth > 4095 || p->spp_end > (1 << 20)) return fail(SRT_ERR_ARG, "render: max_depth <= 4095 and spp_end <= 2^20 (packed path state)");
   // queue sizing: 64 Mi paths in flight (SoA ray/state/hit queues = 112 B/path = 7.5 GB of the 180 GB
   // HBM), never more than the job.  Measured on cfg2: 8 Mi -> 6.94, 64 Mi -> 7.31 Grays/s (fewer
   // iterations, and the depth-50 drain tail weighs less).
   size_t total = npix * (size_t)spp;
   size_t cap = p->wave_spp > 0 ? npix * (size_t)p->wave_spp : (size_t)(64u << 20);
   if (cap > total) cap = total;
+  if (cap < 1) cap = 1;
   if (cap > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: queue of %zu paths too large", cap);
   if (int rc = ensure_wave(s, cap, npix)) return rc;
+  if (spp == 0) {                              // nothing to trace; a multi-GPU rank still owes a zero accumulator
+    if (!d_rgb_sum) { CK(cudaMemsetAsync(s->wb.accum64, 0, sizeof(unsigned long long) * 3 * npix, 0)); CK(cudaStreamSynchronize(0)); }
+    return 0;
+  }
   // The loop runs on the scene's own non-blocking stream (CUDA-graph capture is not allowed on the
   // legacy default stream) but is ordered inside stream 0 by events on both sides, so callers that
   // bracket the call with events / work on the default stream (torch's current stream) stay correct.
@@ -503,17 +788,18 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
   CK(cudaEventRecord(s->ev_in, 0)); CK(cudaStreamWaitEvent(stream, s->ev_in, 0));
   RenderLaunch L = make_launch(s, p);
   const bool profile = p->reserved[0] == 1;
-  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, stream));
+  EventPair tm; CK(tm.create());
+  CK(cudaEventRecord(tm.a, stream));
   WaveBuffers W = s->wb; W.capacity = cap; W.use_graph = p->reserved[1] != 1;
   SrtStats st; std::memset(&st, 0, sizeof(st));
-  srt_wavefront_render(L, W, d_rgb_sum, stream, &st, profile);
-  CK(cudaEventRecord(e1, stream));
+  cudaError_t werr = cudaSuccess;
+  if (srt_wavefront_render(L, W, d_rgb_sum, stream, &st, profile, &werr) < 0)
+    return fail(SRT_ERR_CUDA, "render: the wavefront loop failed: %s", werr == cudaErrorLaunchTimeout ? "the path queue did not drain within its iteration bound" : cudaGetErrorString(werr));
+  CK(cudaEventRecord(tm.b, stream));
   CK(cudaEventRecord(s->ev_out, stream)); CK(cudaStreamWaitEvent(0, s->ev_out, 0));
-  CK(cudaEventSynchronize(e1));
+  CK(cudaEventSynchronize(tm.b));
   CK(cudaGetLastError());
-  float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
   if (stats) {
     *stats = st;
     stats->paths = (uint64_t)total; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
@@ -522,16 +808,56 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
   return 0;
 }
 
-int srt_render_device(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) { return render_impl(s, p, d_rgb_sum, stats); }
+int srt_render_device(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) {
+  if (!d_rgb_sum) return fail(SRT_ERR_ARG, "render_device: null accumulation buffer");
+  return render_impl(s, p, d_rgb_sum, stats);
+}
 
+// params.reserved[2] == 1: rgb_sum is WRITE-ONLY (the frame starts from zero, main.scm:430), which
+// saves the upload of the running sum.
 int srt_render_host(SrtScene* s, const SrtRenderParams* p, float* rgb_sum, SrtStats* stats) {
   if (!s || !p || !rgb_sum) return fail(SRT_ERR_ARG, "render_host: null argument");
   if (p->width <= 0 || p->height <= 0) return fail(SRT_ERR_ARG, "render_host: bad size");
+  USE_DEVICE(s);
   size_t n3 = (size_t)p->width * p->height * 3;
   CK(s->d_accum.ensure(n3));
-  CK(cudaMemcpyAsync(s->d_accum.p, rgb_sum, sizeof(float) * n3, cudaMemcpyHostToDevice, 0));   // running sum in (*raw-data*)
+  if (p->reserved[2] == 1) CK(cudaMemsetAsync(s->d_accum.p, 0, sizeof(float) * n3, 0));
+  else CK(cudaMemcpyAsync(s->d_accum.p, rgb_sum, sizeof(float) * n3, cudaMemcpyHostToDevice, 0));   // running sum in (*raw-data*)
   if (int rc = render_impl(s, p, s->d_accum.p, stats)) return rc;
   CK(cudaMemcpy(rgb_sum, s->d_accum.p, sizeof(float) * n3, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Progressive path (main.scm:452-469 trace-line passes, :493-503 the displayed image): the running
+// sum *raw-data* stays RESIDENT on the device between calls; one call renders samples
+// [spp_begin, spp_end) into it and returns only the 8-bit frame for the spp_end samples so far.
+// spp_begin == 0 (or a change of size) starts a new accumulation.
+int srt_progressive_step(SrtScene* s, const SrtRenderParams* p, uint8_t* image, SrtStats* stats) {
+  if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  if (!p || !image) return fail(SRT_ERR_ARG, "progressive_step: null argument");
+  if (int rc = check_params(p)) return rc;
+  if (p->spp_end <= 0) return fail(SRT_ERR_ARG, "progressive_step: spp_end must be positive");
+  USE_DEVICE(s);
+  const size_t n3 = (size_t)p->width * p->height * 3;
+  if (p->spp_begin == 0 || s->prog_w != p->width || s->prog_h != p->height || !s->d_prog.p) {
+    if (p->spp_begin != 0) return fail(SRT_ERR_ARG, "progressive_step: no running sum of %d x %d to continue from sample %d", p->width, p->height, p->spp_begin);
+    CK(s->d_prog.ensure(n3)); CK(cudaMemsetAsync(s->d_prog.p, 0, sizeof(float) * n3, 0));
+    s->prog_w = p->width; s->prog_h = p->height; s->prog_spp = 0;
+  }
+  if (p->spp_begin != s->prog_spp) return fail(SRT_ERR_ARG, "progressive_step: the running sum holds %d samples, the pass starts at %d", s->prog_spp, p->spp_begin);
+  if (int rc = render_impl(s, p, s->d_prog.p, stats)) return rc;
+  s->prog_spp = p->spp_end;
+  CK(s->d_image.ensure(n3));
+  srt_launch_resolve(s->d_prog.p, (int)n3, p->spp_end, s->d_image.p, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(image, s->d_image.p, n3, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int srt_progressive_read(SrtScene* s, float* rgb_sum, int32_t* spp) {
+  if (!s || !rgb_sum || !s->d_prog.p) return fail(SRT_ERR_ARG, "progressive_read: no running sum");
+  USE_DEVICE(s);
+  CK(cudaMemcpy(rgb_sum, s->d_prog.p, sizeof(float) * 3 * (size_t)s->prog_w * s->prog_h, cudaMemcpyDeviceToHost));
+  if (spp) *spp = s->prog_spp;
   return 0;
 }
 
@@ -544,6 +870,7 @@ int srt_resolve_device(const float* d_rgb_sum, int width, int height, int spp, u
 int srt_resolve_host(const float* rgb_sum, int width, int height, int spp, uint8_t* image) {
   if (!rgb_sum || !image || width <= 0 || height <= 0 || spp <= 0) return fail(SRT_ERR_ARG, "resolve: bad argument");
   if (g_device < 0) return fail(SRT_ERR_NO_DEVICE, "srt_init() has not succeeded (no CPU fallback)");
+  CK(cudaSetDevice(g_device));
   size_t n3 = (size_t)width * height * 3;
   DevBuf<float> d_in; DevBuf<uint8_t> d_out;
   CK(d_in.ensure(n3)); CK(d_out.ensure(n3));
@@ -572,6 +899,7 @@ int srt_save_ppm(const char* path, const uint8_t* image, int width, int height) 
 
 int srt_eval_texture(SrtScene* s, int tex, const float* uvp5, int n, int quirks, float* rgb) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   if (tex < 0 || tex >= (int)s->texs.size() || n < 0 || (n && (!uvp5 || !rgb))) return fail(SRT_ERR_ARG, "eval_texture: bad argument");
   if (n == 0) return 0;
   DevBuf<float> d_in, d_out; CK(d_in.ensure(5 * (size_t)n)); CK(d_out.ensure(3 * (size_t)n));
@@ -584,6 +912,7 @@ int srt_eval_texture(SrtScene* s, int tex, const float* uvp5, int n, int quirks,
 }
 int srt_eval_raygen(SrtScene* s, const SrtRenderParams* p, int n, const int32_t* pixel, const int32_t* sample, SrtRay* out) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
+  USE_DEVICE(s);
   if (!p || n < 0 || (n && (!pixel || !sample || !out))) return fail(SRT_ERR_ARG, "eval_raygen: bad argument");
   if (n == 0) return 0;
   DevBuf<int> d_px, d_sm; DevBuf<SrtRay> d_out; CK(d_px.ensure(n)); CK(d_sm.ensure(n)); CK(d_out.ensure(n));

@@ -450,10 +450,17 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
   else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; aux = hdr.w; }
   float t = 0.f, u = 0.f, v = 0.f; bool ok = false;
   if (HAS_SPHERE && type == SRT_PRIM_SPHERE) {
-    ok = isect_sphere(xyz(a), a.w, o, d, inv_a, tmin, t);
+    // an instanced sphere (geometry.scm:465-543 above a sphere leaf): the rigid transform keeps t, so
+    // the ray goes to object space and t comes back unchanged.  Sphere-only kernels (SINGLE_KIND) never
+    // see one: such scenes are routed to a variant that reads the header (variant_of, wavefront.cu).
+    float3 oo = o, dd = d;
+    if (!SINGLE_KIND && xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
+    ok = isect_sphere(xyz(a), a.w, oo, dd, inv_a, tmin, t);
   } else if (HAS_MOVING && type == SRT_PRIM_MOVING_SPHERE) {
     float4 b = __ldg(&sc.prim_b[id]), c = __ldg(&sc.prim_c[id]);
-    ok = isect_sphere(moving_center(a, b, c, time), a.w, o, d, inv_a, tmin, t);
+    float3 oo = o, dd = d;
+    if (!SINGLE_KIND && xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
+    ok = isect_sphere(moving_center(a, b, c, time), a.w, oo, dd, inv_a, tmin, t);
   } else if (HAS_RECT && type <= SRT_PRIM_YZ_RECT) {
     float k = __int_as_float(aux);                       // plane constant, carried in the header (srt_api.cu)
     float3 oo = o, dd = d; float ti = 0.f; bool have_t = false;
@@ -522,7 +529,10 @@ __device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t
     float3 c = xyz(a);
     if (type == SRT_PRIM_MOVING_SPHERE) c = moving_center(a, __ldg(&sc.prim_b[prim]), __ldg(&sc.prim_c[prim]), time);
     p = madd(d, t, o);
-    n = (p - c) * (1.0f / a.w);
+    if (hdr.z >= 0) {                                  // instanced: normal in object space, rotated back (geometry.scm:473, 526-535)
+      Xf x = load_xf(sc, hdr.z);
+      n = xf_vec_to_world(x, (xf_point_to_obj(x, p) - c) * (1.0f / a.w));
+    } else n = (p - c) * (1.0f / a.w);
   } else if (type <= SRT_PRIM_YZ_RECT) {
     n = v3(type == SRT_PRIM_YZ_RECT ? 1.f : 0.f, type == SRT_PRIM_XZ_RECT ? 1.f : 0.f, type == SRT_PRIM_XY_RECT ? 1.f : 0.f);
     if (hdr.z >= 0) {

@@ -2,7 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "srt_device.cuh"
+
+#define SRT_MAX_DEVICES 16
+#define SRT_MASK_XF_SPHERE 0x200            // prim_mask bit: a sphere / moving sphere sits under a translate / rotate-y chain
 
 struct LbvhBuffers {
   float* d_aabb = nullptr;                 // 6 per primitive (by primitive id)
@@ -38,16 +42,33 @@ struct WaveBuffers {
   void* h_ctrl = nullptr;                  // 2 x WaveCtrl (pinned host)
   void* poll_events = nullptr;             // 2 x cudaEvent_t
   bool use_graph = true;                   // replay the iteration batches as a CUDA graph
+  struct GraphCache* graph = nullptr;      // executable graph of one iteration batch, cached on the scene
 };
+
+// The captured batch of wavefront iterations.  `key` = the bytes of everything baked into the
+// graph's kernel nodes (scene tables, camera, parameters without the sample range, buffers, kernel
+// variant); a later render with an equal key replays `exec` instead of capturing again.
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr;
+  std::vector<unsigned char> key; int launches_per_batch = 0;
+};
+void srt_graph_cache_release(GraphCache& c);
 
 struct RenderLaunch {
   DScene sc; DCamera cam; SrtRenderParams p;
   int sm_count; bool bvh_in_smem; size_t extend_smem;
-  int prim_mask;                            // bit k set = primitive kind k present (extend kernel variant)
+  int prim_mask;                            // bit k set = primitive kind k present (extend kernel variant); SRT_MASK_XF_SPHERE
+  int device;                               // CUDA device the scene lives on (index of the per-device variant cache)
 };
 
-// returns number of kernel launches; d_rgb_sum accumulates W*H*3 floats
-int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile);
+// returns the number of kernel launches or a negative SrtError (*cuda_err = the failing CUDA status);
+// d_rgb_sum accumulates W*H*3 floats, nullptr = leave the frame in W.accum64 (multi-GPU reduce first)
+int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile, cudaError_t* cuda_err);
+int srt_launch_accum_to_float(int sm_count, int n3, const unsigned long long* accum64, float* d_rgb_sum, cudaStream_t stream);
+// multi-GPU combine on the root device: accum64 += sum of the peers' accumulators (read over NVLink
+// peer access), then rgb_sum += accum64 / 2^36 and, if d_image != nullptr, the gamma-corrected 8-bit image
+int srt_launch_reduce_peers(int sm_count, int n3, unsigned long long* accum64, const unsigned long long* const* peer_ptrs /* host array */, int n_peers,
+                            float* d_rgb_sum, float spp_total, uint8_t* d_image, cudaStream_t stream);
 size_t srt_wave_ctrl_bytes();
 void srt_extend_prepare(const RenderLaunch& L);
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,

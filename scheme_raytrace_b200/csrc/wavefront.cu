@@ -14,6 +14,9 @@
 // batch of samples.  Iterations are enqueued in batches of 8 that are captured once into a CUDA
 // graph and replayed; the host polls the control block one batch behind.  The recursive estimator `color` is run in its iterative form
 // L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
+#include <mutex>
+#include <cstring>
+#include <cstdlib>
 #include "srt_device.cuh"
 #include "srt_host.h"
 
@@ -31,18 +34,30 @@ constexpr int SHD_THREADS = 256;
 //   qcount[g]     live length of queue generation g (read by extend / shade)
 //   survivors[g]  compaction cursor: shade(g^1) atomically appends survivors into generation g
 //   next_path[k]  first camera path not yet generated, as seen by the regen of parity k
+//   spp_begin     first sample of the range this call renders (kept here, not in the kernel
+//                 arguments, so that the captured iteration graph is reusable across calls)
 struct WaveCtrl {
   int qcount[2]; int survivors[2];
   unsigned long long next_path[2];
   unsigned long long total_paths;
   unsigned long long rays;          // sum of qcount over iterations = closest-hit queries
   unsigned long long iterations;
+  unsigned long long nonfinite;     // radiance contributions dropped because they were NaN / Inf
+  unsigned long long bounce_hist[8];// closest-hit queries by bounce (0..6, >= 7), profile mode only
+  int spp_begin; int tail_runs;     // tail_runs: how many times the drain kernel took over
 };
 #define SRT_ACC_SCALE 68719476736.0f   // 2^36: radiance accumulates in 64-bit fixed point
+#define SRT_ACC_MAX 6.7e7f             // per-contribution clamp: 2^26 * 2^36 = 2^62 stays inside the signed 64-bit sum
 
-__device__ __forceinline__ void accumulate_fixed(unsigned long long* __restrict__ acc, int pixel, float3 L) {
-  // order-independent (integer) accumulation: the image is bit-identical for any scheduling,
-  // queue size or sample-range split.  main.scm:480 running sum.
+// Order-independent (integer) accumulation: WITHIN ONE CALL the image is bit-identical for any
+// scheduling, queue size, number of GPUs (the multi-GPU reduce adds these integers) and sample-range
+// split; across calls the float running sum rgb_sum += ... rounds once per call.  main.scm:480 running sum.
+// A NaN / Inf contribution (outside the reference's domain: Gauche would carry the NaN into the
+// pixel) is dropped and counted in SrtStats.nonfinite instead of poisoning the integer sum; a finite
+// one is clamped to SRT_ACC_MAX, so a call's per-pixel sum is exact up to 2^27 (spp x radiance).
+__device__ __forceinline__ void accumulate_fixed(unsigned long long* __restrict__ acc, int pixel, float3 L, unsigned long long* __restrict__ nonfinite) {
+  if (!(fabsf(L.x) <= 3.0e38f) || !(fabsf(L.y) <= 3.0e38f) || !(fabsf(L.z) <= 3.0e38f)) { atomicAdd(nonfinite, 1ull); return; }
+  L.x = fminf(fmaxf(L.x, -SRT_ACC_MAX), SRT_ACC_MAX); L.y = fminf(fmaxf(L.y, -SRT_ACC_MAX), SRT_ACC_MAX); L.z = fminf(fmaxf(L.z, -SRT_ACC_MAX), SRT_ACC_MAX);
   if (L.x != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 0], (unsigned long long)__float2ll_rn(L.x * SRT_ACC_SCALE));
   if (L.y != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 1], (unsigned long long)__float2ll_rn(L.y * SRT_ACC_SCALE));
   if (L.z != 0.f) atomicAdd(&acc[3 * (size_t)pixel + 2], (unsigned long long)__float2ll_rn(L.z * SRT_ACC_SCALE));
@@ -58,6 +73,7 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
                                                 WaveCtrl* __restrict__ ctrl) {
   const int surv = ctrl->survivors[g];
   const unsigned long long next = ctrl->next_path[parity], total = ctrl->total_paths;
+  const int spp_begin = ctrl->spp_begin;
   unsigned long long room = (unsigned long long)(capacity - surv), left = total - next;
   const int n_new = (int)(room < left ? room : left);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
@@ -65,7 +81,7 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
     unsigned int sl = (unsigned int)(id / (unsigned long long)npix);
     int pixel = (int)(id - (unsigned long long)sl * (unsigned long long)npix);
     int y = pixel / p.width, x = pixel - y * p.width;
-    unsigned int sample = (unsigned int)p.spp_begin + sl;
+    unsigned int sample = (unsigned int)spp_begin + sl;
     RngAddr addr{p.seed, (uint32_t)pixel, sample, 0u};
     float4 xi = rng_block(addr, 0);
     float u = ((float)x + xi.x) / (float)p.width;       // y = 0 is the bottom row
@@ -420,8 +436,39 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// shade: one bounce of `color` (main.scm:100-121) for every live path + compaction of survivors
-// into the other queue generation (warp ballot -> per-warp count -> one atomic per CTA).
+// One bounce of `color` (main.scm:100-121) for one path: hit-record completion, emitted / sky into
+// the accumulator, scatter.  Returns true when the path continues; the new ray / state are written
+// to (no4, nd4, ns4) in the queue layout.  Shared by k_shade (wavefront) and k_tail (drain).
+template <int EST>
+__device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderParams& p, float4 h4, float4 o4, float4 d4, float4 s4,
+                                           unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl,
+                                           float4& no4, float4& nd4, float4& ns4) {
+  const int prim = __float_as_int(h4.y);
+  float3 thr = xyz(s4); const int pixel = __float_as_int(s4.w); const int sd = __float_as_int(d4.w);
+  const int depth = sd & 0xfff; const unsigned int sample = (unsigned int)sd >> 12;
+  const float3 o = xyz(o4), d = xyz(d4);
+  if (p.reserved[0] == 1) atomicAdd(&ctrl->bounce_hist[depth < 7 ? depth : 7], 1ull);     // profile mode: rays per bounce
+  if (prim < 0) {                                              // main.scm:120 sky
+    accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d), &ctrl->nonfinite);
+    return false;
+  }
+  float3 pt, n; int material;
+  complete_hit(sc, prim, h4.x, h4.z, h4.w, o, d, o4.w, pt, n, material);
+  RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
+  Scatter s = scatter<EST>(sc, prim, d, pt, n, h4.z, h4.w, addr, p.quirks);
+  if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
+    accumulate_fixed(accum, pixel, thr * s.emitted, &ctrl->nonfinite);
+  if (!(s.valid && depth < p.max_depth)) return false;       // main.scm:112
+  thr = thr * s.weight;
+  const float ntime = (p.quirks & SRT_Q6_SCATTER_TIME0) ? 0.0f : o4.w;   // Q6: make-ray forces time 0
+  no4 = make_float4(pt.x, pt.y, pt.z, ntime);
+  nd4 = make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float(sd + 1));
+  ns4 = make_float4(thr.x, thr.y, thr.z, __int_as_float(pixel));
+  return true;
+}
+
+// shade: one bounce for every live path + compaction of survivors into the other queue generation
+// (warp ballot -> per-warp count -> one atomic per CTA).
 template <int EST>
 __global__ void __launch_bounds__(SHD_THREADS, 4)
 k_shade(DScene sc, SrtRenderParams p, int g,
@@ -436,30 +483,8 @@ k_shade(DScene sc, SrtRenderParams p, int g,
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {   // block-uniform trip count
     int i = base + threadIdx.x;
     bool alive = false;
-    float3 no = v3(0, 0, 0), nd = v3(0, 0, 0), thr = v3(0, 0, 0); float ntime = 0.f; int pixel = 0, sd = 0;
-    if (i < count) {
-      float4 h4 = hit[i], o4 = ray_o[i], d4 = ray_d[i], s4 = state[i];
-      int prim = __float_as_int(h4.y);
-      thr = xyz(s4); pixel = __float_as_int(s4.w); sd = __float_as_int(d4.w);
-      const int depth = sd & 0xfff; const unsigned int sample = (unsigned int)sd >> 12;
-      float3 o = xyz(o4), d = xyz(d4);
-      if (prim < 0) {                                              // main.scm:120 sky
-        accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d));
-      } else {
-        float3 pt, n; int material;
-        complete_hit(sc, prim, h4.x, h4.z, h4.w, o, d, o4.w, pt, n, material);
-        RngAddr addr{p.seed, (uint32_t)pixel, sample, (uint32_t)(depth + 1)};
-        Scatter s = scatter<EST>(sc, prim, d, pt, n, h4.z, h4.w, addr, p.quirks);
-        if (s.emitted.x != 0.f || s.emitted.y != 0.f || s.emitted.z != 0.f)    // main.scm:113/119 emitted
-          accumulate_fixed(accum, pixel, thr * s.emitted);
-        if (s.valid && depth < p.max_depth) {                      // main.scm:112
-          alive = true;
-          thr = thr * s.weight;
-          no = pt; nd = s.dir; sd += 1;
-          ntime = (p.quirks & SRT_Q6_SCATTER_TIME0) ? 0.0f : o4.w;   // Q6: make-ray forces time 0
-        }
-      }
-    }
+    float4 no4 = make_float4(0.f, 0.f, 0.f, 0.f), nd4 = no4, ns4 = no4;
+    if (i < count) alive = shade_path<EST>(sc, p, hit[i], ray_o[i], ray_d[i], state[i], accum, ctrl, no4, nd4, ns4);
     unsigned ballot = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
@@ -472,12 +497,75 @@ k_shade(DScene sc, SrtRenderParams p, int g,
     __syncthreads();
     if (alive) {
       int pos = s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
-      ray_o_next[pos] = make_float4(no.x, no.y, no.z, ntime);
-      ray_d_next[pos] = make_float4(nd.x, nd.y, nd.z, __int_as_float(sd));
-      state_next[pos] = make_float4(thr.x, thr.y, thr.z, __int_as_float(pixel));
+      ray_o_next[pos] = no4; ray_d_next[pos] = nd4; state_next[pos] = ns4;
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail: the drain of the streaming wavefront in ONE launch.  Once every camera path has been
+// generated and the queue holds at most `tail_max` paths (about one wave of resident threads), the
+// remaining iterations of the wavefront are ~max_depth launch-bound, nearly empty extend / shade /
+// regen triples (main.scm:26 +max-depth+ is what makes the tail: a path may live 50 bounces).  Here
+// every thread takes one queued path and runs extend -> shade -> extend ... until the path ends
+// (the same device functions, the same Philox addresses (pixel, sample, bounce) and the same
+// integer accumulator, so the image is bit-identical to the wavefront's).  The kernel is part of
+// every iteration batch and returns at once while its condition does not hold; k_tail_done (one
+// thread) then empties the queue, so the remaining launches of the batch find nothing to do.
+__device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int parity, int tail_max) {
+  const int c = ctrl->qcount[g];
+  return c > 0 && c <= tail_max && ctrl->next_path[parity] >= ctrl->total_paths;
+}
+template <int MASK, int EST>
+__global__ void __launch_bounds__(EXT_THREADS, 2)
+k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
+       const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
+       unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {
+  extern __shared__ float4 smem[];
+  if (!tail_condition(ctrl, g, parity, tail_max)) return;
+  const int count = ctrl->qcount[g];
+  if ((int)(blockIdx.x * blockDim.x) >= count) return;
+  const int nn = 4 * sc.n_nodes, np = sc.n_prims;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = sc.nodes[i];
+  int4* sh = (int4*)(smem + nn);
+  float4* sa = smem + nn + np;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
+  __syncthreads();
+  const PrimShared ps{sh, sa};
+  Trav T;
+  T.sp0 = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np) + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("" : "+r"(sbase));
+  T.ra.seed = p.seed; T.ra.pixel = 0u; T.ra.sample = 0u; T.ra.bounce = 0u;
+  unsigned int nrays = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    float4 o4 = ray_o[i], d4 = ray_d[i], s4 = state[i];
+    for (;;) {
+      trav_init(T, o4, d4, SRT_MAX_FLOAT, i);
+      ++nrays;
+      if (sc.n_surf > 0) {
+        for (int k = 0; k < sc.n_global; ++k)
+          intersect_prim<MASK>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
+        bool more = sc.n_items > 0;
+        while (more) {
+          int pend0 = -1, pend1 = -1;
+          more = node_step<true, TRAV_STACK>(T, smem, sbase, p.t_min, pend0, pend1);
+          while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h); pend0 = pend1; pend1 = -1; }
+        }
+      }
+      float4 no4, nd4, ns4;
+      if (!shade_path<EST>(sc, p, make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v), o4, d4, s4, accum, ctrl, no4, nd4, ns4)) break;
+      o4 = no4; d4 = nd4; s4 = ns4;
+    }
+  }
+  for (int o = 16; o; o >>= 1) nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
+  if ((threadIdx.x & 31) == 0 && nrays) atomicAdd(&ctrl->rays, (unsigned long long)nrays);
+}
+__global__ void k_tail_done(int g, int parity, int tail_max, WaveCtrl* ctrl) {
+  if (!tail_condition(ctrl, g, parity, tail_max)) return;
+  ctrl->rays -= (unsigned long long)ctrl->qcount[g];    // the regen that filled this generation already counted its first query
+  ctrl->qcount[g] = 0; ctrl->iterations += 1ull; ctrl->tail_runs += 1;
 }
 
 // end of render: rgb_sum += fixed-point accumulator (main.scm:480 running sum, *raw-data*)
@@ -485,9 +573,11 @@ __global__ void k_accum_to_float(int n3, const unsigned long long* __restrict__ 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x)
     rgb_sum[i] += (float)((double)(long long)accum[i] * (1.0 / 68719476736.0));
 }
-__global__ void k_ctrl_init(WaveCtrl* ctrl, unsigned long long total_paths) {
+__global__ void k_ctrl_init(WaveCtrl* ctrl, unsigned long long total_paths, int spp_begin) {
   ctrl->qcount[0] = ctrl->qcount[1] = 0; ctrl->survivors[0] = ctrl->survivors[1] = 0;
   ctrl->next_path[0] = ctrl->next_path[1] = 0ull; ctrl->total_paths = total_paths; ctrl->rays = 0ull; ctrl->iterations = 0ull;
+  ctrl->nonfinite = 0ull; ctrl->spp_begin = spp_begin; ctrl->tail_runs = 0;
+  for (int k = 0; k < 8; ++k) ctrl->bounce_hist[k] = 0ull;
 }
 
 // main.scm:123-124, 481-487: correct-gamma (sqrt) + floor(255.99 * min(1, c)); negative sums
@@ -497,6 +587,23 @@ __global__ void k_resolve(const float* __restrict__ rgb_sum, int n3, float spp, 
     float c = __fdiv_rn(rgb_sum[i], spp);
     c = sqrtf(fmaxf(c, 0.0f));
     image[i] = (uint8_t)floorf(255.99f * fminf(1.0f, c));
+  }
+}
+
+// Multi-GPU combine on the root GPU, one kernel: frame = own accumulator + the peers' accumulators
+// read directly over NVLink peer access (integer adds: exact, order-independent), then
+// rgb_sum += frame * 2^-36 (main.scm:480) and, optionally, gamma + 8-bit (main.scm:481-487) for the
+// `spp` samples the running sum now holds.  With no peers it is the single-GPU epilogue.
+struct PeerPtrs { const unsigned long long* p[SRT_MAX_DEVICES]; };
+__global__ void __launch_bounds__(256) k_reduce_peers(int n3, unsigned long long* __restrict__ accum, PeerPtrs peers, int n_peers,
+                                                      float* __restrict__ rgb_sum, float spp, uint8_t* __restrict__ image) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+    unsigned long long a = accum[i];
+    for (int k = 0; k < n_peers; ++k) a += peers.p[k][i];
+    if (n_peers) accum[i] = a;
+    const float v = rgb_sum[i] + (float)((double)(long long)a * (1.0 / 68719476736.0));
+    rgb_sum[i] = v;
+    if (image) { float c = sqrtf(fmaxf(__fdiv_rn(v, spp), 0.0f)); image[i] = (uint8_t)floorf(255.99f * fminf(1.0f, c)); }
   }
 }
 
@@ -590,17 +697,26 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
 // =================================================================================================
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
-// Kernel variants by primitive mix.
+// Kernel variants by primitive mix.  The cache (function attribute + occupancy query) is kept per
+// DEVICE: scenes on different GPUs of one process (srt_render_multi) each see their own entry.
 typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t, int);
+typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
-static ExtendVariant g_variants[2][5][3];
+struct TailVariant { TailFn fn; size_t smem; int bps; };
+static ExtendVariant g_variants[SRT_MAX_DEVICES][2][5][3];
+static TailVariant g_tail_variants[SRT_MAX_DEVICES][3][2];
+static std::mutex g_variant_mu;
 
 // spheres | + moving spheres | + rects / instances | + bicubic patches | everything (curves, media, Klein).
 // The patch variant exists because the curve's subdivision stack (1.3 KB of local memory per thread) and
 // the Klein / medium code cost the patch scenes 14 % when merely compiled in (cfg5_teapot 2.61 -> 2.96 Grays/s).
+// SRT_MASK_XF_SPHERE (an instanced sphere: translate / rotate-y above a sphere leaf, geometry.scm:465-543)
+// needs the primitive header, which the sphere-only variant 0 does not read: such scenes use variant 1.
 static int variant_of(int mask) {
-  if ((mask & ~0x01) == 0) return 0;
-  if ((mask & ~0x03) == 0) return 1;
+  const bool xf_sphere = mask & SRT_MASK_XF_SPHERE;
+  mask &= SRT_MASK_ALL;
+  if ((mask & ~0x01) == 0 && !xf_sphere) return 0;
+  if ((mask & ~0x03) == 0) return 1;                 // two kinds: the header (and its xform) is read
   if ((mask & 0x1e0) == 0) return 2;
   if ((mask & 0x160) == 0) return 3;
   return 4;
@@ -619,16 +735,24 @@ static ExtendFn variant_fn(bool smem, int v, int trav) {
   if (trav == TRAV_CACHE) return smem ? variant_fn_m<true, TRAV_CACHE>(v) : variant_fn_m<false, TRAV_CACHE>(v);
   return smem ? variant_fn_m<true, TRAV_TRAIL>(v) : variant_fn_m<false, TRAV_TRAIL>(v);
 }
-// persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
-static const ExtendVariant& extend_variant(const RenderLaunch& L) {
-  int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
+static int trav_mode(const RenderLaunch& L, int v, size_t* stack_bytes) {
+  const int which = L.bvh_in_smem ? 1 : 0;
   // 16-bit node ids: shared-memory stack when it fits beside the staged scene, else the register cache
   const int threads = v >= 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
   const size_t stack = (size_t)2 * trav_stack_stride(L.sc.bvh_depth) * threads;
   const bool small_ids = L.sc.n_nodes < 65536;
-  const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling
-  int trav = !small_ids ? TRAV_TRAIL : ((!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE);
-  ExtendVariant& e = g_variants[which][v][trav];
+  static const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling
+  *stack_bytes = stack;
+  return !small_ids ? TRAV_TRAIL : ((!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE);
+}
+// persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
+static ExtendVariant extend_variant(const RenderLaunch& L) {
+  const int which = L.bvh_in_smem ? 1 : 0, v = variant_of(L.prim_mask);
+  size_t stack = 0;
+  const int trav = trav_mode(L, v, &stack);
+  const int threads = v >= 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
+  std::lock_guard<std::mutex> lock(g_variant_mu);
+  ExtendVariant& e = g_variants[L.device][which][v][trav];
   size_t smem = (which ? L.extend_smem : 0) + (trav == TRAV_STACK ? stack : 0);
   if (!e.fn || e.smem != smem) {
     e.fn = variant_fn(which, v, trav); e.smem = smem; e.threads = threads;
@@ -639,12 +763,36 @@ static const ExtendVariant& extend_variant(const RenderLaunch& L) {
   }
   return e;
 }
+// The drain kernel exists for the cheap variants with the tree staged in shared memory and the
+// shared-memory traversal stack (every reference scene); other scenes drain through the wavefront.
+static bool tail_variant(const RenderLaunch& L, TailVariant* out) {
+  const int v = variant_of(L.prim_mask);
+  size_t stack = 0;
+  if (v > 2 || !L.bvh_in_smem || trav_mode(L, v, &stack) != TRAV_STACK) return false;
+  static const bool off = getenv("SRT_NO_TAIL") != nullptr;                          // A/B switch
+  if (off) return false;
+  const int est = L.p.estimator == SRT_EST_MIXTURE ? 1 : 0;
+  std::lock_guard<std::mutex> lock(g_variant_mu);
+  TailVariant& t = g_tail_variants[L.device][v][est];
+  const size_t smem = L.extend_smem + stack;
+  if (!t.fn || t.smem != smem) {
+    if (est) t.fn = v == 0 ? k_tail<0x01, SRT_EST_MIXTURE> : (v == 1 ? k_tail<0x03, SRT_EST_MIXTURE> : k_tail<0x1f, SRT_EST_MIXTURE>);
+    else t.fn = v == 0 ? k_tail<0x01, SRT_EST_REFERENCE> : (v == 1 ? k_tail<0x03, SRT_EST_REFERENCE> : k_tail<0x1f, SRT_EST_REFERENCE>);
+    t.smem = smem;
+    if (smem) cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, t.fn, EXT_THREADS, smem);
+    t.bps = bps < 1 ? 1 : bps;
+  }
+  *out = t;
+  return true;
+}
 
 void srt_extend_prepare(const RenderLaunch& L) { (void)extend_variant(L); }
 
 int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* ray_d, const float4* state, float4* hit, const int* d_count, int count,
                       float tmin, float tmax, uint32_t seed, cudaStream_t stream) {
-  const ExtendVariant& e = extend_variant(L);
+  const ExtendVariant e = extend_variant(L);
   // deferred-test tuning (heavy variant only): park vote | refill threshold << 8; env overrides are for A/B runs
   static const int tune = [] {
     const char* a = getenv("SRT_PARK_VOTE"); const char* b = getenv("SRT_REFILL_MIN");
@@ -658,10 +806,20 @@ int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* 
 
 size_t srt_wave_ctrl_bytes() { return sizeof(WaveCtrl); }
 
+void srt_graph_cache_release(GraphCache& c) {
+  if (c.exec) cudaGraphExecDestroy((cudaGraphExec_t)c.exec);
+  if (c.graph) cudaGraphDestroy((cudaGraph_t)c.graph);
+  c.exec = nullptr; c.graph = nullptr; c.key.clear();
+}
+
 // The streaming wavefront: iterate extend -> shade -> regen until every camera path of the sample
 // range has been generated and the queue has drained.  The host enqueues iterations in batches
 // and polls the control block (pinned copy) one batch behind, so the GPU never waits on the host.
-int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile) {
+// Returns the number of kernels launched, or a negative SrtError: every CUDA call of the loop is
+// checked, and the loop is bounded, so a sticky device error cannot leave the host spinning.
+// d_rgb_sum == nullptr leaves the frame in the 64-bit accumulator (multi-GPU: reduced first).
+#define WCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = e_; goto fail; } } while (0)
+int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum, cudaStream_t stream, SrtStats* stats, bool profile, cudaError_t* cuda_err) {
   const SrtRenderParams& p = L.p;
   const int npix = p.width * p.height;
   const unsigned long long total = (unsigned long long)npix * (unsigned long long)(p.spp_end - p.spp_begin);
@@ -669,67 +827,124 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   WaveCtrl* ctrl = (WaveCtrl*)W.ctrl;
   int launches = 0;
   const int shade_grid = L.sm_count * 8, regen_grid = L.sm_count * 8;
-  cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream);
-  k_ctrl_init<<<1, 1, 0, stream>>>(ctrl, total); ++launches;
-  k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, p, npix, cap, 0, 0, W.ray_o[0], W.ray_d[0], W.state[0], ctrl); ++launches;
+  cudaError_t err = cudaSuccess;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   float acc_ext = 0.f, acc_shd = 0.f; int n_ext = 0;
-  if (profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
-  const int BATCH = 8;                          // even, so every batch has identical launch parameters
   WaveCtrl* h = (WaveCtrl*)W.h_ctrl;            // pinned, 2 slots
   cudaEvent_t* ev = (cudaEvent_t*)W.poll_events;
-  int g = 0, parity = 1, batch = 0;
-  auto enqueue_batch = [&]() {
-    for (int k = 0; k < BATCH; ++k) {
-      if (profile) cudaEventRecord(e0, stream);
-      launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.state[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, p.seed, stream);
-      if (profile) cudaEventRecord(e1, stream);
-      (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, p, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
-                                                       W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
-      if (profile) { cudaEventRecord(e2, stream); cudaEventSynchronize(e2); float a, b; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); acc_ext += a; acc_shd += b; ++n_ext; }
-      k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, p, npix, cap, g ^ 1, parity, W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], ctrl);
-      launches += 2;
-      g ^= 1; parity ^= 1;
-    }
+  // kernels read the sample range from the control block, so the captured graph (and its key) do
+  // not depend on it: progressive passes replay the same executable graph
+  SrtRenderParams pk = p; pk.spp_begin = 0; pk.spp_end = 0; pk.wave_spp = 0; pk.reserved[1] = pk.reserved[2] = pk.reserved[3] = 0;
+  TailVariant tv; const bool have_tail = p.reserved[3] != 1 && tail_variant(L, &tv);
+  const int tail_grid = have_tail ? L.sm_count * tv.bps : 0;
+  const int tail_max = have_tail ? tail_grid * EXT_THREADS * 2 : 0;   // about two waves of resident threads
+  auto launch_tail = [&](int g, int parity) {
+    tv.fn<<<tail_grid, EXT_THREADS, tv.smem, stream>>>(L.sc, pk, g, parity, tail_max, W.ray_o[g], W.ray_d[g], W.state[g], W.accum64, ctrl);
+    k_tail_done<<<1, 1, 0, stream>>>(g, parity, tail_max, ctrl);
+    launches += 2;
   };
-  // The batch of 8 iterations (24 launches) is captured once into a CUDA graph and replayed: the
-  // deep-path drain tail and small frames (cfg1: 320k paths) are launch-bound otherwise.
-  cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
-  if (!profile && W.use_graph) {
-    srt_extend_prepare(L);                      // function attributes / occupancy query outside the capture
-    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      int l0 = launches;
-      enqueue_batch();
-      launches = l0;
-      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) { gexec = nullptr; cudaGetLastError(); }
-    } else cudaGetLastError();
-  }
-  bool done = false;
-  while (!done) {
-    if (gexec) { cudaGraphLaunch(gexec, stream); launches += 3 * BATCH; }
-    else enqueue_batch();
-    cudaMemcpyAsync(&h[batch & 1], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
-    cudaEventRecord(ev[batch & 1], stream);
-    if (batch >= 1) {                             // look at the PREVIOUS batch while this one runs
-      cudaEventSynchronize(ev[(batch - 1) & 1]);
-      const WaveCtrl& c = h[(batch - 1) & 1];
-      if (c.qcount[0] == 0 && c.qcount[1] == 0 && c.next_path[0] >= total && c.next_path[1] >= total) done = true;
+  WCK(cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream));
+  k_ctrl_init<<<1, 1, 0, stream>>>(ctrl, total, p.spp_begin); ++launches;
+  k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, pk, npix, cap, 0, 0, W.ray_o[0], W.ray_d[0], W.state[0], ctrl); ++launches;
+  if (have_tail && !profile && total <= (unsigned long long)tail_max && total <= (unsigned long long)cap) {
+    // small frame (cfg1: 320k paths): the whole frame is one wave - regen + tail, no iteration graph, no polling
+    launch_tail(0, 1);
+  } else {
+    if (profile) { WCK(cudaEventCreate(&e0)); WCK(cudaEventCreate(&e1)); WCK(cudaEventCreate(&e2)); }
+    const int BATCH = 8;                          // even, so every batch has identical launch parameters
+    int g = 0, parity = 1;
+    auto enqueue_batch = [&]() {
+      if (have_tail && !profile) launch_tail(g, parity);
+      for (int k = 0; k < BATCH; ++k) {
+        if (profile) cudaEventRecord(e0, stream);
+        launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.state[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, p.seed, stream);
+        if (profile) cudaEventRecord(e1, stream);
+        (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, pk, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
+                                                         W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
+        if (profile) { cudaEventRecord(e2, stream); cudaEventSynchronize(e2); float a = 0.f, b = 0.f; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); acc_ext += a; acc_shd += b; ++n_ext; }
+        k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, pk, npix, cap, g ^ 1, parity, W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], ctrl);
+        launches += 2;
+        g ^= 1; parity ^= 1;
+      }
+    };
+    // The batch of 8 iterations (2 + 24 launches) is captured once into a CUDA graph and replayed: the
+    // deep-path drain tail and small frames are launch-bound otherwise.  The executable graph is
+    // CACHED on the scene (W.graph) and reused by later calls with the same scene tables, buffers
+    // and parameters; only a re-commit or a change of size / estimator / quirks / seed re-captures.
+    cudaGraphExec_t gexec = nullptr;
+    int launches_per_batch = 0;
+    if (!profile && W.use_graph && W.graph) {
+      const ExtendVariant e = extend_variant(L);  // function attributes / occupancy query outside the capture
+      struct Key { DScene sc; DCamera cam; SrtRenderParams p; WaveBuffers w; void* fn; size_t smem; int bps, device, tail_max; } key;
+      std::memset(&key, 0, sizeof(key));
+      key.sc = L.sc; key.cam = L.cam; key.p = pk; key.fn = (void*)e.fn; key.smem = e.smem; key.bps = e.bps; key.device = L.device; key.tail_max = tail_max;
+      key.w.capacity = W.capacity; key.w.hit = W.hit; key.w.accum64 = W.accum64; key.w.ctrl = W.ctrl;
+      for (int k = 0; k < 2; ++k) { key.w.ray_o[k] = W.ray_o[k]; key.w.ray_d[k] = W.ray_d[k]; key.w.state[k] = W.state[k]; }
+      GraphCache& C = *W.graph;
+      if (!C.exec || C.key.size() != sizeof(key) || std::memcmp(C.key.data(), &key, sizeof(key)) != 0) {
+        srt_graph_cache_release(C);
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          const int l0 = launches;
+          enqueue_batch();
+          C.launches_per_batch = launches - l0; launches = l0;
+          cudaGraph_t graph = nullptr; cudaGraphExec_t ex = nullptr;
+          if (cudaStreamEndCapture(stream, &graph) == cudaSuccess && cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) {
+            C.graph = graph; C.exec = ex; C.key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+          } else { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); }
+        } else cudaGetLastError();
+      }
+      gexec = (cudaGraphExec_t)C.exec; launches_per_batch = C.launches_per_batch;
     }
-    ++batch;
+    // bound on the number of iterations: a queue fill lives at most max_depth + 1 iterations
+    const unsigned long long max_iter = ((total + (unsigned long long)cap - 1ull) / (unsigned long long)cap + 1ull) * (unsigned long long)(p.max_depth + 2) + 64ull;
+    bool done = false; int batch = 0;
+    while (!done) {
+      if ((unsigned long long)batch * BATCH > max_iter + 2ull * BATCH) { err = cudaErrorLaunchTimeout; goto fail; }   // the queue does not drain: give up loudly
+      if (gexec) { WCK(cudaGraphLaunch(gexec, stream)); launches += launches_per_batch; }
+      else { enqueue_batch(); WCK(cudaPeekAtLastError()); }
+      WCK(cudaMemcpyAsync(&h[batch & 1], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream));
+      WCK(cudaEventRecord(ev[batch & 1], stream));
+      if (batch >= 1) {                             // look at the PREVIOUS batch while this one runs
+        WCK(cudaEventSynchronize(ev[(batch - 1) & 1]));
+        const WaveCtrl& c = h[(batch - 1) & 1];
+        if (c.qcount[0] == 0 && c.qcount[1] == 0 && c.next_path[0] >= total && c.next_path[1] >= total) done = true;
+      }
+      ++batch;
+    }
   }
-  if (gexec) cudaGraphExecDestroy(gexec);
-  if (graph) cudaGraphDestroy(graph);
-  k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches;
-  cudaMemcpyAsync(&h[0], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream);
-  cudaStreamSynchronize(stream);
+  if (d_rgb_sum) { k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches; }
+  WCK(cudaMemcpyAsync(&h[0], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream));
+  WCK(cudaStreamSynchronize(stream));
+  WCK(cudaGetLastError());
   if (profile) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
   if (stats) {
     stats->rays = h[0].rays; stats->waves = (int)h[0].iterations; stats->kernel_launches = launches;
     stats->ms_extend = acc_ext; stats->ms_shade = acc_shd; stats->extend_launches = n_ext;
+    stats->nonfinite = h[0].nonfinite; stats->tail_runs = h[0].tail_runs;
+    for (int k = 0; k < 8; ++k) stats->rays_per_bounce[k] = h[0].bounce_hist[k];
   }
   return launches;
+fail:
+  if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2);
+  { cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone; if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { cudaGraph_t gdead = nullptr; cudaStreamEndCapture(stream, &gdead); if (gdead) cudaGraphDestroy(gdead); } }
+  if (cuda_err) *cuda_err = err;
+  return SRT_ERR_CUDA;
+}
+#undef WCK
+
+// Adds the 64-bit accumulator of a finished render into the float running sum (multi-GPU: after the reduce).
+int srt_launch_accum_to_float(int sm_count, int n3, const unsigned long long* accum64, float* d_rgb_sum, cudaStream_t stream) {
+  k_accum_to_float<<<sm_count * 4, 256, 0, stream>>>(n3, accum64, d_rgb_sum);
+  return 1;
 }
 
+int srt_launch_reduce_peers(int sm_count, int n3, unsigned long long* accum64, const unsigned long long* const* peer_ptrs, int n_peers,
+                            float* d_rgb_sum, float spp_total, uint8_t* d_image, cudaStream_t stream) {
+  PeerPtrs pp; std::memset(&pp, 0, sizeof(pp));
+  for (int k = 0; k < n_peers && k < SRT_MAX_DEVICES; ++k) pp.p[k] = peer_ptrs[k];
+  k_reduce_peers<<<sm_count * 8, 256, 0, stream>>>(n3, accum64, pp, n_peers, d_rgb_sum, spp_total, d_image);
+  return 1;
+}
 int srt_launch_complete_hits(const DScene& sc, const float4* ray_o, const float4* ray_d, const float4* hit, int n, SrtHit* d_out, cudaStream_t stream) {
   if (n > 0) k_complete_hits<<<(n + 127) / 128, 128, 0, stream>>>(sc, ray_o, ray_d, hit, n, d_out);
   return 1;

@@ -21,7 +21,7 @@ class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("ms_total", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("waves", C.c_int32), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32),
                 ("rays_per_bounce", C.c_uint64 * 8), ("ms_extend", C.c_float), ("ms_shade", C.c_float),
-                ("extend_launches", C.c_int32), ("pad", C.c_int32)]
+                ("extend_launches", C.c_int32), ("tail_runs", C.c_int32), ("nonfinite", C.c_uint64)]
 
 
 # every symbol include/srt.h declares (tests check the library exports all of them)
@@ -31,6 +31,7 @@ SYMBOLS = [
     "srt_scene_set_images", "srt_scene_set_perlin", "srt_scene_set_camera", "srt_scene_set_lights", "srt_scene_commit", "srt_bvh_node_count", "srt_bvh_readback",
     "srt_bvh_keys_readback", "srt_bvh_items_readback", "srt_prim_bounds_readback", "srt_trace_batch", "srt_render_host", "srt_render_device",
     "srt_resolve_device", "srt_resolve_host", "srt_save_ppm", "srt_eval_texture", "srt_eval_raygen",
+    "srt_init_multi", "srt_multi_device_count", "srt_multi_reduce_mode", "srt_render_multi", "srt_progressive_step", "srt_progressive_read",
 ]
 
 _lib = None
@@ -68,6 +69,12 @@ def load():
     lib.srt_trace_batch.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp]
     lib.srt_render_host.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
     lib.srt_render_device.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
+    lib.srt_init_multi.argtypes = [i32]
+    lib.srt_multi_device_count.restype = i32
+    lib.srt_multi_reduce_mode.argtypes = [C.POINTER(i32)]
+    lib.srt_render_multi.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(Stats)]
+    lib.srt_progressive_step.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
+    lib.srt_progressive_read.argtypes = [vp, vp, C.POINTER(i32)]
     lib.srt_resolve_device.argtypes = [vp, i32, i32, i32, vp]
     lib.srt_resolve_host.argtypes = [vp, i32, i32, i32, vp]
     lib.srt_save_ppm.argtypes = [C.c_char_p, vp, i32, i32]

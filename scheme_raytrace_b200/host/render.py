@@ -21,9 +21,16 @@ class Renderer:
     """Owns one committed scene on one GPU.  Replaces the in-process closure evaluation of
     trace-all -> color -> g:hit / m:scatter (main.scm:100-121, 471-491)."""
 
-    def __init__(self, scene, device=0, perlin_seed=3, lights=(), perlin=None):
+    def __init__(self, scene, device=0, perlin_seed=3, lights=(), perlin=None, gpus=1):
+        """gpus > 1 (0 = every visible GPU): the scene is committed on that many GPUs of this process
+        (srt_init_multi) and `render_multi` shards a frame's samples over them."""
         self.lib = ffi.load()
-        ffi.check(self.lib.srt_init(int(device)), "srt_init")
+        self.gpus = int(gpus)
+        if self.gpus != 1:
+            ffi.check(self.lib.srt_init_multi(self.gpus), "srt_init_multi")
+            self.gpus = self.lib.srt_multi_device_count()
+        else:
+            ffi.check(self.lib.srt_init(int(device)), "srt_init")
         self.flat = scene if isinstance(scene, FlatScene) else flatten_scene(scene)
         self.perlin = perlin if perlin is not None else perlin_generate(perlin_seed)   # (ranvec, perm-x, perm-y, perm-z), perlin.scm:10-30
         self.lights = np.ascontiguousarray(list(lights), dtype=np.int32)   # primitive ids for the hittable pdf (make-hitable-pdf)
@@ -134,6 +141,35 @@ class Renderer:
         return st
 
 
+    def render_multi(self, width, height, spp, max_depth=50, seed=1, quirks=ffi.QUIRKS_REFERENCE, spp_begin=0, rgb_sum=None, estimator=0, want_image=True):
+        """(trace-all scene k) over every GPU of srt_init_multi from this one process: samples
+        [spp_begin, spp_begin+spp) are split into one contiguous range per GPU, the integer accumulators are
+        combined with one reduce over NVLink.  Returns (rgb_sum, image8 or None, stats); host buffers."""
+        fresh = rgb_sum is None
+        if fresh:
+            rgb_sum = np.zeros((height, width, 3), dtype=np.float32)
+        image = np.zeros((height, width, 3), dtype=np.uint8) if want_image else None
+        p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, estimator=estimator)
+        p.reserved[2] = 1 if fresh else 0
+        st = ffi.Stats()
+        ffi.check(self.lib.srt_render_multi(self.h, C.byref(p), _ptr(rgb_sum), _ptr(image) if want_image else None, C.byref(st)), "render_multi")
+        return rgb_sum, image, st
+
+    def progressive_step(self, width, height, spp_begin, spp_end, max_depth=100, seed=1, quirks=ffi.QUIRKS_REFERENCE):
+        """One progressive pass with the running sum resident on the device: returns the 8-bit frame only."""
+        image = np.zeros((height, width, 3), dtype=np.uint8)
+        p = self.params(width, height, spp_begin, spp_end, max_depth, seed, quirks)
+        st = ffi.Stats()
+        ffi.check(self.lib.srt_progressive_step(self.h, C.byref(p), _ptr(image), C.byref(st)), "progressive_step")
+        return image, st
+
+    def progressive_read(self, width, height):
+        out = np.zeros((height, width, 3), dtype=np.float32)
+        n = C.c_int32(0)
+        ffi.check(self.lib.srt_progressive_read(self.h, _ptr(out), C.byref(n)), "progressive_read")
+        return out, n.value
+
+
 class ProgressiveRenderer:
     """The reference's progressive viewer semantics (main.scm:452-469, 533-544: one new sample per
     pixel per pass, running sum, 8-bit image re-derived after every pass) without the GLUT window:
@@ -142,16 +178,23 @@ class ProgressiveRenderer:
     def __init__(self, scene, width=200, height=200, max_depth=100, seed=1, quirks=ffi.QUIRKS_REFERENCE, device=0):
         self.r = Renderer(scene, device=device)
         self.width, self.height, self.max_depth, self.seed, self.quirks = width, height, max_depth, seed, quirks
-        self.raw_data = np.zeros((height, width, 3), dtype=np.float32)     # *raw-data* main.scm:430
         self.sample_count = 0                                              # *sample-count*
         self.image = np.zeros((height, width, 3), dtype=np.uint8)          # *image* main.scm:429
 
     def step(self, samples=1):
-        self.r.render(self.width, self.height, samples, max_depth=self.max_depth, seed=self.seed, quirks=self.quirks,
-                      spp_begin=self.sample_count, rgb_sum=self.raw_data)
+        """One pass: the running sum (*raw-data*, main.scm:430) never leaves the device; only the 8-bit
+        frame comes back (srt_progressive_step)."""
+        self.image, self.stats = self.r.progressive_step(self.width, self.height, self.sample_count, self.sample_count + samples,
+                                                         max_depth=self.max_depth, seed=self.seed, quirks=self.quirks)
         self.sample_count += samples
-        self.image = correct_gamma_quantise(self.raw_data, self.sample_count)
         return self.image
+
+    @property
+    def raw_data(self):
+        """*raw-data* read back from the device on demand (inspection / tests)."""
+        if self.sample_count == 0:
+            return np.zeros((self.height, self.width, 3), dtype=np.float32)
+        return self.r.progressive_read(self.width, self.height)[0]
 
     def save(self, path="test.ppm"):                                       # key 'S' main.scm:551-552
         save_as_ppm(path, self.image)

@@ -768,11 +768,15 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
         # pass.  Same draws => it must leave the same *raw-data* / *image* behind as trace-all did.
         it.eval(forms["*image*"], main)
         it.eval(forms["*raw-data*"], main)
+        passes = []                                            # *raw-data* / *image* as the viewer shows them after every pass
         for s in range(spp):
             state["pixel"] = 0
             rng.path, rng.k = (seed, 0, s), 0
             for y in range(size):
                 it.call("main", "trace-line", scene, y, s + 1)
+            praw = [list(x) for x in main.lookup(Sym("*raw-data*"))]
+            pund = [any(c < 0 for c in px) for px in praw]
+            passes.append(dict(raw_data=praw, image=[-1 if pund[i // 3] else q for i, q in enumerate(list(main.lookup(Sym("*image*"))))]))
         assert [list(x) for x in main.lookup(Sym("*raw-data*"))] == raw and list(main.lookup(Sym("*image*"))) == img, "trace-line != trace-all"
         import tempfile
         cwd = os.getcwd()
@@ -791,7 +795,7 @@ def make_color(ref, main, rng, size=10, spp=2, seed=7, max_depth=12):
             img = [-1 if undefined[i // 3] else q for i, q in enumerate(img)]
             ppm = None
         out.append(dict(scene=name, width=size, height=size, spp=spp, seed=seed, max_depth=max_depth, raw_data=raw, image=img, ppm=ppm,
-                        trace_line_equals_trace_all=True))
+                        trace_line_equals_trace_all=True, trace_line_passes=passes))
         print(f"color/{name}: mean radiance {np.mean(raw) / spp:.4f}")
     rng.path, rng.lens = None, False
     main.vars[Sym("color")] = color
@@ -812,6 +816,9 @@ def main():
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(obj, f)
         print("wrote", name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KB")
+    if "--only-color" in sys.argv:                             # the other files do not depend on it
+        dump("ref_color.json", make_color(ref, main_mod, rng))
+        return
     dump("ref_prims.json", make_prims(ref))
     dump("ref_scenes.json", make_scenes(ref, main_mod))
     dump("ref_prims2.json", make_prims(ref, PRIM_CASES2, 300))

@@ -33,6 +33,15 @@ WORKERS = int(os.environ.get("SRT_WORKERS", "8"))
 #   SRT_RENDER_BATCH=1 python tests/golden/make_reference_render.py
 BATCH = int(os.environ.get("SRT_RENDER_BATCH", "0"))
 ONLY = [x for x in os.environ.get("SRT_RENDER_SCENES", "").split(",") if x]          # e.g. SRT_RENDER_SCENES=test-bezier
+# round 2: larger thumbnails into a second file, e.g.
+#   SRT_RENDER_SIZE=32 SRT_RENDER_SPP=384 SRT_WORKERS=6 SRT_RENDER_OUT=ref_render32.npz SRT_RENDER_SCENES=cornell-box,test-bezier python ...
+OUT = os.environ.get("SRT_RENDER_OUT", "ref_render.npz")
+if os.environ.get("SRT_RENDER_SIZE"):
+    for _c in SCENES.values():
+        _c["width"] = _c["height"] = int(os.environ["SRT_RENDER_SIZE"])
+if os.environ.get("SRT_RENDER_SPP"):
+    for _c in SCENES.values():
+        _c["spp"] = int(os.environ["SRT_RENDER_SPP"])
 
 
 def _worker(args):
@@ -87,7 +96,7 @@ def main():
         res[key + "_sum"], res[key + "_sumsq"] = s1, s2
         res[key + "_meta"] = np.array([cfg["width"], cfg["height"], cfg["spp"]])
         print(f"{name}: {cfg['width']}x{cfg['height']} @ {cfg['spp']} spp, mean radiance {s1.mean() / cfg['spp']:.4f}, {time.time() - t0:.0f} s", flush=True)
-    path = os.path.join(HERE, "ref_render.npz")
+    path = os.path.join(HERE, OUT)
     if os.path.exists(path) and (BATCH > 0 or ONLY):             # accumulate into / keep the other scenes of an existing file
         old = np.load(path)
         for k in list(res):
@@ -96,7 +105,7 @@ def main():
         for k in old.files:
             res.setdefault(k, old[k])
     np.savez_compressed(path, **res)
-    print("wrote ref_render.npz", {k: int(res[k][2]) for k in res if k.endswith("_meta")})
+    print("wrote", OUT, {k: int(res[k][2]) for k in res if k.endswith("_meta")})
 
 
 if __name__ == "__main__":

@@ -28,23 +28,35 @@ def test_reference_more_scene_hits(idx):
     _check(host_scene(case["name"]), case, case["name"])
 
 
-@pytest.mark.parametrize("key", ["cornell_box", "test_bezier"])
-def test_converged_image_against_the_references_own_render(key):
+def _render_files():
+    import os
+    from tests.test_reference_golden import GOLD, RENDER_SCENES
+    import numpy as np
+    out = [("ref_render.npz", k) for k in RENDER_SCENES]
+    big = os.path.join(GOLD, "ref_render32.npz")           # round 2: 32 x 32 thumbnails of the scenes HEAD's `color` can run
+    if os.path.exists(big):
+        out += [("ref_render32.npz", k[:-5]) for k in np.load(big).files if k.endswith("_meta")]
+    return out
+
+
+@pytest.mark.parametrize("fname,key", _render_files())
+def test_converged_image_against_the_references_own_render(fname, key):
     """North star, second criterion, on the CUDA path: a 16384-spp render of the scene against the image the REFERENCE
-    rendered on the CPU (tests/golden/ref_render.npz, independent random numbers); judged against the reference
-    render's own Monte-Carlo standard error, same bars as tests/test_reference_golden.py."""
+    rendered on the CPU (tests/golden/ref_render*.npz, independent random numbers); judged against the reference
+    render's own Monte-Carlo standard error, same bars as tests/test_reference_golden.py (all four scenes: Cornell box,
+    curves, constant media, Perlin textures under small lights)."""
     import os
     import numpy as np
     import scheme_raytrace_b200 as srt
-    from tests.test_reference_golden import GOLD, RENDER_SCENES, render_stats
-    gold = np.load(os.path.join(GOLD, "ref_render.npz"))
+    from tests.test_reference_golden import GOLD, RENDER_SCENES, RENDER_TAILS, render_stats
+    gold = np.load(os.path.join(GOLD, fname))
     w, h, n = (int(x) for x in gold[key + "_meta"])
     r = srt.Renderer(host_scene(RENDER_SCENES[key], w, h), device=0)
     spp = 16384
     img, st = r.render(w, h, spp, max_depth=100, seed=78)
     r.close()
     s = render_stats(gold, key, img.astype(np.float64) / spp, spp)
-    print(f"\n[reference render {key}, CUDA path] rays={st.rays} {s}")
-    assert 0.45 <= s["median_abs_z"] <= 0.95 and s["frac_within_3"] >= 0.975 and s["frac_within_4"] >= 0.995
+    print(f"\n[reference render {fname}:{key} {w}x{h}@{n}spp, CUDA path] rays={st.rays} {s}")
+    assert 0.45 <= s["median_abs_z"] <= 0.95 and s["frac_within_3"] >= RENDER_TAILS[key][0] and s["frac_within_4"] >= RENDER_TAILS[key][1]
     assert abs(s["bias_z"]) <= 4.0 and abs(s["rel_mean"] - 1.0) <= 0.02
     assert s["rmse"] <= 1.3 * s["expected_rmse"]

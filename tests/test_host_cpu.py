@@ -30,10 +30,26 @@ def test_no_cpu_fallback_without_gpu():
         srt.Renderer(scenes.cfg1_weekend(8, 8))
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes / numpy mirrors against include/srt.h as a C compiler lays it out (sizes and the
+    offsets of the fields the host writes or reads)."""
     import ctypes as C
-    assert C.sizeof(ffi.RenderParams) == 64 and C.sizeof(ffi.Stats) == 120
-    assert flatten.PRIM_DTYPE.itemsize == 80 and flatten.CAMERA_DTYPE.itemsize == 96
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "srt.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SrtRenderParams), sizeof(SrtStats), sizeof(SrtPrim),'
+        ' sizeof(SrtCamera), sizeof(SrtXform), sizeof(SrtMaterial), sizeof(SrtTexture), sizeof(SrtBvhNode), sizeof(SrtRay), sizeof(SrtHit),'
+        ' offsetof(SrtStats, nonfinite), offsetof(SrtStats, rays_per_bounce)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    from scheme_raytrace_b200.host import render
+    want = [C.sizeof(ffi.RenderParams), C.sizeof(ffi.Stats), flatten.PRIM_DTYPE.itemsize, flatten.CAMERA_DTYPE.itemsize, flatten.XFORM_DTYPE.itemsize,
+            flatten.MATERIAL_DTYPE.itemsize, flatten.TEXTURE_DTYPE.itemsize, render.BVH_NODE_DTYPE.itemsize, render.RAY_DTYPE.itemsize, render.HIT_DTYPE.itemsize,
+            ffi.Stats.nonfinite.offset, ffi.Stats.rays_per_bounce.offset]
+    assert got == want, (got, want)
+    assert C.sizeof(ffi.RenderParams) == 64 and C.sizeof(ffi.Stats) == 128
 
 
 def test_flatten_order_and_instances():

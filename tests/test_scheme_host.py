@@ -264,3 +264,15 @@ def test_vec_modules_agree_with_the_references():
             py.append(list(r) if isinstance(r, tuple) else float(r))
     py.append(list(v.scale(vs[0], 2.5)))
     assert py == ref
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference sources only exist in the build container")
+def test_chain_fixtures_are_what_the_reference_scene_text_produces(tmp_path):
+    """tests/golden/chain_<scene>.srt (the committed first half of the drop-in chain, see make_chain_fixtures.py) must be,
+    byte for byte, what main.scm's unmodified scene definitions write through the repo's Scheme host today; the GPU half
+    (tests/test_gpu_chain.py) feeds these files to cli/srt_render and compares the PPM with the reference-written one."""
+    from tests.golden.make_chain_fixtures import write_chain_files, CHAIN_SCENES
+    write_chain_files(str(tmp_path))
+    gold = os.path.join(ROOT, "tests", "golden")
+    for name in CHAIN_SCENES:
+        assert open(os.path.join(gold, f"chain_{name}.srt")).read() == open(tmp_path / f"chain_{name}.srt").read(), name

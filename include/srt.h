@@ -104,7 +104,8 @@ typedef struct {
   int32_t reserved[5];         /* [0] = 1: time extend/shade launches separately and count rays per bounce (slower);
                                 * [1] = 1: no CUDA graph; [2] = 1: rgb_sum of srt_render_host / _multi is write-only
                                 * (the frame starts from zero: skips the upload of the running sum);
-                                * [3] = 1: drain through the wavefront instead of the one-launch tail kernel (A/B, tests) */
+                                * [3] = 1: drain through the wavefront instead of the one-launch tail kernel (A/B, tests);
+                                * [4] = 2: split the sample range over two concurrent streaming pipelines (A/B, tests; default one) */
 } SrtRenderParams;
 
 typedef struct {
@@ -120,6 +121,8 @@ typedef struct {
   int32_t extend_launches;     /* extend launches timed for ms_extend                    */
   int32_t tail_runs;           /* times the one-launch drain kernel finished the queue   */
   uint64_t nonfinite;          /* NaN / Inf radiance contributions dropped (0 inside the reference's domain) */
+  int32_t pipes;               /* concurrent streaming pipelines the call used on its GPU (1 or 2) */
+  int32_t pad;
 } SrtStats;
 
 /* 64-byte node of the LBVH as the traversal kernel reads it: the two child boxes as centre and

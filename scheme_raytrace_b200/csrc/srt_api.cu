@@ -7,6 +7,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <cmath>
 #include <thread>
 #include <mutex>
 #include <dlfcn.h>
@@ -122,16 +123,25 @@ struct SrtScene {
   std::vector<int> item_prim, global_prims;
   DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
   int n_nodes = 0, n_surf = 0, n_items = 0, bvh_depth = 0; float ms_commit = 0.f; int commit_launches = 0;
-  // wavefront
-  WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned long long> w_accum; DevBuf<unsigned char> w_ctrl;
-  void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
-  cudaStream_t work = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // graph capture needs a non-legacy stream
+  // wavefront: SRT_MAX_PIPES independent streaming pipelines (queues, control block, stream, cached graph each) that
+  // share the frame's 64-bit accumulator.  A render splits its sample range over them and runs them CONCURRENTLY on
+  // half-size persistent grids, so that one pipeline's shade (waiting on HBM) and the other's extend (ALU-bound)
+  // share every SM ("two pipelines").
+  struct Pipe {
+    WaveBuffers wb; DevBuf<float4> w_ro[2], w_rd[2], w_st[2], w_hit; DevBuf<unsigned char> w_ctrl;
+    void* h_ctrl = nullptr; cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    cudaStream_t work = nullptr; cudaEvent_t ev_out = nullptr;   // graph capture needs a non-legacy stream
+    GraphCache gcache;
+  };
+  Pipe pipe[SRT_MAX_PIPES];
+  DevBuf<unsigned long long> w_accum;
+  cudaEvent_t ev_in = nullptr;
   DevBuf<float> d_accum;     // staging accumulation buffer for srt_render_host / srt_render_multi
   DevBuf<uint8_t> d_image;   // 8-bit frame of srt_render_multi / srt_progressive_step
   DevBuf<float> d_prog; int prog_w = 0, prog_h = 0, prog_spp = 0;   // device-resident running sum of the progressive path (*raw-data*, main.scm:430)
   DevBuf<unsigned long long> d_stage;   // multi-GPU: peers' accumulators staged on the root when peer access is unavailable
-  GraphCache gcache;         // executable graph of one iteration batch (wavefront.cu)
   int device = 0;            // the CUDA device this scene lives on
+  bool leaf32_ok = false;    // every sphere inside the LBVH is small against the scene (|r| < extent / 64): fp32 sphere test
   bool multi = false;        // created under srt_init_multi: commit keeps one replica per GPU, srt_render_multi uses them
   unsigned long long version = 0;       // bumped by every set_*; replicas re-commit when it differs
   std::vector<SrtScene*> replicas;      // srt_render_multi: one copy of the scene per extra GPU (owned)
@@ -150,24 +160,27 @@ static void fill_dscene(SrtScene* s) {
   d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.img_texels = s->d_img_texels.p; d.imgs = s->d_imgs.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
 }
 
-static int ensure_wave(SrtScene* s, size_t paths, size_t npix) {
-  WaveBuffers& W = s->wb;
+static int ensure_wave(SrtScene* s, int k, size_t paths, size_t npix) {
+  SrtScene::Pipe& P = s->pipe[k];
+  WaveBuffers& W = P.wb;
   if (paths > W.capacity) {
-    for (int g = 0; g < 2; ++g) { CK(s->w_ro[g].ensure(paths)); CK(s->w_rd[g].ensure(paths)); CK(s->w_st[g].ensure(paths)); }
-    CK(s->w_hit.ensure(paths));
-    for (int g = 0; g < 2; ++g) { W.ray_o[g] = s->w_ro[g].p; W.ray_d[g] = s->w_rd[g].p; W.state[g] = s->w_st[g].p; }
-      W.hit = s->w_hit.p; W.capacity = paths;
+    for (int g = 0; g < 2; ++g) { CK(P.w_ro[g].ensure(paths)); CK(P.w_rd[g].ensure(paths)); CK(P.w_st[g].ensure(paths)); }
+    CK(P.w_hit.ensure(paths));
+    for (int g = 0; g < 2; ++g) { W.ray_o[g] = P.w_ro[g].p; W.ray_d[g] = P.w_rd[g].p; W.state[g] = P.w_st[g].p; }
+    W.hit = P.w_hit.p; W.capacity = paths;
   }
-  W.graph = &s->gcache;
-  if (npix) { CK(s->w_accum.ensure(3 * npix)); W.accum64 = s->w_accum.p; }
-  if (!W.ctrl) { CK(s->w_ctrl.ensure(srt_wave_ctrl_bytes())); W.ctrl = s->w_ctrl.p; }
-  if (!s->h_ctrl) {
-    CK(cudaMallocHost(&s->h_ctrl, 2 * srt_wave_ctrl_bytes()));
-    CK(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
-    W.h_ctrl = s->h_ctrl; W.poll_events = s->poll_ev;
-    CK(cudaStreamCreateWithFlags(&s->work, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
+  W.graph = &P.gcache;
+  if (npix) CK(s->w_accum.ensure(3 * npix));
+  W.accum64 = s->w_accum.p;
+  if (!W.ctrl) { CK(P.w_ctrl.ensure(srt_wave_ctrl_bytes())); W.ctrl = P.w_ctrl.p; }
+  if (!P.h_ctrl) {
+    CK(cudaMallocHost(&P.h_ctrl, 2 * srt_wave_ctrl_bytes()));
+    CK(cudaEventCreateWithFlags(&P.poll_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&P.poll_ev[1], cudaEventDisableTiming));
+    W.h_ctrl = P.h_ctrl; W.poll_events = P.poll_ev;
+    CK(cudaStreamCreateWithFlags(&P.work, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&P.ev_out, cudaEventDisableTiming));
   }
+  if (!s->ev_in) CK(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
   return 0;
 }
 
@@ -181,6 +194,7 @@ static RenderLaunch make_launch(SrtScene* s, const SrtRenderParams* p) {
     L.prim_mask |= 1 << q.type;
     if (q.xform >= 0 && q.type <= SRT_PRIM_MOVING_SPHERE) L.prim_mask |= SRT_MASK_XF_SPHERE;
   }
+  if (s->leaf32_ok) L.prim_mask |= SRT_MASK_LEAF32;
   return L;
 }
 #define USE_DEVICE(s) CK(cudaSetDevice((s)->device))
@@ -226,20 +240,23 @@ void srt_scene_destroy(SrtScene* s) {
   for (SrtScene* r : s->replicas) srt_scene_destroy(r);
   s->replicas.clear();
   cudaSetDevice(s->device);
-  srt_graph_cache_release(s->gcache);
   s->d_image.release(); s->d_prog.release(); s->d_stage.release();
   if (s->ev_done) cudaEventDestroy(s->ev_done);
   s->d_tree_area.release(); s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
   s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
-  for (int g = 0; g < 2; ++g) { s->w_ro[g].release(); s->w_rd[g].release(); s->w_st[g].release(); }
-  s->w_hit.release(); s->w_accum.release(); s->w_ctrl.release(); s->d_accum.release();
-  if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
-  for (int i = 0; i < 2; ++i) if (s->poll_ev[i]) cudaEventDestroy(s->poll_ev[i]);
+  for (SrtScene::Pipe& P : s->pipe) {
+    srt_graph_cache_release(P.gcache);
+    for (int g = 0; g < 2; ++g) { P.w_ro[g].release(); P.w_rd[g].release(); P.w_st[g].release(); }
+    P.w_hit.release(); P.w_ctrl.release();
+    if (P.h_ctrl) cudaFreeHost(P.h_ctrl);
+    for (int i = 0; i < 2; ++i) if (P.poll_ev[i]) cudaEventDestroy(P.poll_ev[i]);
+    if (P.ev_out) cudaEventDestroy(P.ev_out);
+    if (P.work) cudaStreamDestroy(P.work);
+  }
+  s->w_accum.release(); s->d_accum.release();
   if (s->ev_in) cudaEventDestroy(s->ev_in);
-  if (s->ev_out) cudaEventDestroy(s->ev_out);
-  if (s->work) cudaStreamDestroy(s->work);
   delete s;
 }
 
@@ -368,7 +385,33 @@ static int commit_impl(SrtScene* s) {
       case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
       case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
       case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
-      case SRT_PRIM_PATCH: a[i] = make_float4(q[0], 0, 0, 0); b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0); break;
+      case SRT_PRIM_PATCH: {
+        // a = bounding SLAB of the leaf sub-patch, |n'.p - d'| <= 1: n = normal of the plane through the corner
+        // diagonals, [dmin, dmax] = extent of the 16 control points along it (the surface lies in their convex
+        // hull), padded for fp32 and for Newton's +-1e-3 domain slack.  The extend kernel intersects the ray with
+        // it inside the leaf's box interval before it parks the full test: 38 % of the box hits are culled
+        // (profiles/README.md, round 2).  Degenerate normal: n' = 0, d' = 0 (never culls).
+        const float* cp = s->patches.data() + 48 * (size_t)q[0];
+        auto P = [&](int k, int c) { return (double)cp[3 * k + c]; };
+        double e1[3], e2[3], nn[3];
+        for (int c = 0; c < 3; ++c) { e1[c] = P(15, c) - P(0, c); e2[c] = P(12, c) - P(3, c); }
+        nn[0] = e1[1] * e2[2] - e1[2] * e2[1]; nn[1] = e1[2] * e2[0] - e1[0] * e2[2]; nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        const double len = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+        float4 slab = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (len > 1e-20) {
+          double dmin = 1e300, dmax = -1e300, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
+          for (int k = 0; k < 16; ++k) {
+            double dk = 0.0;
+            for (int c = 0; c < 3; ++c) { dk += nn[c] / len * P(k, c); lo[c] = std::min(lo[c], P(k, c)); hi[c] = std::max(hi[c], P(k, c)); amax = std::max(amax, std::fabs(P(k, c))); }
+            dmin = std::min(dmin, dk); dmax = std::max(dmax, dk);
+          }
+          const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+          const double half = 0.5 * (dmax - dmin) * 1.001 + 4e-3 * diag + 4e-6 * amax;
+          slab = make_float4((float)(nn[0] / len / half), (float)(nn[1] / len / half), (float)(nn[2] / len / half), (float)(0.5 * (dmin + dmax) / half));
+        }
+        a[i] = slab; b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0);
+        break;
+      }
       case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
       default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
     }
@@ -520,6 +563,13 @@ static int commit_impl(SrtScene* s) {
     }
   }
   if (extra.empty() || chosen != (int)extra.size()) { if (build_with(chosen) < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed"); }
+  {   // fp32 sphere test for the tree's leaves iff every sphere in the tree is small against the scene (srt_device.cuh, isect_sphere32)
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = 0; i < ns; ++i) { if (s->prims[i].type == SRT_PRIM_KLEIN) continue; for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], hb[6 * i + k]); hi[k] = std::max(hi[k], hb[6 * i + 3 + k]); } }
+    float E = 0.f; for (int k = 0; k < 3; ++k) E = std::max(E, hi[k] - lo[k]);
+    s->leaf32_ok = ns > 0;
+    for (int i : s->item_prim) if (s->prims[i].type <= SRT_PRIM_MOVING_SPHERE && !(std::fabs(s->prims[i].p[3]) < E * (1.0f / 64.0f))) s->leaf32_ok = false;
+  }
   fill_dscene(s);
   CK(cudaGetLastError());
   int depth = 0;
@@ -652,26 +702,26 @@ int srt_render_multi(SrtScene* s, const SrtRenderParams* p, float* rgb_sum, uint
     int e = 0;
     for (int r = 0; r < n && e == 0; ++r) {
       SrtScene* sc = r == 0 ? s : s->replicas[r - 1];
-      e = M.nccl.Reduce(sc->wb.accum64, sc->wb.accum64, n3, 5 /* ncclUint64 */, 0 /* ncclSum */, 0, M.comms[r], sc->work);
+      e = M.nccl.Reduce(sc->w_accum.p, sc->w_accum.p, n3, 5 /* ncclUint64 */, 0 /* ncclSum */, 0, M.comms[r], sc->pipe[0].work);
     }
     const int e2 = M.nccl.GroupEnd();
     if (e || e2) return fail(SRT_ERR_CUDA, "render_multi: ncclReduce failed: %s", M.nccl.GetErrorString ? M.nccl.GetErrorString(e ? e : e2) : "?");
     USE_DEVICE(s);
-    CK(cudaStreamSynchronize(s->work));
+    CK(cudaStreamSynchronize(s->pipe[0].work));
     launches += n;
-    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->wb.accum64, nullptr, 0, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
+    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->w_accum.p, nullptr, 0, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
   } else {
     const unsigned long long* peers[SRT_MAX_DEVICES]; int np = 0;
     for (int r = 1; r < n; ++r) {
       SrtScene* sc = s->replicas[r - 1];
-      if (M.peer[r]) peers[np++] = sc->wb.accum64;
+      if (M.peer[r]) peers[np++] = sc->w_accum.p;
       else {                                   // no peer access: stage the accumulator on the root first
         CK(s->d_stage.ensure((size_t)(n - 1) * n3));
-        CK(cudaMemcpyPeerAsync(s->d_stage.p + (size_t)(r - 1) * n3, s->device, sc->wb.accum64, sc->device, sizeof(unsigned long long) * n3, 0));
+        CK(cudaMemcpyPeerAsync(s->d_stage.p + (size_t)(r - 1) * n3, s->device, sc->w_accum.p, sc->device, sizeof(unsigned long long) * n3, 0));
         peers[np++] = s->d_stage.p + (size_t)(r - 1) * n3;
       }
     }
-    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->wb.accum64, peers, np, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
+    srt_launch_reduce_peers(g_dev[s->device].sm_count, (int)n3, s->w_accum.p, peers, np, s->d_accum.p, (float)p->spp_end, image ? s->d_image.p : nullptr, 0); ++launches;
   }
   CK(cudaGetLastError());
   if (rgb_sum) CK(cudaMemcpyAsync(rgb_sum, s->d_accum.p, sizeof(float) * n3, cudaMemcpyDeviceToHost, 0));
@@ -731,15 +781,16 @@ int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t
   USE_DEVICE(s);
   if (n < 0 || (n && (!rays || !out))) return fail(SRT_ERR_ARG, "trace_batch: bad argument");
   if (n == 0) return 0;
-  if (int rc = ensure_wave(s, (size_t)n, 0)) return rc;
+  if (int rc = ensure_wave(s, 0, (size_t)n, 0)) return rc;
+  const WaveBuffers& wb0 = s->pipe[0].wb;
   cudaStream_t stream = 0;
   DevBuf<SrtRay> d_rays; DevBuf<SrtHit> d_out;
   CK(d_rays.ensure(n)); CK(d_out.ensure(n));
   CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(SrtRay) * (size_t)n, cudaMemcpyHostToDevice, stream));
   RenderLaunch L = make_launch(s, nullptr);
-  srt_launch_upload_rays(d_rays.p, n, s->wb.ray_o[0], s->wb.ray_d[0], stream);
-  srt_launch_extend(L, s->wb.ray_o[0], s->wb.ray_d[0], nullptr, s->wb.hit, nullptr, n, t_min, t_max, 0u, stream);   // the renderer's extend kernel
-  srt_launch_complete_hits(s->ds, s->wb.ray_o[0], s->wb.ray_d[0], s->wb.hit, n, d_out.p, stream);
+  srt_launch_upload_rays(d_rays.p, n, wb0.ray_o[0], wb0.ray_d[0], stream);
+  srt_launch_extend(L, wb0.ray_o[0], wb0.ray_d[0], nullptr, wb0.hit, nullptr, n, t_min, t_max, 0u, stream);   // the renderer's extend kernel
+  srt_launch_complete_hits(s->ds, wb0.ray_o[0], wb0.ray_d[0], wb0.hit, n, d_out.p, stream);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, d_out.p, sizeof(SrtHit) * (size_t)n, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
@@ -768,42 +819,81 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
   const size_t npix = (size_t)p->width * p->height;
   const int spp = p->spp_end - p->spp_begin;
   if (stats) std::memset(stats, 0, sizeof(*stats));
-  // queue sizing: 64 Mi paths in flight (SoA ray/state/hit queues = 112 B/path = 7.5 GB of the 180 GB
+  // Pipelines: the sample range CAN be split over SRT_MAX_PIPES concurrent streaming wavefronts (own queues, stream,
+  // cached graph; shared integer accumulator), each on a 1/n share of the persistent grids, so that one pipeline's
+  // shade (waiting on HBM) overlaps the other's extend (ALU-bound) on every SM.  Measured on B200 (profiles/README.md,
+  // round 2): cfg2 +2.5 %, but cfg3 -15 % and cfg4 -20 % (kernels of the two streams co-reside poorly: 3 resident
+  // extend CTAs do not halve, and the shared-memory carve-out differs between extend and shade) - so ONE pipeline is
+  // the default; SRT_PIPES=2 or params.reserved[4] == 2 selects two (kept bit-identical by tests/test_gpu_round2.py).
+  RenderLaunch L = make_launch(s, p);
+  static const int pipes_env = getenv("SRT_PIPES") ? atoi(getenv("SRT_PIPES")) : 1;
+  const size_t total = npix * (size_t)spp;
+  int npipes = 1;
+  const int want = p->reserved[4] == 2 ? 2 : (p->reserved[4] == 1 ? 1 : pipes_env);
+  if (!(L.prim_mask & 0x1e0) && p->reserved[0] != 1 && spp >= 2 && total >= ((size_t)16 << 20))
+    npipes = std::max(1, std::min(std::min(want, SRT_MAX_PIPES), spp));
+  L.grid_div = npipes;
+  // queue sizing: 64 Mi paths in flight in all (SoA ray/state/hit queues = 112 B/path = 7.5 GB of the 180 GB
   // HBM), never more than the job.  Measured on cfg2: 8 Mi -> 6.94, 64 Mi -> 7.31 Grays/s (fewer
   // iterations, and the depth-50 drain tail weighs less).
-  size_t total = npix * (size_t)spp;
-  size_t cap = p->wave_spp > 0 ? npix * (size_t)p->wave_spp : (size_t)(64u << 20);
-  if (cap > total) cap = total;
-  if (cap < 1) cap = 1;
-  if (cap > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: queue of %zu paths too large", cap);
-  if (int rc = ensure_wave(s, cap, npix)) return rc;
+  size_t caps[SRT_MAX_PIPES]; SrtRenderParams pp[SRT_MAX_PIPES];
+  for (int k = 0; k < npipes; ++k) {
+    pp[k] = *p;
+    pp[k].spp_begin = p->spp_begin + (int)((long long)k * spp / npipes); pp[k].spp_end = p->spp_begin + (int)((long long)(k + 1) * spp / npipes);
+    const size_t tk = npix * (size_t)(pp[k].spp_end - pp[k].spp_begin);
+    size_t cap = p->wave_spp > 0 ? npix * (size_t)p->wave_spp : (size_t)(64u << 20);
+    cap = std::max<size_t>(1, std::min(cap / npipes, tk));
+    if (cap > ((size_t)1 << 30)) return fail(SRT_ERR_ARG, "render: queue of %zu paths too large", cap);
+    caps[k] = cap;
+    if (int rc = ensure_wave(s, k, cap, npix)) return rc;
+  }
   if (spp == 0) {                              // nothing to trace; a multi-GPU rank still owes a zero accumulator
-    if (!d_rgb_sum) { CK(cudaMemsetAsync(s->wb.accum64, 0, sizeof(unsigned long long) * 3 * npix, 0)); CK(cudaStreamSynchronize(0)); }
+    if (!d_rgb_sum) { CK(cudaMemsetAsync(s->w_accum.p, 0, sizeof(unsigned long long) * 3 * npix, 0)); CK(cudaStreamSynchronize(0)); }
     return 0;
   }
-  // The loop runs on the scene's own non-blocking stream (CUDA-graph capture is not allowed on the
-  // legacy default stream) but is ordered inside stream 0 by events on both sides, so callers that
-  // bracket the call with events / work on the default stream (torch's current stream) stay correct.
-  cudaStream_t stream = s->work;
-  CK(cudaEventRecord(s->ev_in, 0)); CK(cudaStreamWaitEvent(stream, s->ev_in, 0));
-  RenderLaunch L = make_launch(s, p);
+  // The loops run on the pipes' own non-blocking streams (CUDA-graph capture is not allowed on the legacy
+  // default stream) but are ordered inside stream 0 by events on both sides, so callers that bracket the call
+  // with events / work on the default stream (torch's current stream) stay correct.
   const bool profile = p->reserved[0] == 1;
   EventPair tm; CK(tm.create());
-  CK(cudaEventRecord(tm.a, stream));
-  WaveBuffers W = s->wb; W.capacity = cap; W.use_graph = p->reserved[1] != 1;
-  SrtStats st; std::memset(&st, 0, sizeof(st));
-  cudaError_t werr = cudaSuccess;
-  if (srt_wavefront_render(L, W, d_rgb_sum, stream, &st, profile, &werr) < 0)
-    return fail(SRT_ERR_CUDA, "render: the wavefront loop failed: %s", werr == cudaErrorLaunchTimeout ? "the path queue did not drain within its iteration bound" : cudaGetErrorString(werr));
-  CK(cudaEventRecord(tm.b, stream));
-  CK(cudaEventRecord(s->ev_out, stream)); CK(cudaStreamWaitEvent(0, s->ev_out, 0));
+  CK(cudaEventRecord(tm.a, 0));
+  CK(cudaMemsetAsync(s->w_accum.p, 0, sizeof(unsigned long long) * 3 * npix, 0));
+  CK(cudaEventRecord(s->ev_in, 0));
+  SrtStats st[SRT_MAX_PIPES]; int rcs[SRT_MAX_PIPES]; cudaError_t werr[SRT_MAX_PIPES];
+  auto run = [&](int k) {
+    cudaSetDevice(s->device);
+    SrtScene::Pipe& P = s->pipe[k];
+    std::memset(&st[k], 0, sizeof(SrtStats)); werr[k] = cudaSuccess;
+    if (cudaStreamWaitEvent(P.work, s->ev_in, 0) != cudaSuccess) { rcs[k] = SRT_ERR_CUDA; werr[k] = cudaGetLastError(); return; }
+    RenderLaunch Lk = L; Lk.p = pp[k];
+    WaveBuffers W = P.wb; W.capacity = caps[k]; W.use_graph = p->reserved[1] != 1; W.own_accum = false;
+    rcs[k] = srt_wavefront_render(Lk, W, nullptr, P.work, &st[k], profile, &werr[k]);
+    if (rcs[k] >= 0) cudaEventRecord(P.ev_out, P.work);
+  };
+  {
+    std::vector<std::thread> th;
+    for (int k = 1; k < npipes; ++k) th.emplace_back(run, k);
+    run(0);
+    for (std::thread& t : th) t.join();
+  }
+  for (int k = 0; k < npipes; ++k)
+    if (rcs[k] < 0) return fail(SRT_ERR_CUDA, "render: the wavefront loop failed: %s", werr[k] == cudaErrorLaunchTimeout ? "the path queue did not drain within its iteration bound" : cudaGetErrorString(werr[k]));
+  for (int k = 0; k < npipes; ++k) CK(cudaStreamWaitEvent(0, s->pipe[k].ev_out, 0));
+  int extra = 0;
+  if (d_rgb_sum) extra += srt_launch_accum_to_float(L.sm_count, (int)(3 * npix), s->w_accum.p, d_rgb_sum, 0);
+  CK(cudaEventRecord(tm.b, 0));
   CK(cudaEventSynchronize(tm.b));
   CK(cudaGetLastError());
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
   if (stats) {
-    *stats = st;
+    for (int k = 0; k < npipes; ++k) {
+      stats->rays += st[k].rays; stats->kernel_launches += st[k].kernel_launches; stats->nonfinite += st[k].nonfinite; stats->tail_runs += st[k].tail_runs;
+      stats->waves = std::max(stats->waves, st[k].waves); stats->ms_extend += st[k].ms_extend; stats->ms_shade += st[k].ms_shade; stats->extend_launches += st[k].extend_launches;
+      for (int b = 0; b < 8; ++b) stats->rays_per_bounce[b] += st[k].rays_per_bounce[b];
+    }
+    stats->kernel_launches += extra;
     stats->paths = (uint64_t)total; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
-    stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth;
+    stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth; stats->pipes = npipes;
   }
   return 0;
 }

@@ -151,14 +151,47 @@ __device__ __forceinline__ bool isect_sphere(float3 c, float r, float3 o, float3
   // divide (<= 2 ulp each: ~2e-7 relative on t, far inside the 1e-4 parity tolerance and the 1e-5
   // near-tie filter) instead of the ~8-instruction IEEE sequences: this runs for every ray x
   // every primitive kept outside the tree, and at ~5/32 lanes for leaf tests
-  float sq; asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"((float)disc));
+  float sq; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"((float)disc));
   float q = -(bf + copysignf(sq, bf));
-  float ta = q * inv_a, tb = __fdividef(ccf, q); // the two roots (-b -/+ sqrt(disc))/a in some order
+  float tb; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(tb) : "f"(ccf), "f"(q));
+  float ta = q * inv_a;                          // the two roots (-b -/+ sqrt(disc))/a in some order
   float t1 = fminf(ta, tb), t2 = fmaxf(ta, tb);
   if (t1 > tmin) { t = t1; return true; }        // (< t-min temp ...) strict
   if (t2 > tmin) { t = t2; return true; }
   return false;
 }
+// The same test in fp32 only, for spheres that are SMALL against the scene (|r| < extent / 64, decided
+// at commit: SRT_MASK_LEAF32) - the many small spheres of random-scene, never the r = 100 / 1000 grounds.
+// Conditioning comes from the formulation instead of from FP64 (Haines / Guenther / Akenine-Moeller,
+// "Precision improvements for ray / sphere intersection"): the discriminant is taken from the
+// distance of the centre to the ray, disc / a = r^2 - |oc - (b / a) d|^2, which does not cancel for far
+// origins (b^2 - a c does: both terms ~ |oc|^2 |d|^2); c = oc.oc - r^2 only cancels for origins within
+// ~r / 300 of the surface (relative error of t ~ eps r / 2h), and the root that uses it is then ~0 and
+// rejected by t-min.  Same acceptance rule as above (miss iff disc <= 0, strict t-min).  No F2F / DFMA:
+// this runs at ~5 of 32 lanes in the leaf loop, where the FP64 form was 10 conversions on the
+// quarter-rate XU pipe plus ~17 half-rate FP64 instructions per test.
+__device__ __forceinline__ bool isect_sphere32(float3 c, float r, float3 o, float3 d, float inv_a, float tmin, float& t) {
+  const float3 oc = o - c;
+  const float b = dot(oc, d);
+  const float k = b * inv_a;
+  const float3 l = v3(fmaf(-k, d.x, oc.x), fmaf(-k, d.y, oc.y), fmaf(-k, d.z, oc.z));   // centre -> closest point of the ray
+  const float discr = fmaf(r, r, -dot(l, l));                                            // = disc / a
+  if (!(discr > 0.0f)) return false;
+  const float a = dot(d, d);
+  // approximate sqrt / divide, flush-to-zero forms: one MUFU each, no denormal rescue code (<= 2 ulp; see isect_sphere)
+  float sq; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(a * discr));
+  const float q = -(b + copysignf(sq, b));
+  const float cc = fmaf(-r, r, dot(oc, oc));
+  float tb; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(tb) : "f"(cc), "f"(q));
+  const float ta = q * inv_a;
+  const float t1 = fminf(ta, tb), t2 = fmaxf(ta, tb);
+  if (t1 > tmin) { t = t1; return true; }
+  if (t2 > tmin) { t = t2; return true; }
+  return false;
+}
+// An INSTANCED sphere (translate / rotate-y above a sphere leaf, geometry.scm:465-543): the ray goes to object space,
+// the rigid transform keeps t.  Out of line on purpose (see intersect_prim).
+static __device__ __noinline__ bool isect_sphere_instanced(const DScene& sc, int xform, float3 c, float r, float3 o, float3 d, float inv_a, float tmin, float& t);
 // geometry.scm:178-182 moving-sphere centre at the ray's time
 __device__ __forceinline__ float3 moving_center(float4 a, float4 b, float4 c, float time) {
   float3 c0 = xyz(a), c1 = xyz(b);
@@ -193,6 +226,11 @@ __device__ __forceinline__ float rect_t_f64(const Xf& x, int type, float k, floa
   if (type == SRT_PRIM_XY_RECT) { num = (double)k - ((double)x.s * qx + (double)x.c * qz); den = (double)x.s * (double)d.x + (double)x.c * (double)d.z; }
   else { num = (double)k - ((double)x.c * qx - (double)x.s * qz); den = (double)x.c * (double)d.x - (double)x.s * (double)d.z; }
   return __fdiv_rn((float)num, (float)den);
+}
+
+static __device__ __noinline__ bool isect_sphere_instanced(const DScene& sc, int xform, float3 c, float r, float3 o, float3 d, float inv_a, float tmin, float& t) {
+  const Xf x = load_xf(sc, xform);
+  return isect_sphere(c, r, xf_point_to_obj(x, o), xf_vec_to_obj(x, d), inv_a, tmin, t);
 }
 
 // bezier.scm — cubic Bezier curve with width; recursive subdivision with an explicit stack.
@@ -370,6 +408,17 @@ static __device__ __forceinline__ bool isect_patch(const float4* __restrict__ cp
   return true;
 }
 
+// Bounding slab of a leaf sub-patch (srt_api.cu fills prim_a = (n', d') with |n'.p - d'| <= 1 on the whole
+// convex hull of its control net): true iff the ray stays outside the slab over the leaf's box interval
+// [tb0, tb1], i.e. the full test (projection, hull cull, Newton) cannot find a hit.  b = 0 (ray parallel to
+// the slab) gives +-inf bounds of the right sign; a degenerate slab (n' = 0) never culls.
+__device__ __forceinline__ bool patch_slab_culled(float4 sl, float3 o, float3 d, float tb0, float tb1) {
+  const float a = dot(xyz(sl), o) - sl.w, b = dot(xyz(sl), d);
+  const float ib = __frcp_rn(b);
+  const float t0 = (-1.0f - a) * ib, t1 = (1.0f - a) * ib;
+  return fmaxf(fminf(t0, t1), tb0) > fminf(fmaxf(t0, t1), tb1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // geometry.scm:590-664 Klein / IIS fractal: inversion in six spheres (<= 10 times), sphere-traced
 // <= 100 steps, central-difference normal.  Evaluated in FP64: the finite-difference normal of a
@@ -439,11 +488,13 @@ struct Hit { float t; int prim; float u, v; bool incl; };
 #ifndef SRT_MASK_ALL
 #define SRT_MASK_ALL 0x1ff
 #endif
+#define SRT_MASK_LEAF32 0x400   // not a primitive kind: "the spheres inside the LBVH are small against the scene" (fp32 sphere test)
 template <int MASK, class PrimSrc>
 __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& ps, int id, float3 o, float3 d, float time, float inv_a, float tmin,
                                                const RngAddr& ra, Hit& h) {
   constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40, HAS_PATCH = MASK & 0x80, HAS_KLEIN = MASK & 0x100;
-  constexpr bool SINGLE_KIND = (MASK & (MASK - 1)) == 0;
+  constexpr bool LEAF32 = MASK & SRT_MASK_LEAF32;           // small spheres: the fp32 formulation (isect_sphere32)
+  constexpr bool SINGLE_KIND = ((MASK & SRT_MASK_ALL) & ((MASK & SRT_MASK_ALL) - 1)) == 0;
   float4 a = ps.a(id);
   int type, xform = -1, aux = 0;
   if (SINGLE_KIND && (MASK & 0x23)) type = HAS_SPHERE ? SRT_PRIM_SPHERE : (HAS_MOVING ? SRT_PRIM_MOVING_SPHERE : SRT_PRIM_BEZIER);
@@ -453,14 +504,15 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     // an instanced sphere (geometry.scm:465-543 above a sphere leaf): the rigid transform keeps t, so
     // the ray goes to object space and t comes back unchanged.  Sphere-only kernels (SINGLE_KIND) never
     // see one: such scenes are routed to a variant that reads the header (variant_of, wavefront.cu).
-    float3 oo = o, dd = d;
-    if (!SINGLE_KIND && xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
-    ok = isect_sphere(xyz(a), a.w, oo, dd, inv_a, tmin, t);
+    // (the instanced case is a rare out-of-line call: inlined, its transform code cost the curve / patch variant
+    // 13 % on cfg5, where no sphere is instanced)
+    if (!SINGLE_KIND && xform >= 0) ok = isect_sphere_instanced(sc, xform, xyz(a), a.w, o, d, inv_a, tmin, t);
+    else ok = LEAF32 ? isect_sphere32(xyz(a), a.w, o, d, inv_a, tmin, t) : isect_sphere(xyz(a), a.w, o, d, inv_a, tmin, t);
   } else if (HAS_MOVING && type == SRT_PRIM_MOVING_SPHERE) {
     float4 b = __ldg(&sc.prim_b[id]), c = __ldg(&sc.prim_c[id]);
-    float3 oo = o, dd = d;
-    if (!SINGLE_KIND && xform >= 0) { Xf x = load_xf(sc, xform); oo = xf_point_to_obj(x, o); dd = xf_vec_to_obj(x, d); }
-    ok = isect_sphere(moving_center(a, b, c, time), a.w, oo, dd, inv_a, tmin, t);
+    const float3 ctr = moving_center(a, b, c, time);
+    if (!SINGLE_KIND && xform >= 0) ok = isect_sphere_instanced(sc, xform, ctr, a.w, o, d, inv_a, tmin, t);
+    else ok = LEAF32 ? isect_sphere32(ctr, a.w, o, d, inv_a, tmin, t) : isect_sphere(ctr, a.w, o, d, inv_a, tmin, t);
   } else if (HAS_RECT && type <= SRT_PRIM_YZ_RECT) {
     float k = __int_as_float(aux);                       // plane constant, carried in the header (srt_api.cu)
     float3 oo = o, dd = d; float ti = 0.f; bool have_t = false;
@@ -574,6 +626,24 @@ __device__ __forceinline__ float perlin_noise(const DScene& sc, float3 p, int qu
   float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
   const bool alias = quirks & SRT_Q4_PERLIN_ALIAS;   // Q4 perlin.scm:76: c[i][j][k] = grad(i+1, j+1, k+dk)
   float acc = 0.0f;
+  if (alias) {
+    // Under the reference's aliasing the eight corners hold only TWO distinct gradients (dk = 0, 1): 5 table
+    // loads per call instead of 32 - the marble texture (7 octaves) goes from 224 to 35 loads per hit.  Same
+    // terms in the same order as the general loop below.
+    const int ixy = __ldg(&sc.perm[(i + 1) & 255]) ^ __ldg(&sc.perm[256 + ((j + 1) & 255)]);
+    const float3 g0 = xyz(__ldg(&sc.ranvec[ixy ^ __ldg(&sc.perm[512 + (k & 255)])]));
+    const float3 g1 = xyz(__ldg(&sc.ranvec[ixy ^ __ldg(&sc.perm[512 + ((k + 1) & 255)])]));
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float wa = a ? uu : 1.0f - uu, wb = b ? vv : 1.0f - vv, wc = c ? ww : 1.0f - ww;
+          acc += wa * wb * wc * dot(v3(u - a, v - b, w - c), c ? g1 : g0);
+        }
+    return acc;
+  }
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll

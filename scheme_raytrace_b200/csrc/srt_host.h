@@ -6,6 +6,7 @@
 #include "srt_device.cuh"
 
 #define SRT_MAX_DEVICES 16
+#define SRT_MAX_PIPES 2                     // concurrent streaming pipelines per render call (srt_api.cu render_impl)
 #define SRT_MASK_XF_SPHERE 0x200            // prim_mask bit: a sphere / moving sphere sits under a translate / rotate-y chain
 
 struct LbvhBuffers {
@@ -42,6 +43,7 @@ struct WaveBuffers {
   void* h_ctrl = nullptr;                  // 2 x WaveCtrl (pinned host)
   void* poll_events = nullptr;             // 2 x cudaEvent_t
   bool use_graph = true;                   // replay the iteration batches as a CUDA graph
+  bool own_accum = true;                   // false: the caller zeroes accum64 before and converts it after (several pipelines share it)
   struct GraphCache* graph = nullptr;      // executable graph of one iteration batch, cached on the scene
 };
 
@@ -59,6 +61,7 @@ struct RenderLaunch {
   int sm_count; bool bvh_in_smem; size_t extend_smem;
   int prim_mask;                            // bit k set = primitive kind k present (extend kernel variant); SRT_MASK_XF_SPHERE
   int device;                               // CUDA device the scene lives on (index of the per-device variant cache)
+  int grid_div;                             // this launch's share of the persistent grids is 1 / grid_div (concurrent pipelines)
 };
 
 // returns the number of kernel launches or a negative SrtError (*cuda_err = the failing CUDA status);

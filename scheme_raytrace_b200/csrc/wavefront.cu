@@ -17,6 +17,7 @@
 #include <mutex>
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 #include "srt_device.cuh"
 #include "srt_host.h"
 
@@ -109,10 +110,15 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
 // default; the stackless fallback keeps a bit trail - bit k from the LSB = "the far child at the
 // k-th level above is still pending" - and follows parent links up to the lowest set bit, then
 // enters the sibling).  No local memory in either mode.
+// staged primitive tables, addressed through 32-bit shared-space addresses (through generic pointers
+// the compiler re-derives the shared window - S2UR SR_CgaCtaId + LEA - at every leaf test)
 struct PrimShared {
-  const int4* h; const float4* pa;
-  __device__ __forceinline__ int4 hdr(int i) const { return h[i]; }
-  __device__ __forceinline__ float4 a(int i) const { return pa[i]; }
+  uint32_t h, pa;
+  __device__ __forceinline__ PrimShared(const int4* hp, const float4* ap) : h((uint32_t)__cvta_generic_to_shared(hp)), pa((uint32_t)__cvta_generic_to_shared(ap)) {
+    asm volatile("" : "+r"(h), "+r"(pa));    // opaque: held in registers, not re-derived per test
+  }
+  __device__ __forceinline__ int4 hdr(int i) const { int4 r; asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(h + 16u * (uint32_t)i)); return r; }
+  __device__ __forceinline__ float4 a(int i) const { float4 r; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(pa + 16u * (uint32_t)i)); return r; }
 };
 struct PrimGlobal {
   const int4* h; const float4* pa;
@@ -127,6 +133,7 @@ struct Trav {
   RngAddr ra;                                // only read by constant-medium primitives
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
   uint32_t sp, sp0;                         // TRAV_STACK: shared-space address of the next free / first stack slot
+  int n_nodes;                              // plane stride of the staged node layout
 #ifdef SRT_COUNT_STEPS
   int nsteps, ntests, nmiss, maxsp;         // instrumented build only (tools/step_stats.py); maxsp = deepest stack use
 #endif
@@ -142,7 +149,7 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
   T.ainv = v3(fabsf(T.inv.x), fabsf(T.inv.y), fabsf(T.inv.z));
   T.inv_a = 1.0f / dot(T.d, T.d);
   T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
-  T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0; T.sp = T.sp0;
+  T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0;      // T.sp: back above the sentinel after every finished traversal
 #ifdef SRT_COUNT_STEPS
   T.nsteps = 0; T.ntests = 0; T.nmiss = 0; T.maxsp = 0;
 #endif
@@ -173,6 +180,45 @@ __device__ __forceinline__ float4 ld_node(const float4* __restrict__ nodes, uint
   return __ldg(&nodes[idx]);
 }
 
+// STAGED node layout (shared memory only; the global array keeps the 64-byte SrtBvhNode the bit-exact
+// LBVH check reads back).  Word-major ("SoA") and child-interleaved:
+//   plane 0 [node] = (lc.x rc.x lc.y rc.y)   plane 1 = (lc.z rc.z le.x re.x)
+//   plane 2 [node] = (le.y re.y le.z re.z)   plane 3 = (left right parent sibling)
+// Word-major: the lanes of a quarter-warp read 16-byte words of DIFFERENT nodes; as 64-byte records all
+// of them fall on 2 of the 8 16-byte bank groups (ncu r1: 31 % of the shared wavefronts were conflict
+// replays), as planes they spread over all 8 by node id.  Child-interleaved: (left, right) of one
+// coordinate sit in an aligned register pair, which is what the packed FFMA2 of sm_100 takes.
+#ifndef SRT_NODE_AOS
+#define SRT_NODE_PLANES 1
+#else
+#define SRT_NODE_PLANES 0
+#endif
+__device__ __forceinline__ void stage_nodes(float4* __restrict__ smem, const float4* __restrict__ nodes, int n_nodes) {
+#if SRT_NODE_PLANES
+  for (int i = threadIdx.x; i < n_nodes; i += blockDim.x) {
+    const float4 a = nodes[4 * i], b = nodes[4 * i + 1], c = nodes[4 * i + 2], d = nodes[4 * i + 3];
+    // global: a = (lc.x lc.y lc.z le.x) b = (le.y le.z rc.x rc.y) c = (rc.z re.x re.y re.z)
+    smem[i] = make_float4(a.x, b.z, a.y, b.w);
+    smem[n_nodes + i] = make_float4(a.z, c.x, a.w, c.y);
+    smem[2 * n_nodes + i] = make_float4(b.x, c.z, b.y, c.w);
+    smem[3 * n_nodes + i] = d;
+  }
+#else
+  for (int i = threadIdx.x; i < 4 * n_nodes; i += blockDim.x) smem[i] = nodes[i];
+#endif
+}
+// packed fp32x2 FMA of sm_100 (FFMA2): (a.x, a.y) * b + (c.x, c.y), b broadcast; one issue slot for two FMAs
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+  return r;
+}
+__device__ __forceinline__ float2 ffma2s(float2 a, float b, float c) { return ffma2(a, b, make_float2(c, c)); }
+
 // Backtracking modes (template parameter TRAV):
 //  TRAV_STACK  per-thread stack of 16-bit node ids in shared memory, bvh_depth + 1 entries (a thread
 //              never has more far children pending than internal nodes on its root path): push =
@@ -181,24 +227,48 @@ __device__ __forceinline__ float4 ld_node(const float4* __restrict__ nodes, uint
 //              two 64-bit registers.
 //  TRAV_TRAIL  the bit trail alone (>= 65536 nodes).
 enum { TRAV_TRAIL = 0, TRAV_CACHE = 1, TRAV_STACK = 2 };
-__host__ __device__ __forceinline__ int trav_stack_stride(int bvh_depth) { return (bvh_depth + 1) | 1; }   // halfwords per thread, odd: spreads banks
+// halfwords per thread, odd (spreads banks): bvh_depth + 1 pending far children + the SENTINEL 0xffff at
+// the bottom, written once per thread: "pop" needs no compare against the stack base, the empty stack
+// answers with the sentinel (node ids are < 65535 in this mode)
+__host__ __device__ __forceinline__ int trav_stack_stride(int bvh_depth) { return (bvh_depth + 2) | 1; }
+#define SRT_STACK_SENTINEL 0xffffu
+__device__ __forceinline__ uint32_t trav_stack_init(uint32_t base) {
+  asm volatile("st.shared.u16 [%0], %1;" :: "r"(base), "h"((unsigned short)SRT_STACK_SENTINEL) : "memory");
+  return base + 2u;
+}
 
-template <bool SMEM, int TRAV>
-__device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, uint32_t sbase, float tmin, int& pend0, int& pend1) {
+// WANT_T: also returns the box intervals [t0, t1] of the stashed leaf children (ivl = {pend0's t0, t1,
+// pend1's t0, t1}; already clipped to [tmin, closest hit so far]) for the patch variants' slab cull.
+template <bool SMEM, int TRAV, bool WANT_T = false>
+__device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, uint32_t sbase, float tmin, int& pend0, int& pend1, float4* ivl = nullptr) {
   const int node = T.node;
 #ifdef SRT_COUNT_STEPS
   T.nsteps++;
 #endif
-  const float4 n0 = ld_node<SMEM>(nodes, sbase, 4 * node), n1 = ld_node<SMEM>(nodes, sbase, 4 * node + 1),
-               n2 = ld_node<SMEM>(nodes, sbase, 4 * node + 2), n3 = ld_node<SMEM>(nodes, sbase, 4 * node + 3);
   const float3 inv = T.inv, oi = T.oi, ai = T.ainv;
-  // left: c = (n0.x n0.y n0.z) e = (n0.w n1.x n1.y); right: c = (n1.z n1.w n2.x) e = (n2.y n2.z n2.w)
-  float lcx = fmaf(n0.x, inv.x, -oi.x), lcy = fmaf(n0.y, inv.y, -oi.y), lcz = fmaf(n0.z, inv.z, -oi.z);
-  float rcx = fmaf(n1.z, inv.x, -oi.x), rcy = fmaf(n1.w, inv.y, -oi.y), rcz = fmaf(n2.x, inv.z, -oi.z);
-  float lt0 = fmaxf(fmaxf(fmaf(-n0.w, ai.x, lcx), fmaf(-n1.x, ai.y, lcy)), fmaxf(fmaf(-n1.y, ai.z, lcz), tmin));
-  float lt1 = fminf(fminf(fmaf(n0.w, ai.x, lcx), fmaf(n1.x, ai.y, lcy)), fminf(fmaf(n1.y, ai.z, lcz), T.h.t));
-  float rt0 = fmaxf(fmaxf(fmaf(-n2.y, ai.x, rcx), fmaf(-n2.z, ai.y, rcy)), fmaxf(fmaf(-n2.w, ai.z, rcz), tmin));
-  float rt1 = fminf(fminf(fmaf(n2.y, ai.x, rcx), fmaf(n2.z, ai.y, rcy)), fminf(fmaf(n2.w, ai.z, rcz), T.h.t));
+  float lt0, lt1, rt0, rt1; float4 n3;
+  if (SMEM && SRT_NODE_PLANES) {
+    // staged planes: both children of a coordinate in one register pair, 9 FFMA2 for the two slab tests
+    const int N = T.n_nodes;
+    const float4 w0 = ld_node<true>(nodes, sbase, node), w1 = ld_node<true>(nodes, sbase, N + node), w2 = ld_node<true>(nodes, sbase, 2 * N + node);
+    n3 = ld_node<true>(nodes, sbase, 3 * N + node);
+    const float2 cx = ffma2s(make_float2(w0.x, w0.y), inv.x, -oi.x), cy = ffma2s(make_float2(w0.z, w0.w), inv.y, -oi.y), cz = ffma2s(make_float2(w1.x, w1.y), inv.z, -oi.z);
+    const float2 ex = make_float2(w1.z, w1.w), ey = make_float2(w2.x, w2.y), ez = make_float2(w2.z, w2.w);
+    const float2 nx = ffma2(ex, -ai.x, cx), ny = ffma2(ey, -ai.y, cy), nz = ffma2(ez, -ai.z, cz);
+    const float2 fx = ffma2(ex, ai.x, cx), fy = ffma2(ey, ai.y, cy), fz = ffma2(ez, ai.z, cz);
+    lt0 = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, tmin)); lt1 = fminf(fminf(fx.x, fy.x), fminf(fz.x, T.h.t));
+    rt0 = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, tmin)); rt1 = fminf(fminf(fx.y, fy.y), fminf(fz.y, T.h.t));
+  } else {
+    const float4 n0 = ld_node<SMEM>(nodes, sbase, 4 * node), n1 = ld_node<SMEM>(nodes, sbase, 4 * node + 1), n2 = ld_node<SMEM>(nodes, sbase, 4 * node + 2);
+    n3 = ld_node<SMEM>(nodes, sbase, 4 * node + 3);
+    // left: c = (n0.x n0.y n0.z) e = (n0.w n1.x n1.y); right: c = (n1.z n1.w n2.x) e = (n2.y n2.z n2.w)
+    float lcx = fmaf(n0.x, inv.x, -oi.x), lcy = fmaf(n0.y, inv.y, -oi.y), lcz = fmaf(n0.z, inv.z, -oi.z);
+    float rcx = fmaf(n1.z, inv.x, -oi.x), rcy = fmaf(n1.w, inv.y, -oi.y), rcz = fmaf(n2.x, inv.z, -oi.z);
+    lt0 = fmaxf(fmaxf(fmaf(-n0.w, ai.x, lcx), fmaf(-n1.x, ai.y, lcy)), fmaxf(fmaf(-n1.y, ai.z, lcz), tmin));
+    lt1 = fminf(fminf(fmaf(n0.w, ai.x, lcx), fmaf(n1.x, ai.y, lcy)), fminf(fmaf(n1.y, ai.z, lcz), T.h.t));
+    rt0 = fmaxf(fmaxf(fmaf(-n2.y, ai.x, rcx), fmaf(-n2.z, ai.y, rcy)), fmaxf(fmaf(-n2.w, ai.z, rcz), tmin));
+    rt1 = fminf(fminf(fmaf(n2.y, ai.x, rcx), fmaf(n2.z, ai.y, rcy)), fminf(fmaf(n2.w, ai.z, rcz), T.h.t));
+  }
   const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
   const bool hl0 = lt0 <= lt1, hr0 = rt0 <= rt1;
   // hit leaf children go to (pend0, pend1) - select form: as branches this was a divergent region
@@ -206,6 +276,7 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   const bool ll = hl0 & (left < 0), rl = hr0 & (right < 0);
   pend0 = ll ? ~left : (rl ? ~right : -1);
   pend1 = (ll & rl) ? ~right : -1;
+  if (WANT_T) *ivl = make_float4(ll ? lt0 : rt0, ll ? lt1 : rt1, rt0, rt1);
   const bool hl = hl0 & (left >= 0), hr = hr0 & (right >= 0);
   if (hl | hr) {
     bool both = hl & hr;
@@ -231,10 +302,10 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
     return true;
   }
   if (TRAV == TRAV_STACK) {
-    if (T.sp == T.sp0) return false;
-    T.sp -= 2u;
     unsigned short id;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(id) : "r"(T.sp) : "memory");
+    asm volatile("ld.shared.u16 %0, [%1+-2];" : "=h"(id) : "r"(T.sp) : "memory");
+    if (id == SRT_STACK_SENTINEL) return false;              // empty: sp stays just above the sentinel, ready for the next ray
+    T.sp -= 2u;
     T.node = (int)id;
     return true;
   }
@@ -250,7 +321,7 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   }
   int par = __float_as_int(n3.z), sib = __float_as_int(n3.w);
   for (int k = 0; k < up; ++k) {
-    const float4 m = ld_node<SMEM>(nodes, sbase, 4 * par + 3);
+    const float4 m = (SMEM && SRT_NODE_PLANES) ? ld_node<true>(nodes, sbase, 3 * T.n_nodes + par) : ld_node<SMEM>(nodes, sbase, 4 * par + 3);
     par = __float_as_int(m.z); sib = __float_as_int(m.w);
   }
   T.node = sib;
@@ -268,7 +339,10 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
     return;
   }
   Trav T;
+  T.n_nodes = sc.n_nodes;
   T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+  T.sp = T.sp0;
+  if (TRAV == TRAV_STACK) T.sp = T.sp0 = trav_stack_init(T.sp0);
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   // the next ray of this thread is fetched while the current one is traversed
@@ -285,8 +359,8 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
       T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
       T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
     }
-    for (int g = 0; g < sc.n_global; ++g)      // huge primitives first, all lanes together (uniform control flow)
-      intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+    for (int g = 0; g < sc.n_global; ++g)      // huge primitives first, all lanes together (uniform control flow); FP64 sphere terms
+      intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
     bool more = sc.n_items > 0;
     while (more) {
       int pend0 = -1, pend1 = -1;
@@ -334,7 +408,10 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
   }
   const int vote = tune & 0xff, refill = (tune >> 8) & 0xff;
   Trav T;
+  T.n_nodes = sc.n_nodes;
   T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+  T.sp = T.sp0;
+  if (TRAV == TRAV_STACK) T.sp = T.sp0 = trav_stack_init(T.sp0);
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   const int stride = gridDim.x * blockDim.x;
@@ -387,17 +464,22 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
     }
     if (ray >= 0 && more && !parked) {
       int pend0 = -1, pend1 = -1;
-      more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
+      float4 ivl = make_float4(0.f, 0.f, 0.f, 0.f);
+      more = node_step<SMEM, TRAV, (MASK & 0x80) != 0>(T, nodes, sbase, tmin, pend0, pend1, &ivl);
       while (pend0 >= 0) {
         const int type = ps.hdr(pend0).x & 0xff;
-        if (type >= SRT_PRIM_BEZIER) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
-        else {
+        if (type >= SRT_PRIM_BEZIER) {
+          // a patch leaf is parked only if the ray meets its bounding slab inside the leaf's box interval
+          // (15 instructions here against a ~300-instruction projection + hull cull inside the parked test)
+          const bool culled = (MASK & 0x80) && type == SRT_PRIM_PATCH && patch_slab_culled(ps.a(pend0), T.o, T.d, ivl.x, ivl.y);
+          if (!culled) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
+        } else {
 #ifdef SRT_COUNT_STEPS
           T.ntests++;
 #endif
           intersect_prim<MASK & 0x1f>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
         }
-        pend0 = pend1; pend1 = -1;
+        pend0 = pend1; pend1 = -1; ivl.x = ivl.z; ivl.y = ivl.w;
       }
     }
   }
@@ -418,12 +500,12 @@ k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__
     // stage the whole LBVH + primitive headers ("shared-memory staging of BVH top levels":
     // for the <= few-thousand-primitive scenes of the reference the top levels are all levels)
     int nn = 4 * sc.n_nodes, np = sc.n_prims;
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = sc.nodes[i];
+    stage_nodes(smem, sc.nodes, sc.n_nodes);
     int4* sh = (int4*)(smem + nn);
     float4* sa = smem + nn + np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
     __syncthreads();
-    PrimShared ps{sh, sa};
+    PrimShared ps(sh, sa);
     const uint32_t stack_base = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np);      // TRAV_STACK: after the staged scene
     if (MASK & 0x1e0) extend_loop_deferred<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base, tune);
     else extend_loop<true, MASK, TRAV>(sc, smem, ps, ray_o, ray_d, state, hit, count, tmin, tmax, seed, stack_base);
@@ -447,7 +529,6 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
   float3 thr = xyz(s4); const int pixel = __float_as_int(s4.w); const int sd = __float_as_int(d4.w);
   const int depth = sd & 0xfff; const unsigned int sample = (unsigned int)sd >> 12;
   const float3 o = xyz(o4), d = xyz(d4);
-  if (p.reserved[0] == 1) atomicAdd(&ctrl->bounce_hist[depth < 7 ? depth : 7], 1ull);     // profile mode: rays per bounce
   if (prim < 0) {                                              // main.scm:120 sky
     accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d), &ctrl->nonfinite);
     return false;
@@ -468,7 +549,9 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
 }
 
 // shade: one bounce for every live path + compaction of survivors into the other queue generation
-// (warp ballot -> per-warp count -> one atomic per CTA).
+// (warp ballot -> per-warp count -> one atomic per CTA).  Measured and NOT adopted (profiles/README.md,
+// round 2): the per-primitive tables staged in shared memory (+1 % cfg2, -2 % cfg3) and a software
+// prefetch of the next tile's queue entries (-9 % at 4 CTAs/SM with spills, -24 % at 3 CTAs/SM).
 template <int EST>
 __global__ void __launch_bounds__(SHD_THREADS, 4)
 k_shade(DScene sc, SrtRenderParams p, int g,
@@ -477,14 +560,21 @@ k_shade(DScene sc, SrtRenderParams p, int g,
         unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {
   __shared__ int s_warp[SHD_THREADS / 32];
   __shared__ int s_base;
+  __shared__ unsigned s_hist[8];
   const int count = ctrl->qcount[g];
   int* next_count = &ctrl->survivors[g ^ 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.reserved[0] == 1) { if (threadIdx.x < 8) s_hist[threadIdx.x] = 0u; __syncthreads(); }
   for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {   // block-uniform trip count
-    int i = base + threadIdx.x;
+    const int i = base + threadIdx.x;
     bool alive = false;
-    float4 no4 = make_float4(0.f, 0.f, 0.f, 0.f), nd4 = no4, ns4 = no4;
-    if (i < count) alive = shade_path<EST>(sc, p, hit[i], ray_o[i], ray_d[i], state[i], accum, ctrl, no4, nd4, ns4);
+    float4 no4 = make_float4(0.f, 0.f, 0.f, 0.f), nd4 = no4, ns4 = no4, d4 = no4;
+    if (i < count) { d4 = ray_d[i]; alive = shade_path<EST>(sc, p, hit[i], ray_o[i], d4, state[i], accum, ctrl, no4, nd4, ns4); }
+    if (p.reserved[0] == 1) {                     // profile mode: closest-hit queries per bounce (per-CTA histogram in shared memory)
+      const int bucket = i < count ? min(__float_as_int(d4.w) & 0xfff, 7) : 8;
+      const unsigned peers = __match_any_sync(0xffffffffu, bucket);
+      if (bucket < 8 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bucket], (unsigned)__popc(peers));
+    }
     unsigned ballot = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
@@ -501,6 +591,7 @@ k_shade(DScene sc, SrtRenderParams p, int g,
     }
     __syncthreads();
   }
+  if (p.reserved[0] == 1 && threadIdx.x < 8 && s_hist[threadIdx.x]) atomicAdd(&ctrl->bounce_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,37 +618,49 @@ k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
   const int count = ctrl->qcount[g];
   if ((int)(blockIdx.x * blockDim.x) >= count) return;
   const int nn = 4 * sc.n_nodes, np = sc.n_prims;
-  for (int i = threadIdx.x; i < nn; i += blockDim.x) smem[i] = sc.nodes[i];
+  stage_nodes(smem, sc.nodes, sc.n_nodes);
   int4* sh = (int4*)(smem + nn);
   float4* sa = smem + nn + np;
   for (int i = threadIdx.x; i < np; i += blockDim.x) { sh[i] = sc.prim_hdr[i]; sa[i] = sc.prim_a[i]; }
   __syncthreads();
-  const PrimShared ps{sh, sa};
+  const PrimShared ps(sh, sa);
   Trav T;
+  T.n_nodes = sc.n_nodes;
   T.sp0 = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np) + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+  T.sp = T.sp0 = trav_stack_init(T.sp0);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("" : "+r"(sbase));
   T.ra.seed = p.seed; T.ra.pixel = 0u; T.ra.sample = 0u; T.ra.bounce = 0u;
   unsigned int nrays = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    float4 o4 = ray_o[i], d4 = ray_d[i], s4 = state[i];
-    for (;;) {
-      trav_init(T, o4, d4, SRT_MAX_FLOAT, i);
-      ++nrays;
-      if (sc.n_surf > 0) {
-        for (int k = 0; k < sc.n_global; ++k)
-          intersect_prim<MASK>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
-        bool more = sc.n_items > 0;
-        while (more) {
-          int pend0 = -1, pend1 = -1;
-          more = node_step<true, TRAV_STACK>(T, smem, sbase, p.t_min, pend0, pend1);
-          while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h); pend0 = pend1; pend1 = -1; }
-        }
-      }
-      float4 no4, nd4, ns4;
-      if (!shade_path<EST>(sc, p, make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v), o4, d4, s4, accum, ctrl, no4, nd4, ns4)) break;
-      o4 = no4; d4 = nd4; s4 = ns4;
+  // Every LANE runs its own sequence of paths (grid-stride) and takes the next one the moment its
+  // current path ends: one trip of the loop is one bounce for every lane that still has work, so the
+  // lanes of a warp stay busy although their paths have different lengths (no queue, no compaction,
+  // no HBM traffic between bounces - the path state lives in registers).
+  int next = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  bool alive = false;
+  float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, s4 = o4;
+  for (;;) {
+    if (!alive) {
+      if (next >= count) break;
+      o4 = ray_o[next]; d4 = ray_d[next]; s4 = state[next];
+      next += stride; alive = true;
     }
+    trav_init(T, o4, d4, SRT_MAX_FLOAT, 0);
+    ++nrays;
+    if (sc.n_surf > 0) {
+      for (int k = 0; k < sc.n_global; ++k)
+        intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
+      bool more = sc.n_items > 0;
+      while (more) {
+        int pend0 = -1, pend1 = -1;
+        more = node_step<true, TRAV_STACK>(T, smem, sbase, p.t_min, pend0, pend1);
+        while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h); pend0 = pend1; pend1 = -1; }
+      }
+    }
+    float4 no4, nd4, ns4;
+    alive = shade_path<EST>(sc, p, make_float4(T.h.t, __int_as_float(T.h.prim), T.h.u, T.h.v), o4, d4, s4, accum, ctrl, no4, nd4, ns4);
+    if (alive) { o4 = no4; d4 = nd4; s4 = ns4; }
   }
   for (int o = 16; o; o >>= 1) nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
   if ((threadIdx.x & 31) == 0 && nrays) atomicAdd(&ctrl->rays, (unsigned long long)nrays);
@@ -703,8 +806,8 @@ typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, fl
 typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
 struct TailVariant { TailFn fn; size_t smem; int bps; };
-static ExtendVariant g_variants[SRT_MAX_DEVICES][2][5][3];
-static TailVariant g_tail_variants[SRT_MAX_DEVICES][3][2];
+static ExtendVariant g_variants[SRT_MAX_DEVICES][2][5][3][2];
+static TailVariant g_tail_variants[SRT_MAX_DEVICES][3][2][2];
 static std::mutex g_variant_mu;
 
 // spheres | + moving spheres | + rects / instances | + bicubic patches | everything (curves, media, Klein).
@@ -721,19 +824,23 @@ static int variant_of(int mask) {
   if ((mask & 0x160) == 0) return 3;
   return 4;
 }
-template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v) {
+template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v, bool leaf32) {
   switch (v) {
-    case 0: return k_extend<SMEM, 0x01, TRAV>;
-    case 1: return k_extend<SMEM, 0x03, TRAV>;
-    case 2: return k_extend<SMEM, 0x1f, TRAV>;
+    case 0: return leaf32 ? k_extend<SMEM, 0x01 | SRT_MASK_LEAF32, TRAV> : k_extend<SMEM, 0x01, TRAV>;
+    case 1: return leaf32 ? k_extend<SMEM, 0x03 | SRT_MASK_LEAF32, TRAV> : k_extend<SMEM, 0x03, TRAV>;
+    case 2: return leaf32 ? k_extend<SMEM, 0x1f | SRT_MASK_LEAF32, TRAV> : k_extend<SMEM, 0x1f, TRAV>;
     case 3: return k_extend<SMEM, 0x9f, TRAV>;
     default: return k_extend<SMEM, SRT_MASK_ALL, TRAV>;
   }
 }
-static ExtendFn variant_fn(bool smem, int v, int trav) {
-  if (trav == TRAV_STACK) return smem ? variant_fn_m<true, TRAV_STACK>(v) : variant_fn_m<false, TRAV_STACK>(v);
-  if (trav == TRAV_CACHE) return smem ? variant_fn_m<true, TRAV_CACHE>(v) : variant_fn_m<false, TRAV_CACHE>(v);
-  return smem ? variant_fn_m<true, TRAV_TRAIL>(v) : variant_fn_m<false, TRAV_TRAIL>(v);
+static ExtendFn variant_fn(bool smem, int v, int trav, bool leaf32) {
+  if (trav == TRAV_STACK) return smem ? variant_fn_m<true, TRAV_STACK>(v, leaf32) : variant_fn_m<false, TRAV_STACK>(v, leaf32);
+  if (trav == TRAV_CACHE) return smem ? variant_fn_m<true, TRAV_CACHE>(v, leaf32) : variant_fn_m<false, TRAV_CACHE>(v, leaf32);
+  return smem ? variant_fn_m<true, TRAV_TRAIL>(v, leaf32) : variant_fn_m<false, TRAV_TRAIL>(v, leaf32);
+}
+static bool leaf32_of(const RenderLaunch& L, int v) {
+  static const bool off = getenv("SRT_NO_LEAF32") != nullptr;                        // A/B switch
+  return !off && v <= 2 && (L.prim_mask & SRT_MASK_LEAF32);
 }
 static int trav_mode(const RenderLaunch& L, int v, size_t* stack_bytes) {
   const int which = L.bvh_in_smem ? 1 : 0;
@@ -751,11 +858,12 @@ static ExtendVariant extend_variant(const RenderLaunch& L) {
   size_t stack = 0;
   const int trav = trav_mode(L, v, &stack);
   const int threads = v >= 3 ? EXT_THREADS_HEAVY : EXT_THREADS;
+  const bool leaf32 = leaf32_of(L, v);
   std::lock_guard<std::mutex> lock(g_variant_mu);
-  ExtendVariant& e = g_variants[L.device][which][v][trav];
+  ExtendVariant& e = g_variants[L.device][which][v][trav][leaf32 ? 1 : 0];
   size_t smem = (which ? L.extend_smem : 0) + (trav == TRAV_STACK ? stack : 0);
   if (!e.fn || e.smem != smem) {
-    e.fn = variant_fn(which, v, trav); e.smem = smem; e.threads = threads;
+    e.fn = variant_fn(which, v, trav, leaf32); e.smem = smem; e.threads = threads;
     if (smem) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, e.fn, threads, smem);
@@ -772,11 +880,15 @@ static bool tail_variant(const RenderLaunch& L, TailVariant* out) {
   static const bool off = getenv("SRT_NO_TAIL") != nullptr;                          // A/B switch
   if (off) return false;
   const int est = L.p.estimator == SRT_EST_MIXTURE ? 1 : 0;
+  const bool leaf32 = leaf32_of(L, v);
   std::lock_guard<std::mutex> lock(g_variant_mu);
-  TailVariant& t = g_tail_variants[L.device][v][est];
+  TailVariant& t = g_tail_variants[L.device][v][est][leaf32 ? 1 : 0];
   const size_t smem = L.extend_smem + stack;
   if (!t.fn || t.smem != smem) {
-    if (est) t.fn = v == 0 ? k_tail<0x01, SRT_EST_MIXTURE> : (v == 1 ? k_tail<0x03, SRT_EST_MIXTURE> : k_tail<0x1f, SRT_EST_MIXTURE>);
+    constexpr int L32 = SRT_MASK_LEAF32;
+    if (est && leaf32) t.fn = v == 0 ? k_tail<0x01 | L32, SRT_EST_MIXTURE> : (v == 1 ? k_tail<0x03 | L32, SRT_EST_MIXTURE> : k_tail<0x1f | L32, SRT_EST_MIXTURE>);
+    else if (est) t.fn = v == 0 ? k_tail<0x01, SRT_EST_MIXTURE> : (v == 1 ? k_tail<0x03, SRT_EST_MIXTURE> : k_tail<0x1f, SRT_EST_MIXTURE>);
+    else if (leaf32) t.fn = v == 0 ? k_tail<0x01 | L32, SRT_EST_REFERENCE> : (v == 1 ? k_tail<0x03 | L32, SRT_EST_REFERENCE> : k_tail<0x1f | L32, SRT_EST_REFERENCE>);
     else t.fn = v == 0 ? k_tail<0x01, SRT_EST_REFERENCE> : (v == 1 ? k_tail<0x03, SRT_EST_REFERENCE> : k_tail<0x1f, SRT_EST_REFERENCE>);
     t.smem = smem;
     if (smem) cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -800,7 +912,8 @@ int srt_launch_extend(const RenderLaunch& L, const float4* ray_o, const float4* 
     vote = vote < 1 ? 1 : (vote > 32 ? 32 : vote); refill = refill < 1 ? 1 : (refill > 32 ? 32 : refill);
     return vote | (refill << 8);
   }();
-  e.fn<<<L.sm_count * e.bps, e.threads, e.smem, stream>>>(L.sc, ray_o, ray_d, state, hit, d_count, count, tmin, tmax, seed, tune);
+  const int div = L.grid_div > 1 ? L.grid_div : 1;
+  e.fn<<<L.sm_count * std::max(1, e.bps / div), e.threads, e.smem, stream>>>(L.sc, ray_o, ray_d, state, hit, d_count, count, tmin, tmax, seed, tune);
   return 1;
 }
 
@@ -826,7 +939,10 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   const int cap = (int)W.capacity;
   WaveCtrl* ctrl = (WaveCtrl*)W.ctrl;
   int launches = 0;
-  const int shade_grid = L.sm_count * 8, regen_grid = L.sm_count * 8;
+  const int div = L.grid_div > 1 ? L.grid_div : 1;
+  const int shade_grid = L.sm_count * std::max(1, 8 / div), regen_grid = L.sm_count * std::max(1, 8 / div);
+  typedef void (*ShadeFn)(DScene, SrtRenderParams, int, const float4*, const float4*, const float4*, const float4*, float4*, float4*, float4*, unsigned long long*, WaveCtrl*);
+  const ShadeFn shade_fn = p.estimator == SRT_EST_MIXTURE ? (ShadeFn)k_shade<SRT_EST_MIXTURE> : (ShadeFn)k_shade<SRT_EST_REFERENCE>;
   cudaError_t err = cudaSuccess;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   float acc_ext = 0.f, acc_shd = 0.f; int n_ext = 0;
@@ -836,14 +952,19 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   // not depend on it: progressive passes replay the same executable graph
   SrtRenderParams pk = p; pk.spp_begin = 0; pk.spp_end = 0; pk.wave_spp = 0; pk.reserved[1] = pk.reserved[2] = pk.reserved[3] = 0;
   TailVariant tv; const bool have_tail = p.reserved[3] != 1 && tail_variant(L, &tv);
-  const int tail_grid = have_tail ? L.sm_count * tv.bps : 0;
-  const int tail_max = have_tail ? tail_grid * EXT_THREADS * 2 : 0;   // about two waves of resident threads
+  const int tail_grid = have_tail ? L.sm_count * std::max(1, tv.bps / div) : 0;
+  // The drain takes over below 384 Ki queued paths (measured sweep, profiles/README.md, round 2): per ray the
+  // kernel is SLOWER than the wavefront (a whole 60 M-path fill through it: 35.0 vs 23.2 ms on cfg2), so it only
+  // pays where the wavefront is launch-bound - small frames (cfg1: 0.79 -> 0.36 ms) and the last, nearly
+  // empty iterations of a drain; larger thresholds lose (cfg3 at 2 Mi: +7 %).  SRT_TAIL_MAX overrides for A/B runs.
+  static const long long tail_env = getenv("SRT_TAIL_MAX") ? atoll(getenv("SRT_TAIL_MAX")) : -1;
+  const int tail_max = !have_tail ? 0 : (tail_env >= 0 ? (int)std::min<long long>(tail_env, 1ll << 30) : (384 << 10));
   auto launch_tail = [&](int g, int parity) {
     tv.fn<<<tail_grid, EXT_THREADS, tv.smem, stream>>>(L.sc, pk, g, parity, tail_max, W.ray_o[g], W.ray_d[g], W.state[g], W.accum64, ctrl);
     k_tail_done<<<1, 1, 0, stream>>>(g, parity, tail_max, ctrl);
     launches += 2;
   };
-  WCK(cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream));
+  if (W.own_accum) WCK(cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream));
   k_ctrl_init<<<1, 1, 0, stream>>>(ctrl, total, p.spp_begin); ++launches;
   k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, pk, npix, cap, 0, 0, W.ray_o[0], W.ray_d[0], W.state[0], ctrl); ++launches;
   if (have_tail && !profile && total <= (unsigned long long)tail_max && total <= (unsigned long long)cap) {
@@ -854,13 +975,13 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
     const int BATCH = 8;                          // even, so every batch has identical launch parameters
     int g = 0, parity = 1;
     auto enqueue_batch = [&]() {
-      if (have_tail && !profile) launch_tail(g, parity);
       for (int k = 0; k < BATCH; ++k) {
+        if (have_tail && !profile && (k & 3) == 0) launch_tail(g, parity);     // twice per batch: takes over as soon as the queue is small
         if (profile) cudaEventRecord(e0, stream);
         launches += srt_launch_extend(L, W.ray_o[g], W.ray_d[g], W.state[g], W.hit, &ctrl->qcount[g], 0, p.t_min, SRT_MAX_FLOAT, p.seed, stream);
         if (profile) cudaEventRecord(e1, stream);
-        (p.estimator == SRT_EST_MIXTURE ? k_shade<SRT_EST_MIXTURE> : k_shade<SRT_EST_REFERENCE>)<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, pk, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
-                                                         W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
+        shade_fn<<<shade_grid, SHD_THREADS, 0, stream>>>(L.sc, pk, g, W.ray_o[g], W.ray_d[g], W.state[g], W.hit,
+                                                                  W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], W.accum64, ctrl);
         if (profile) { cudaEventRecord(e2, stream); cudaEventSynchronize(e2); float a = 0.f, b = 0.f; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); acc_ext += a; acc_shd += b; ++n_ext; }
         k_regen<<<regen_grid, 256, 0, stream>>>(L.cam, pk, npix, cap, g ^ 1, parity, W.ray_o[g ^ 1], W.ray_d[g ^ 1], W.state[g ^ 1], ctrl);
         launches += 2;
@@ -875,9 +996,9 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
     int launches_per_batch = 0;
     if (!profile && W.use_graph && W.graph) {
       const ExtendVariant e = extend_variant(L);  // function attributes / occupancy query outside the capture
-      struct Key { DScene sc; DCamera cam; SrtRenderParams p; WaveBuffers w; void* fn; size_t smem; int bps, device, tail_max; } key;
+      struct Key { DScene sc; DCamera cam; SrtRenderParams p; WaveBuffers w; void* fn; void* sfn; size_t smem; int bps, device, tail_max, grid_div; } key;
       std::memset(&key, 0, sizeof(key));
-      key.sc = L.sc; key.cam = L.cam; key.p = pk; key.fn = (void*)e.fn; key.smem = e.smem; key.bps = e.bps; key.device = L.device; key.tail_max = tail_max;
+      key.sc = L.sc; key.cam = L.cam; key.p = pk; key.fn = (void*)e.fn; key.sfn = (void*)shade_fn; key.smem = e.smem; key.bps = e.bps; key.device = L.device; key.tail_max = tail_max; key.grid_div = div;
       key.w.capacity = W.capacity; key.w.hit = W.hit; key.w.accum64 = W.accum64; key.w.ctrl = W.ctrl;
       for (int k = 0; k < 2; ++k) { key.w.ray_o[k] = W.ray_o[k]; key.w.ray_d[k] = W.ray_d[k]; key.w.state[k] = W.state[k]; }
       GraphCache& C = *W.graph;
@@ -912,7 +1033,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
       ++batch;
     }
   }
-  if (d_rgb_sum) { k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches; }
+  if (d_rgb_sum && W.own_accum) { k_accum_to_float<<<L.sm_count * 4, 256, 0, stream>>>(3 * npix, W.accum64, d_rgb_sum); ++launches; }
   WCK(cudaMemcpyAsync(&h[0], ctrl, sizeof(WaveCtrl), cudaMemcpyDeviceToHost, stream));
   WCK(cudaStreamSynchronize(stream));
   WCK(cudaGetLastError());

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libsrt.so")
+# SRT_LIB selects an experimental build of the same library for A/B runs (tools/ab.py); the default is the in-tree build
+LIB_PATH = os.environ.get("SRT_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libsrt.so")
 
 
 # quirk bits of include/srt.h (SURVEY 8a Q rows + Q15); QUIRKS_REFERENCE reproduces upstream HEAD
@@ -21,7 +22,8 @@ class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("ms_total", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("waves", C.c_int32), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32),
                 ("rays_per_bounce", C.c_uint64 * 8), ("ms_extend", C.c_float), ("ms_shade", C.c_float),
-                ("extend_launches", C.c_int32), ("tail_runs", C.c_int32), ("nonfinite", C.c_uint64)]
+                ("extend_launches", C.c_int32), ("tail_runs", C.c_int32), ("nonfinite", C.c_uint64),
+                ("pipes", C.c_int32), ("pad", C.c_int32)]
 
 
 # every symbol include/srt.h declares (tests check the library exports all of them)
@@ -69,12 +71,13 @@ def load():
     lib.srt_trace_batch.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp]
     lib.srt_render_host.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
     lib.srt_render_device.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
-    lib.srt_init_multi.argtypes = [i32]
-    lib.srt_multi_device_count.restype = i32
-    lib.srt_multi_reduce_mode.argtypes = [C.POINTER(i32)]
-    lib.srt_render_multi.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(Stats)]
-    lib.srt_progressive_step.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
-    lib.srt_progressive_read.argtypes = [vp, vp, C.POINTER(i32)]
+    if hasattr(lib, "srt_init_multi"):              # (absent only from older experimental builds loaded through SRT_LIB)
+        lib.srt_init_multi.argtypes = [i32]
+        lib.srt_multi_device_count.restype = i32
+        lib.srt_multi_reduce_mode.argtypes = [C.POINTER(i32)]
+        lib.srt_render_multi.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(Stats)]
+        lib.srt_progressive_step.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(Stats)]
+        lib.srt_progressive_read.argtypes = [vp, vp, C.POINTER(i32)]
     lib.srt_resolve_device.argtypes = [vp, i32, i32, i32, vp]
     lib.srt_resolve_host.argtypes = [vp, i32, i32, i32, vp]
     lib.srt_save_ppm.argtypes = [C.c_char_p, vp, i32, i32]

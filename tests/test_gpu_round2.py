@@ -16,9 +16,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LAMB = m.make_lambertian(t.constant_texture((0.5, 0.5, 0.5)))
 
 
-def _render(r, w, h, spp, seed=3, depth=50, spp_begin=0, no_tail=False, no_graph=False, wave_spp=0, profile=False):
+def _render(r, w, h, spp, seed=3, depth=50, spp_begin=0, no_tail=False, no_graph=False, wave_spp=0, profile=False, two_pipes=False):
     p = r.params(w, h, spp_begin, spp_begin + spp, depth, seed, wave_spp=wave_spp)
-    p.reserved[0], p.reserved[1], p.reserved[2], p.reserved[3] = int(profile), int(no_graph), 1, int(no_tail)
+    p.reserved[0], p.reserved[1], p.reserved[2], p.reserved[3], p.reserved[4] = int(profile), int(no_graph), 1, int(no_tail), 2 if two_pipes else 0
     out = np.zeros((h, w, 3), dtype=np.float32)
     st = ffi.Stats()
     ffi.check(r.lib.srt_render_host(r.h, C.byref(p), out.ctypes.data_as(C.c_void_p), C.byref(st)), "render_host")
@@ -40,6 +40,23 @@ def test_tail_kernel_is_bit_identical_to_the_wavefront_drain(name):
         assert sa.rays == sb.rays == sc.rays and np.array_equal(a, b) and np.array_equal(a, c)
         assert sa.kernel_launches < sb.kernel_launches
         print(f"\n[tail {name} spp={spp} wave={wave}] rays={sa.rays} launches {sa.kernel_launches} vs {sb.kernel_launches}  ms {sa.ms_total:.3f} vs {sb.ms_total:.3f}")
+    r.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
+def test_two_concurrent_pipelines_equal_one(name):
+    """Optional mode (params.reserved[4] == 2): the sample range split over two streaming pipelines that run concurrently
+    on half-size grids and share the integer accumulator: frame and ray count must equal the single-pipeline render bit
+    for bit (odd spp, queue refills)."""
+    cfg = scenes.CONFIGS[name]
+    w, h, spp = 640, 480, 57                     # 17.5 M paths: above the two-pipeline threshold
+    r = srt.Renderer(cfg["scene"](w, h), device=0)
+    a, sa = _render(r, w, h, spp, wave_spp=16, two_pipes=True)
+    b, sb = _render(r, w, h, spp, wave_spp=16)
+    c, sc = _render(r, w, h, spp, two_pipes=True)
+    assert sa.pipes == 2 and sb.pipes == 1
+    assert sa.rays == sb.rays == sc.rays and np.array_equal(a, b) and np.array_equal(a, c)
+    print(f"\n[pipes {name}] rays={sa.rays}  two pipelines {sa.ms_total:.2f} ms  one {sb.ms_total:.2f} ms")
     r.close()
 
 
@@ -107,8 +124,15 @@ def test_instanced_spheres_against_the_oracle(orc):
     scene = g.make_scene(objs, scenes.default_camera(), scenes.sky_color)
     r = srt.Renderer(scene, device=0)
     S = orc.OracleScene(scene, flat=r.flat)
-    lo, hi = raybatch.interest_bounds(r.flat)
-    rays = np.concatenate([raybatch.camera_grid(r, 48, 48), raybatch.random_rays((lo, hi), 40000, 11)])
+    # rays aimed at the instanced spheres' WORLD positions (rotate-y(40) of (2,0,0) etc.) from all around, plus a random batch
+    rs = np.random.RandomState(12)
+    centres = np.array([(1.0, 0.25, -2.0), (2 * np.cos(np.radians(40)), 0.0, -2 * np.sin(np.radians(40))),
+                        (np.cos(np.radians(65)) - 1.0, 0.5, np.sin(np.radians(65)) - 1.5), (-2.0, 0.75, -2.0)])
+    c = centres[rs.randint(0, 4, 20000)]
+    o = c + rs.normal(size=(20000, 3)) * 2.0
+    d = (c + rs.normal(size=(20000, 3)) * 0.35 - o) * rs.uniform(0.5, 2.0, (20000, 1))
+    aimed = np.concatenate([o, d, rs.random_sample((20000, 1))], axis=1).astype(np.float32)
+    rays = np.concatenate([raybatch.camera_grid(r, 48, 48), aimed, raybatch.random_rays(raybatch.interest_bounds(r.flat), 20000, 11)])
     rays64 = rays.astype(np.float64)
     got = r.trace_batch(rays)
     o64 = S.trace_batch(rays64)

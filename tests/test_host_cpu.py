@@ -49,7 +49,7 @@ def test_struct_layouts_match_header(tmp_path):
             flatten.MATERIAL_DTYPE.itemsize, flatten.TEXTURE_DTYPE.itemsize, render.BVH_NODE_DTYPE.itemsize, render.RAY_DTYPE.itemsize, render.HIT_DTYPE.itemsize,
             ffi.Stats.nonfinite.offset, ffi.Stats.rays_per_bounce.offset]
     assert got == want, (got, want)
-    assert C.sizeof(ffi.RenderParams) == 64 and C.sizeof(ffi.Stats) == 128
+    assert C.sizeof(ffi.RenderParams) == 64 and C.sizeof(ffi.Stats) == 136
 
 
 def test_flatten_order_and_instances():

@@ -2,7 +2,7 @@
 // tree emit -> bottom-up refit.  Supersedes the reference's CPU builders make-bvh-node
 // (geometry.scm:226-260) and make-bvh-with-sah (geometry.scm:294-371); tree topology is not a
 // parity target, the build is instead bit-exact against the sequential host reference
-// oracle/lbvh_ref.cpp over the same AABBs (tests/test_lbvh.py).
+// oracle/lbvh_ref.cpp over the same AABBs (tests/test_gpu_parity.py: test_lbvh_bit_exact).
 //
 // Algorithm specification (DESIGN.md "LBVH"); every fp32 op below is an explicitly rounded
 // intrinsic so that the host reference (compiled with -ffp-contract=off) produces the same bits:
@@ -121,10 +121,7 @@ __device__ __forceinline__ unsigned long long expand21(unsigned int v) {
   x = (x | x << 2) & 0x1249249249249249ull;
   return x;
 }
-__global__ void k_morton(int n, const int* __restrict__ item_prim, const float* __restrict__ aabb, const int* __restrict__ b, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* q = aabb + 6 * (size_t)item_prim[i];
+__device__ __forceinline__ unsigned long long morton_key(const float* __restrict__ q, const int* b) {
   unsigned int g[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -136,7 +133,12 @@ __global__ void k_morton(int n, const int* __restrict__ item_prim, const float* 
     unsigned int gi = (unsigned int)scv;
     g[k] = gi < 2097151u ? gi : 2097151u;
   }
-  keys[i] = (expand21(g[0]) << 2) | (expand21(g[1]) << 1) | expand21(g[2]);
+  return (expand21(g[0]) << 2) | (expand21(g[1]) << 1) | expand21(g[2]);
+}
+__global__ void k_morton(int n, const int* __restrict__ item_prim, const float* __restrict__ aabb, const int* __restrict__ b, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = morton_key(aabb + 6 * (size_t)item_prim[i], b);
   vals[i] = i;
 }
 
@@ -200,21 +202,19 @@ __global__ void k_rs_scatter(const unsigned long long* __restrict__ kin, const i
     int off = 0;
     for (int w = 0; w < warp; ++w) off += wc[w][d];
     int pos = hist[d * nblk + blockIdx.x] + off + rank;
-    kout[pos] = key; vout[pos] = val;
+    if (SRT_BOUNDS_OK(pos >= 0 && pos < n, 301)) { kout[pos] = key; vout[pos] = val; }
   }
 }
 
 // ---- 5. Karras 2012 radix tree ------------------------------------------------------------------
-__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+__device__ __forceinline__ int delta(const unsigned long long* keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
   unsigned long long a = keys[i], b = keys[j];
   if (a != b) return __clzll((long long)(a ^ b));
   return 64 + __clz(i ^ j);
 }
-__global__ void k_karras(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ order, const int* __restrict__ item_prim,
-                         int4* __restrict__ links /* left right parent sibling per node */, int* __restrict__ leaf_parent) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
+__device__ __forceinline__ void karras_node(int i, int n, const unsigned long long* keys, const int* order, const int* __restrict__ item_prim,
+                                            int4* links /* left right parent sibling per node */, int* leaf_parent) {
   int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
   int dmin = delta(keys, n, i, i - d);
   int lmax = 2;
@@ -227,6 +227,7 @@ __global__ void k_karras(int n, const unsigned long long* __restrict__ keys, con
   do { t = (t + 1) >> 1; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
   int gamma = i + s * d + min(d, 0);
   int a = min(i, j), b = max(i, j);
+  if (!SRT_BOUNDS_OK(j >= 0 && j < n && gamma >= 0 && gamma + 1 < n, 311)) return;
   int left = (a == gamma) ? ~item_prim[order[gamma]] : gamma;          // leaf reference = ~primitive id
   int right = (b == gamma + 1) ? ~item_prim[order[gamma + 1]] : gamma + 1;
   links[i].x = left; links[i].y = right;
@@ -234,14 +235,18 @@ __global__ void k_karras(int n, const unsigned long long* __restrict__ keys, con
   if (right >= 0) { links[right].z = i; links[right].w = left; } else leaf_parent[gamma + 1] = i;
   if (i == 0) { links[0].z = -1; links[0].w = -1; }
 }
+__global__ void k_karras(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ order, const int* __restrict__ item_prim,
+                         int4* __restrict__ links, int* __restrict__ leaf_parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  karras_node(i, n, keys, order, item_prim, links, leaf_parent);
+}
 
 // ---- 6. bottom-up refit with atomic visit counters ----------------------------------------------
 // nbox[i] = unpadded box of internal node i (scratch); stored child boxes are padded on write.
-__global__ void k_refit(int n, const int* __restrict__ order, const float* __restrict__ aabb, const int4* __restrict__ links,
-                        const int* __restrict__ leaf_parent, const int* __restrict__ b, float* nbox, int* visit,
-                        float4* __restrict__ nodes, int* __restrict__ depth_out) {
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= n) return;
+__device__ __forceinline__ void refit_from_leaf(int pos, int n, const float* __restrict__ aabb, const int4* links,
+                                                const int* leaf_parent, const int* b, float* nbox, int* visit,
+                                                float4* nodes, int* depth_out) {
   const float pad = __fmul_rn(ord2f(b[6]), 1.0f / 2097152.0f);
   int node = leaf_parent[pos];
   int depth = 0;   // internal ancestors of this leaf
@@ -250,6 +255,7 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
     atomicMax(depth_out, depth);
   }
   while (node >= 0) {
+    if (!SRT_BOUNDS_OK(node < n - 1, 321)) return;
     __threadfence();
     if (atomicAdd(&visit[node], 1) == 0) return;      // first arrival: the sibling subtree finishes this node
     int4 lk = links[node];
@@ -273,6 +279,14 @@ __global__ void k_refit(int n, const int* __restrict__ order, const float* __res
     nodes[4 * node + 3] = make_float4(__int_as_float(lk.x), __int_as_float(lk.y), __int_as_float(lk.z), __int_as_float(lk.w));
     node = lk.z;
   }
+}
+__global__ void k_refit(int n, const int* __restrict__ order, const float* __restrict__ aabb, const int4* __restrict__ links,
+                        const int* __restrict__ leaf_parent, const int* __restrict__ b, float* nbox, int* visit,
+                        float4* __restrict__ nodes, int* __restrict__ depth_out) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  (void)order;
+  refit_from_leaf(pos, n, aabb, links, leaf_parent, b, nbox, visit, nodes, depth_out);
 }
 
 // n <= 1: a single node.
@@ -298,11 +312,10 @@ __global__ void k_single_node(int n, const int* __restrict__ item_prim, const fl
 // Surface-area sums of a built tree: out[0] = sum over internal nodes, out[1] = sum over leaf
 // (child) boxes, out[2] = root.  One CTA, per-thread strided partial sums in double and a fixed
 // shared-memory tree: the result does not depend on scheduling.
-__global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __restrict__ nodes, double* __restrict__ out) {
-  __shared__ double sh[2][256];
+__device__ __forceinline__ void tree_area_256(int n_items, const float4* nodes, double* __restrict__ out, double (*sh)[256]) {
   const int n_nodes = n_items > 1 ? n_items - 1 : 1;
   double a_int = 0.0, a_leaf = 0.0, a_root = 0.0;
-  for (int i = threadIdx.x; i < n_nodes; i += 256) {
+  for (int i = threadIdx.x < 256 ? (int)threadIdx.x : n_nodes; i < n_nodes; i += 256) {   // (the single-CTA build calls this with 1024 threads: 256 of them sum)
     const float4 f0 = nodes[4 * i], f1 = nodes[4 * i + 1], f2 = nodes[4 * i + 2], f3 = nodes[4 * i + 3];
     const double le[3] = {f0.w, f1.x, f1.y}, re[3] = {f2.y, f2.z, f2.w};
     const double al = 8.0 * (le[0] * le[1] + le[1] * le[2] + le[0] * le[2]), ar = 8.0 * (re[0] * re[1] + re[1] * re[2] + re[0] * re[2]);
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __
       a_root = 2.0 * (d[0] * d[1] + d[1] * d[2] + d[0] * d[2]);
     }
   }
-  sh[0][threadIdx.x] = a_int; sh[1][threadIdx.x] = a_leaf;
+  if (threadIdx.x < 256) { sh[0][threadIdx.x] = a_int; sh[1][threadIdx.x] = a_leaf; }
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
@@ -323,8 +336,92 @@ __global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __
   }
   if (threadIdx.x == 0) { out[0] = sh[0][0] + a_root; out[1] = sh[1][0]; out[2] = a_root; }
 }
+__global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __restrict__ nodes, double* __restrict__ out) {
+  __shared__ double sh[2][256];
+  tree_area_256(n_items, nodes, out, sh);
+}
+
+// ---- single-CTA build for small scenes -----------------------------------------------------------
+// Every scene of the reference has at most a few hundred primitives; the multi-kernel build above is then ~29
+// launches of one or two CTAs each, and the commit-time search for the primitives kept outside the tree builds up
+// to nine candidate trees (srt_api.cu) - 0.7 ms of launch latency for cfg2.  Here ONE CTA builds one candidate from
+// bounds to surface-area sums, and the candidates of a commit run side by side as the CTAs of one launch.  Same
+// arithmetic (the device functions above), same tree: the sort is a bitonic network on (key, index) pairs, which is
+// the order the stable LSD radix sort produces; the refit uses the same visit-counter protocol.
+constexpr int SMALL_MAX_ITEMS = 2048, SMALL_THREADS = 1024;
+__global__ void __launch_bounds__(SMALL_THREADS) k_lbvh_small(const float* __restrict__ aabb, const SrtSmallJob* __restrict__ jobs) {
+  const SrtSmallJob J = jobs[blockIdx.x];
+  const int n = J.n, tid = threadIdx.x;
+  __shared__ unsigned long long s_key[SMALL_MAX_ITEMS];
+  __shared__ int s_val[SMALL_MAX_ITEMS];
+  __shared__ int s_visit[SMALL_MAX_ITEMS];
+  __shared__ int s_b[8];
+  __shared__ int s_depth;
+  __shared__ double s_red[2][256];
+  if (tid < 3) s_b[tid] = f2ord(BIG); else if (tid < 6) s_b[tid] = f2ord(-BIG); else if (tid == 6) s_b[6] = f2ord(0.0f);
+  if (tid == 0) s_depth = 0;
+  __syncthreads();
+  {   // centroid bounds + S (exact min / max: independent of the order)
+    float cmin[3] = {BIG, BIG, BIG}, cmax[3] = {-BIG, -BIG, -BIG}, S = 0.0f;
+    for (int i = tid; i < n; i += SMALL_THREADS) {
+      const float* q = aabb + 6 * (size_t)J.item_prim[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float c = __fmul_rn(0.5f, __fadd_rn(q[k], q[3 + k]));
+        cmin[k] = fminf(cmin[k], c); cmax[k] = fmaxf(cmax[k], c);
+        S = fmaxf(S, fmaxf(fabsf(q[k]), fabsf(q[3 + k])));
+      }
+    }
+    for (int k = 0; k < 3; ++k) { atomicMin(&s_b[k], f2ord(cmin[k])); atomicMax(&s_b[3 + k], f2ord(cmax[k])); }
+    atomicMax(&s_b[6], f2ord(S));
+  }
+  __syncthreads();
+  int npad = 2; while (npad < n) npad <<= 1;
+  for (int i = tid; i < npad; i += SMALL_THREADS) {
+    if (i < n) { s_key[i] = morton_key(aabb + 6 * (size_t)J.item_prim[i], s_b); s_val[i] = i; }
+    else { s_key[i] = ~0ull; s_val[i] = 0x7fffffff; }
+  }
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < npad; i += SMALL_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long ka = s_key[i], kb = s_key[l]; const int va = s_val[i], vb = s_val[l];
+          const bool gt = ka > kb || (ka == kb && va > vb);
+          if (gt == ((i & k) == 0)) { s_key[i] = kb; s_key[l] = ka; s_val[i] = vb; s_val[l] = va; }
+        }
+      }
+    }
+  __syncthreads();
+  for (int i = tid; i < n; i += SMALL_THREADS) { J.keys[i] = s_key[i]; J.order[i] = s_val[i]; s_visit[i] = 0; }
+  for (int i = tid; i < n - 1; i += SMALL_THREADS) karras_node(i, n, s_key, s_val, J.item_prim, J.links, J.leaf_parent);
+  __syncthreads();
+  for (int pos = tid; pos < n; pos += SMALL_THREADS) refit_from_leaf(pos, n, aabb, J.links, J.leaf_parent, s_b, J.nbox, s_visit, J.nodes, &s_depth);
+  __syncthreads();
+  tree_area_256(n, J.nodes, J.area, s_red);
+  if (tid == 0) { *J.depth = s_depth; for (int k = 0; k < 7; ++k) J.bounds[k] = s_b[k]; }
+}
 
 }  // namespace
+
+unsigned long long srt_bounds_violations_lbvh(int* first) {
+#ifdef SRT_BOUNDS_CHECK
+  unsigned long long v = 0ull; int f = 0;
+  cudaMemcpyFromSymbol(&v, d_srt_violations, sizeof(v)); cudaMemcpyFromSymbol(&f, d_srt_first_violation, sizeof(f));
+  if (first) *first = f;
+  return v;
+#else
+  if (first) *first = 0;
+  return 0ull;
+#endif
+}
+
+// The candidate trees of one commit (n_jobs <= 16, each 2 <= n <= SRT_SMALL_MAX_ITEMS items), one CTA each.
+int srt_lbvh_build_small(const float* d_aabb, const SrtSmallJob* d_jobs, int n_jobs, cudaStream_t stream) {
+  k_lbvh_small<<<n_jobs, SMALL_THREADS, 0, stream>>>(d_aabb, d_jobs);
+  return 1;
+}
 
 // Surface-area sums of the tree just built (see k_tree_area); d_out = 3 doubles on the device.
 int srt_lbvh_tree_area(int n_items, LbvhBuffers& B, double* d_out, cudaStream_t stream) {

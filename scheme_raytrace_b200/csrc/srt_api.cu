@@ -113,12 +113,17 @@ struct SrtScene {
   std::vector<uint8_t> img_texels; std::vector<int4> imgs;   // image-texture data (srt_scene_set_images)
   float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
   SrtCamera cam; bool has_cam = false;
-  std::vector<int32_t> lights; DevBuf<int> d_lights;
-  std::vector<float> patches; DevBuf<float4> d_patches; DevBuf<int> d_logical;
+  std::vector<int32_t> lights; std::vector<float> patches;
   bool committed = false;
   // device tables
-  DevBuf<int4> d_hdr; DevBuf<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; DevBuf<int4> d_mats, d_imgs; DevBuf<double> d_tree_area; DevBuf<uint8_t> d_perm, d_img_texels;
+  // device tables: views into ONE allocation (d_tables), uploaded from ONE pinned staging blob (h_tables) per commit
+  template <class T> struct View { T* p = nullptr; };
+  View<int> d_lights, d_logical; View<float4> d_patches;
+  View<int4> d_hdr; View<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; View<int4> d_mats, d_imgs; View<uint8_t> d_perm, d_img_texels;
+  DevBuf<unsigned char> d_tables; void* h_tables = nullptr; size_t h_tables_bytes = 0;
+  DevBuf<double> d_tree_area;
   // LBVH
+  DevBuf<unsigned char> d_small;   // slots of the single-CTA candidate builds (small scenes)
   LbvhBuffers lb; DevBuf<float> d_aabb, d_nbox; DevBuf<int> d_bounds, d_order0, d_order1, d_hist, d_leaf_parent, d_visit, d_depth, d_item_prim;
   std::vector<int> item_prim, global_prims;
   DevBuf<unsigned long long> d_keys0, d_keys1; DevBuf<int4> d_links; DevBuf<float4> d_nodes;
@@ -157,7 +162,7 @@ static void fill_dscene(SrtScene* s) {
   d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
-  d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.img_texels = s->d_img_texels.p; d.imgs = s->d_imgs.p; d.nodes = s->d_nodes.p; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
+  d.xf = s->d_xf.p; d.prim_shade = s->d_shade.p; d.img_texels = s->d_img_texels.p; d.imgs = s->d_imgs.p; d.nodes = s->lb.d_nodes; d.mats = s->d_mats.p; d.tex = s->d_tex.p; d.ranvec = s->d_ranvec.p; d.perm = s->d_perm.p; d.lights = s->d_lights.p; d.n_lights = (int)s->lights.size(); d.patch_cp = s->d_patches.p; d.prim_logical = s->d_logical.p;
 }
 
 static int ensure_wave(SrtScene* s, int k, size_t paths, size_t npix) {
@@ -198,6 +203,16 @@ static RenderLaunch make_launch(SrtScene* s, const SrtRenderParams* p) {
   return L;
 }
 #define USE_DEVICE(s) CK(cudaSetDevice((s)->device))
+// bounds-checked build: every entry point that launched kernels ends with this
+static int bounds_verdict(const char* where) {
+#ifdef SRT_BOUNDS_CHECK
+  int f1 = 0, f2 = 0;
+  const unsigned long long v1 = srt_bounds_violations_wavefront(&f1), v2 = srt_bounds_violations_lbvh(&f2);
+  if (v1 + v2) return fail(SRT_ERR_CUDA, "%s: bounds-checked build counted %llu violations (first codes %d / %d)", where, v1 + v2, f1, f2);
+#endif
+  (void)where;
+  return 0;
+}
 
 extern "C" {
 
@@ -242,8 +257,9 @@ void srt_scene_destroy(SrtScene* s) {
   cudaSetDevice(s->device);
   s->d_image.release(); s->d_prog.release(); s->d_stage.release();
   if (s->ev_done) cudaEventDestroy(s->ev_done);
-  s->d_tree_area.release(); s->d_img_texels.release(); s->d_imgs.release(); s->d_shade.release(); s->d_hdr.release(); s->d_a.release(); s->d_b.release(); s->d_c.release(); s->d_d.release(); s->d_xf.release(); s->d_tex.release();
-  s->d_ranvec.release(); s->d_lights.release(); s->d_patches.release(); s->d_logical.release(); s->d_mats.release(); s->d_perm.release(); s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
+  s->d_small.release(); s->d_tree_area.release(); s->d_tables.release();
+  if (s->h_tables) cudaFreeHost(s->h_tables);
+  s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
   for (SrtScene::Pipe& P : s->pipe) {
@@ -310,6 +326,32 @@ int srt_scene_set_lights(SrtScene* s, const int32_t* prim_ids, int n) {
   s->lights.assign(prim_ids, prim_ids + n); s->committed = false; ++s->version; return 0;
 }
 
+// Bounding SLAB of a leaf sub-patch, |n'.p - d'| <= 1 (returned as (n', d')): n = normal of the plane through the
+// corner diagonals, [dmin, dmax] = extent of the 16 control points along it (the surface lies in their convex hull),
+// padded for fp32 and for Newton's +-1e-3 domain slack.  The extend kernel intersects the ray with it inside the
+// leaf's box interval before it parks the full test: 38 % of the box hits are culled (profiles/README.md, round 2).
+// Degenerate normal: n' = 0, d' = 0 (never culls).
+static float4 patch_slab(const float* cp) {
+  auto P = [&](int k, int c) { return (double)cp[3 * k + c]; };
+  double e1[3], e2[3], nn[3];
+  for (int c = 0; c < 3; ++c) { e1[c] = P(15, c) - P(0, c); e2[c] = P(12, c) - P(3, c); }
+  nn[0] = e1[1] * e2[2] - e1[2] * e2[1]; nn[1] = e1[2] * e2[0] - e1[0] * e2[2]; nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+  const double len = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+  float4 slab = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (len > 1e-20) {
+    double dmin = 1e300, dmax = -1e300, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
+    for (int k = 0; k < 16; ++k) {
+      double dk = 0.0;
+      for (int c = 0; c < 3; ++c) { dk += nn[c] / len * P(k, c); lo[c] = std::min(lo[c], P(k, c)); hi[c] = std::max(hi[c], P(k, c)); amax = std::max(amax, std::fabs(P(k, c))); }
+      dmin = std::min(dmin, dk); dmax = std::max(dmax, dk);
+    }
+    const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    const double half = 0.5 * (dmax - dmin) * 1.001 + 4e-3 * diag + 4e-6 * amax;
+    slab = make_float4((float)(nn[0] / len / half), (float)(nn[1] / len / half), (float)(nn[2] / len / half), (float)(0.5 * (dmin + dmax) / half));
+  }
+  return slab;
+}
+
 static int commit_impl(SrtScene* s) {
   if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
   if (int rc = ensure_device(s->device)) return rc;
@@ -361,16 +403,11 @@ static int commit_impl(SrtScene* s) {
   EventPair tm; CK(tm.create());
   cudaEvent_t e0 = tm.a, e1 = tm.b;
   CK(cudaEventRecord(e0, stream));
-  {
-    size_t np16 = s->patches.size() / 3;
-    std::vector<float4> pc(np16 ? np16 : 1);
-    for (size_t k = 0; k < np16; ++k) pc[k] = make_float4(s->patches[3 * k], s->patches[3 * k + 1], s->patches[3 * k + 2], 0.f);
-    CK(s->d_patches.ensure(np16));
-    if (np16) CK(cudaMemcpy(s->d_patches.p, pc.data(), sizeof(float4) * np16, cudaMemcpyHostToDevice));
-  }
-  CK(s->d_lights.ensure(s->lights.size()));
-  if (!s->lights.empty()) CK(cudaMemcpyAsync(s->d_lights.p, s->lights.data(), sizeof(int) * s->lights.size(), cudaMemcpyHostToDevice, stream));
-  // ---- host SoA staging + H2D ---------------------------------------------------------------
+  // ---- host SoA staging: every table goes into ONE pinned blob and up in ONE H2D copy ---------------
+  // (sixteen separate small copies were 0.1 ms of the commit; the device tables are views into s->d_tables)
+  const size_t np16 = s->patches.size() / 3;
+  std::vector<float4> pc(np16 ? np16 : 1);
+  for (size_t k = 0; k < np16; ++k) pc[k] = make_float4(s->patches[3 * k], s->patches[3 * k + 1], s->patches[3 * k + 2], 0.f);
   std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
   for (int i = 0; i < n; ++i) {
     const SrtPrim& p = s->prims[i]; const float* q = p.p;
@@ -385,63 +422,21 @@ static int commit_impl(SrtScene* s) {
       case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
       case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
       case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
-      case SRT_PRIM_PATCH: {
-        // a = bounding SLAB of the leaf sub-patch, |n'.p - d'| <= 1: n = normal of the plane through the corner
-        // diagonals, [dmin, dmax] = extent of the 16 control points along it (the surface lies in their convex
-        // hull), padded for fp32 and for Newton's +-1e-3 domain slack.  The extend kernel intersects the ray with
-        // it inside the leaf's box interval before it parks the full test: 38 % of the box hits are culled
-        // (profiles/README.md, round 2).  Degenerate normal: n' = 0, d' = 0 (never culls).
-        const float* cp = s->patches.data() + 48 * (size_t)q[0];
-        auto P = [&](int k, int c) { return (double)cp[3 * k + c]; };
-        double e1[3], e2[3], nn[3];
-        for (int c = 0; c < 3; ++c) { e1[c] = P(15, c) - P(0, c); e2[c] = P(12, c) - P(3, c); }
-        nn[0] = e1[1] * e2[2] - e1[2] * e2[1]; nn[1] = e1[2] * e2[0] - e1[0] * e2[2]; nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
-        const double len = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-        float4 slab = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (len > 1e-20) {
-          double dmin = 1e300, dmax = -1e300, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
-          for (int k = 0; k < 16; ++k) {
-            double dk = 0.0;
-            for (int c = 0; c < 3; ++c) { dk += nn[c] / len * P(k, c); lo[c] = std::min(lo[c], P(k, c)); hi[c] = std::max(hi[c], P(k, c)); amax = std::max(amax, std::fabs(P(k, c))); }
-            dmin = std::min(dmin, dk); dmax = std::max(dmax, dk);
-          }
-          const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
-          const double half = 0.5 * (dmax - dmin) * 1.001 + 4e-3 * diag + 4e-6 * amax;
-          slab = make_float4((float)(nn[0] / len / half), (float)(nn[1] / len / half), (float)(nn[2] / len / half), (float)(0.5 * (dmin + dmax) / half));
-        }
-        a[i] = slab; b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0);
-        break;
-      }
+      case SRT_PRIM_PATCH: { a[i] = patch_slab(s->patches.data() + 48 * (size_t)q[0]); b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0); break; }
       case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
       default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
     }
   }
-  {
-    std::vector<int> logical(n ? n : 1);
-    for (int i = 0; i < n; ++i) logical[i] = s->prims[i].p[15] > 0.f ? (int)s->prims[i].p[15] - 1 : i;   // p[15] = logical id + 1, 0 = array index
-    CK(s->d_logical.ensure(n));
-    if (n) CK(cudaMemcpy(s->d_logical.p, logical.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-  }
-  {   // per-primitive shading record (see DScene::prim_shade)
-    std::vector<float4> sh(2 * (size_t)(n ? n : 1));
-    for (int i = 0; i < n; ++i) {
-      const SrtMaterial& m = s->mats[s->prims[i].material];
-      float r = 1.f, g = 1.f, b = 1.f; int is_const = 0;
-      if (m.kind != SRT_MAT_DIELECTRIC && s->texs[m.tex].kind == SRT_TEX_CONSTANT) { const SrtTexture& t = s->texs[m.tex]; r = t.rgb[0]; g = t.rgb[1]; b = t.rgb[2]; is_const = 1; }
-      if (m.kind == SRT_MAT_DIELECTRIC) is_const = 1;
-      float fk, ft, fc; int tex = m.tex; std::memcpy(&fk, &m.kind, 4); std::memcpy(&ft, &tex, 4); std::memcpy(&fc, &is_const, 4);
-      sh[2 * i] = make_float4(r, g, b, m.param); sh[2 * i + 1] = make_float4(fk, ft, fc, 0.f);
-    }
-    CK(s->d_shade.ensure(2 * (size_t)n));
-    if (n) CK(cudaMemcpy(s->d_shade.p, sh.data(), sizeof(float4) * 2 * (size_t)n, cudaMemcpyHostToDevice));
-  }
-  CK(s->d_hdr.ensure(n)); CK(s->d_a.ensure(n)); CK(s->d_b.ensure(n)); CK(s->d_c.ensure(n)); CK(s->d_d.ensure(n));
-  if (n) {
-    CK(cudaMemcpyAsync(s->d_hdr.p, hdr.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(s->d_a.p, a.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(s->d_b.p, b.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(s->d_c.p, c.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(s->d_d.p, d.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream));
+  std::vector<int> logical(n ? n : 1);
+  for (int i = 0; i < n; ++i) logical[i] = s->prims[i].p[15] > 0.f ? (int)s->prims[i].p[15] - 1 : i;   // p[15] = logical id + 1, 0 = array index
+  std::vector<float4> sh(2 * (size_t)(n ? n : 1));     // per-primitive shading record (see DScene::prim_shade)
+  for (int i = 0; i < n; ++i) {
+    const SrtMaterial& m = s->mats[s->prims[i].material];
+    float r = 1.f, g = 1.f, bl = 1.f; int is_const = 0;
+    if (m.kind != SRT_MAT_DIELECTRIC && s->texs[m.tex].kind == SRT_TEX_CONSTANT) { const SrtTexture& t = s->texs[m.tex]; r = t.rgb[0]; g = t.rgb[1]; bl = t.rgb[2]; is_const = 1; }
+    if (m.kind == SRT_MAT_DIELECTRIC) is_const = 1;
+    float fk, ft, fc; int tex = m.tex; std::memcpy(&fk, &m.kind, 4); std::memcpy(&ft, &tex, 4); std::memcpy(&fc, &is_const, 4);
+    sh[2 * i] = make_float4(r, g, bl, m.param); sh[2 * i + 1] = make_float4(fk, ft, fc, 0.f);
   }
   size_t nx = s->xforms.size(), nm = s->mats.size(), nt = s->texs.size();
   std::vector<float4> xf(2 * (nx ? nx : 1)), tx(2 * (nt ? nt : 1)); std::vector<int4> mt(nm ? nm : 1);
@@ -451,19 +446,33 @@ static int commit_impl(SrtScene* s) {
     const SrtTexture& t = s->texs[i]; float fk, fe, fo; std::memcpy(&fk, &t.kind, 4); std::memcpy(&fe, &t.even, 4); std::memcpy(&fo, &t.odd, 4);
     tx[2 * i] = make_float4(fk, fe, fo, t.scale); tx[2 * i + 1] = make_float4(t.rgb[0], t.rgb[1], t.rgb[2], 0);
   }
-  CK(s->d_xf.ensure(2 * nx)); CK(s->d_mats.ensure(nm)); CK(s->d_tex.ensure(2 * nt));
-  if (nx) CK(cudaMemcpyAsync(s->d_xf.p, xf.data(), sizeof(float4) * 2 * nx, cudaMemcpyHostToDevice, stream));
-  if (nm) CK(cudaMemcpyAsync(s->d_mats.p, mt.data(), sizeof(int4) * nm, cudaMemcpyHostToDevice, stream));
-  CK(s->d_imgs.ensure(s->imgs.size())); CK(s->d_img_texels.ensure(s->img_texels.size()));
-  if (!s->imgs.empty()) CK(cudaMemcpyAsync(s->d_imgs.p, s->imgs.data(), sizeof(int4) * s->imgs.size(), cudaMemcpyHostToDevice, stream));
-  if (!s->img_texels.empty()) CK(cudaMemcpyAsync(s->d_img_texels.p, s->img_texels.data(), s->img_texels.size(), cudaMemcpyHostToDevice, stream));
-  if (nt) CK(cudaMemcpyAsync(s->d_tex.p, tx.data(), sizeof(float4) * 2 * nt, cudaMemcpyHostToDevice, stream));
   std::vector<float4> rv(256); std::vector<uint8_t> pm(768);
   for (int i = 0; i < 256; ++i) rv[i] = s->has_perlin ? make_float4(s->ranvec[3 * i], s->ranvec[3 * i + 1], s->ranvec[3 * i + 2], 0) : make_float4(0, 0, 0, 0);
   for (int k = 0; k < 3; ++k) for (int i = 0; i < 256; ++i) pm[256 * k + i] = s->has_perlin ? (uint8_t)(s->perm[k][i] & 255) : (uint8_t)i;
-  CK(s->d_ranvec.ensure(256)); CK(s->d_perm.ensure(768));
-  CK(cudaMemcpyAsync(s->d_ranvec.p, rv.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(s->d_perm.p, pm.data(), 768, cudaMemcpyHostToDevice, stream));
+  {
+    struct Item { void** dst; const void* src; size_t bytes, off; };
+    std::vector<Item> items; size_t total = 0;
+    auto add = [&](void** dst, const void* src, size_t bytes) { items.push_back(Item{dst, src, bytes, total}); total += (bytes + 255) & ~(size_t)255; if (!bytes) total += 256; };
+    add((void**)&s->d_patches.p, pc.data(), sizeof(float4) * np16);
+    add((void**)&s->d_lights.p, s->lights.data(), sizeof(int) * s->lights.size());
+    add((void**)&s->d_logical.p, logical.data(), sizeof(int) * (size_t)n);
+    add((void**)&s->d_shade.p, sh.data(), sizeof(float4) * 2 * (size_t)n);
+    add((void**)&s->d_hdr.p, hdr.data(), sizeof(int4) * (size_t)n);
+    add((void**)&s->d_a.p, a.data(), sizeof(float4) * (size_t)n); add((void**)&s->d_b.p, b.data(), sizeof(float4) * (size_t)n);
+    add((void**)&s->d_c.p, c.data(), sizeof(float4) * (size_t)n); add((void**)&s->d_d.p, d.data(), sizeof(float4) * (size_t)n);
+    add((void**)&s->d_xf.p, xf.data(), sizeof(float4) * 2 * nx); add((void**)&s->d_mats.p, mt.data(), sizeof(int4) * nm);
+    add((void**)&s->d_tex.p, tx.data(), sizeof(float4) * 2 * nt);
+    add((void**)&s->d_imgs.p, s->imgs.data(), sizeof(int4) * s->imgs.size()); add((void**)&s->d_img_texels.p, s->img_texels.data(), s->img_texels.size());
+    add((void**)&s->d_ranvec.p, rv.data(), sizeof(float4) * 256); add((void**)&s->d_perm.p, pm.data(), 768);
+    CK(s->d_tables.ensure(total));
+    if (total > s->h_tables_bytes) {
+      if (s->h_tables) cudaFreeHost(s->h_tables);
+      s->h_tables = nullptr; s->h_tables_bytes = 0;
+      CK(cudaMallocHost(&s->h_tables, total)); s->h_tables_bytes = total;
+    }
+    for (const Item& it : items) { if (it.bytes) std::memcpy((unsigned char*)s->h_tables + it.off, it.src, it.bytes); *it.dst = s->d_tables.p + it.off; }
+    CK(cudaMemcpyAsync(s->d_tables.p, s->h_tables, total, cudaMemcpyHostToDevice, stream));
+  }
   // camera (by value in kernel params)
   if (s->has_cam) {
     const SrtCamera& cm = s->cam; DCamera& dc = s->dcam;
@@ -543,26 +552,77 @@ static int commit_impl(SrtScene* s) {
     return nitems;
   };
   int chosen = 0;
-  if (!extra.empty()) {
-    const double C_LEAF = 2.0, C_GLOBAL = 0.25;
-    const int nk = (int)extra.size() + 1;
-    CK(s->d_tree_area.ensure(3 * (size_t)nk));
-    for (int k = 0; k < nk; ++k) {
-      const int nitems = build_with(k);
-      if (nitems < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed");
-      s->commit_launches += srt_lbvh_tree_area(nitems, B, s->d_tree_area.p + 3 * k, stream);
-    }
-    std::vector<double> area(3 * (size_t)nk);
-    CK(cudaMemcpyAsync(area.data(), s->d_tree_area.p, sizeof(double) * area.size(), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
+  const double C_LEAF = 2.0, C_GLOBAL = 0.25;
+  const int nk = (int)extra.size() + 1;
+  auto pick = [&](const std::vector<double>& area) {
     double best = 0.0;
     for (int k = 0; k < nk; ++k) {
       const double c = (area[3 * k] + C_LEAF * area[3 * k + 1]) / area[2] + C_GLOBAL * k;
       if (getenv("SRT_DEBUG_COMMIT")) std::fprintf(stderr, "[srt commit] k=%d prim=%d internal %.3f leaf %.3f cost %.3f\n", k, k ? extra[k - 1] : -1, area[3 * k] / area[2], area[3 * k + 1] / area[2], c);
       if (k == 0 || c < best) { best = c; chosen = k; }
     }
+  };
+  const int n0 = ns - (int)base.size();                    // items of candidate k = 0; candidate k has n0 - k
+  static const bool small_off = getenv("SRT_NO_SMALL_LBVH") != nullptr;              // A/B switch
+  if (!small_off && n0 <= SRT_SMALL_MAX_ITEMS && n0 - (nk - 1) >= 2) {
+    // Small scene (every scene of the reference): all nk candidate trees are built by ONE launch, one CTA each
+    // (k_lbvh_small), into per-candidate slots of one scratch allocation; the chosen slot IS the committed tree.
+    const size_t N = (size_t)n0;
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_items = 0, o_keys = up(o_items + 4 * N), o_order = up(o_keys + 8 * N), o_links = up(o_order + 4 * N), o_lp = up(o_links + 16 * N),
+                 o_nbox = up(o_lp + 4 * N), o_nodes = up(o_nbox + 24 * N), o_misc = up(o_nodes + 64 * N), slot = up(o_misc + 64);   // misc: area[3] f64, depth, bounds[8]
+    const size_t o_jobs = slot * (size_t)nk, bytes = o_jobs + sizeof(SrtSmallJob) * (size_t)nk;
+    CK(s->d_small.ensure(bytes));
+    unsigned char* D = s->d_small.p;
+    std::vector<unsigned char> hblob(bytes, 0);
+    std::vector<std::vector<int>> items(nk), globs(nk);
+    for (int k = 0; k < nk; ++k) {
+      std::vector<int> g(base); g.insert(g.end(), extra.begin(), extra.begin() + k);
+      std::sort(g.begin(), g.end());
+      size_t gi = 0;
+      for (int i = 0; i < ns; ++i) { if (gi < g.size() && g[gi] == i) { ++gi; continue; } items[k].push_back(i); }
+      globs[k] = g;
+      unsigned char* S = D + slot * (size_t)k;
+      std::memcpy(hblob.data() + slot * (size_t)k + o_items, items[k].data(), sizeof(int) * items[k].size());
+      SrtSmallJob J;
+      J.item_prim = (const int*)(S + o_items); J.n = (int)items[k].size();
+      J.keys = (unsigned long long*)(S + o_keys); J.order = (int*)(S + o_order); J.links = (int4*)(S + o_links); J.leaf_parent = (int*)(S + o_lp);
+      J.nbox = (float*)(S + o_nbox); J.nodes = (float4*)(S + o_nodes); J.area = (double*)(S + o_misc); J.depth = (int*)(S + o_misc + 24); J.bounds = (int*)(S + o_misc + 32);
+      std::memcpy(hblob.data() + o_jobs + sizeof(SrtSmallJob) * (size_t)k, &J, sizeof(J));
+    }
+    // one H2D for the item lists + job table (the rest of the blob is scratch, its host bytes are never sent)
+    for (int k = 0; k < nk; ++k) CK(cudaMemcpyAsync(D + slot * (size_t)k + o_items, hblob.data() + slot * (size_t)k + o_items, sizeof(int) * items[k].size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(D + o_jobs, hblob.data() + o_jobs, sizeof(SrtSmallJob) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+    s->commit_launches += srt_lbvh_build_small(B.d_aabb, (const SrtSmallJob*)(D + o_jobs), nk, stream);
+    std::vector<unsigned char> misc(64 * (size_t)nk);
+    for (int k = 0; k < nk; ++k) CK(cudaMemcpyAsync(misc.data() + 64 * (size_t)k, D + slot * (size_t)k + o_misc, 64, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (nk > 1) {
+      std::vector<double> area(3 * (size_t)nk);
+      for (int k = 0; k < nk; ++k) std::memcpy(&area[3 * k], misc.data() + 64 * (size_t)k, 24);
+      pick(area);
+    }
+    unsigned char* S = D + slot * (size_t)chosen;
+    s->global_prims = globs[chosen]; s->item_prim = items[chosen];
+    s->n_items = (int)items[chosen].size(); s->n_nodes = s->n_items - 1;
+    B.d_item_prim = (int*)(S + o_items); B.d_keys[0] = (unsigned long long*)(S + o_keys); B.d_order[0] = (int*)(S + o_order); B.sorted = 0;
+    B.d_links = (int4*)(S + o_links); B.d_leaf_parent = (int*)(S + o_lp); B.d_nbox = (float*)(S + o_nbox); B.d_nodes = (float4*)(S + o_nodes);
+    B.d_depth = (int*)(S + o_misc + 24); B.d_bounds = (int*)(S + o_misc + 32);
+  } else {
+    if (!extra.empty()) {
+      CK(s->d_tree_area.ensure(3 * (size_t)nk));
+      for (int k = 0; k < nk; ++k) {
+        const int nitems = build_with(k);
+        if (nitems < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed");
+        s->commit_launches += srt_lbvh_tree_area(nitems, B, s->d_tree_area.p + 3 * k, stream);
+      }
+      std::vector<double> area(3 * (size_t)nk);
+      CK(cudaMemcpyAsync(area.data(), s->d_tree_area.p, sizeof(double) * area.size(), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      pick(area);
+    }
+    if (extra.empty() || chosen != (int)extra.size()) { if (build_with(chosen) < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed"); }
   }
-  if (extra.empty() || chosen != (int)extra.size()) { if (build_with(chosen) < 0) return fail(SRT_ERR_CUDA, "commit: item upload failed"); }
   {   // fp32 sphere test for the tree's leaves iff every sphere in the tree is small against the scene (srt_device.cuh, isect_sphere32)
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
     for (int i = 0; i < ns; ++i) { if (s->prims[i].type == SRT_PRIM_KLEIN) continue; for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], hb[6 * i + k]); hi[k] = std::max(hi[k], hb[6 * i + 3 + k]); } }
@@ -579,6 +639,7 @@ static int commit_impl(SrtScene* s) {
   CK(cudaEventElapsedTime(&s->ms_commit, e0, e1));
   s->bvh_depth = depth; s->ds.bvh_depth = depth;
   if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level traversal bound", depth);
+  if (int rc = bounds_verdict("commit")) return rc;
   s->committed = true;
   return 0;
 }
@@ -745,7 +806,7 @@ int srt_bvh_readback(SrtScene* s, SrtBvhNode* nodes, int cap) {
   if (!s || !s->committed) return fail(SRT_ERR_NOT_COMMITTED, "scene not committed");
   USE_DEVICE(s);
   if (cap < s->n_nodes || !nodes) return fail(SRT_ERR_ARG, "bvh_readback: capacity %d < %d nodes", cap, s->n_nodes);
-  CK(cudaMemcpy(nodes, s->d_nodes.p, sizeof(SrtBvhNode) * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(nodes, s->lb.d_nodes, sizeof(SrtBvhNode) * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
   return 0;
 }
 int srt_bvh_items_readback(SrtScene* s, int32_t* item_prim, int cap, int32_t* global_prims8, int32_t* n_global) {
@@ -795,7 +856,7 @@ int srt_trace_batch(SrtScene* s, const SrtRay* rays, int n, float t_min, float t
   CK(cudaMemcpyAsync(out, d_out.p, sizeof(SrtHit) * (size_t)n, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   d_rays.release(); d_out.release();
-  return 0;
+  return bounds_verdict("trace_batch");
 }
 
 static int check_params(const SrtRenderParams* p) {
@@ -895,7 +956,7 @@ static int render_impl(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, 
     stats->paths = (uint64_t)total; stats->ms_total = ms; stats->ms_commit = s->ms_commit;
     stats->bvh_nodes = s->n_nodes; stats->bvh_depth = s->bvh_depth; stats->pipes = npipes;
   }
-  return 0;
+  return bounds_verdict("render");
 }
 
 int srt_render_device(SrtScene* s, const SrtRenderParams* p, float* d_rgb_sum, SrtStats* stats) {

@@ -7,6 +7,20 @@
 #include <stdint.h>
 #include "../../include/srt.h"
 
+// ---- bounds-checked build (-DSRT_BOUNDS_CHECK; tools/r2_bounds.sh) ---------------------------------------------------
+// compute-sanitizer is not available on the B200 pool (profiles/r2_sanitizer_unavailable.txt), so the indices the
+// kernels trust - queue slots, compaction positions, node / primitive / material / texture ids, traversal-stack
+// pointers, pixel ids, radix-sort scatter positions - are checked by the kernels themselves in this build: a
+// violation is counted (per translation unit), the access is skipped, and the entry point fails with the code of
+// the first violation.  The release build compiles the checks away.
+#ifdef SRT_BOUNDS_CHECK
+static __device__ unsigned long long d_srt_violations = 0ull;
+static __device__ int d_srt_first_violation = 0;
+#define SRT_BOUNDS_OK(cond, code) ((cond) ? true : (atomicAdd(&d_srt_violations, 1ull), atomicCAS(&d_srt_first_violation, 0, (code)), false))
+#else
+#define SRT_BOUNDS_OK(cond, code) true
+#endif
+
 #define SRT_PI 3.14159265358979323846f
 #define SRT_MAX_FLOAT 999999999999.0f  // constant.scm:6
 #define SRT_MAX_GLOBAL 8
@@ -494,11 +508,12 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
                                                const RngAddr& ra, Hit& h) {
   constexpr bool HAS_SPHERE = MASK & 1, HAS_MOVING = MASK & 2, HAS_RECT = MASK & 0x1c, HAS_BEZIER = MASK & 0x20, HAS_MEDIUM = MASK & 0x40, HAS_PATCH = MASK & 0x80, HAS_KLEIN = MASK & 0x100;
   constexpr bool LEAF32 = MASK & SRT_MASK_LEAF32;           // small spheres: the fp32 formulation (isect_sphere32)
+  if (!SRT_BOUNDS_OK(id >= 0 && id < sc.n_prims, 101)) return;
   constexpr bool SINGLE_KIND = ((MASK & SRT_MASK_ALL) & ((MASK & SRT_MASK_ALL) - 1)) == 0;
   float4 a = ps.a(id);
   int type, xform = -1, aux = 0;
   if (SINGLE_KIND && (MASK & 0x23)) type = HAS_SPHERE ? SRT_PRIM_SPHERE : (HAS_MOVING ? SRT_PRIM_MOVING_SPHERE : SRT_PRIM_BEZIER);
-  else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; aux = hdr.w; }
+  else { int4 hdr = ps.hdr(id); type = hdr.x & 0xff; xform = hdr.z; aux = hdr.w; if (!SRT_BOUNDS_OK(xform < sc.n_xforms, 102)) return; }
   float t = 0.f, u = 0.f, v = 0.f; bool ok = false;
   if (HAS_SPHERE && type == SRT_PRIM_SPHERE) {
     // an instanced sphere (geometry.scm:465-543 above a sphere leaf): the rigid transform keeps t, so
@@ -531,10 +546,10 @@ __device__ __forceinline__ void intersect_prim(const DScene& sc, const PrimSrc& 
     // xi = block (16 + id) of the ray's (pixel, sample, bounce) stream (upstream: (random-real)).
     const int first = (int)a.y, cnt = (int)a.z;
     Hit h1; h1.t = SRT_MAX_FLOAT; h1.prim = -1; h1.u = h1.v = 0.f; h1.incl = false;
-    for (int j = first; j < first + cnt; ++j) intersect_prim<MASK & 0x1d>(sc, ps, j, o, d, time, inv_a, -SRT_MAX_FLOAT, ra, h1);
+    for (int j = first; j < first + cnt; ++j) intersect_prim<0x1d>(sc, ps, j, o, d, time, inv_a, -SRT_MAX_FLOAT, ra, h1);   // boundaries: spheres / rects (commit checks)
     if (h1.prim >= 0) {
       Hit h2; h2.t = SRT_MAX_FLOAT; h2.prim = -1; h2.u = h2.v = 0.f; h2.incl = false;
-      for (int j = first; j < first + cnt; ++j) intersect_prim<MASK & 0x1d>(sc, ps, j, o, d, time, inv_a, h1.t + 0.0001f, ra, h2);
+      for (int j = first; j < first + cnt; ++j) intersect_prim<0x1d>(sc, ps, j, o, d, time, inv_a, h1.t + 0.0001f, ra, h2);
       if (h2.prim >= 0) {
         float t1 = fmaxf(fmaxf(h1.t, tmin), 0.0f);
         float len = length(d);
@@ -573,9 +588,11 @@ __device__ __forceinline__ float3 patch_normal(const float4* __restrict__ cp, fl
 // geometry.scm:158-160 (sphere), :386-387 (rects), :438 (flip), :473/:526-535 (instances),
 // bezier.scm:209-211 (Q9: p along the raw direction, normal = -dir).
 __device__ __forceinline__ void complete_hit(const DScene& sc, int prim, float t, float hu, float hv, float3 o, float3 d, float time, float3& p, float3& n, int& material) {
+  if (!SRT_BOUNDS_OK(prim >= 0 && prim < sc.n_prims, 111)) { p = o; n = v3(0.f, 1.f, 0.f); material = 0; return; }
   int4 hdr = __ldg(&sc.prim_hdr[prim]);
   int type = hdr.x & 0xff;
   material = hdr.y;
+  (void)SRT_BOUNDS_OK(material >= 0 && material < sc.n_mats && hdr.z < sc.n_xforms, 112);
   float4 a = __ldg(&sc.prim_a[prim]);
   if (type <= SRT_PRIM_MOVING_SPHERE) {
     float3 c = xyz(a);
@@ -665,6 +682,7 @@ __device__ __forceinline__ float perlin_turb(const DScene& sc, float3 p, int qui
 }
 __device__ __forceinline__ float3 tex_value(const DScene& sc, int tex, float u, float v, float3 p, int quirks) {
   for (int guard = 0; guard < 64; ++guard) {
+    if (!SRT_BOUNDS_OK(tex >= 0 && tex < sc.n_tex, 121)) return v3(0.f, 0.f, 0.f);
     float4 t0 = __ldg(&sc.tex[2 * tex]);
     int kind = __float_as_int(t0.x);
     if (kind == SRT_TEX_CONSTANT) return xyz(__ldg(&sc.tex[2 * tex + 1]));                    // texture.scm:12

@@ -25,6 +25,13 @@ struct LbvhBuffers {
   int sorted = 0;                          // which of d_keys/d_order holds the sorted result
 };
 
+// One candidate tree of the single-CTA build (device pointers; see k_lbvh_small in lbvh.cu)
+#define SRT_SMALL_MAX_ITEMS 2048
+struct SrtSmallJob {
+  const int* item_prim; int n;
+  unsigned long long* keys; int* order; int4* links; int* leaf_parent; float* nbox; float4* nodes; int* depth; double* area; int* bounds;
+};
+int srt_lbvh_build_small(const float* d_aabb, const SrtSmallJob* d_jobs, int n_jobs, cudaStream_t stream);
 int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);
 int srt_lbvh_build(int n_items, LbvhBuffers& B, cudaStream_t stream);
 int srt_lbvh_tree_area(int n_items, LbvhBuffers& B, double* d_out3, cudaStream_t stream);
@@ -83,3 +90,6 @@ int srt_launch_eval_texture(const DScene& sc, int tex, const float* d_uvp5, int 
 int srt_launch_eval_raygen(const RenderLaunch& L, int n, const int* d_pixel, const int* d_sample, SrtRay* d_out, cudaStream_t stream);
 size_t srt_extend_smem_bytes(const DScene& sc);
 float srt_measure_fma_tflops(int sm_count, cudaStream_t stream);
+// bounds-checked build (-DSRT_BOUNDS_CHECK): violations counted by the kernels of each translation unit
+unsigned long long srt_bounds_violations_wavefront(int* first);
+unsigned long long srt_bounds_violations_lbvh(int* first);

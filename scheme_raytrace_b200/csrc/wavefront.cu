@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
     float3 o, d; float time;
     get_ray(cam, u, v, xi.z, addr, o, d, time);
     int slot = surv + j;
+    if (!SRT_BOUNDS_OK(slot >= 0 && slot < capacity, 211)) continue;
     ray_o[slot] = make_float4(o.x, o.y, o.z, time);
     ray_d[slot] = make_float4(d.x, d.y, d.z, __int_as_float((int)(sample << 12)));
     state[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(pixel));
@@ -134,6 +135,9 @@ struct Trav {
   unsigned long long s0, s1; int nstk;      // register-packed cache of the 8 most recent pending far children (16-bit ids)
   uint32_t sp, sp0;                         // TRAV_STACK: shared-space address of the next free / first stack slot
   int n_nodes;                              // plane stride of the staged node layout
+#ifdef SRT_BOUNDS_CHECK
+  int stack_slots;                          // halfwords of this thread's stack (bounds-checked build)
+#endif
 #ifdef SRT_COUNT_STEPS
   int nsteps, ntests, nmiss, maxsp;         // instrumented build only (tools/step_stats.py); maxsp = deepest stack use
 #endif
@@ -225,8 +229,10 @@ __device__ __forceinline__ float2 ffma2s(float2 a, float b, float c) { return ff
 //              STS.U16, pop = LDS.U16.  Used whenever the tree has < 65536 nodes and the stack fits.
 //  TRAV_CACHE  stackless bit trail + parent/sibling climb, with the 8 most recent far children in
 //              two 64-bit registers.
-//  TRAV_TRAIL  the bit trail alone (>= 65536 nodes).
-enum { TRAV_TRAIL = 0, TRAV_CACHE = 1, TRAV_STACK = 2 };
+//  TRAV_STACK32 the same stack with 32-bit entries, for trees with >= 65536 nodes (never staged, so the stack
+//              always fits): replaced the bare bit trail, whose parent / sibling climb is a chain of dependent
+//              GLOBAL loads on such trees (70,000-sphere cloud: profiles/README.md, round 2).
+enum { TRAV_STACK32 = 0, TRAV_CACHE = 1, TRAV_STACK = 2 };
 // halfwords per thread, odd (spreads banks): bvh_depth + 1 pending far children + the SENTINEL 0xffff at
 // the bottom, written once per thread: "pop" needs no compare against the stack base, the empty stack
 // answers with the sentinel (node ids are < 65535 in this mode)
@@ -236,12 +242,18 @@ __device__ __forceinline__ uint32_t trav_stack_init(uint32_t base) {
   asm volatile("st.shared.u16 [%0], %1;" :: "r"(base), "h"((unsigned short)SRT_STACK_SENTINEL) : "memory");
   return base + 2u;
 }
+__device__ __forceinline__ uint32_t trav_stack32_init(uint32_t base) {       // TRAV_STACK32: words, sentinel 0xffffffff
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(base), "r"(0xffffffffu) : "memory");
+  return base + 4u;
+}
 
 // WANT_T: also returns the box intervals [t0, t1] of the stashed leaf children (ivl = {pend0's t0, t1,
 // pend1's t0, t1}; already clipped to [tmin, closest hit so far]) for the patch variants' slab cull.
 template <bool SMEM, int TRAV, bool WANT_T = false>
 __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ nodes, uint32_t sbase, float tmin, int& pend0, int& pend1, float4* ivl = nullptr) {
   const int node = T.node;
+  if (!SRT_BOUNDS_OK(node >= 0 && node < T.n_nodes, 231)) return false;
+  if (TRAV != TRAV_CACHE && !SRT_BOUNDS_OK(T.sp >= T.sp0 && T.sp <= T.sp0 + (TRAV == TRAV_STACK32 ? 4u : 2u) * (uint32_t)(T.stack_slots - 1), 232)) return false;
 #ifdef SRT_COUNT_STEPS
   T.nsteps++;
 #endif
@@ -271,20 +283,30 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
   }
   const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
   const bool hl0 = lt0 <= lt1, hr0 = rt0 <= rt1;
-  // hit leaf children go to (pend0, pend1) - select form: as branches this was a divergent region
-  // plus byte-packed booleans carried across it
+  // hit leaf children go to (pend0, pend1) as RAW leaf references (negative: ~primitive id; 0 = none) - select
+  // form: as branches this was a divergent region plus byte-packed booleans carried across it.  The node loop
+  // is bound by the ALU pipe (compares, selects, min / max: ncu r2), so the logic below is written for
+  // predicates: no boolean is materialised in a register, the leaf reference is decoded at the leaf test.
   const bool ll = hl0 & (left < 0), rl = hr0 & (right < 0);
-  pend0 = ll ? ~left : (rl ? ~right : -1);
-  pend1 = (ll & rl) ? ~right : -1;
+  pend0 = ll ? left : (rl ? right : 0);
+  pend1 = (ll & rl) ? right : 0;
   if (WANT_T) *ivl = make_float4(ll ? lt0 : rt0, ll ? lt1 : rt1, rt0, rt1);
   const bool hl = hl0 & (left >= 0), hr = hr0 & (right >= 0);
   if (hl | hr) {
-    bool both = hl & hr;
-    bool go_left = both ? (lt0 <= rt0) : hl;                  // near child first
-    T.node = go_left ? left : right;
+    const bool both = hl & hr;
+    const bool right_first = !hl | (hr & (rt0 < lt0));          // near child first; a single hit child is "near"
+    const int nearc = right_first ? right : left, farc = right_first ? left : right;
+    T.node = nearc;
+    if (TRAV == TRAV_STACK32) {
+      if (both) {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(T.sp), "r"((uint32_t)farc) : "memory");
+        T.sp += 4u;
+      }
+      return true;
+    }
     if (TRAV == TRAV_STACK) {
       if (both) {
-        asm volatile("st.shared.u16 [%0], %1;" :: "r"(T.sp), "h"((unsigned short)(go_left ? right : left)) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(T.sp), "h"((unsigned short)farc) : "memory");
         T.sp += 2u;
 #ifdef SRT_COUNT_STEPS
         T.maxsp = max(T.maxsp, (int)((T.sp - T.sp0) >> 1));
@@ -292,6 +314,7 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
       }
       return true;
     }
+    const bool go_left = !right_first;
     T.trail = (T.trail << 1) | (both ? 1ull : 0ull);
     if (TRAV == TRAV_CACHE && both) {
       unsigned long long far_id = (unsigned long long)(unsigned)(go_left ? right : left);
@@ -299,6 +322,14 @@ __device__ __forceinline__ bool node_step(Trav& T, const float4* __restrict__ no
       T.s0 = (T.s0 << 16) | far_id;
       T.nstk = min(T.nstk + 1, 8);
     }
+    return true;
+  }
+  if (TRAV == TRAV_STACK32) {
+    uint32_t id;
+    asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(id) : "r"(T.sp) : "memory");
+    if (id == 0xffffffffu) return false;
+    T.sp -= 4u;
+    T.node = (int)id;
     return true;
   }
   if (TRAV == TRAV_STACK) {
@@ -340,9 +371,13 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
   }
   Trav T;
   T.n_nodes = sc.n_nodes;
-  T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+#ifdef SRT_BOUNDS_CHECK
+  T.stack_slots = trav_stack_stride(sc.bvh_depth) - 1;     // slots above the sentinel
+#endif
+  T.sp0 = stack_base + (TRAV == TRAV_STACK32 ? 4u : 2u) * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   T.sp = T.sp0;
   if (TRAV == TRAV_STACK) T.sp = T.sp0 = trav_stack_init(T.sp0);
+  if (TRAV == TRAV_STACK32) T.sp = T.sp0 = trav_stack32_init(T.sp0);
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   // the next ray of this thread is fetched while the current one is traversed
@@ -363,13 +398,13 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
       intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
     bool more = sc.n_items > 0;
     while (more) {
-      int pend0 = -1, pend1 = -1;
+      int pend0 = 0, pend1 = 0;                  // raw leaf references (negative), 0 = none
       more = node_step<SMEM, TRAV>(T, nodes, sbase, tmin, pend0, pend1);
-      while (pend0 >= 0) {
+      while (pend0 < 0) {
 #ifdef SRT_COUNT_STEPS
         T.ntests++;
 #endif
-        intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h); pend0 = pend1; pend1 = -1;
+        intersect_prim<MASK>(sc, ps, ~pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h); pend0 = pend1; pend1 = 0;
       }
     }
 #ifdef SRT_COUNT_STEPS
@@ -409,9 +444,13 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
   const int vote = tune & 0xff, refill = (tune >> 8) & 0xff;
   Trav T;
   T.n_nodes = sc.n_nodes;
-  T.sp0 = stack_base + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
+#ifdef SRT_BOUNDS_CHECK
+  T.stack_slots = trav_stack_stride(sc.bvh_depth) - 1;     // slots above the sentinel
+#endif
+  T.sp0 = stack_base + (TRAV == TRAV_STACK32 ? 4u : 2u) * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   T.sp = T.sp0;
   if (TRAV == TRAV_STACK) T.sp = T.sp0 = trav_stack_init(T.sp0);
+  if (TRAV == TRAV_STACK32) T.sp = T.sp0 = trav_stack32_init(T.sp0);
   uint32_t sbase = SMEM ? (uint32_t)__cvta_generic_to_shared(nodes) : 0u;
   asm volatile("" : "+r"(sbase));            // opaque: keep it in a register instead of re-deriving it per iteration
   const int stride = gridDim.x * blockDim.x;
@@ -457,29 +496,30 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
 #ifdef SRT_COUNT_STEPS
         T.ntests++;
 #endif
-        intersect_prim<MASK>(sc, ps, park0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+        intersect_prim<MASK & 0x1e0>(sc, ps, park0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);   // only the expensive kinds are ever parked
         park0 = park1; park1 = -1;
       }
       continue;
     }
     if (ray >= 0 && more && !parked) {
-      int pend0 = -1, pend1 = -1;
+      int pend0 = 0, pend1 = 0;                  // raw leaf references (negative), 0 = none
       float4 ivl = make_float4(0.f, 0.f, 0.f, 0.f);
       more = node_step<SMEM, TRAV, (MASK & 0x80) != 0>(T, nodes, sbase, tmin, pend0, pend1, &ivl);
-      while (pend0 >= 0) {
-        const int type = ps.hdr(pend0).x & 0xff;
+      while (pend0 < 0) {
+        const int leaf = ~pend0;
+        const int type = ps.hdr(leaf).x & 0xff;
         if (type >= SRT_PRIM_BEZIER) {
           // a patch leaf is parked only if the ray meets its bounding slab inside the leaf's box interval
           // (15 instructions here against a ~300-instruction projection + hull cull inside the parked test)
-          const bool culled = (MASK & 0x80) && type == SRT_PRIM_PATCH && patch_slab_culled(ps.a(pend0), T.o, T.d, ivl.x, ivl.y);
-          if (!culled) { if (park0 < 0) park0 = pend0; else park1 = pend0; }
+          const bool culled = (MASK & 0x80) && type == SRT_PRIM_PATCH && patch_slab_culled(ps.a(leaf), T.o, T.d, ivl.x, ivl.y);
+          if (!culled) { if (park0 < 0) park0 = leaf; else park1 = leaf; }
         } else {
 #ifdef SRT_COUNT_STEPS
           T.ntests++;
 #endif
-          intersect_prim<MASK & 0x1f>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+          intersect_prim<MASK & 0x1f>(sc, ps, leaf, T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
         }
-        pend0 = pend1; pend1 = -1; ivl.x = ivl.z; ivl.y = ivl.w;
+        pend0 = pend1; pend1 = 0; ivl.x = ivl.z; ivl.y = ivl.w;
       }
     }
   }
@@ -529,6 +569,7 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
   float3 thr = xyz(s4); const int pixel = __float_as_int(s4.w); const int sd = __float_as_int(d4.w);
   const int depth = sd & 0xfff; const unsigned int sample = (unsigned int)sd >> 12;
   const float3 o = xyz(o4), d = xyz(d4);
+  if (!SRT_BOUNDS_OK(pixel >= 0 && pixel < p.width * p.height && depth <= p.max_depth, 201)) return false;
   if (prim < 0) {                                              // main.scm:120 sky
     accumulate_fixed(accum, pixel, thr * sky_value(p.sky, d), &ctrl->nonfinite);
     return false;
@@ -587,7 +628,9 @@ k_shade(DScene sc, SrtRenderParams p, int g,
     __syncthreads();
     if (alive) {
       int pos = s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
-      ray_o_next[pos] = no4; ray_d_next[pos] = nd4; state_next[pos] = ns4;
+      if (SRT_BOUNDS_OK(pos >= 0 && pos < count, 221)) {       // survivors of a generation never outnumber it
+        ray_o_next[pos] = no4; ray_d_next[pos] = nd4; state_next[pos] = ns4;
+      }
     }
     __syncthreads();
   }
@@ -626,6 +669,9 @@ k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
   const PrimShared ps(sh, sa);
   Trav T;
   T.n_nodes = sc.n_nodes;
+#ifdef SRT_BOUNDS_CHECK
+  T.stack_slots = trav_stack_stride(sc.bvh_depth) - 1;     // slots above the sentinel
+#endif
   T.sp0 = (uint32_t)__cvta_generic_to_shared(smem + nn + 2 * np) + 2u * (uint32_t)trav_stack_stride(sc.bvh_depth) * threadIdx.x;
   T.sp = T.sp0 = trav_stack_init(T.sp0);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
@@ -653,9 +699,9 @@ k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
         intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
       bool more = sc.n_items > 0;
       while (more) {
-        int pend0 = -1, pend1 = -1;
+        int pend0 = 0, pend1 = 0;
         more = node_step<true, TRAV_STACK>(T, smem, sbase, p.t_min, pend0, pend1);
-        while (pend0 >= 0) { intersect_prim<MASK>(sc, ps, pend0, T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h); pend0 = pend1; pend1 = -1; }
+        while (pend0 < 0) { intersect_prim<MASK>(sc, ps, ~pend0, T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h); pend0 = pend1; pend1 = 0; }
       }
     }
     float4 no4, nd4, ns4;
@@ -797,6 +843,19 @@ float srt_measure_fma_tflops(int sm_count, cudaStream_t stream) {
   return best;
 }
 
+// bounds-checked build: violations counted by the kernels of this translation unit (0 in the release build)
+unsigned long long srt_bounds_violations_wavefront(int* first) {
+#ifdef SRT_BOUNDS_CHECK
+  unsigned long long v = 0ull; int f = 0;
+  cudaMemcpyFromSymbol(&v, d_srt_violations, sizeof(v)); cudaMemcpyFromSymbol(&f, d_srt_first_violation, sizeof(f));
+  if (first) *first = f;
+  return v;
+#else
+  if (first) *first = 0;
+  return 0ull;
+#endif
+}
+
 // =================================================================================================
 size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes + (size_t)32 * sc.n_prims; }
 
@@ -806,13 +865,14 @@ typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, fl
 typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
 struct TailVariant { TailFn fn; size_t smem; int bps; };
-static ExtendVariant g_variants[SRT_MAX_DEVICES][2][5][3][2];
+static ExtendVariant g_variants[SRT_MAX_DEVICES][2][6][3][2];
 static TailVariant g_tail_variants[SRT_MAX_DEVICES][3][2][2];
 static std::mutex g_variant_mu;
 
-// spheres | + moving spheres | + rects / instances | + bicubic patches | everything (curves, media, Klein).
-// The patch variant exists because the curve's subdivision stack (1.3 KB of local memory per thread) and
-// the Klein / medium code cost the patch scenes 14 % when merely compiled in (cfg5_teapot 2.61 -> 2.96 Grays/s).
+// spheres | + moving spheres | + rects / instances | + bicubic patches | everything (curves, media, Klein) |
+// patches + curves.  The patch variant exists because the curve's subdivision stack (1.3 KB of local memory per
+// thread) and the Klein / medium code cost the patch scenes 14 % when merely compiled in (cfg5_teapot 2.61 -> 2.96
+// Grays/s); variant 5 is the same argument for cfg5 (patches AND the reference's curves, no medium / Klein).
 // SRT_MASK_XF_SPHERE (an instanced sphere: translate / rotate-y above a sphere leaf, geometry.scm:465-543)
 // needs the primitive header, which the sphere-only variant 0 does not read: such scenes use variant 1.
 static int variant_of(int mask) {
@@ -822,6 +882,7 @@ static int variant_of(int mask) {
   if ((mask & ~0x03) == 0) return 1;                 // two kinds: the header (and its xform) is read
   if ((mask & 0x1e0) == 0) return 2;
   if ((mask & 0x160) == 0) return 3;
+  if ((mask & 0x140) == 0) return 5;
   return 4;
 }
 template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v, bool leaf32) {
@@ -830,13 +891,14 @@ template <bool SMEM, int TRAV> static ExtendFn variant_fn_m(int v, bool leaf32) 
     case 1: return leaf32 ? k_extend<SMEM, 0x03 | SRT_MASK_LEAF32, TRAV> : k_extend<SMEM, 0x03, TRAV>;
     case 2: return leaf32 ? k_extend<SMEM, 0x1f | SRT_MASK_LEAF32, TRAV> : k_extend<SMEM, 0x1f, TRAV>;
     case 3: return k_extend<SMEM, 0x9f, TRAV>;
+    case 5: return k_extend<SMEM, 0xbf, TRAV>;
     default: return k_extend<SMEM, SRT_MASK_ALL, TRAV>;
   }
 }
 static ExtendFn variant_fn(bool smem, int v, int trav, bool leaf32) {
   if (trav == TRAV_STACK) return smem ? variant_fn_m<true, TRAV_STACK>(v, leaf32) : variant_fn_m<false, TRAV_STACK>(v, leaf32);
   if (trav == TRAV_CACHE) return smem ? variant_fn_m<true, TRAV_CACHE>(v, leaf32) : variant_fn_m<false, TRAV_CACHE>(v, leaf32);
-  return smem ? variant_fn_m<true, TRAV_TRAIL>(v, leaf32) : variant_fn_m<false, TRAV_TRAIL>(v, leaf32);
+  return smem ? variant_fn_m<true, TRAV_STACK32>(v, leaf32) : variant_fn_m<false, TRAV_STACK32>(v, leaf32);
 }
 static bool leaf32_of(const RenderLaunch& L, int v) {
   static const bool off = getenv("SRT_NO_LEAF32") != nullptr;                        // A/B switch
@@ -850,7 +912,8 @@ static int trav_mode(const RenderLaunch& L, int v, size_t* stack_bytes) {
   const bool small_ids = L.sc.n_nodes < 65536;
   static const bool force_cache = getenv("SRT_TRAV_CACHE") != nullptr;             // A/B switch for profiling
   *stack_bytes = stack;
-  return !small_ids ? TRAV_TRAIL : ((!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE);
+  if (!small_ids) { *stack_bytes = 2 * stack; return TRAV_STACK32; }      // never staged (>= 4 MB of nodes): the 32-bit stack always fits
+  return (!force_cache && (which ? L.extend_smem : 0) + stack <= (size_t)200 * 1024) ? TRAV_STACK : TRAV_CACHE;
 }
 // persistent grid: SM count x resident CTAs per SM (queried; depends on the staged-BVH size)
 static ExtendVariant extend_variant(const RenderLaunch& L) {
@@ -861,7 +924,7 @@ static ExtendVariant extend_variant(const RenderLaunch& L) {
   const bool leaf32 = leaf32_of(L, v);
   std::lock_guard<std::mutex> lock(g_variant_mu);
   ExtendVariant& e = g_variants[L.device][which][v][trav][leaf32 ? 1 : 0];
-  size_t smem = (which ? L.extend_smem : 0) + (trav == TRAV_STACK ? stack : 0);
+  size_t smem = (which ? L.extend_smem : 0) + (trav != TRAV_CACHE ? stack : 0);
   if (!e.fn || e.smem != smem) {
     e.fn = variant_fn(which, v, trav, leaf32); e.smem = smem; e.threads = threads;
     if (smem) cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

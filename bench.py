@@ -323,12 +323,13 @@ def main():
             dist.barrier(group=cpu_group)
             try:
                 rm = srt.Renderer(flat, gpus=world)
-                host = np.zeros((H, W, 3), dtype=np.float32)
-                rm.render_multi(W, H, SPP, max_depth=D, seed=SEED, rgb_sum=None)      # warm-up: replicas, graphs, NCCL channels
+                host_sum = torch.empty(H, W, 3, dtype=torch.float32).pin_memory().numpy()      # *raw-data* / *image* land in pinned host memory
+                host_img8 = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory().numpy()
+                rm.render_multi(W, H, SPP, max_depth=D, seed=SEED, rgb_sum=host_sum, image=host_img8, write_only=True)      # warm-up: replicas, graphs, NCCL channels
                 t0 = time.perf_counter(); nr = 0
                 for _ in range(K):
                     rm.commit()
-                    _, _, stm = rm.render_multi(W, H, SPP, max_depth=D, seed=SEED)
+                    _, _, stm = rm.render_multi(W, H, SPP, max_depth=D, seed=SEED, rgb_sum=host_sum, image=host_img8, write_only=True)
                     nr += stm.rays
                 dt = time.perf_counter() - t0
                 import ctypes as C

@@ -529,8 +529,13 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
 // expensive primitives needs 128 registers, i.e. at most 512 threads per SM; it runs as ONE 512-thread
 // CTA per SM so that those 16 warps share one staged copy of the scene (as 2 x 256 the teapot scene's
 // 147 KB tree allowed a single 256-thread CTA: 8 warps/SM, issue slots 39 % busy).
+// (round 2: the rect / instance variant also runs 4 CTAs per SM - 62 registers with 56 B of spills beat 80 registers
+// at 3 CTAs: cfg4 8.96 -> 9.36, cfg3 6.79 -> 6.96 Grays/s)
+#ifndef SRT_RECT_CTAS
+#define SRT_RECT_CTAS 4
+#endif
 template <bool SMEM, int MASK, int TRAV>
-__global__ void __launch_bounds__((MASK & 0x1e0) ? EXT_THREADS_HEAVY : EXT_THREADS, (MASK & 0x1e0) ? 1 : ((MASK & 0x1c) ? 3 : 4))
+__global__ void __launch_bounds__((MASK & 0x1e0) ? EXT_THREADS_HEAVY : EXT_THREADS, (MASK & 0x1e0) ? 1 : ((MASK & 0x1c) ? SRT_RECT_CTAS : 4))
 k_extend(DScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
          float4* __restrict__ hit, const int* __restrict__ count_ptr, int count_fixed, float tmin, float tmax, uint32_t seed, int tune) {
   extern __shared__ float4 smem[];

@@ -449,25 +449,33 @@ RENDER_SCENES = {"cornell_box": "cornell-box", "test_bezier": "test-bezier", "co
 RENDER_TAILS = {"cornell_box": (0.975, 0.995), "test_bezier": (0.975, 0.995), "cornell_smoke": (0.975, 0.995), "test_scene2": (0.92, 0.94)}
 
 
-@pytest.mark.parametrize("key", list(RENDER_SCENES))
-def test_converged_image_against_the_references_own_render(orc, key):
+def _render_cases():
+    out = [("ref_render.npz", k) for k in RENDER_SCENES]
+    big = os.path.join(GOLD, "ref_render32.npz")            # round 2: 32 x 32 thumbnails (make_reference_render.py, SRT_RENDER_SIZE=32)
+    if os.path.exists(big):
+        out += [("ref_render32.npz", k[:-5]) for k in np.load(big).files if k.endswith("_meta")]
+    return out
+
+
+@pytest.mark.parametrize("fname,key", _render_cases())
+def test_converged_image_against_the_references_own_render(orc, fname, key):
     """North star, second criterion: the converged image must match the reference's CPU render.  The oracle renders the
     same scene at 4096 spp with its own Philox stream; tolerance, stated: per channel value the difference is within the
     reference render's Monte-Carlo standard error - median |z| in [0.45, 0.95] (0.674 for pure noise), >= 97.5 % of the
     values within 3 se and >= 99.5 % within 4 se (looser, stated in RENDER_TAILS, for the two scenes lit only by small emitters), no global bias beyond 4 se of the summed image (per channel), mean radiance within 2 %, RMSE of the clamped
     linear image <= 1.3 x the noise-predicted RMSE.  Without Q15 (quirks = 15: one cosine direction per scatter instead
     of the three the `local` macro evaluates) the Cornell box FAILS the same test - the quirk is visible in the image."""
-    gold = np.load(os.path.join(GOLD, "ref_render.npz"))
+    gold = np.load(os.path.join(GOLD, fname))
     w, h, n = (int(x) for x in gold[key + "_meta"])
     S = orc.OracleScene(host_scene(RENDER_SCENES[key], w, h), quantise=False)
     spp = 4096
     img, _ = S.render(w, h, spp, max_depth=100, seed=77)
     st = render_stats(gold, key, img / spp, spp)
-    print(f"\n[reference render {key}] {st}")
+    print(f"\n[reference render {fname}:{key} {w}x{h}@{n}] {st}")
     assert 0.45 <= st["median_abs_z"] <= 0.95 and st["frac_within_3"] >= RENDER_TAILS[key][0] and st["frac_within_4"] >= RENDER_TAILS[key][1]
     assert abs(st["bias_z"]) <= 4.0 and abs(st["rel_mean"] - 1.0) <= 0.02
     assert st["rmse"] <= 1.3 * st["expected_rmse"]
-    if key == "cornell_box":
+    if key == "cornell_box" and fname == "ref_render.npz":
         img15, _ = S.render(w, h, spp, max_depth=100, seed=77, quirks=15)
         st15 = render_stats(gold, key, img15 / spp, spp)
         print(f"[reference render {key}, quirks=15] {st15}")

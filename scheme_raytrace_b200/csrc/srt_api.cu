@@ -146,6 +146,7 @@ struct SrtScene {
   DevBuf<float> d_prog; int prog_w = 0, prog_h = 0, prog_spp = 0;   // device-resident running sum of the progressive path (*raw-data*, main.scm:430)
   DevBuf<unsigned long long> d_stage;   // multi-GPU: peers' accumulators staged on the root when peer access is unavailable
   int device = 0;            // the CUDA device this scene lives on
+  int global_small = 0;      // bit g: global_prims[g] is a small sphere (fp32 test)
   bool leaf32_ok = false;    // every sphere inside the LBVH is small against the scene (|r| < extent / 64): fp32 sphere test
   bool multi = false;        // created under srt_init_multi: commit keeps one replica per GPU, srt_render_multi uses them
   unsigned long long version = 0;       // bumped by every set_*; replicas re-commit when it differs
@@ -159,6 +160,7 @@ static void fill_dscene(SrtScene* s) {
   DScene& d = s->ds;
   std::memset(&d, 0, sizeof(d));             // padding too: the bytes are part of the graph-cache key
   d.n_prims = (int)s->prims.size(); d.n_surf = s->n_surf; d.n_nodes = s->n_nodes; d.n_items = s->n_items;
+  d.global_small = s->global_small;
   d.n_global = (int)s->global_prims.size(); for (int i = 0; i < SRT_MAX_GLOBAL; ++i) d.global_prims[i] = i < d.n_global ? s->global_prims[i] : 0; d.n_xforms = (int)s->xforms.size();
   d.n_mats = (int)s->mats.size(); d.n_tex = (int)s->texs.size(); d.bvh_depth = s->bvh_depth;
   d.prim_hdr = s->d_hdr.p; d.prim_a = s->d_a.p; d.prim_b = s->d_b.p; d.prim_c = s->d_c.p; d.prim_d = s->d_d.p;
@@ -629,6 +631,11 @@ static int commit_impl(SrtScene* s) {
     float E = 0.f; for (int k = 0; k < 3; ++k) E = std::max(E, hi[k] - lo[k]);
     s->leaf32_ok = ns > 0;
     for (int i : s->item_prim) if (s->prims[i].type <= SRT_PRIM_MOVING_SPHERE && !(std::fabs(s->prims[i].p[3]) < E * (1.0f / 64.0f))) s->leaf32_ok = false;
+    s->global_small = 0;
+    for (size_t g = 0; g < s->global_prims.size(); ++g) {
+      const SrtPrim& q = s->prims[s->global_prims[g]];
+      if (q.type <= SRT_PRIM_MOVING_SPHERE && q.xform < 0 && std::fabs(q.p[3]) < E * (1.0f / 64.0f)) s->global_small |= 1 << g;
+    }
   }
   fill_dscene(s);
   CK(cudaGetLastError());

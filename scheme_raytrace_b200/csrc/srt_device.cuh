@@ -31,6 +31,8 @@ struct DScene {
   int n_prims, n_surf, n_nodes, n_xforms, n_mats, n_tex, bvh_depth;   // n_surf = scene surfaces; the rest are medium boundaries
   int n_items;              // surfaces inside the LBVH
   int n_global; int global_prims[SRT_MAX_GLOBAL];   // huge surfaces tested linearly before traversal
+  int global_small;         // bit g: global_prims[g] is a sphere that is small against the scene (an "outlier" taken out of the
+                            // tree by the cost search, e.g. the three r = 1 spheres of random-scene): fp32 sphere test
   const int4* prim_hdr;     // x = type | flags << 8, y = material, z = xform, w = 0
   const float4* prim_a;     // sphere: c.xyz r | rect: a0 a1 b0 b1 | bezier: A.xyz width
   const float4* prim_b;     // moving: c1.xyz time0 | rect: k | bezier: B.xyz

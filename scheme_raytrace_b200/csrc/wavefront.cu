@@ -394,8 +394,11 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
       T.ra.seed = seed; T.ra.pixel = state ? (uint32_t)__float_as_int(state[i].w) : (uint32_t)i;
       T.ra.sample = (uint32_t)sd >> 12; T.ra.bounce = (uint32_t)(sd & 0xfff) + 1u;
     }
-    for (int g = 0; g < sc.n_global; ++g)      // huge primitives first, all lanes together (uniform control flow); FP64 sphere terms
-      intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+    for (int g = 0; g < sc.n_global; ++g) {    // primitives kept outside the tree first, all lanes together (uniform control flow)
+      // FP64 sphere terms for the huge ones (ground spheres); the small outliers take the fp32 test like the tree's leaves
+      if ((MASK & SRT_MASK_LEAF32) && ((sc.global_small >> g) & 1)) intersect_prim<MASK>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+      else intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[g], T.o, T.d, T.time, T.inv_a, tmin, T.ra, T.h);
+    }
     bool more = sc.n_items > 0;
     while (more) {
       int pend0 = 0, pend1 = 0;                  // raw leaf references (negative), 0 = none
@@ -598,8 +601,11 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
 // (warp ballot -> per-warp count -> one atomic per CTA).  Measured and NOT adopted (profiles/README.md,
 // round 2): the per-primitive tables staged in shared memory (+1 % cfg2, -2 % cfg3) and a software
 // prefetch of the next tile's queue entries (-9 % at 4 CTAs/SM with spills, -24 % at 3 CTAs/SM).
+#ifndef SRT_SHADE_CTAS
+#define SRT_SHADE_CTAS 4
+#endif
 template <int EST>
-__global__ void __launch_bounds__(SHD_THREADS, 4)
+__global__ void __launch_bounds__(SHD_THREADS, SRT_SHADE_CTAS)
 k_shade(DScene sc, SrtRenderParams p, int g,
         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
         float4* __restrict__ ray_o_next, float4* __restrict__ ray_d_next, float4* __restrict__ state_next,
@@ -700,8 +706,10 @@ k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
     trav_init(T, o4, d4, SRT_MAX_FLOAT, 0);
     ++nrays;
     if (sc.n_surf > 0) {
-      for (int k = 0; k < sc.n_global; ++k)
-        intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
+      for (int k = 0; k < sc.n_global; ++k) {
+        if ((MASK & SRT_MASK_LEAF32) && ((sc.global_small >> k) & 1)) intersect_prim<MASK>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
+        else intersect_prim<MASK & ~SRT_MASK_LEAF32>(sc, ps, sc.global_prims[k], T.o, T.d, T.time, T.inv_a, p.t_min, T.ra, T.h);
+      }
       bool more = sc.n_items > 0;
       while (more) {
         int pend0 = 0, pend1 = 0;

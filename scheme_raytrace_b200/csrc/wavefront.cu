@@ -45,7 +45,7 @@ struct WaveCtrl {
   unsigned long long iterations;
   unsigned long long nonfinite;     // radiance contributions dropped because they were NaN / Inf
   unsigned long long bounce_hist[8];// closest-hit queries by bounce (0..6, >= 7), profile mode only
-  int spp_begin; int tail_runs;     // tail_runs: how many times the drain kernel took over
+  int spp_begin; int tail_runs;     // tail_runs: how many times the one-launch tail kernel took over
 };
 #define SRT_ACC_SCALE 68719476736.0f   // 2^36: radiance accumulates in 64-bit fixed point
 #define SRT_ACC_MAX 6.7e7f             // per-contribution clamp: 2^26 * 2^36 = 2^62 stays inside the signed 64-bit sum
@@ -601,6 +601,46 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
 // (warp ballot -> per-warp count -> one atomic per CTA).  Measured and NOT adopted (profiles/README.md,
 // round 2): the per-primitive tables staged in shared memory (+1 % cfg2, -2 % cfg3) and a software
 // prefetch of the next tile's queue entries (-9 % at 4 CTAs/SM with spills, -24 % at 3 CTAs/SM).
+struct ShadeShared { int warp[SHD_THREADS / 32]; int base; unsigned hist[8]; };
+// One pass over queue generation g: shade every path, compact the survivors behind *next_count (shared by the
+// wavefront's k_shade and the persistent drain kernel).  blockDim.x == SHD_THREADS.
+template <int EST>
+__device__ __forceinline__ void shade_tiles(const DScene& sc, const SrtRenderParams& p, int count,
+                                            const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
+                                            float4* __restrict__ ray_o_next, float4* __restrict__ ray_d_next, float4* __restrict__ state_next,
+                                            unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl, int* next_count, ShadeShared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.reserved[0] == 1) { if (threadIdx.x < 8) S.hist[threadIdx.x] = 0u; __syncthreads(); }
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {   // block-uniform trip count
+    const int i = base + threadIdx.x;
+    bool alive = false;
+    float4 no4 = make_float4(0.f, 0.f, 0.f, 0.f), nd4 = no4, ns4 = no4, d4 = no4;
+    if (i < count) { d4 = ray_d[i]; alive = shade_path<EST>(sc, p, hit[i], ray_o[i], d4, state[i], accum, ctrl, no4, nd4, ns4); }
+    if (p.reserved[0] == 1) {                     // profile mode: closest-hit queries per bounce (per-CTA histogram in shared memory)
+      const int bucket = i < count ? min(__float_as_int(d4.w) & 0xfff, 7) : 8;
+      const unsigned peers = __match_any_sync(0xffffffffu, bucket);
+      if (bucket < 8 && lane == __ffs(peers) - 1) atomicAdd(&S.hist[bucket], (unsigned)__popc(peers));
+    }
+    unsigned ballot = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) S.warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < SHD_THREADS / 32; ++w) { int c = S.warp[w]; S.warp[w] = tot; tot += c; }
+      S.base = tot ? atomicAdd(next_count, tot) : 0;
+    }
+    __syncthreads();
+    if (alive) {
+      int pos = S.base + S.warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+      if (SRT_BOUNDS_OK(pos >= 0 && pos < count, 221)) {       // survivors of a generation never outnumber it
+        ray_o_next[pos] = no4; ray_d_next[pos] = nd4; state_next[pos] = ns4;
+      }
+    }
+    __syncthreads();
+  }
+  if (p.reserved[0] == 1 && threadIdx.x < 8 && S.hist[threadIdx.x]) atomicAdd(&ctrl->bounce_hist[threadIdx.x], (unsigned long long)S.hist[threadIdx.x]);
+}
 #ifndef SRT_SHADE_CTAS
 #define SRT_SHADE_CTAS 4
 #endif
@@ -610,42 +650,8 @@ k_shade(DScene sc, SrtRenderParams p, int g,
         const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state, const float4* __restrict__ hit,
         float4* __restrict__ ray_o_next, float4* __restrict__ ray_d_next, float4* __restrict__ state_next,
         unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {
-  __shared__ int s_warp[SHD_THREADS / 32];
-  __shared__ int s_base;
-  __shared__ unsigned s_hist[8];
-  const int count = ctrl->qcount[g];
-  int* next_count = &ctrl->survivors[g ^ 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (p.reserved[0] == 1) { if (threadIdx.x < 8) s_hist[threadIdx.x] = 0u; __syncthreads(); }
-  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {   // block-uniform trip count
-    const int i = base + threadIdx.x;
-    bool alive = false;
-    float4 no4 = make_float4(0.f, 0.f, 0.f, 0.f), nd4 = no4, ns4 = no4, d4 = no4;
-    if (i < count) { d4 = ray_d[i]; alive = shade_path<EST>(sc, p, hit[i], ray_o[i], d4, state[i], accum, ctrl, no4, nd4, ns4); }
-    if (p.reserved[0] == 1) {                     // profile mode: closest-hit queries per bounce (per-CTA histogram in shared memory)
-      const int bucket = i < count ? min(__float_as_int(d4.w) & 0xfff, 7) : 8;
-      const unsigned peers = __match_any_sync(0xffffffffu, bucket);
-      if (bucket < 8 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bucket], (unsigned)__popc(peers));
-    }
-    unsigned ballot = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) s_warp[warp] = __popc(ballot);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < SHD_THREADS / 32; ++w) { int c = s_warp[w]; s_warp[w] = tot; tot += c; }
-      s_base = tot ? atomicAdd(next_count, tot) : 0;
-    }
-    __syncthreads();
-    if (alive) {
-      int pos = s_base + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
-      if (SRT_BOUNDS_OK(pos >= 0 && pos < count, 221)) {       // survivors of a generation never outnumber it
-        ray_o_next[pos] = no4; ray_d_next[pos] = nd4; state_next[pos] = ns4;
-      }
-    }
-    __syncthreads();
-  }
-  if (p.reserved[0] == 1 && threadIdx.x < 8 && s_hist[threadIdx.x]) atomicAdd(&ctrl->bounce_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+  __shared__ ShadeShared S;
+  shade_tiles<EST>(sc, p, ctrl->qcount[g], ray_o, ray_d, state, hit, ray_o_next, ray_d_next, state_next, accum, ctrl, &ctrl->survivors[g ^ 1], S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -658,6 +664,12 @@ k_shade(DScene sc, SrtRenderParams p, int g,
 // integer accumulator, so the image is bit-identical to the wavefront's).  The kernel is part of
 // every iteration batch and returns at once while its condition does not hold; k_tail_done (one
 // thread) then empties the queue, so the remaining launches of the batch find nothing to do.
+// (Also measured, round 2, and rejected: a PERSISTENT drain for larger queues - one launch that loops
+// extend | grid barrier | shade | grid barrier per bounce with the tree staged once.  Bit-identical, fewer
+// launches (63 instead of 227 for one GPU's share of cfg2 on an 8-GPU box), but slower: cfg2 at 63 spp 24.0 vs
+// 22.7 ms, full frame 176.5 vs 173.5 ms, cfg3 29.6 vs 30.0, cfg4 equal - the fused kernel's shade phase runs
+// with the extend phase's shared-memory carve-out (211 KB of tree copies per SM, ~17 KB of L1 left for the
+// material tables) and without the oversubscribed grid that balances k_shade's tiles.)
 __device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int parity, int tail_max) {
   const int c = ctrl->qcount[g];
   return c > 0 && c <= tail_max && ctrl->next_path[parity] >= ctrl->total_paths;
@@ -876,6 +888,7 @@ size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes 
 // DEVICE: scenes on different GPUs of one process (srt_render_multi) each see their own entry.
 typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t, int);
 typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
+
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
 struct TailVariant { TailFn fn; size_t smem; int bps; };
 static ExtendVariant g_variants[SRT_MAX_DEVICES][2][6][3][2];

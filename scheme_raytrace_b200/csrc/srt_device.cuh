@@ -646,22 +646,24 @@ __device__ __forceinline__ float perlin_noise(const DScene& sc, float3 p, int qu
   const bool alias = quirks & SRT_Q4_PERLIN_ALIAS;   // Q4 perlin.scm:76: c[i][j][k] = grad(i+1, j+1, k+dk)
   float acc = 0.0f;
   if (alias) {
-    // Under the reference's aliasing the eight corners hold only TWO distinct gradients (dk = 0, 1): 5 table
-    // loads per call instead of 32 - the marble texture (7 octaves) goes from 224 to 35 loads per hit.  Same
-    // terms in the same order as the general loop below.
+    // Under the reference's aliasing the eight corners hold only TWO distinct gradients g0, g1 (dk = 0, 1): 5 table
+    // loads per call instead of 32 - the marble texture (7 octaves) goes from 224 to 35 loads per hit - and the sum
+    // over the four (a, b) corners collapses: with sum_a w_a = 1 and sum_a w_a a = uu,
+    //   sum_{a,b} w_a w_b ((u - a) g.x + (v - b) g.y + (w - c) g.z) = (u - uu) g.x + (v - vv) g.y + (w - c) g.z,
+    // so noise = (1 - ww) (..g0, c = 0) + ww (..g1, c = 1): ~15 flops instead of ~80.  Algebraically the reference's
+    // trilinear sum (perlin.scm:51-67); the rounding differs at the 1e-7 level (parity bar on textures: 2e-4).
     const int ixy = __ldg(&sc.perm[(i + 1) & 255]) ^ __ldg(&sc.perm[256 + ((j + 1) & 255)]);
     const float3 g0 = xyz(__ldg(&sc.ranvec[ixy ^ __ldg(&sc.perm[512 + (k & 255)])]));
     const float3 g1 = xyz(__ldg(&sc.ranvec[ixy ^ __ldg(&sc.perm[512 + ((k + 1) & 255)])]));
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float wa = a ? uu : 1.0f - uu, wb = b ? vv : 1.0f - vv, wc = c ? ww : 1.0f - ww;
-          acc += wa * wb * wc * dot(v3(u - a, v - b, w - c), c ? g1 : g0);
-        }
-    return acc;
+    // every operation explicitly rounded: the function is instantiated in k_shade and in k_tail, whose frames must
+    // stay bit-identical - a contraction the compiler is free to make in one of them (u - A * B -> fma) would show
+    const float hu = __fmul_rn(__fmul_rn(u, u), __fsub_rn(3.0f, __fmul_rn(2.0f, u)));
+    const float hv = __fmul_rn(__fmul_rn(v, v), __fsub_rn(3.0f, __fmul_rn(2.0f, v)));
+    const float hw = __fmul_rn(__fmul_rn(w, w), __fsub_rn(3.0f, __fmul_rn(2.0f, w)));
+    const float du = __fsub_rn(u, hu), dv = __fsub_rn(v, hv);
+    const float n0 = fmaf(w, g0.z, fmaf(dv, g0.y, __fmul_rn(du, g0.x)));
+    const float n1 = fmaf(__fsub_rn(w, 1.0f), g1.z, fmaf(dv, g1.y, __fmul_rn(du, g1.x)));
+    return fmaf(hw, __fsub_rn(n1, n0), n0);
   }
 #pragma unroll
   for (int a = 0; a < 2; ++a)

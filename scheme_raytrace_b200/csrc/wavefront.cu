@@ -670,17 +670,23 @@ k_shade(DScene sc, SrtRenderParams p, int g,
 // 22.7 ms, full frame 176.5 vs 173.5 ms, cfg3 29.6 vs 30.0, cfg4 equal - the fused kernel's shade phase runs
 // with the extend phase's shared-memory carve-out (211 KB of tree copies per SM, ~17 KB of L1 left for the
 // material tables) and without the oversubscribed grid that balances k_shade's tiles.)
-__device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int parity, int tail_max) {
-  const int c = ctrl->qcount[g];
-  return c > 0 && c <= tail_max && ctrl->next_path[parity] >= ctrl->total_paths;
+// Two thresholds: a queue of <= tail_max paths always goes to the tail kernel; one of <= tail_slow paths only when it
+// has stopped shrinking (>= 90 % of the previous iteration's length): those are the long-lived paths - in
+// random-scene 3.5 % of the paths bounce inside glass until the depth limit, ~2 M paths for 40 iterations on one
+// GPU's share of an 8-GPU frame - which the kernel carries in registers, while a queue that still decays fast
+// (cfg3: -30 % per iteration) is cheaper to finish through the wavefront (measured: profiles/README.md, round 2).
+__device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int parity, int tail_max, int tail_slow) {
+  const int c = ctrl->qcount[g], prev = ctrl->qcount[g ^ 1];      // prev: the queue one iteration ago
+  if (c <= 0 || ctrl->next_path[parity] < ctrl->total_paths) return false;
+  return c <= tail_max || (c <= tail_slow && 10ll * c >= 9ll * prev);
 }
 template <int MASK, int EST>
 __global__ void __launch_bounds__(EXT_THREADS, 2)
-k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
+k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max, int tail_slow,
        const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
        unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {
   extern __shared__ float4 smem[];
-  if (!tail_condition(ctrl, g, parity, tail_max)) return;
+  if (!tail_condition(ctrl, g, parity, tail_max, tail_slow)) return;
   const int count = ctrl->qcount[g];
   if ((int)(blockIdx.x * blockDim.x) >= count) return;
   const int nn = 4 * sc.n_nodes, np = sc.n_prims;
@@ -736,8 +742,8 @@ k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max,
   for (int o = 16; o; o >>= 1) nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
   if ((threadIdx.x & 31) == 0 && nrays) atomicAdd(&ctrl->rays, (unsigned long long)nrays);
 }
-__global__ void k_tail_done(int g, int parity, int tail_max, WaveCtrl* ctrl) {
-  if (!tail_condition(ctrl, g, parity, tail_max)) return;
+__global__ void k_tail_done(int g, int parity, int tail_max, int tail_slow, WaveCtrl* ctrl) {
+  if (!tail_condition(ctrl, g, parity, tail_max, tail_slow)) return;
   ctrl->rays -= (unsigned long long)ctrl->qcount[g];    // the regen that filled this generation already counted its first query
   ctrl->qcount[g] = 0; ctrl->iterations += 1ull; ctrl->tail_runs += 1;
 }
@@ -887,7 +893,7 @@ size_t srt_extend_smem_bytes(const DScene& sc) { return (size_t)64 * sc.n_nodes 
 // Kernel variants by primitive mix.  The cache (function attribute + occupancy query) is kept per
 // DEVICE: scenes on different GPUs of one process (srt_render_multi) each see their own entry.
 typedef void (*ExtendFn)(DScene, const float4*, const float4*, const float4*, float4*, const int*, int, float, float, uint32_t, int);
-typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
+typedef void (*TailFn)(DScene, SrtRenderParams, int, int, int, int, const float4*, const float4*, const float4*, unsigned long long*, WaveCtrl*);
 
 struct ExtendVariant { ExtendFn fn; int bps; size_t smem; int threads; };
 struct TailVariant { TailFn fn; size_t smem; int bps; };
@@ -1048,9 +1054,11 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   // empty iterations of a drain; larger thresholds lose (cfg3 at 2 Mi: +7 %).  SRT_TAIL_MAX overrides for A/B runs.
   static const long long tail_env = getenv("SRT_TAIL_MAX") ? atoll(getenv("SRT_TAIL_MAX")) : -1;
   const int tail_max = !have_tail ? 0 : (tail_env >= 0 ? (int)std::min<long long>(tail_env, 1ll << 30) : (384 << 10));
+  static const long long slow_env = getenv("SRT_TAIL_SLOW") ? atoll(getenv("SRT_TAIL_SLOW")) : -1;
+  const int tail_slow = !have_tail ? 0 : (slow_env >= 0 ? (int)std::min<long long>(slow_env, 1ll << 30) : (2 << 20));
   auto launch_tail = [&](int g, int parity) {
-    tv.fn<<<tail_grid, EXT_THREADS, tv.smem, stream>>>(L.sc, pk, g, parity, tail_max, W.ray_o[g], W.ray_d[g], W.state[g], W.accum64, ctrl);
-    k_tail_done<<<1, 1, 0, stream>>>(g, parity, tail_max, ctrl);
+    tv.fn<<<tail_grid, EXT_THREADS, tv.smem, stream>>>(L.sc, pk, g, parity, tail_max, tail_slow, W.ray_o[g], W.ray_d[g], W.state[g], W.accum64, ctrl);
+    k_tail_done<<<1, 1, 0, stream>>>(g, parity, tail_max, tail_slow, ctrl);
     launches += 2;
   };
   if (W.own_accum) WCK(cudaMemsetAsync(W.accum64, 0, sizeof(unsigned long long) * 3 * (size_t)npix, stream));
@@ -1087,7 +1095,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
       const ExtendVariant e = extend_variant(L);  // function attributes / occupancy query outside the capture
       struct Key { DScene sc; DCamera cam; SrtRenderParams p; WaveBuffers w; void* fn; void* sfn; size_t smem; int bps, device, tail_max, grid_div; } key;
       std::memset(&key, 0, sizeof(key));
-      key.sc = L.sc; key.cam = L.cam; key.p = pk; key.fn = (void*)e.fn; key.sfn = (void*)shade_fn; key.smem = e.smem; key.bps = e.bps; key.device = L.device; key.tail_max = tail_max; key.grid_div = div;
+      key.sc = L.sc; key.cam = L.cam; key.p = pk; key.fn = (void*)e.fn; key.sfn = (void*)shade_fn; key.smem = e.smem; key.bps = e.bps; key.device = L.device; key.tail_max = tail_max + 7 * tail_slow; key.grid_div = div;
       key.w.capacity = W.capacity; key.w.hit = W.hit; key.w.accum64 = W.accum64; key.w.ctrl = W.ctrl;
       for (int k = 0; k < 2; ++k) { key.w.ray_o[k] = W.ray_o[k]; key.w.ray_d[k] = W.ray_d[k]; key.w.state[k] = W.state[k]; }
       GraphCache& C = *W.graph;

@@ -48,7 +48,7 @@ def test_converged_image_against_the_references_own_render(fname, key):
     import os
     import numpy as np
     import scheme_raytrace_b200 as srt
-    from tests.test_reference_golden import GOLD, RENDER_SCENES, RENDER_TAILS, render_stats
+    from tests.test_reference_golden import GOLD, RENDER_SCENES, render_tails, render_stats
     gold = np.load(os.path.join(GOLD, fname))
     w, h, n = (int(x) for x in gold[key + "_meta"])
     r = srt.Renderer(host_scene(RENDER_SCENES[key], w, h), device=0)
@@ -57,6 +57,6 @@ def test_converged_image_against_the_references_own_render(fname, key):
     r.close()
     s = render_stats(gold, key, img.astype(np.float64) / spp, spp)
     print(f"\n[reference render {fname}:{key} {w}x{h}@{n}spp, CUDA path] rays={st.rays} {s}")
-    assert 0.45 <= s["median_abs_z"] <= 0.95 and s["frac_within_3"] >= RENDER_TAILS[key][0] and s["frac_within_4"] >= RENDER_TAILS[key][1]
+    assert 0.45 <= s["median_abs_z"] <= 0.95 and s["frac_within_3"] >= render_tails(fname, key)[0] and s["frac_within_4"] >= render_tails(fname, key)[1]
     assert abs(s["bias_z"]) <= 4.0 and abs(s["rel_mean"] - 1.0) <= 0.02
     assert s["rmse"] <= 1.3 * s["expected_rmse"]

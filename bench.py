@@ -329,7 +329,7 @@ def main():
                 t0 = time.perf_counter(); nr = 0
                 for _ in range(K):
                     rm.commit()
-                    _, _, stm = rm.render_multi(W, H, SPP, max_depth=D, seed=SEED, rgb_sum=host_sum, image=host_img8, write_only=True)
+                    _, _, stm = rm.render_multi(W, H, SPP, max_depth=D, seed=SEED, image=host_img8, want_sum=False)     # the step's result: the 8-bit frame (*image*)
                     nr += stm.rays
                 dt = time.perf_counter() - t0
                 import ctypes as C
@@ -341,7 +341,7 @@ def main():
                 one = {"value": nr / dt / 1e6, "unit": "Mrays/s", "sec_per_frame": dt / K, "gpus": rm.gpus,
                        "reduce": "ncclReduce(uint64 accumulators)" if mode == 0 else "peer-read reduce kernel over NVLink", "nccl_version": ver.value,
                        "bit_identical_to_one_gpu": bool(np.array_equal(full, alone)),
-                       "h2d_bytes_per_step": (flat.h2d_bytes() + 3072 + 3 * 1024) * world, "d2h_bytes_per_step": W * H * 3 * 4 + W * H * 3}
+                       "h2d_bytes_per_step": (flat.h2d_bytes() + 3072 + 3 * 1024) * world, "d2h_bytes_per_step": W * H * 3}
                 rm.close()
             except Exception as ex:                       # never lose the bench line to the optional leg
                 one = {"error": str(ex)[:300]}

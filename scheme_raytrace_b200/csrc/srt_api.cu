@@ -10,6 +10,9 @@
 #include <cmath>
 #include <thread>
 #include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <dlfcn.h>
 #include "srt_host.h"
 
@@ -62,6 +65,28 @@ template <class T> struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+
+// One persistent host thread per replica (srt_render_multi / multi-GPU commit): a frame on an 8-GPU box is ~23 ms, and
+// creating + joining seven threads twice per frame was a measurable part of the one-process overhead.
+class Worker {
+ public:
+  Worker() : th_([this] { loop(); }) {}
+  ~Worker() { { std::lock_guard<std::mutex> l(mu_); quit_ = true; } cv_.notify_all(); th_.join(); }
+  void start(std::function<void()> job) { { std::lock_guard<std::mutex> l(mu_); job_ = std::move(job); busy_ = true; } cv_.notify_all(); }
+  void wait() { std::unique_lock<std::mutex> l(mu_); done_.wait(l, [this] { return !busy_; }); }
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()> job;
+      { std::unique_lock<std::mutex> l(mu_); cv_.wait(l, [this] { return quit_ || (busy_ && job_); }); if (quit_) return; job = std::move(job_); job_ = nullptr; }
+      job();
+      { std::lock_guard<std::mutex> l(mu_); busy_ = false; }
+      done_.notify_all();
+    }
+  }
+  std::mutex mu_; std::condition_variable cv_, done_; std::function<void()> job_; bool busy_ = false, quit_ = false;
+  std::thread th_;
+};
 
 // ---- multi-GPU state (srt_init_multi) -------------------------------------------------------------
 // One process drives n GPUs (the caller the path replaces, (trace-all scene k) main.scm:471-491, is
@@ -151,6 +176,7 @@ struct SrtScene {
   bool multi = false;        // created under srt_init_multi: commit keeps one replica per GPU, srt_render_multi uses them
   unsigned long long version = 0;       // bumped by every set_*; replicas re-commit when it differs
   std::vector<SrtScene*> replicas;      // srt_render_multi: one copy of the scene per extra GPU (owned)
+  std::vector<std::unique_ptr<Worker>> workers;   // one persistent host thread per replica
   unsigned long long replica_version = ~0ull;
   cudaEvent_t ev_done = nullptr;        // multi-GPU: "this replica's accumulator is complete"
   DScene ds; DCamera dcam;
@@ -254,6 +280,7 @@ SrtScene* srt_scene_create(void) {
 
 void srt_scene_destroy(SrtScene* s) {
   if (!s) return;
+  s->workers.clear();                      // joins the replica threads
   for (SrtScene* r : s->replicas) srt_scene_destroy(r);
   s->replicas.clear();
   cudaSetDevice(s->device);
@@ -675,14 +702,14 @@ int srt_scene_commit(SrtScene* s) {
     if (!r) return fail(SRT_ERR_CUDA, "commit: cannot create the replica for device %d", g_multi.devs[s->replicas.size() + 1]);
     s->replicas.push_back(r);
   }
+  while ((int)s->workers.size() < n - 1) s->workers.emplace_back(new Worker());
   std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
-  std::vector<std::thread> th;
   for (int r = 1; r < n; ++r) {
     copy_tables(s->replicas[r - 1], s);
-    th.emplace_back([&, r] { rc[r] = commit_impl(s->replicas[r - 1]); if (rc[r]) msg[r] = g_err; });
+    s->workers[r - 1]->start([&, r] { rc[r] = commit_impl(s->replicas[r - 1]); if (rc[r]) msg[r] = g_err; });
   }
   rc[0] = commit_impl(s);
-  for (std::thread& t : th) t.join();
+  for (int r = 1; r < n; ++r) s->workers[r - 1]->wait();
   if (rc[0]) return rc[0];
   for (int r = 1; r < n; ++r) if (rc[r]) return fail(rc[r], "commit on device %d: %s", g_multi.devs[r], msg[r].c_str());
   s->replica_version = s->version;
@@ -756,10 +783,9 @@ int srt_render_multi(SrtScene* s, const SrtRenderParams* p, float* rgb_sum, uint
     rc[r] = render_impl(sc, &q, nullptr, &st[r]);
     if (rc[r]) msg[r] = g_err;
   };
-  std::vector<std::thread> th;
-  for (int r = 1; r < n; ++r) th.emplace_back(work, r);
+  for (int r = 1; r < n; ++r) s->workers[r - 1]->start([&work, r] { work(r); });
   work(0);
-  for (std::thread& t : th) t.join();
+  for (int r = 1; r < n; ++r) s->workers[r - 1]->wait();
   for (int r = 0; r < n; ++r) if (rc[r]) return fail(rc[r], "render on device %d: %s", M.devs[r], msg[r].c_str());
   // every rank's accumulator is complete (render_impl returns synchronised).  Combine on the root.
   USE_DEVICE(s);

@@ -142,14 +142,14 @@ class Renderer:
 
 
     def render_multi(self, width, height, spp, max_depth=50, seed=1, quirks=ffi.QUIRKS_REFERENCE, spp_begin=0, rgb_sum=None, estimator=0, want_image=True,
-                     image=None, write_only=False):
+                     image=None, write_only=False, want_sum=True):
         """(trace-all scene k) over every GPU of srt_init_multi from this one process: samples
         [spp_begin, spp_begin+spp) are split into one contiguous range per GPU, the integer accumulators are
         combined with one reduce over NVLink.  Returns (rgb_sum, image8 or None, stats); host buffers.
         `rgb_sum` given: the running sum the frame is added to (write_only=True: an output buffer only, e.g. pinned
         memory reused across frames); `image`: optional preallocated (H, W, 3) uint8 output."""
         fresh = rgb_sum is None
-        if fresh:
+        if fresh and want_sum:
             rgb_sum = np.empty((height, width, 3), dtype=np.float32)
         if want_image and image is None:
             image = np.empty((height, width, 3), dtype=np.uint8)
@@ -158,7 +158,7 @@ class Renderer:
         p = self.params(width, height, spp_begin, spp_begin + spp, max_depth, seed, quirks, estimator=estimator)
         p.reserved[2] = 1 if (fresh or write_only) else 0
         st = ffi.Stats()
-        ffi.check(self.lib.srt_render_multi(self.h, C.byref(p), _ptr(rgb_sum), _ptr(image) if want_image else None, C.byref(st)), "render_multi")
+        ffi.check(self.lib.srt_render_multi(self.h, C.byref(p), _ptr(rgb_sum) if rgb_sum is not None else None, _ptr(image) if want_image else None, C.byref(st)), "render_multi")
         return rgb_sum, image, st
 
     def progressive_step(self, width, height, spp_begin, spp_end, max_depth=100, seed=1, quirks=ffi.QUIRKS_REFERENCE):

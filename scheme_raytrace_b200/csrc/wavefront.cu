@@ -77,10 +77,19 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
   const int spp_begin = ctrl->spp_begin;
   unsigned long long room = (unsigned long long)(capacity - surv), left = total - next;
   const int n_new = (int)(room < left ? room : left);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
-    unsigned long long id = next + (unsigned long long)j;
-    unsigned int sl = (unsigned int)(id / (unsigned long long)npix);
-    int pixel = (int)(id - (unsigned long long)sl * (unsigned long long)npix);
+  // path id -> (sample, pixel) needs a 64-bit division (ids pass 2^32 on cfg4 / cfg5): done ONCE per thread, the
+  // grid-stride loop then advances (sample, pixel) by the precomputed quotient / remainder of its stride
+  const int stride = gridDim.x * blockDim.x;
+  const unsigned int s_q = (unsigned int)(stride / npix), s_r = (unsigned int)(stride % npix);
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int sl = 0u; int pixel = 0;
+  if (j < n_new) {
+    const unsigned long long id = next + (unsigned long long)j;
+    sl = (unsigned int)(id / (unsigned long long)npix);
+    pixel = (int)(id - (unsigned long long)sl * (unsigned long long)npix);
+  }
+  for (; j < n_new; j += stride, sl += s_q, pixel += (int)s_r) {
+    if (pixel >= npix) { pixel -= npix; ++sl; }
     int y = pixel / p.width, x = pixel - y * p.width;
     unsigned int sample = (unsigned int)spp_begin + sl;
     RngAddr addr{p.seed, (uint32_t)pixel, sample, 0u};
@@ -147,11 +156,12 @@ __device__ __forceinline__ void trav_init(Trav& T, float4 o4, float4 d4, float t
   // reciprocal direction; (near-)zero components become +-1e18 instead of +-inf so that the FMA
   // slab form never produces inf - inf (boxes are padded, see lbvh.cu, so the sign of
   // (b - o) * 1e18 is exact for every ray that can reach a primitive inside the box)
-  T.inv = v3(fabsf(T.d.x) > 1e-18f ? 1.0f / T.d.x : copysignf(1e18f, T.d.x), fabsf(T.d.y) > 1e-18f ? 1.0f / T.d.y : copysignf(1e18f, T.d.y),
-             fabsf(T.d.z) > 1e-18f ? 1.0f / T.d.z : copysignf(1e18f, T.d.z));
+  // (__frcp_rn is the correctly rounded reciprocal, i.e. the value of 1.0f / x, without the division's slow-path check)
+  T.inv = v3(fabsf(T.d.x) > 1e-18f ? __frcp_rn(T.d.x) : copysignf(1e18f, T.d.x), fabsf(T.d.y) > 1e-18f ? __frcp_rn(T.d.y) : copysignf(1e18f, T.d.y),
+             fabsf(T.d.z) > 1e-18f ? __frcp_rn(T.d.z) : copysignf(1e18f, T.d.z));
   T.oi = v3(T.o.x * T.inv.x, T.o.y * T.inv.y, T.o.z * T.inv.z);
   T.ainv = v3(fabsf(T.inv.x), fabsf(T.inv.y), fabsf(T.inv.z));
-  T.inv_a = 1.0f / dot(T.d, T.d);
+  T.inv_a = __frcp_rn(dot(T.d, T.d));
   T.h.t = tmax; T.h.prim = -1; T.h.u = 0.f; T.h.v = 0.f; T.h.incl = false;
   T.node = 0; T.trail = 0ull; T.s0 = T.s1 = 0ull; T.nstk = 0;      // T.sp: back above the sentinel after every finished traversal
 #ifdef SRT_COUNT_STEPS

@@ -4,15 +4,19 @@
 // 471-491; camera.scm:80-92; geometry.scm:14-15; material.scm:15-22).  STREAMING wavefront: one
 // queue of up to `capacity` paths is kept full; every iteration runs
 //   k_extend  closest hit: LBVH traversal (near child first, per-thread stack of 16-bit node ids in
-//             shared memory; stackless bit-trail fallback for huge trees), the whole node array +
-//             primitive headers staged in shared memory
+//             shared memory - 32-bit for trees of >= 65536 nodes), the whole node array (as four
+//             child-interleaved planes: FFMA2 slab test of both children) + primitive headers staged
+//             in shared memory
 //   k_shade   hit-record completion, material scatter / emitted, sky on miss; terminated paths add
 //             their radiance into a 64-bit fixed-point accumulator; survivors are compacted
 //             (warp ballot + one atomic per CTA) into the other queue generation
 //   k_regen   fresh camera paths (Philox bounce slot 0) are appended behind the survivors
 // so the long thin tail of deep paths (depth <= max_depth) is paid once per frame, not once per
 // batch of samples.  Iterations are enqueued in batches of 8 that are captured once into a CUDA
-// graph and replayed; the host polls the control block one batch behind.  The recursive estimator `color` is run in its iterative form
+// graph (cached on the scene) and replayed; the host polls the control block one batch behind.
+//   k_tail    once every path is generated and the queue is small (or has stopped shrinking: the
+//             long-lived glass paths), ONE launch runs the remaining paths to their end
+// The recursive estimator `color` is run in its iterative form
 // L = sum_k (prod_{j<k} w_j) e_k; paths carry (throughput, pixel, sample, depth).
 #include <mutex>
 #include <cstring>
@@ -538,7 +542,7 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
   }
 }
 
-// CTA size: 256 threads, 4 (spheres) or 3 (+ rects / instances) CTAs per SM.  The variant with the
+// CTA size: 256 threads, 4 CTAs per SM for the sphere and the rect / instance variants.  The variant with the
 // expensive primitives needs 128 registers, i.e. at most 512 threads per SM; it runs as ONE 512-thread
 // CTA per SM so that those 16 warps share one staged copy of the scene (as 2 x 256 the teapot scene's
 // 147 KB tree allowed a single 256-thread CTA: 8 warps/SM, issue slots 39 % busy).

@@ -447,6 +447,12 @@ __device__ __forceinline__ void extend_loop(const DScene& sc, const float4* __re
 // 5.4 in its Newton loop, 9.3 in the node loop).  For the cheap sphere / rect variants the same
 // refill was measured slower (bookkeeping > idle lanes recovered, profiles/README.md); here one test
 // is worth hundreds of node steps.
+// node steps per bookkeeping round of the deferred loop (measured, round 2, Grays/s on cfg5 / cfg5_teapot / cfg5_curves:
+// 1: 2.73 / 3.21 / 3.39, 2: 2.83 / 3.36 / 3.49, 4: 2.97 / 3.55 / 3.53, 6: 3.00 / 3.59 / 3.51, 8: 3.01 / 3.58 / 3.52,
+// 12: 2.99 / 3.54 / 3.52, unbounded: 2.93 / 3.34 / 3.52)
+#ifndef SRT_DEFER_STEPS
+#define SRT_DEFER_STEPS 6
+#endif
 constexpr int EXT_PARK_VOTE = 16, EXT_REFILL_MIN = 16;   // measured sweep: profiles/README.md (tools/sweep_deferred.sh)
 template <bool SMEM, int MASK, int TRAV, class PrimSrc>
 __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const float4* __restrict__ nodes, const PrimSrc& ps,
@@ -518,7 +524,10 @@ __device__ __forceinline__ void extend_loop_deferred(const DScene& sc, const flo
       }
       continue;
     }
-    if (ray >= 0 && more && !parked) {
+    // up to SRT_DEFER_STEPS node steps per round of the bookkeeping above (three ballots, the refill and vote logic:
+    // ~40 instructions, as much as a node step itself); a lane that parks or finishes early waits for the round to end
+#pragma unroll 1
+    for (int k = 0; k < SRT_DEFER_STEPS && ray >= 0 && more && park0 < 0; ++k) {
       int pend0 = 0, pend1 = 0;                  // raw leaf references (negative), 0 = none
       float4 ivl = make_float4(0.f, 0.f, 0.f, 0.f);
       more = node_step<SMEM, TRAV, (MASK & 0x80) != 0>(T, nodes, sbase, tmin, pend0, pend1, &ivl);

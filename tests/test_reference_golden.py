@@ -447,10 +447,11 @@ RENDER_SCENES = {"cornell_box": "cornell-box", "test_bezier": "test-bezier", "co
 # under-estimate their standard error, so the tails are heavy (cornell-smoke needed 768 spp to meet the common bars).
 # The image-wide figures (bias, mean radiance, RMSE against the predicted RMSE) do not suffer from that and keep the same bars.
 RENDER_TAILS = {"cornell_box": (0.975, 0.995), "test_bezier": (0.975, 0.995), "cornell_smoke": (0.975, 0.995), "test_scene2": (0.92, 0.94)}
-# the same for the 32 x 32 renders of ref_render32.npz: cornell-smoke has 384 spp there (the 16 x 16 render needed 768 to meet the
-# common bars: the free-flight paths through the media are rare and bright), so its tail bars are stated looser until a second batch
-# of samples is added (SRT_RENDER_BATCH=1); every image-wide figure keeps the common bar
-RENDER_TAILS32 = dict(RENDER_TAILS, cornell_smoke=(0.97, 0.98))
+# the same for the 32 x 32 renders of ref_render32.npz: cornell-smoke (768 spp there: two batches of 384) still has heavier tails
+# than the common bar allows - the free-flight paths through the media are rare and bright, so a pixel's SAMPLE variance
+# under-estimates its standard error (384 spp: 97.6 % / 98.7 %; 768 spp: 98.2 % / 99.3 % within 3 / 4 se) - and states 99 %
+# within 4 se; every image-wide figure keeps the common bar
+RENDER_TAILS32 = dict(RENDER_TAILS, cornell_smoke=(0.975, 0.99))
 
 
 def render_tails(fname, key):

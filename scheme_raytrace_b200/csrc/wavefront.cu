@@ -623,7 +623,8 @@ __device__ __forceinline__ bool shade_path(const DScene& sc, const SrtRenderPara
 // shade: one bounce for every live path + compaction of survivors into the other queue generation
 // (warp ballot -> per-warp count -> one atomic per CTA).  Measured and NOT adopted (profiles/README.md,
 // round 2): the per-primitive tables staged in shared memory (+1 % cfg2, -2 % cfg3) and a software
-// prefetch of the next tile's queue entries (-9 % at 4 CTAs/SM with spills, -24 % at 3 CTAs/SM).
+// prefetch of the next tile's queue entries (-9 % at 4 CTAs/SM with spills, -24 % at 3 CTAs/SM); one atomic per WARP
+// instead of the two barriers + one atomic per CTA (shade 2x slower: 16 M single-address atomics per launch serialise in L2).
 struct ShadeShared { int warp[SHD_THREADS / 32]; int base; unsigned hist[8]; };
 // One pass over queue generation g: shade every path, compact the survivors behind *next_count (shared by the
 // wavefront's k_shade and the persistent drain kernel).  blockDim.x == SHD_THREADS.

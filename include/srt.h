@@ -112,7 +112,7 @@ typedef struct {
   uint64_t rays;               /* closest-hit queries (primary + every bounce)           */
   uint64_t paths;              /* camera samples                                         */
   float ms_total;              /* device time, first ray-gen launch .. accumulation done */
-  float ms_commit;             /* last commit: H2D + LBVH build                          */
+  float ms_commit;             /* last commit: host wall clock of srt_scene_commit (staging + H2D + LBVH build) */
   int32_t kernel_launches;     /* kernels launched by this call                          */
   int32_t waves;               /* extend/shade/regen iterations of the streaming wavefront */
   int32_t bvh_nodes, bvh_depth;

@@ -244,6 +244,9 @@ __global__ void k_karras(int n, const unsigned long long* __restrict__ keys, con
 
 // ---- 6. bottom-up refit with atomic visit counters ----------------------------------------------
 // nbox[i] = unpadded box of internal node i (scratch); stored child boxes are padded on write.
+// CTA_SCOPE: boxes and counters live in shared memory (single-CTA build): a block-scope fence orders them; the device-scope
+// fence of the multi-CTA build would also wait for the node stores of every level to reach L2 (~1 us per level).
+template <bool CTA_SCOPE = false>
 __device__ __forceinline__ void refit_from_leaf(int pos, int n, const float* __restrict__ aabb, const int4* links,
                                                 const int* leaf_parent, const int* b, float* nbox, int* visit,
                                                 float4* nodes, int* depth_out) {
@@ -256,7 +259,7 @@ __device__ __forceinline__ void refit_from_leaf(int pos, int n, const float* __r
   }
   while (node >= 0) {
     if (!SRT_BOUNDS_OK(node < n - 1, 321)) return;
-    __threadfence();
+    if (CTA_SCOPE) __threadfence_block(); else __threadfence();
     if (atomicAdd(&visit[node], 1) == 0) return;      // first arrival: the sibling subtree finishes this node
     int4 lk = links[node];
     float cb[2][6];
@@ -349,12 +352,20 @@ __global__ void __launch_bounds__(256) k_tree_area(int n_items, const float4* __
 // arithmetic (the device functions above), same tree: the sort is a bitonic network on (key, index) pairs, which is
 // the order the stable LSD radix sort produces; the refit uses the same visit-counter protocol.
 constexpr int SMALL_MAX_ITEMS = 2048, SMALL_THREADS = 1024;
+// Everything the build chases pointers through lives in shared memory (keys, order, links, leaf parents, the unpadded node
+// boxes and the visit counters: 120 KB): the refit walks ~depth dependent steps per leaf, each of which was an L2 round trip
+// (~0.5 us) when links / boxes were in global memory.  Only the results (keys, order, nodes, area, depth) are written out.
+constexpr size_t SMALL_SMEM = (size_t)SMALL_MAX_ITEMS * (8 + 16 + 24 + 4 + 4 + 4);
 __global__ void __launch_bounds__(SMALL_THREADS) k_lbvh_small(const float* __restrict__ aabb, const SrtSmallJob* __restrict__ jobs) {
   const SrtSmallJob J = jobs[blockIdx.x];
   const int n = J.n, tid = threadIdx.x;
-  __shared__ unsigned long long s_key[SMALL_MAX_ITEMS];
-  __shared__ int s_val[SMALL_MAX_ITEMS];
-  __shared__ int s_visit[SMALL_MAX_ITEMS];
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  unsigned long long* s_key = (unsigned long long*)s_raw;
+  int4* s_links = (int4*)(s_raw + (size_t)SMALL_MAX_ITEMS * 8);
+  float* s_nbox = (float*)(s_raw + (size_t)SMALL_MAX_ITEMS * 24);
+  int* s_val = (int*)(s_raw + (size_t)SMALL_MAX_ITEMS * 48);
+  int* s_visit = s_val + SMALL_MAX_ITEMS;
+  int* s_lp = s_visit + SMALL_MAX_ITEMS;
   __shared__ int s_b[8];
   __shared__ int s_depth;
   __shared__ double s_red[2][256];
@@ -372,8 +383,17 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_lbvh_small(const float* __res
         S = fmaxf(S, fmaxf(fabsf(q[k]), fabsf(q[3 + k])));
       }
     }
-    for (int k = 0; k < 3; ++k) { atomicMin(&s_b[k], f2ord(cmin[k])); atomicMax(&s_b[3 + k], f2ord(cmax[k])); }
-    atomicMax(&s_b[6], f2ord(S));
+    // warp reduction first: 7 shared atomics per warp instead of per thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { cmin[k] = fminf(cmin[k], __shfl_xor_sync(0xffffffffu, cmin[k], o)); cmax[k] = fmaxf(cmax[k], __shfl_xor_sync(0xffffffffu, cmax[k], o)); }
+      S = fmaxf(S, __shfl_xor_sync(0xffffffffu, S, o));
+    }
+    if ((tid & 31) == 0 && tid < ((n + 31) & ~31)) {
+      for (int k = 0; k < 3; ++k) { atomicMin(&s_b[k], f2ord(cmin[k])); atomicMax(&s_b[3 + k], f2ord(cmax[k])); }
+      atomicMax(&s_b[6], f2ord(S));
+    }
   }
   __syncthreads();
   int npad = 2; while (npad < n) npad <<= 1;
@@ -381,9 +401,13 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_lbvh_small(const float* __res
     if (i < n) { s_key[i] = morton_key(aabb + 6 * (size_t)J.item_prim[i], s_b); s_val[i] = i; }
     else { s_key[i] = ~0ull; s_val[i] = 0x7fffffff; }
   }
+  // bitonic network; element i belongs to thread i % SMALL_THREADS, so partners at distance j < 32 are exchanged inside
+  // one warp: those steps need a warp barrier only (35 of the 45 steps for 512 items)
+  int jprev = 1;
   for (int k = 2; k <= npad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncthreads();
+      if (j >= 32 || jprev >= 32) __syncthreads(); else __syncwarp();
+      jprev = j;
       for (int i = tid; i < npad; i += SMALL_THREADS) {
         const int l = i ^ j;
         if (l > i) {
@@ -395,9 +419,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_lbvh_small(const float* __res
     }
   __syncthreads();
   for (int i = tid; i < n; i += SMALL_THREADS) { J.keys[i] = s_key[i]; J.order[i] = s_val[i]; s_visit[i] = 0; }
-  for (int i = tid; i < n - 1; i += SMALL_THREADS) karras_node(i, n, s_key, s_val, J.item_prim, J.links, J.leaf_parent);
+  for (int i = tid; i < n - 1; i += SMALL_THREADS) karras_node(i, n, s_key, s_val, J.item_prim, s_links, s_lp);
   __syncthreads();
-  for (int pos = tid; pos < n; pos += SMALL_THREADS) refit_from_leaf(pos, n, aabb, J.links, J.leaf_parent, s_b, J.nbox, s_visit, J.nodes, &s_depth);
+  for (int pos = tid; pos < n; pos += SMALL_THREADS) refit_from_leaf<true>(pos, n, aabb, s_links, s_lp, s_b, s_nbox, s_visit, J.nodes, &s_depth);
   __syncthreads();
   tree_area_256(n, J.nodes, J.area, s_red);
   if (tid == 0) { *J.depth = s_depth; for (int k = 0; k < 7; ++k) J.bounds[k] = s_b[k]; }
@@ -419,7 +443,13 @@ unsigned long long srt_bounds_violations_lbvh(int* first) {
 
 // The candidate trees of one commit (n_jobs <= 16, each 2 <= n <= SRT_SMALL_MAX_ITEMS items), one CTA each.
 int srt_lbvh_build_small(const float* d_aabb, const SrtSmallJob* d_jobs, int n_jobs, cudaStream_t stream) {
-  k_lbvh_small<<<n_jobs, SMALL_THREADS, 0, stream>>>(d_aabb, d_jobs);
+  static bool attr_set[SRT_MAX_DEVICES] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev >= 0 && dev < SRT_MAX_DEVICES && !attr_set[dev]) {
+    if (cudaFuncSetAttribute(k_lbvh_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) != cudaSuccess) return -1;
+    attr_set[dev] = true;
+  }
+  k_lbvh_small<<<n_jobs, SMALL_THREADS, SMALL_SMEM, stream>>>(d_aabb, d_jobs);
   return 1;
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <vector>
+#include <chrono>
 #include <string>
 #include <algorithm>
 #include <cmath>
@@ -138,7 +139,7 @@ struct SrtScene {
   std::vector<uint8_t> img_texels; std::vector<int4> imgs;   // image-texture data (srt_scene_set_images)
   float ranvec[768]; int32_t perm[3][256]; bool has_perlin = false;
   SrtCamera cam; bool has_cam = false;
-  std::vector<int32_t> lights; std::vector<float> patches;
+  std::vector<int32_t> lights; std::vector<float> patches; std::vector<float4> patch_slabs;   // slab (n', d') per patch-table entry, see patch_slab()
   bool committed = false;
   // device tables
   // device tables: views into ONE allocation (d_tables), uploaded from ONE pinned staging blob (h_tables) per commit
@@ -146,6 +147,7 @@ struct SrtScene {
   View<int> d_lights, d_logical; View<float4> d_patches;
   View<int4> d_hdr; View<float4> d_a, d_b, d_c, d_d, d_xf, d_tex, d_ranvec, d_shade; View<int4> d_mats, d_imgs; View<uint8_t> d_perm, d_img_texels;
   DevBuf<unsigned char> d_tables; void* h_tables = nullptr; size_t h_tables_bytes = 0;
+  void* h_scratch = nullptr; size_t h_scratch_bytes = 0;      // pinned: bounds read-back, candidate item lists + jobs, per-candidate results
   DevBuf<double> d_tree_area;
   // LBVH
   DevBuf<unsigned char> d_small;   // slots of the single-CTA candidate builds (small scenes)
@@ -288,6 +290,7 @@ void srt_scene_destroy(SrtScene* s) {
   if (s->ev_done) cudaEventDestroy(s->ev_done);
   s->d_small.release(); s->d_tree_area.release(); s->d_tables.release();
   if (s->h_tables) cudaFreeHost(s->h_tables);
+  if (s->h_scratch) cudaFreeHost(s->h_scratch);
   s->d_aabb.release(); s->d_nbox.release(); s->d_bounds.release();
   s->d_order0.release(); s->d_order1.release(); s->d_hist.release(); s->d_leaf_parent.release(); s->d_item_prim.release(); s->d_visit.release(); s->d_depth.release();
   s->d_keys0.release(); s->d_keys1.release(); s->d_links.release(); s->d_nodes.release();
@@ -345,9 +348,13 @@ int srt_scene_set_camera(SrtScene* s, const SrtCamera* c) {
   s->cam = *c; s->has_cam = true; s->committed = false; ++s->version; return 0;
 }
 
+static float4 patch_slab(const float* cp);
 int srt_scene_set_patches(SrtScene* s, const float* cp48, int n) {
   if (!s || n < 0 || (n && !cp48)) return fail(SRT_ERR_ARG, "set_patches: bad argument");
-  s->patches.assign(cp48, cp48 + 48 * (size_t)n); s->committed = false; ++s->version; return 0;
+  s->patches.assign(cp48, cp48 + 48 * (size_t)n);
+  s->patch_slabs.resize((size_t)n);
+  for (int i = 0; i < n; ++i) s->patch_slabs[i] = patch_slab(cp48 + 48 * (size_t)i);     // a property of the table, not of a commit
+  s->committed = false; ++s->version; return 0;
 }
 
 int srt_scene_set_lights(SrtScene* s, const int32_t* prim_ids, int n) {
@@ -368,10 +375,11 @@ static float4 patch_slab(const float* cp) {
   const double len = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
   float4 slab = make_float4(0.f, 0.f, 0.f, 0.f);
   if (len > 1e-20) {
+    const double un[3] = {nn[0] / len, nn[1] / len, nn[2] / len};
     double dmin = 1e300, dmax = -1e300, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, amax = 0.0;
     for (int k = 0; k < 16; ++k) {
       double dk = 0.0;
-      for (int c = 0; c < 3; ++c) { dk += nn[c] / len * P(k, c); lo[c] = std::min(lo[c], P(k, c)); hi[c] = std::max(hi[c], P(k, c)); amax = std::max(amax, std::fabs(P(k, c))); }
+      for (int c = 0; c < 3; ++c) { dk += un[c] * P(k, c); lo[c] = std::min(lo[c], P(k, c)); hi[c] = std::max(hi[c], P(k, c)); amax = std::max(amax, std::fabs(P(k, c))); }
       dmin = std::min(dmin, dk); dmax = std::max(dmax, dk);
     }
     const double diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
@@ -383,6 +391,7 @@ static float4 patch_slab(const float* cp) {
 
 static int commit_impl(SrtScene* s) {
   if (!s) return fail(SRT_ERR_ARG, "commit: null scene");
+  const auto t_enter = std::chrono::steady_clock::now();     // ms_commit = host wall clock of this (synchronous) call
   if (int rc = ensure_device(s->device)) return rc;
   USE_DEVICE(s);
   const int n = (int)s->prims.size();
@@ -429,77 +438,79 @@ static int commit_impl(SrtScene* s) {
     if (!shape_ok || p.xform >= 0 || (p.flags & SRT_PRIM_FLAG_BOUNDARY)) return fail(SRT_ERR_ARG, "light %zu: only un-instanced spheres and rects can be sampled (pdf.scm:28-32)", i);
   }
   cudaStream_t stream = 0;
-  EventPair tm; CK(tm.create());
-  cudaEvent_t e0 = tm.a, e1 = tm.b;
-  CK(cudaEventRecord(e0, stream));
-  // ---- host SoA staging: every table goes into ONE pinned blob and up in ONE H2D copy ---------------
+  static const bool dbg_time = getenv("SRT_DEBUG_COMMIT_TIME") != nullptr;
+  double tp[8] = {0}; int ntp = 0;
+  auto stamp = [&]() { if (dbg_time && ntp < 8) tp[ntp++] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  stamp();
+  // ---- host SoA staging: every table is written straight into ONE pinned blob and goes up in ONE H2D copy ------
   // (sixteen separate small copies were 0.1 ms of the commit; the device tables are views into s->d_tables)
   const size_t np16 = s->patches.size() / 3;
-  std::vector<float4> pc(np16 ? np16 : 1);
-  for (size_t k = 0; k < np16; ++k) pc[k] = make_float4(s->patches[3 * k], s->patches[3 * k + 1], s->patches[3 * k + 2], 0.f);
-  std::vector<int4> hdr(n ? n : 1); std::vector<float4> a(n ? n : 1), b(n ? n : 1), c(n ? n : 1), d(n ? n : 1);
-  for (int i = 0; i < n; ++i) {
-    const SrtPrim& p = s->prims[i]; const float* q = p.p;
-    // aux: patch index for patches; the bits of the plane constant k for rects (saves the extend
-    // kernel a global load per rect test: the header is staged in shared memory)
-    int aux = 0;
-    if (p.type == SRT_PRIM_PATCH) aux = (int)q[0];
-    else if (p.type >= SRT_PRIM_XY_RECT && p.type <= SRT_PRIM_YZ_RECT) std::memcpy(&aux, &q[4], 4);
-    hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, aux);
-    a[i] = b[i] = c[i] = d[i] = make_float4(0, 0, 0, 0);
-    switch (p.type) {
-      case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
-      case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
-      case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
-      case SRT_PRIM_PATCH: { a[i] = patch_slab(s->patches.data() + 48 * (size_t)q[0]); b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0); break; }
-      case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
-      default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
-    }
+  const size_t nx = s->xforms.size(), nm = s->mats.size(), nt = s->texs.size();
+  size_t total = 0;
+  auto place = [&](size_t bytes) { const size_t off = total; total += bytes ? (bytes + 255) & ~(size_t)255 : 256; return off; };
+  const size_t o_patches = place(sizeof(float4) * np16), o_lights = place(sizeof(int) * s->lights.size()), o_logical = place(sizeof(int) * (size_t)n),
+               o_shade = place(sizeof(float4) * 2 * (size_t)n), o_hdr = place(sizeof(int4) * (size_t)n), o_a = place(sizeof(float4) * (size_t)n),
+               o_b = place(sizeof(float4) * (size_t)n), o_c = place(sizeof(float4) * (size_t)n), o_d = place(sizeof(float4) * (size_t)n),
+               o_xf = place(sizeof(float4) * 2 * nx), o_mats = place(sizeof(int4) * nm), o_tex = place(sizeof(float4) * 2 * nt),
+               o_imgs = place(sizeof(int4) * s->imgs.size()), o_texels = place(s->img_texels.size()), o_ranvec = place(sizeof(float4) * 256), o_perm = place(768);
+  CK(s->d_tables.ensure(total));
+  if (total > s->h_tables_bytes) {
+    if (s->h_tables) cudaFreeHost(s->h_tables);
+    s->h_tables = nullptr; s->h_tables_bytes = 0;
+    CK(cudaMallocHost(&s->h_tables, total)); s->h_tables_bytes = total;
   }
-  std::vector<int> logical(n ? n : 1);
-  for (int i = 0; i < n; ++i) logical[i] = s->prims[i].p[15] > 0.f ? (int)s->prims[i].p[15] - 1 : i;   // p[15] = logical id + 1, 0 = array index
-  std::vector<float4> sh(2 * (size_t)(n ? n : 1));     // per-primitive shading record (see DScene::prim_shade)
-  for (int i = 0; i < n; ++i) {
-    const SrtMaterial& m = s->mats[s->prims[i].material];
-    float r = 1.f, g = 1.f, bl = 1.f; int is_const = 0;
-    if (m.kind != SRT_MAT_DIELECTRIC && s->texs[m.tex].kind == SRT_TEX_CONSTANT) { const SrtTexture& t = s->texs[m.tex]; r = t.rgb[0]; g = t.rgb[1]; bl = t.rgb[2]; is_const = 1; }
-    if (m.kind == SRT_MAT_DIELECTRIC) is_const = 1;
-    float fk, ft, fc; int tex = m.tex; std::memcpy(&fk, &m.kind, 4); std::memcpy(&ft, &tex, 4); std::memcpy(&fc, &is_const, 4);
-    sh[2 * i] = make_float4(r, g, bl, m.param); sh[2 * i + 1] = make_float4(fk, ft, fc, 0.f);
-  }
-  size_t nx = s->xforms.size(), nm = s->mats.size(), nt = s->texs.size();
-  std::vector<float4> xf(2 * (nx ? nx : 1)), tx(2 * (nt ? nt : 1)); std::vector<int4> mt(nm ? nm : 1);
-  for (size_t i = 0; i < nx; ++i) { const SrtXform& x = s->xforms[i]; xf[2 * i] = make_float4(x.sin_t, x.cos_t, x.off[0], x.off[1]); xf[2 * i + 1] = make_float4(x.off[2], 0, 0, 0); }
-  for (size_t i = 0; i < nm; ++i) { const SrtMaterial& m = s->mats[i]; int pb; std::memcpy(&pb, &m.param, 4); mt[i] = make_int4(m.kind, m.tex, pb, 0); }
-  for (size_t i = 0; i < nt; ++i) {
-    const SrtTexture& t = s->texs[i]; float fk, fe, fo; std::memcpy(&fk, &t.kind, 4); std::memcpy(&fe, &t.even, 4); std::memcpy(&fo, &t.odd, 4);
-    tx[2 * i] = make_float4(fk, fe, fo, t.scale); tx[2 * i + 1] = make_float4(t.rgb[0], t.rgb[1], t.rgb[2], 0);
-  }
-  std::vector<float4> rv(256); std::vector<uint8_t> pm(768);
-  for (int i = 0; i < 256; ++i) rv[i] = s->has_perlin ? make_float4(s->ranvec[3 * i], s->ranvec[3 * i + 1], s->ranvec[3 * i + 2], 0) : make_float4(0, 0, 0, 0);
-  for (int k = 0; k < 3; ++k) for (int i = 0; i < 256; ++i) pm[256 * k + i] = s->has_perlin ? (uint8_t)(s->perm[k][i] & 255) : (uint8_t)i;
+  unsigned char* H = (unsigned char*)s->h_tables;
+  unsigned char* Dv = s->d_tables.p;
+  s->d_patches.p = (float4*)(Dv + o_patches); s->d_lights.p = (int*)(Dv + o_lights); s->d_logical.p = (int*)(Dv + o_logical); s->d_shade.p = (float4*)(Dv + o_shade);
+  s->d_hdr.p = (int4*)(Dv + o_hdr); s->d_a.p = (float4*)(Dv + o_a); s->d_b.p = (float4*)(Dv + o_b); s->d_c.p = (float4*)(Dv + o_c); s->d_d.p = (float4*)(Dv + o_d);
+  s->d_xf.p = (float4*)(Dv + o_xf); s->d_mats.p = (int4*)(Dv + o_mats); s->d_tex.p = (float4*)(Dv + o_tex); s->d_imgs.p = (int4*)(Dv + o_imgs);
+  s->d_img_texels.p = (unsigned char*)(Dv + o_texels); s->d_ranvec.p = (float4*)(Dv + o_ranvec); s->d_perm.p = (unsigned char*)(Dv + o_perm);
   {
-    struct Item { void** dst; const void* src; size_t bytes, off; };
-    std::vector<Item> items; size_t total = 0;
-    auto add = [&](void** dst, const void* src, size_t bytes) { items.push_back(Item{dst, src, bytes, total}); total += (bytes + 255) & ~(size_t)255; if (!bytes) total += 256; };
-    add((void**)&s->d_patches.p, pc.data(), sizeof(float4) * np16);
-    add((void**)&s->d_lights.p, s->lights.data(), sizeof(int) * s->lights.size());
-    add((void**)&s->d_logical.p, logical.data(), sizeof(int) * (size_t)n);
-    add((void**)&s->d_shade.p, sh.data(), sizeof(float4) * 2 * (size_t)n);
-    add((void**)&s->d_hdr.p, hdr.data(), sizeof(int4) * (size_t)n);
-    add((void**)&s->d_a.p, a.data(), sizeof(float4) * (size_t)n); add((void**)&s->d_b.p, b.data(), sizeof(float4) * (size_t)n);
-    add((void**)&s->d_c.p, c.data(), sizeof(float4) * (size_t)n); add((void**)&s->d_d.p, d.data(), sizeof(float4) * (size_t)n);
-    add((void**)&s->d_xf.p, xf.data(), sizeof(float4) * 2 * nx); add((void**)&s->d_mats.p, mt.data(), sizeof(int4) * nm);
-    add((void**)&s->d_tex.p, tx.data(), sizeof(float4) * 2 * nt);
-    add((void**)&s->d_imgs.p, s->imgs.data(), sizeof(int4) * s->imgs.size()); add((void**)&s->d_img_texels.p, s->img_texels.data(), s->img_texels.size());
-    add((void**)&s->d_ranvec.p, rv.data(), sizeof(float4) * 256); add((void**)&s->d_perm.p, pm.data(), 768);
-    CK(s->d_tables.ensure(total));
-    if (total > s->h_tables_bytes) {
-      if (s->h_tables) cudaFreeHost(s->h_tables);
-      s->h_tables = nullptr; s->h_tables_bytes = 0;
-      CK(cudaMallocHost(&s->h_tables, total)); s->h_tables_bytes = total;
+    float4* pc = (float4*)(H + o_patches);
+    const float* src = s->patches.data();
+    for (size_t k = 0; k < np16; ++k) pc[k] = make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f);
+    if (!s->lights.empty()) std::memcpy(H + o_lights, s->lights.data(), sizeof(int) * s->lights.size());
+    int4* hdr = (int4*)(H + o_hdr); float4 *a = (float4*)(H + o_a), *b = (float4*)(H + o_b), *c = (float4*)(H + o_c), *d = (float4*)(H + o_d);
+    int* logical = (int*)(H + o_logical); float4* sh = (float4*)(H + o_shade);     // sh: per-primitive shading record (see DScene::prim_shade)
+    const float4 zero = make_float4(0, 0, 0, 0);
+    for (int i = 0; i < n; ++i) {
+      const SrtPrim& p = s->prims[i]; const float* q = p.p;
+      // aux: patch index for patches; the bits of the plane constant k for rects (saves the extend
+      // kernel a global load per rect test: the header is staged in shared memory)
+      int aux = 0;
+      if (p.type == SRT_PRIM_PATCH) aux = (int)q[0];
+      else if (p.type >= SRT_PRIM_XY_RECT && p.type <= SRT_PRIM_YZ_RECT) std::memcpy(&aux, &q[4], 4);
+      hdr[i] = make_int4(p.type | (p.flags << 8), p.material, p.xform, aux);
+      a[i] = b[i] = c[i] = d[i] = zero;
+      switch (p.type) {
+        case SRT_PRIM_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); break;
+        case SRT_PRIM_MOVING_SPHERE: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], q[5], q[6], q[7]); c[i] = make_float4(q[8], 0, 0, 0); break;
+        case SRT_PRIM_CONSTANT_MEDIUM: a[i] = make_float4(q[0], q[1], q[2], 0); break;
+        case SRT_PRIM_PATCH: { a[i] = s->patch_slabs[(size_t)q[0]]; b[i] = make_float4(q[1], q[2], q[3] > 0.f ? q[3] : 1.0f, 0); break; }
+        case SRT_PRIM_BEZIER: a[i] = make_float4(q[0], q[1], q[2], q[12]); b[i] = make_float4(q[3], q[4], q[5], 0); c[i] = make_float4(q[6], q[7], q[8], 0); d[i] = make_float4(q[9], q[10], q[11], 0); break;
+        default: a[i] = make_float4(q[0], q[1], q[2], q[3]); b[i] = make_float4(q[4], 0, 0, 0); break;
+      }
+      logical[i] = q[15] > 0.f ? (int)q[15] - 1 : i;                 // p[15] = logical id + 1, 0 = array index
+      const SrtMaterial& m = s->mats[p.material];
+      float r = 1.f, g = 1.f, bl = 1.f; int is_const = 0;
+      if (m.kind != SRT_MAT_DIELECTRIC && s->texs[m.tex].kind == SRT_TEX_CONSTANT) { const SrtTexture& t = s->texs[m.tex]; r = t.rgb[0]; g = t.rgb[1]; bl = t.rgb[2]; is_const = 1; }
+      if (m.kind == SRT_MAT_DIELECTRIC) is_const = 1;
+      float fk, ft, fc; int tex = m.tex; std::memcpy(&fk, &m.kind, 4); std::memcpy(&ft, &tex, 4); std::memcpy(&fc, &is_const, 4);
+      sh[2 * i] = make_float4(r, g, bl, m.param); sh[2 * i + 1] = make_float4(fk, ft, fc, 0.f);
     }
-    for (const Item& it : items) { if (it.bytes) std::memcpy((unsigned char*)s->h_tables + it.off, it.src, it.bytes); *it.dst = s->d_tables.p + it.off; }
+    float4 *xf = (float4*)(H + o_xf), *tx = (float4*)(H + o_tex); int4* mt = (int4*)(H + o_mats);
+    for (size_t i = 0; i < nx; ++i) { const SrtXform& x = s->xforms[i]; xf[2 * i] = make_float4(x.sin_t, x.cos_t, x.off[0], x.off[1]); xf[2 * i + 1] = make_float4(x.off[2], 0, 0, 0); }
+    for (size_t i = 0; i < nm; ++i) { const SrtMaterial& m = s->mats[i]; int pb; std::memcpy(&pb, &m.param, 4); mt[i] = make_int4(m.kind, m.tex, pb, 0); }
+    for (size_t i = 0; i < nt; ++i) {
+      const SrtTexture& t = s->texs[i]; float fk, fe, fo; std::memcpy(&fk, &t.kind, 4); std::memcpy(&fe, &t.even, 4); std::memcpy(&fo, &t.odd, 4);
+      tx[2 * i] = make_float4(fk, fe, fo, t.scale); tx[2 * i + 1] = make_float4(t.rgb[0], t.rgb[1], t.rgb[2], 0);
+    }
+    if (!s->imgs.empty()) std::memcpy(H + o_imgs, s->imgs.data(), sizeof(int4) * s->imgs.size());
+    if (!s->img_texels.empty()) std::memcpy(H + o_texels, s->img_texels.data(), s->img_texels.size());
+    float4* rv = (float4*)(H + o_ranvec); uint8_t* pm = (uint8_t*)(H + o_perm);
+    for (int i = 0; i < 256; ++i) rv[i] = s->has_perlin ? make_float4(s->ranvec[3 * i], s->ranvec[3 * i + 1], s->ranvec[3 * i + 2], 0) : zero;
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < 256; ++i) pm[256 * k + i] = s->has_perlin ? (uint8_t)(s->perm[k][i] & 255) : (uint8_t)i;
+    stamp();
     CK(cudaMemcpyAsync(s->d_tables.p, s->h_tables, total, cudaMemcpyHostToDevice, stream));
   }
   // camera (by value in kernel params)
@@ -525,9 +536,19 @@ static int commit_impl(SrtScene* s) {
   fill_dscene(s);
   // phase A: primitive AABBs on the device, read back (n x 24 B) to pick the huge primitives
   s->commit_launches = srt_lbvh_bounds(s->ds, s->dcam.time0, s->dcam.time1, B, stream);
-  std::vector<float> hb(6 * (size_t)(ns ? ns : 1));
-  if (ns) CK(cudaMemcpyAsync(hb.data(), B.d_aabb, sizeof(float) * 6 * (size_t)ns, cudaMemcpyDeviceToHost, stream));
+  // pinned scratch: [bounds 24 ns | candidate item lists + job table | per-candidate results] (sized for the worst case)
+  const size_t hs_bounds = (sizeof(float) * 6 * (size_t)(ns ? ns : 1) + 255) & ~(size_t)255;
+  const size_t hs_cand = (size_t)(SRT_MAX_GLOBAL + 1) * (((size_t)4 * (ns ? ns : 1) + 15 & ~(size_t)15) + sizeof(SrtSmallJob) + 64) + 256;
+  if (hs_bounds + hs_cand > s->h_scratch_bytes) {
+    if (s->h_scratch) cudaFreeHost(s->h_scratch);
+    s->h_scratch = nullptr; s->h_scratch_bytes = 0;
+    CK(cudaMallocHost(&s->h_scratch, hs_bounds + hs_cand)); s->h_scratch_bytes = hs_bounds + hs_cand;
+  }
+  float* hb = (float*)s->h_scratch;
+  unsigned char* hcand = (unsigned char*)s->h_scratch + hs_bounds;
+  if (ns) CK(cudaMemcpyAsync(hb, B.d_aabb, sizeof(float) * 6 * (size_t)ns, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
+  stamp();
   // Which surfaces stay OUT of the tree ("global": tested by all lanes before traversal).
   //  1. Klein primitives (no bounding box upstream) - forced.
   //  2. huge ones: extent e_i (max side of AABB i) >= 0.5 E, E = max side of the union of all boxes;
@@ -580,7 +601,7 @@ static int commit_impl(SrtScene* s) {
     s->commit_launches += srt_lbvh_build(nitems, B, stream);
     return nitems;
   };
-  int chosen = 0;
+  int chosen = 0, small_depth = -1;        // small_depth: the chosen tree's depth when the one-launch path already read it back
   const double C_LEAF = 2.0, C_GLOBAL = 0.25;
   const int nk = (int)extra.size() + 1;
   auto pick = [&](const std::vector<double>& area) {
@@ -598,45 +619,53 @@ static int commit_impl(SrtScene* s) {
     // (k_lbvh_small), into per-candidate slots of one scratch allocation; the chosen slot IS the committed tree.
     const size_t N = (size_t)n0;
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t o_items = 0, o_keys = up(o_items + 4 * N), o_order = up(o_keys + 8 * N), o_links = up(o_order + 4 * N), o_lp = up(o_links + 16 * N),
-                 o_nbox = up(o_lp + 4 * N), o_nodes = up(o_nbox + 24 * N), o_misc = up(o_nodes + 64 * N), slot = up(o_misc + 64);   // misc: area[3] f64, depth, bounds[8]
-    const size_t o_jobs = slot * (size_t)nk, bytes = o_jobs + sizeof(SrtSmallJob) * (size_t)nk;
+    // device scratch: [item lists of all candidates | job table | results (64 B per candidate: area[3] f64, depth, bounds[8])] then
+    // one slot of build buffers per candidate; the front part mirrors the pinned host block, so it goes up in ONE copy and the
+    // results come back in ONE copy
+    const size_t o_keys = 0, o_order = up(o_keys + 8 * N), o_nodes = up(o_order + 4 * N), slot = up(o_nodes + 64 * N);   // (links, leaf parents, node boxes: shared memory)
+    const size_t items_stride = up(4 * N), o_jobs = items_stride * (size_t)nk, o_res = up(o_jobs + sizeof(SrtSmallJob) * (size_t)nk),
+                 o_slots = up(o_res + 64 * (size_t)nk), bytes = o_slots + slot * (size_t)nk;
     CK(s->d_small.ensure(bytes));
     unsigned char* D = s->d_small.p;
-    std::vector<unsigned char> hblob(bytes, 0);
-    std::vector<std::vector<int>> items(nk), globs(nk);
+    std::vector<std::vector<int>> globs(nk);
+    std::vector<int> n_of(nk);
     for (int k = 0; k < nk; ++k) {
       std::vector<int> g(base); g.insert(g.end(), extra.begin(), extra.begin() + k);
       std::sort(g.begin(), g.end());
-      size_t gi = 0;
-      for (int i = 0; i < ns; ++i) { if (gi < g.size() && g[gi] == i) { ++gi; continue; } items[k].push_back(i); }
-      globs[k] = g;
-      unsigned char* S = D + slot * (size_t)k;
-      std::memcpy(hblob.data() + slot * (size_t)k + o_items, items[k].data(), sizeof(int) * items[k].size());
+      int* items = (int*)(hcand + items_stride * (size_t)k);
+      size_t gi = 0; int m = 0;
+      for (int i = 0; i < ns; ++i) { if (gi < g.size() && g[gi] == i) { ++gi; continue; } items[m++] = i; }
+      globs[k] = g; n_of[k] = m;
+      unsigned char* S = D + o_slots + slot * (size_t)k;
+      unsigned char* R = D + o_res + 64 * (size_t)k;
       SrtSmallJob J;
-      J.item_prim = (const int*)(S + o_items); J.n = (int)items[k].size();
-      J.keys = (unsigned long long*)(S + o_keys); J.order = (int*)(S + o_order); J.links = (int4*)(S + o_links); J.leaf_parent = (int*)(S + o_lp);
-      J.nbox = (float*)(S + o_nbox); J.nodes = (float4*)(S + o_nodes); J.area = (double*)(S + o_misc); J.depth = (int*)(S + o_misc + 24); J.bounds = (int*)(S + o_misc + 32);
-      std::memcpy(hblob.data() + o_jobs + sizeof(SrtSmallJob) * (size_t)k, &J, sizeof(J));
+      J.item_prim = (const int*)(D + items_stride * (size_t)k); J.n = m;
+      J.keys = (unsigned long long*)(S + o_keys); J.order = (int*)(S + o_order);
+      J.nodes = (float4*)(S + o_nodes); J.area = (double*)R; J.depth = (int*)(R + 24); J.bounds = (int*)(R + 32);
+      std::memcpy(hcand + o_jobs + sizeof(SrtSmallJob) * (size_t)k, &J, sizeof(J));
     }
-    // one H2D for the item lists + job table (the rest of the blob is scratch, its host bytes are never sent)
-    for (int k = 0; k < nk; ++k) CK(cudaMemcpyAsync(D + slot * (size_t)k + o_items, hblob.data() + slot * (size_t)k + o_items, sizeof(int) * items[k].size(), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(D + o_jobs, hblob.data() + o_jobs, sizeof(SrtSmallJob) * (size_t)nk, cudaMemcpyHostToDevice, stream));
-    s->commit_launches += srt_lbvh_build_small(B.d_aabb, (const SrtSmallJob*)(D + o_jobs), nk, stream);
-    std::vector<unsigned char> misc(64 * (size_t)nk);
-    for (int k = 0; k < nk; ++k) CK(cudaMemcpyAsync(misc.data() + 64 * (size_t)k, D + slot * (size_t)k + o_misc, 64, cudaMemcpyDeviceToHost, stream));
+    stamp();
+    CK(cudaMemcpyAsync(D, hcand, o_jobs + sizeof(SrtSmallJob) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+    if (srt_lbvh_build_small(B.d_aabb, (const SrtSmallJob*)(D + o_jobs), nk, stream) < 0) return fail(SRT_ERR_CUDA, "commit: the single-CTA LBVH build needs %d KB of shared memory", 120);
+    s->commit_launches += 1;
+    unsigned char* res = hcand + o_res;
+    CK(cudaMemcpyAsync(res, D + o_res, 64 * (size_t)nk, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    stamp();
     if (nk > 1) {
       std::vector<double> area(3 * (size_t)nk);
-      for (int k = 0; k < nk; ++k) std::memcpy(&area[3 * k], misc.data() + 64 * (size_t)k, 24);
+      for (int k = 0; k < nk; ++k) std::memcpy(&area[3 * k], res + 64 * (size_t)k, 24);
       pick(area);
     }
-    unsigned char* S = D + slot * (size_t)chosen;
-    s->global_prims = globs[chosen]; s->item_prim = items[chosen];
-    s->n_items = (int)items[chosen].size(); s->n_nodes = s->n_items - 1;
-    B.d_item_prim = (int*)(S + o_items); B.d_keys[0] = (unsigned long long*)(S + o_keys); B.d_order[0] = (int*)(S + o_order); B.sorted = 0;
-    B.d_links = (int4*)(S + o_links); B.d_leaf_parent = (int*)(S + o_lp); B.d_nbox = (float*)(S + o_nbox); B.d_nodes = (float4*)(S + o_nodes);
-    B.d_depth = (int*)(S + o_misc + 24); B.d_bounds = (int*)(S + o_misc + 32);
+    unsigned char* S = D + o_slots + slot * (size_t)chosen;
+    unsigned char* R = D + o_res + 64 * (size_t)chosen;
+    const int* items = (const int*)(hcand + items_stride * (size_t)chosen);
+    s->global_prims = globs[chosen]; s->item_prim.assign(items, items + n_of[chosen]);
+    s->n_items = n_of[chosen]; s->n_nodes = s->n_items - 1;
+    B.d_item_prim = (int*)(D + items_stride * (size_t)chosen); B.d_keys[0] = (unsigned long long*)(S + o_keys); B.d_order[0] = (int*)(S + o_order); B.sorted = 0;
+    B.d_nodes = (float4*)(S + o_nodes);
+    B.d_depth = (int*)(R + 24); B.d_bounds = (int*)(R + 32);
+    std::memcpy(&small_depth, res + 64 * (size_t)chosen + 24, sizeof(int));
   } else {
     if (!extra.empty()) {
       CK(s->d_tree_area.ensure(3 * (size_t)nk));
@@ -666,11 +695,13 @@ static int commit_impl(SrtScene* s) {
   }
   fill_dscene(s);
   CK(cudaGetLastError());
-  int depth = 0;
-  CK(cudaMemcpyAsync(&depth, B.d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  CK(cudaEventRecord(e1, stream));
-  CK(cudaEventSynchronize(e1));
-  CK(cudaEventElapsedTime(&s->ms_commit, e0, e1));
+  int depth = small_depth;
+  if (depth < 0) CK(cudaMemcpyAsync(&depth, B.d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  if (small_depth < 0) CK(cudaStreamSynchronize(stream));
+  s->ms_commit = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+  stamp();
+  if (dbg_time) std::fprintf(stderr, "[srt commit] us: validate+event %.1f | host staging %.1f | H2D + bounds + D2H %.1f | selection %.1f | H2D + build + D2H %.1f | finish %.1f (n = %d)\n",
+                             0.0, tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], n);
   s->bvh_depth = depth; s->ds.bvh_depth = depth;
   if (depth > 64) return fail(SRT_ERR_BVH_DEPTH, "LBVH depth %d exceeds the 64-level traversal bound", depth);
   if (int rc = bounds_verdict("commit")) return rc;

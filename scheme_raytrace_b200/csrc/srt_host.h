@@ -29,7 +29,7 @@ struct LbvhBuffers {
 #define SRT_SMALL_MAX_ITEMS 2048
 struct SrtSmallJob {
   const int* item_prim; int n;
-  unsigned long long* keys; int* order; int4* links; int* leaf_parent; float* nbox; float4* nodes; int* depth; double* area; int* bounds;
+  unsigned long long* keys; int* order; float4* nodes; int* depth; double* area; int* bounds;
 };
 int srt_lbvh_build_small(const float* d_aabb, const SrtSmallJob* d_jobs, int n_jobs, cudaStream_t stream);
 int srt_lbvh_bounds(const DScene& sc, float cam_t0, float cam_t1, LbvhBuffers& B, cudaStream_t stream);

@@ -72,9 +72,12 @@ __device__ __forceinline__ void accumulate_fixed(unsigned long long* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+#ifndef SRT_TILE_LOG_W
+#define SRT_TILE_LOG_W 4
+#define SRT_TILE_LOG_H 4
+#endif
 // regen: tops queue generation g up with fresh camera paths (main.scm:476-478 + camera.scm:80-92).
-// Path id -> (pixel, sample) with consecutive ids on consecutive pixels, so the appended block of
-// primary rays is coherent.  Path state: ray_o = (o, time), ray_d = (d, sample << 12 | depth),
+// Path id -> (pixel, sample): see "Path order" below.  Path state: ray_o = (o, time), ray_d = (d, sample << 12 | depth),
 // state = (throughput, pixel).
 __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, int npix, int capacity, int g, int parity,
                                                 float4* __restrict__ ray_o, float4* __restrict__ ray_d, float4* __restrict__ state,
@@ -84,20 +87,37 @@ __global__ void __launch_bounds__(256) k_regen(DCamera cam, SrtRenderParams p, i
   const int spp_begin = ctrl->spp_begin;
   unsigned long long room = (unsigned long long)(capacity - surv), left = total - next;
   const int n_new = (int)(room < left ? room : left);
-  // path id -> (sample, pixel) needs a 64-bit division (ids pass 2^32 on cfg4 / cfg5): done ONCE per thread, the
-  // grid-stride loop then advances (sample, pixel) by the precomputed quotient / remainder of its stride
+  // Path order.  Frames that divide into 16 x 16 pixel tiles: TILE-major - all samples of a tile before the next tile, inside a
+  // sample the tile's 256 pixels as eight 8 x 4 blocks - so a warp of fresh paths is an 8 x 4 block (not a 32 x 1 run) and,
+  // more important, what survives many bounces next to each other in the queue still comes from the same tile (with sample-major
+  // order the 32 survivors of a deep-bounce warp were spread over several tiles).  Other frames: sample-major scanlines.  The
+  // image does not depend on the order (Philox is keyed by (pixel, sample, bounce), the sums are integers).
+  // path id -> (outer, inner) = (tile, sample * 256 + pixel in tile) or (sample, pixel) needs a 64-bit division (ids pass 2^32 on
+  // cfg4 / cfg5): done ONCE per thread, the grid-stride loop then advances by the precomputed quotient / remainder of its stride
+  constexpr int TLW = SRT_TILE_LOG_W, TLH = SRT_TILE_LOG_H, TLP = TLW + TLH;          // tile = 2^TLW x 2^TLH pixels
+  const bool tiled = ((p.width & ((1 << TLW) - 1)) | (p.height & ((1 << TLH) - 1))) == 0;
+  const unsigned int n_samples = (unsigned int)(total / (unsigned long long)npix);
+  const unsigned int span = max(tiled ? n_samples << TLP : (unsigned int)npix, 1u);          // paths per outer unit
   const int stride = gridDim.x * blockDim.x;
-  const unsigned int s_q = (unsigned int)(stride / npix), s_r = (unsigned int)(stride % npix);
+  const unsigned int s_q = (unsigned int)stride / span, s_r = (unsigned int)stride % span;
+  const int nbx = p.width >> TLW;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int sl = 0u; int pixel = 0;
+  unsigned int outer = 0u, inner = 0u;
   if (j < n_new) {
     const unsigned long long id = next + (unsigned long long)j;
-    sl = (unsigned int)(id / (unsigned long long)npix);
-    pixel = (int)(id - (unsigned long long)sl * (unsigned long long)npix);
+    outer = (unsigned int)(id / (unsigned long long)span);
+    inner = (unsigned int)(id - (unsigned long long)outer * (unsigned long long)span);
   }
-  for (; j < n_new; j += stride, sl += s_q, pixel += (int)s_r) {
-    if (pixel >= npix) { pixel -= npix; ++sl; }
-    int y = pixel / p.width, x = pixel - y * p.width;
+  for (; j < n_new; j += stride, outer += s_q, inner += s_r) {
+    if (inner >= span) { inner -= span; ++outer; }
+    int x, y; unsigned int sl;
+    if (tiled) {
+      const int r = (int)(inner & ((1u << TLP) - 1u)), by = (int)outer / nbx, bx = (int)outer - by * nbx;
+      const int blk = r >> 5, l = r & 31, bxi = blk & ((1 << (TLW - 3)) - 1), byi = blk >> (TLW - 3);     // 8 x 4 blocks, row-major inside the tile
+      sl = inner >> TLP;
+      x = (bx << TLW) + bxi * 8 + (l & 7); y = (by << TLH) + byi * 4 + (l >> 3);
+    } else { sl = outer; y = (int)inner / p.width; x = (int)inner - y * p.width; }
+    const int pixel = y * p.width + x;
     unsigned int sample = (unsigned int)spp_begin + sl;
     RngAddr addr{p.seed, (uint32_t)pixel, sample, 0u};
     float4 xi = rng_block(addr, 0);

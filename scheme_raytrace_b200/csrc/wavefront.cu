@@ -733,7 +733,10 @@ __device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int 
   return c <= tail_max || (c <= tail_slow && 10ll * c >= 9ll * prev);
 }
 template <int MASK, int EST>
-__global__ void __launch_bounds__(EXT_THREADS, 2)
+#ifndef SRT_TAIL_CTAS
+#define SRT_TAIL_CTAS 4
+#endif
+__global__ void __launch_bounds__(EXT_THREADS, SRT_TAIL_CTAS)
 k_tail(DScene sc, SrtRenderParams p, int g, int parity, int tail_max, int tail_slow,
        const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const float4* __restrict__ state,
        unsigned long long* __restrict__ accum, WaveCtrl* __restrict__ ctrl) {

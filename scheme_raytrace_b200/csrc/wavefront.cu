@@ -727,10 +727,13 @@ k_shade(DScene sc, SrtRenderParams p, int g,
 // random-scene 3.5 % of the paths bounce inside glass until the depth limit, ~2 M paths for 40 iterations on one
 // GPU's share of an 8-GPU frame - which the kernel carries in registers, while a queue that still decays fast
 // (cfg3: -30 % per iteration) is cheaper to finish through the wavefront (measured: profiles/README.md, round 2).
+#ifndef SRT_TAIL_RATIO
+#define SRT_TAIL_RATIO 96      // percent
+#endif
 __device__ __forceinline__ bool tail_condition(const WaveCtrl* ctrl, int g, int parity, int tail_max, int tail_slow) {
   const int c = ctrl->qcount[g], prev = ctrl->qcount[g ^ 1];      // prev: the queue one iteration ago
   if (c <= 0 || ctrl->next_path[parity] < ctrl->total_paths) return false;
-  return c <= tail_max || (c <= tail_slow && 10ll * c >= 9ll * prev);
+  return c <= tail_max || (c <= tail_slow && 100ll * c >= (long long)SRT_TAIL_RATIO * prev);
 }
 template <int MASK, int EST>
 #ifndef SRT_TAIL_CTAS
@@ -1110,7 +1113,7 @@ int srt_wavefront_render(const RenderLaunch& L, WaveBuffers& W, float* d_rgb_sum
   static const long long tail_env = getenv("SRT_TAIL_MAX") ? atoll(getenv("SRT_TAIL_MAX")) : -1;
   const int tail_max = !have_tail ? 0 : (tail_env >= 0 ? (int)std::min<long long>(tail_env, 1ll << 30) : (384 << 10));
   static const long long slow_env = getenv("SRT_TAIL_SLOW") ? atoll(getenv("SRT_TAIL_SLOW")) : -1;
-  const int tail_slow = !have_tail ? 0 : (slow_env >= 0 ? (int)std::min<long long>(slow_env, 1ll << 30) : (2 << 20));
+  const int tail_slow = !have_tail ? 0 : (slow_env >= 0 ? (int)std::min<long long>(slow_env, 1ll << 30) : (16 << 20));
   auto launch_tail = [&](int g, int parity) {
     tv.fn<<<tail_grid, EXT_THREADS, tv.smem, stream>>>(L.sc, pk, g, parity, tail_max, tail_slow, W.ray_o[g], W.ray_d[g], W.state[g], W.accum64, ctrl);
     k_tail_done<<<1, 1, 0, stream>>>(g, parity, tail_max, tail_slow, ctrl);

@@ -722,11 +722,13 @@ k_shade(DScene sc, SrtRenderParams p, int g,
 // 22.7 ms, full frame 176.5 vs 173.5 ms, cfg3 29.6 vs 30.0, cfg4 equal - the fused kernel's shade phase runs
 // with the extend phase's shared-memory carve-out (211 KB of tree copies per SM, ~17 KB of L1 left for the
 // material tables) and without the oversubscribed grid that balances k_shade's tiles.)
-// Two thresholds: a queue of <= tail_max paths always goes to the tail kernel; one of <= tail_slow paths only when it
-// has stopped shrinking (>= 90 % of the previous iteration's length): those are the long-lived paths - in
-// random-scene 3.5 % of the paths bounce inside glass until the depth limit, ~2 M paths for 40 iterations on one
-// GPU's share of an 8-GPU frame - which the kernel carries in registers, while a queue that still decays fast
-// (cfg3: -30 % per iteration) is cheaper to finish through the wavefront (measured: profiles/README.md, round 2).
+// Two rules: a queue of <= tail_max paths always goes to the tail kernel; one of <= tail_slow (16 Mi) paths when it has
+// stopped shrinking (>= SRT_TAIL_RATIO % of the previous iteration's length): those are the long-lived paths - in
+// random-scene 3.5 % of the paths bounce inside glass until the depth limit, ~2 M paths per 62.5 spp for 35-40 more
+// iterations - which the kernel carries in registers, while a queue that still decays fast (cfg3: -30 % per iteration) is
+// cheaper to finish through the wavefront.  The RATIO, not the size, finds the right iteration for every share of a frame:
+// a fixed 2 Mi threshold only fitted one rank's share of an 8-GPU cfg2 frame (profiles/r2_sweep22_tail_rule.txt).
+// 4 CTAs per SM (64 registers, 88 B of spills): the kernel is latency-bound, 2 CTAs at 108 registers were 17 % slower.
 #ifndef SRT_TAIL_RATIO
 #define SRT_TAIL_RATIO 96      // percent
 #endif

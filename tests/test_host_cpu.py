@@ -164,3 +164,40 @@ def test_quirk_bits_match_header():
     hdr = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SRT_(Q\w+)\s+(\d+)", text)}
     mine = {k: v for k, v in vars(ffi).items() if re.fullmatch(r"Q\d+_\w+|QUIRKS_REFERENCE", k)}
     assert hdr == mine and mine["QUIRKS_REFERENCE"] == sum(v for k, v in mine.items() if k != "QUIRKS_REFERENCE") == 31
+
+
+def path_order(path_id, width, height, n_samples, tlw=4, tlh=4):
+    """The path order k_regen uses (csrc/wavefront.cu, "Path order"): path id -> (pixel, sample).  Frames that
+    divide into 2^tlw x 2^tlh tiles are walked tile-major (all samples of a tile, then the next tile; inside a sample the tile's
+    pixels as 8 x 4 blocks, row-major); other frames sample-major in scanlines.  Restated here as the specification the
+    kernel's index arithmetic has to meet; the frame itself cannot depend on it (tests/test_gpu_fullsize.py, additivity and
+    determinism at full size; checksums of both orders in profiles/r2_sweep17_path_order.txt)."""
+    npix = width * height
+    tiled = (width % (1 << tlw) == 0) and (height % (1 << tlh) == 0)
+    if not tiled:
+        sample, pos = divmod(path_id, npix)
+        return pos, sample
+    span = n_samples << (tlw + tlh)
+    tile, inner = divmod(path_id, span)
+    sample, r = divmod(inner, 1 << (tlw + tlh))
+    by, bx = divmod(tile, width >> tlw)
+    blk, lane = divmod(r, 32)
+    byi, bxi = divmod(blk, 1 << (tlw - 3))
+    x = (bx << tlw) + bxi * 8 + (lane & 7)
+    y = (by << tlh) + byi * 4 + (lane >> 3)
+    return y * width + x, sample
+
+
+@pytest.mark.parametrize("w,h,s", [(48, 32, 3), (64, 16, 1), (50, 30, 2), (16, 16, 5)])
+def test_path_order_is_a_bijection_and_keeps_tiles_together(w, h, s):
+    ids = np.arange(w * h * s)
+    pix, smp = np.array([path_order(int(i), w, h, s) for i in ids]).T
+    assert sorted(zip(pix.tolist(), smp.tolist())) == [(p, k) for p in range(w * h) for k in range(s)]      # every (pixel, sample) once
+    if w % 16 == 0 and h % 16 == 0:
+        x, y = pix % w, pix // w
+        for k in range(0, len(ids), 32):                                   # a warp of fresh paths: one 8 x 4 block of one sample
+            assert len(set(smp[k:k + 32])) == 1 and np.ptp(x[k:k + 32]) == 7 and np.ptp(y[k:k + 32]) == 3
+        for k in range(0, len(ids), 256 * s):                              # all samples of one 16 x 16 tile are consecutive
+            assert len(set(zip((x[k:k + 256 * s] // 16).tolist(), (y[k:k + 256 * s] // 16).tolist()))) == 1
+    else:
+        assert np.array_equal(pix, np.tile(np.arange(w * h), s))              # scanlines, sample-major
